@@ -1,0 +1,755 @@
+// Hot path 2 — 3D-memory reprojection kernels (HBM-bound gather/scatter; no tensor cores).
+//
+//   evw_plucker                 utils/plucker_embedding.py:221-255
+//   evw_equi2pers_u8            equilib.Equi2Pers (pyequilib 0.5.8), unified_loop_consistency.py:329
+//   evw_lift_depth              third_party/vggt/vggt/utils/geometry.py:12-111
+//   evw_pack_points             reproject_vggt_open3d_utils.py:286-292 (+ Open3D's f64->f32 upload)
+//   evw_conf_select             reproject_vggt_open3d_utils.py:294-310
+//   evw_splat_cubemap_equirect  reproject_vggt_open3d_utils.py:617-711 + :542-614
+//
+// The integer part of the path (pixel index, z-buffer key, winning point index, cube->equirect
+// gather index) is specified so that it is bit-reproducible: the projection uses explicit fmaf /
+// IEEE division in a fixed order and is mirrored instruction-for-instruction by oracle/reproj_oracle.c.
+#include "common.h"
+#include <math_constants.h>
+
+namespace {
+
+constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Plücker
+// ------------------------------------------------------------------------------------------
+__global__ void plucker_kernel(const float* __restrict__ ray, const float* __restrict__ c2w,
+                               float* __restrict__ out, int T, int HW) {
+  extern __shared__ float s_c2w[];  // [T,12]
+  for (int i = threadIdx.x; i < T * 12; i += blockDim.x) s_c2w[i] = c2w[i];
+  __syncthreads();
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  float dx = ray[p * 3 + 0], dy = ray[p * 3 + 1], dz = ray[p * 3 + 2];
+  for (int n = 0; n < T; ++n) {
+    const float* m = s_c2w + n * 12;
+    // same summation order as a plain i,j loop: ((R0*dx + R1*dy) + R2*dz), no contraction
+    float wx = __fadd_rn(__fadd_rn(__fmul_rn(m[0], dx), __fmul_rn(m[1], dy)), __fmul_rn(m[2], dz));
+    float wy = __fadd_rn(__fadd_rn(__fmul_rn(m[4], dx), __fmul_rn(m[5], dy)), __fmul_rn(m[6], dz));
+    float wz = __fadd_rn(__fadd_rn(__fmul_rn(m[8], dx), __fmul_rn(m[9], dy)), __fmul_rn(m[10], dz));
+    float tx = m[3], ty = m[7], tz = m[11];
+    float* o = out + (size_t)n * 6 * HW + p;
+    o[0 * (size_t)HW] = wx;
+    o[1 * (size_t)HW] = wy;
+    o[2 * (size_t)HW] = wz;
+    o[3 * (size_t)HW] = __fsub_rn(__fmul_rn(ty, wz), __fmul_rn(tz, wy));
+    o[4 * (size_t)HW] = __fsub_rn(__fmul_rn(tz, wx), __fmul_rn(tx, wz));
+    o[5 * (size_t)HW] = __fsub_rn(__fmul_rn(tx, wy), __fmul_rn(ty, wx));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Equirect -> perspective, uint8 bilinear (horizontal and vertical wrap as pyequilib's sampler)
+// ------------------------------------------------------------------------------------------
+__global__ void equi2pers_kernel(const uint8_t* __restrict__ equi, const float* __restrict__ pix2dir,
+                                 uint8_t* __restrict__ out, int C, int He, int We, int Hp, int Wp) {
+  int b = blockIdx.z;
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= Wp || y >= Hp) return;
+  const float* A = pix2dir + b * 9;
+  float fx = (float)x, fy = (float)y;
+  float mx = __fadd_rn(__fadd_rn(__fmul_rn(A[0], fx), __fmul_rn(A[1], fy)), A[2]);
+  float my = __fadd_rn(__fadd_rn(__fmul_rn(A[3], fx), __fmul_rn(A[4], fy)), A[5]);
+  float mz = __fadd_rn(__fadd_rn(__fmul_rn(A[6], fx), __fmul_rn(A[7], fy)), A[8]);
+  float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(mx, mx), __fmul_rn(my, my)), __fmul_rn(mz, mz)));
+  float phi = asinf(__fdiv_rn(mz, nrm));
+  float theta = atan2f(my, mx);
+  const float PI = 3.14159265358979323846f;
+  float ui = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(theta, PI), (float)We), __fmul_rn(2.0f, PI)), 0.5f);
+  float uj = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(phi, __fmul_rn(0.5f, PI)), (float)He), PI), 0.5f);
+  ui = fmodf(ui, (float)We);
+  if (ui < 0.f) ui = __fadd_rn(ui, (float)We);
+  uj = fmodf(uj, (float)He);
+  if (uj < 0.f) uj = __fadd_rn(uj, (float)He);
+  float x0f = floorf(ui), y0f = floorf(uj);
+  float dx = __fsub_rn(ui, x0f), dy = __fsub_rn(uj, y0f);
+  int x0 = ((int)x0f) % We, y0 = ((int)y0f) % He;
+  int x1 = (x0 + 1) % We, y1 = (y0 + 1) % He;
+  float wx0 = __fsub_rn(1.0f, dx), wy0 = __fsub_rn(1.0f, dy);
+  for (int c = 0; c < C; ++c) {
+    const uint8_t* img = equi + ((size_t)b * C + c) * He * We;
+    float q00 = img[(size_t)y0 * We + x0], q01 = img[(size_t)y0 * We + x1];
+    float q10 = img[(size_t)y1 * We + x0], q11 = img[(size_t)y1 * We + x1];
+    float top = __fadd_rn(__fmul_rn(q00, wx0), __fmul_rn(q01, dx));
+    float bot = __fadd_rn(__fmul_rn(q10, wx0), __fmul_rn(q11, dx));
+    float v = __fadd_rn(__fmul_rn(top, wy0), __fmul_rn(bot, dy));
+    v = fminf(fmaxf(v, 0.f), 255.f);
+    out[(((size_t)b * C + c) * Hp + y) * Wp + x] = (uint8_t)v;  // truncation, as astype(uint8)
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Depth lift (float64 world transform as the numpy reference)
+// ------------------------------------------------------------------------------------------
+__global__ void lift_kernel(const float* __restrict__ depth, const float* __restrict__ extr,
+                            const float* __restrict__ intr, double* __restrict__ out64,
+                            float* __restrict__ out32, int H, int W) {
+  int s = blockIdx.y;
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= H * W) return;
+  const float* E = extr + s * 12;
+  const float* K = intr + s * 9;
+  // c2w = [R^T | -R^T t]; the reference evaluates -R^T t in float32 (numpy matmul of f32 arrays)
+  float r[9], t[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r[i * 3 + j] = E[j * 4 + i];
+    float acc = __fmul_rn(E[0 * 4 + i], E[3]);
+    acc = __fadd_rn(acc, __fmul_rn(E[1 * 4 + i], E[7]));
+    acc = __fadd_rn(acc, __fmul_rn(E[2 * 4 + i], E[11]));
+    t[i] = -acc;
+  }
+  int v = p / W, u = p - v * W;
+  double d = (double)depth[(size_t)s * H * W + p];
+  // (u - cu) * depth / fu in float64, then cast to float32 (geometry.py:104-109)
+  float xc = (float)(((double)u - (double)K[2]) * d / (double)K[0]);
+  float yc = (float)(((double)v - (double)K[5]) * d / (double)K[4]);
+  float zc = (float)d;
+  double wx = ((double)xc * r[0] + (double)yc * r[1]) + (double)zc * r[2] + (double)t[0];
+  double wy = ((double)xc * r[3] + (double)yc * r[4]) + (double)zc * r[5] + (double)t[1];
+  double wz = ((double)xc * r[6] + (double)yc * r[7]) + (double)zc * r[8] + (double)t[2];
+  size_t o = ((size_t)s * H * W + p) * 3;
+  if (out64) {
+    out64[o] = wx;
+    out64[o + 1] = wy;
+    out64[o + 2] = wz;
+  }
+  if (out32) {
+    out32[o] = (float)wx;
+    out32[o + 1] = (float)wy;
+    out32[o + 2] = (float)wz;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pack {xyz, rgb} -> float4
+// ------------------------------------------------------------------------------------------
+__global__ void pack_points_kernel(const double* __restrict__ xyz64, const float* __restrict__ xyz32,
+                                   const uint8_t* __restrict__ rgb, const float* __restrict__ images,
+                                   int HW, float4* __restrict__ out, int64_t N) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float x, y, z;
+  if (xyz64) {
+    x = (float)xyz64[i * 3];
+    y = (float)xyz64[i * 3 + 1];
+    z = (float)xyz64[i * 3 + 2];
+  } else {
+    x = xyz32[i * 3];
+    y = xyz32[i * 3 + 1];
+    z = xyz32[i * 3 + 2];
+  }
+  unsigned r, g, b;
+  if (rgb) {
+    r = rgb[i * 3];
+    g = rgb[i * 3 + 1];
+    b = rgb[i * 3 + 2];
+  } else {
+    int64_t s = i / HW, p = i - s * HW;
+    const float* im = images + (size_t)s * 3 * HW + p;
+    r = (unsigned)(uint8_t)(int)__fmul_rn(im[0], 255.0f);
+    g = (unsigned)(uint8_t)(int)__fmul_rn(im[(size_t)HW], 255.0f);
+    b = (unsigned)(uint8_t)(int)__fmul_rn(im[2 * (size_t)HW], 255.0f);
+  }
+  out[i] = make_float4(x, y, z, __uint_as_float(r | (g << 8) | (b << 16)));
+}
+
+// ------------------------------------------------------------------------------------------
+// Confidence select: exact k-th order statistics by 3-pass radix select on float bits, numpy-lerp
+// threshold, then order-preserving stream compaction.
+// ------------------------------------------------------------------------------------------
+struct SelectState {
+  unsigned prefix;        // resolved high bits of the k_lo-th key
+  unsigned mask;          // which bits of prefix are resolved
+  unsigned long long k;   // remaining rank inside the current prefix bucket
+  unsigned long long cnt_le;  // #keys <= key(k_lo)
+  unsigned next_key;      // min key > key(k_lo)
+  unsigned nan_count;
+  float thr;
+  unsigned pad;
+};
+
+__device__ __forceinline__ unsigned float_key(float f) {
+  unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(unsigned k) {
+  unsigned b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+  return __uint_as_float(b);
+}
+
+__host__ __device__ constexpr int radix_bits(int pass) { return pass == 2 ? 10 : 11; }
+__host__ __device__ constexpr int radix_shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
+
+__global__ void select_init_kernel(SelectState* st, unsigned* hist, long long k_lo) {
+  for (int i = threadIdx.x; i < 3 * 2048; i += blockDim.x) hist[i] = 0;
+  if (threadIdx.x == 0) {
+    st->prefix = 0;
+    st->mask = 0;
+    st->k = (unsigned long long)k_lo;
+    st->cnt_le = 0;
+    st->next_key = 0xFFFFFFFFu;
+    st->nan_count = 0;
+    st->thr = 0.f;
+  }
+}
+
+template <int PASS>
+__global__ void select_hist_kernel(const float* __restrict__ conf, int64_t n,
+                                   const SelectState* __restrict__ st, unsigned* __restrict__ hist) {
+  __shared__ unsigned sh[2048];
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const unsigned prefix = st->prefix, mask = st->mask;
+  constexpr int shift = radix_shift(PASS);
+  constexpr unsigned dmask = (1u << radix_bits(PASS)) - 1u;
+  unsigned nan_local = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float f = conf[i];
+    if (PASS == 0 && f != f) {
+      ++nan_local;
+      continue;
+    }
+    if (f != f) continue;
+    unsigned k = float_key(f);
+    if ((k & mask) == prefix) atomicAdd(&sh[(k >> shift) & dmask], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+    if (sh[i]) atomicAdd(&hist[PASS * 2048 + i], sh[i]);
+  if (PASS == 0 && nan_local) atomicAdd(const_cast<unsigned*>(&st->nan_count), nan_local);
+}
+
+template <int PASS>
+__global__ void select_scan_kernel(SelectState* st, const unsigned* __restrict__ hist) {
+  // single thread: 2048 bins, negligible
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  constexpr int nb = 1 << radix_bits(PASS);
+  unsigned long long k = st->k, run = 0;
+  int bin = nb - 1;
+  for (int i = 0; i < nb; ++i) {
+    unsigned long long c = hist[PASS * 2048 + i];
+    if (run + c > k) {
+      bin = i;
+      break;
+    }
+    run += c;
+  }
+  st->k = k - run;
+  st->prefix |= ((unsigned)bin) << radix_shift(PASS);
+  st->mask |= ((1u << radix_bits(PASS)) - 1u) << radix_shift(PASS);
+}
+
+__global__ void select_next_kernel(const float* __restrict__ conf, int64_t n, SelectState* st) {
+  const unsigned key_a = st->prefix;
+  unsigned long long cnt = 0;
+  unsigned nxt = 0xFFFFFFFFu;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float f = conf[i];
+    if (f != f) continue;
+    unsigned k = float_key(f);
+    if (k <= key_a) ++cnt;
+    else nxt = min(nxt, k);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    nxt = min(nxt, __shfl_xor_sync(0xffffffffu, nxt, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (cnt) atomicAdd(&st->cnt_le, cnt);
+    if (nxt != 0xFFFFFFFFu) atomicMin(&st->next_key, nxt);
+  }
+}
+
+// thr = numpy _lerp(a, b, t) in float32:  a + (b-a)*t, and for t >= 0.5:  b - (b-a)*(1-t)
+__global__ void select_thr_kernel(SelectState* st, long long k_hi, float gamma, int use_threshold,
+                                  float* out_thr) {
+  if (threadIdx.x != 0) return;
+  float thr;
+  if (!use_threshold) {
+    thr = 0.0f;
+  } else if (st->nan_count) {
+    thr = CUDART_NAN_F;
+  } else {
+    float a = key_float(st->prefix);
+    float b = (st->cnt_le >= (unsigned long long)k_hi + 1ull) ? a : key_float(st->next_key);
+    float diff = __fsub_rn(b, a);
+    thr = __fadd_rn(a, __fmul_rn(diff, gamma));
+    if (gamma >= 0.5f) thr = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, gamma)));
+  }
+  st->thr = thr;
+  if (out_thr) *out_thr = thr;
+}
+
+constexpr int kCompactThreads = 256;
+constexpr int kCompactItems = 8;  // items per thread, consecutive
+constexpr int kCompactTile = kCompactThreads * kCompactItems;
+
+__global__ void compact_count_kernel(const float* __restrict__ conf, int64_t n,
+                                     const SelectState* __restrict__ st,
+                                     unsigned* __restrict__ block_counts) {
+  const float thr = st->thr;
+  int64_t base = (int64_t)blockIdx.x * kCompactTile + (int64_t)threadIdx.x * kCompactItems;
+  unsigned c = 0;
+#pragma unroll
+  for (int j = 0; j < kCompactItems; ++j) {
+    int64_t i = base + j;
+    if (i < n && conf[i] >= thr) ++c;
+  }
+  __shared__ unsigned sw[kCompactThreads / 32];
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned s = 0;
+    for (int w = 0; w < kCompactThreads / 32; ++w) s += sw[w];
+    block_counts[blockIdx.x] = s;
+  }
+}
+
+// single block exclusive scan over block_counts -> block_offsets (int64), total -> out_count
+__global__ void compact_scan_kernel(const unsigned* __restrict__ block_counts, int nblocks,
+                                    long long* __restrict__ block_offsets, long long* out_count) {
+  __shared__ long long s_part[1024];
+  const int tid = threadIdx.x;
+  const int per = (nblocks + blockDim.x - 1) / blockDim.x;
+  const int lo = tid * per, hi = min(nblocks, lo + per);
+  long long sum = 0;
+  for (int i = lo; i < hi; ++i) sum += block_counts[i];
+  s_part[tid] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    long long run = 0;
+    for (int i = 0; i < (int)blockDim.x; ++i) {
+      long long v = s_part[i];
+      s_part[i] = run;
+      run += v;
+    }
+    *out_count = run;
+  }
+  __syncthreads();
+  long long run = s_part[tid];
+  for (int i = lo; i < hi; ++i) {
+    block_offsets[i] = run;
+    run += block_counts[i];
+  }
+}
+
+__global__ void compact_scatter_kernel(const float* __restrict__ conf, const float4* __restrict__ pts,
+                                       int64_t n, const SelectState* __restrict__ st,
+                                       const long long* __restrict__ block_offsets,
+                                       float4* __restrict__ out, long long* __restrict__ keep_idx) {
+  const float thr = st->thr;
+  int64_t base = (int64_t)blockIdx.x * kCompactTile + (int64_t)threadIdx.x * kCompactItems;
+  unsigned flags = 0, c = 0;
+#pragma unroll
+  for (int j = 0; j < kCompactItems; ++j) {
+    int64_t i = base + j;
+    if (i < n && conf[i] >= thr) {
+      flags |= 1u << j;
+      ++c;
+    }
+  }
+  // block exclusive scan of c
+  __shared__ unsigned sw[kCompactThreads / 32];
+  unsigned incl = c;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) sw[warp] = incl;
+  __syncthreads();
+  unsigned woff = 0;
+  for (int w = 0; w < warp; ++w) woff += sw[w];
+  long long pos = block_offsets[blockIdx.x] + woff + (incl - c);
+#pragma unroll
+  for (int j = 0; j < kCompactItems; ++j) {
+    if (flags & (1u << j)) {
+      int64_t i = base + j;
+      if (out) out[pos] = pts[i];
+      if (keep_idx) keep_idx[pos] = i;
+      ++pos;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Splat: project every point into the 6 faces of G views, 64-bit atomicMin z-buffer
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void splat_one(const float* __restrict__ m, float x, float y, float z,
+                                          float focal, float c, float z_near, int res,
+                                          unsigned long long* __restrict__ zface, unsigned idx) {
+  float zc = fmaf(m[8], x, fmaf(m[9], y, fmaf(m[10], z, m[11])));
+  if (!(zc > z_near)) return;
+  float xc = fmaf(m[0], x, fmaf(m[1], y, fmaf(m[2], z, m[3])));
+  float yc = fmaf(m[4], x, fmaf(m[5], y, fmaf(m[6], z, m[7])));
+  float u = fmaf(focal, __fdiv_rn(xc, zc), c);
+  float v = fmaf(focal, __fdiv_rn(yc, zc), c);
+  float fres = (float)res;
+  if (!(u >= 0.f && u < fres && v >= 0.f && v < fres)) return;
+  int px = (int)floorf(u), py = (int)floorf(v);
+  unsigned long long key = ((unsigned long long)__float_as_uint(zc) << 32) | idx;
+  unsigned long long* cell = zface + (size_t)py * res + px;
+  // cheap pre-test (plain L2 read) saves most of the losing atomics
+  if (key < *((volatile unsigned long long*)cell)) atomicMin(cell, key);
+}
+
+template <int G>
+__global__ void __launch_bounds__(256)
+splat_kernel(const float4* __restrict__ pts, int64_t n_cap, const long long* __restrict__ n_dev,
+             const float* __restrict__ w2c /*[G,6,12]*/, int res, float focal, float z_near,
+             unsigned long long* __restrict__ zbuf /*[G,6,res,res]*/) {
+  __shared__ float s_m[G * 6 * 12];
+  for (int i = threadIdx.x; i < G * 72; i += blockDim.x) s_m[i] = w2c[i];
+  __syncthreads();
+  int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
+  const float c = 0.5f * (float)res;
+  const size_t face_sz = (size_t)res * res;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 p = ld_stream_f4(pts + i);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+      for (int f = 0; f < 6; ++f)
+        splat_one(s_m + (g * 6 + f) * 12, p.x, p.y, p.z, focal, c, z_near, res,
+                  zbuf + (size_t)(g * 6 + f) * face_sz, (unsigned)i);
+    }
+  }
+}
+
+// resolve: 4 output pixels per thread (12 bytes = 3 x u32 stores)
+__global__ void resolve_kernel(const unsigned long long* __restrict__ zbuf /*[6,res,res]*/,
+                               const float4* __restrict__ pts, const uint32_t* __restrict__ lut,
+                               int res, int64_t npix, uint8_t* __restrict__ out) {
+  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // quad index
+  int64_t p0 = q * 4;
+  if (p0 >= npix) return;
+  unsigned rgb[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    rgb[j] = 0;
+    int64_t p = p0 + j;
+    if (p < npix) {
+      uint32_t e = lut[p];
+      if (e != 0xFFFFFFFFu) {
+        unsigned face = e >> 28, row = (e >> 14) & 0x3FFFu, col = e & 0x3FFFu;
+        unsigned long long key = zbuf[((size_t)face * res + row) * res + col];
+        if (key != kEmptyKey) {
+          unsigned idx = (unsigned)(key & 0xFFFFFFFFull);
+          rgb[j] = __float_as_uint(__ldg(&pts[idx].w)) & 0xFFFFFFu;
+        }
+      }
+    }
+  }
+  if (p0 + 3 < npix) {
+    uint32_t w0 = rgb[0] | (rgb[1] << 24);
+    uint32_t w1 = (rgb[1] >> 8) | (rgb[2] << 16);
+    uint32_t w2 = (rgb[2] >> 16) | (rgb[3] << 8);
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + p0 * 3);  // p0*3 is a multiple of 12
+    o[0] = w0;
+    o[1] = w1;
+    o[2] = w2;
+  } else {
+    for (int j = 0; j < 4 && p0 + j < npix; ++j) {
+      out[(p0 + j) * 3 + 0] = rgb[j] & 0xFF;
+      out[(p0 + j) * 3 + 1] = (rgb[j] >> 8) & 0xFF;
+      out[(p0 + j) * 3 + 2] = (rgb[j] >> 16) & 0xFF;
+    }
+  }
+}
+
+__global__ void zbuf_to_index_kernel(const unsigned long long* __restrict__ zbuf, int64_t n,
+                                     long long* __restrict__ idx) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long k = zbuf[i];
+  idx[i] = (k == kEmptyKey) ? -1ll : (long long)(k & 0xFFFFFFFFull);
+}
+
+// face images from the z-buffer: out [6,res,res,3] u8 (HWC, as render_to_image returns)
+__global__ void zbuf_to_rgb_kernel(const unsigned long long* __restrict__ zbuf,
+                                   const float4* __restrict__ pts, int64_t n, uint8_t* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long k = zbuf[i];
+  unsigned rgb = 0;
+  if (k != kEmptyKey) rgb = __float_as_uint(__ldg(&pts[(unsigned)(k & 0xFFFFFFFFull)].w)) & 0xFFFFFFu;
+  out[i * 3 + 0] = rgb & 0xFF;
+  out[i * 3 + 1] = (rgb >> 8) & 0xFF;
+  out[i * 3 + 2] = (rgb >> 16) & 0xFF;
+}
+
+// cube faces [B,6,3,res,res] u8 (CHW per face) -> equirect [B,H,W,3] through the lookup table
+__global__ void cube_gather_kernel(const uint8_t* __restrict__ faces, const uint32_t* __restrict__ lut,
+                                   int res, int64_t npix, uint8_t* __restrict__ out) {
+  int b = blockIdx.y;
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  uint32_t e = lut[p];
+  uint8_t r = 0, g = 0, bl = 0;
+  if (e != 0xFFFFFFFFu) {
+    unsigned face = e >> 28, row = (e >> 14) & 0x3FFFu, col = e & 0x3FFFu;
+    const size_t plane = (size_t)res * res;
+    const uint8_t* f = faces + ((size_t)b * 6 + face) * 3 * plane + (size_t)row * res + col;
+    r = f[0];
+    g = f[plane];
+    bl = f[2 * plane];
+  }
+  uint8_t* o = out + ((size_t)b * npix + p) * 3;
+  o[0] = r;
+  o[1] = g;
+  o[2] = bl;
+}
+
+template <int G>
+int launch_splat(const float4* pts, int64_t n_cap, const long long* n_dev, const float* w2c, int res,
+                 float focal, float z_near, unsigned long long* zbuf, cudaStream_t st) {
+  int64_t want = (n_cap + 255) / 256;
+  int grid = (int)(want < (int64_t)evw::sm_count() * 8 ? (want > 0 ? want : 1)
+                                                         : (int64_t)evw::sm_count() * 8);
+  splat_kernel<G><<<grid, 256, 0, st>>>(pts, n_cap, n_dev, w2c, res, focal, z_near, zbuf);
+  return 0;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" int evw_plucker(const float* ray, const float* c2w, float* out, int T, int H, int W,
+                           void* stream) {
+  EVW_CHECK_ARG(ray && c2w && out, "evw_plucker: null pointer");
+  EVW_CHECK_ARG(T > 0 && H > 0 && W > 0 && T <= 4096, "evw_plucker: bad shape T=%d H=%d W=%d", T, H, W);
+  int HW = H * W;
+  plucker_kernel<<<(HW + 255) / 256, 256, T * 12 * sizeof(float), (cudaStream_t)stream>>>(
+      ray, c2w, out, T, HW);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+
+extern "C" int evw_equi2pers_u8(const uint8_t* equi, const float* pix2dir, uint8_t* out, int B, int C,
+                                int He, int We, int Hp, int Wp, void* stream) {
+  EVW_CHECK_ARG(equi && pix2dir && out, "evw_equi2pers_u8: null pointer");
+  EVW_CHECK_ARG(B > 0 && C > 0 && He > 0 && We > 0 && Hp > 0 && Wp > 0 && B <= 65535,
+                "evw_equi2pers_u8: bad shape");
+  dim3 blk(32, 8), grd((Wp + 31) / 32, (Hp + 7) / 8, B);
+  equi2pers_kernel<<<grd, blk, 0, (cudaStream_t)stream>>>(equi, pix2dir, out, C, He, We, Hp, Wp);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+
+extern "C" int evw_lift_depth(const float* depth, const float* extr, const float* intr,
+                              double* out_f64, float* out_f32, int S, int H, int W, void* stream) {
+  EVW_CHECK_ARG(depth && extr && intr, "evw_lift_depth: null pointer");
+  EVW_CHECK_ARG(out_f64 || out_f32, "evw_lift_depth: no output buffer");
+  EVW_CHECK_ARG(S > 0 && H > 0 && W > 0 && S <= 65535, "evw_lift_depth: bad shape");
+  dim3 grd((H * W + 255) / 256, S);
+  lift_kernel<<<grd, 256, 0, (cudaStream_t)stream>>>(depth, extr, intr, out_f64, out_f32, H, W);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+
+extern "C" int evw_pack_points(const double* xyz_f64, const float* xyz_f32, const uint8_t* rgb_u8,
+                               const float* images_f32, int S, int HW, float* out_pts4, int64_t N,
+                               void* stream) {
+  EVW_CHECK_ARG((xyz_f64 != nullptr) != (xyz_f32 != nullptr), "evw_pack_points: exactly one xyz source");
+  EVW_CHECK_ARG((rgb_u8 != nullptr) != (images_f32 != nullptr), "evw_pack_points: exactly one colour source");
+  EVW_CHECK_ARG(out_pts4 && N >= 0, "evw_pack_points: bad output");
+  if (images_f32) EVW_CHECK_ARG((int64_t)S * HW == N, "evw_pack_points: N != S*HW");
+  if (N == 0) return EVW_OK;
+  pack_points_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      xyz_f64, xyz_f32, rgb_u8, images_f32, HW, reinterpret_cast<float4*>(out_pts4), N);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+
+static int64_t compact_blocks(int64_t n) { return (n + kCompactTile - 1) / kCompactTile; }
+
+extern "C" int64_t evw_conf_select_workspace(int64_t n) {
+  int64_t nb = compact_blocks(n > 0 ? n : 1);
+  return 256 /*state*/ + 3 * 2048 * 4 /*hist*/ + evw::align_up(nb * 4, 256) + evw::align_up(nb * 8, 256);
+}
+
+extern "C" int evw_conf_select(const float* conf, const float* pts4_in, int64_t n, int64_t k_lo,
+                               int64_t k_hi, float gamma, int use_threshold, float* pts4_out,
+                               int64_t* keep_idx, int64_t* out_count, float* out_thr, void* workspace,
+                               int64_t workspace_bytes, void* stream) {
+  EVW_CHECK_ARG(conf && out_count && workspace, "evw_conf_select: null pointer");
+  EVW_CHECK_ARG(n > 0 && n < (1ll << 32), "evw_conf_select: n=%lld out of range", (long long)n);
+  EVW_CHECK_ARG((pts4_in == nullptr) == (pts4_out == nullptr), "evw_conf_select: pts in/out mismatch");
+  EVW_CHECK_ARG(0 <= k_lo && k_lo <= k_hi && k_hi < n, "evw_conf_select: bad ranks");
+  if (workspace_bytes < evw_conf_select_workspace(n)) {
+    evw::set_error("evw_conf_select: workspace %lld < %lld", (long long)workspace_bytes,
+                   (long long)evw_conf_select_workspace(n));
+    return EVW_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  SelectState* state = (SelectState*)ws;
+  unsigned* hist = (unsigned*)(ws + 256);
+  int64_t nb = compact_blocks(n);
+  unsigned* bcount = (unsigned*)(ws + 256 + 3 * 2048 * 4);
+  long long* boff = (long long*)((char*)bcount + evw::align_up(nb * 4, 256));
+  int grid = evw::sm_count() * 4;
+  select_init_kernel<<<1, 256, 0, st>>>(state, hist, (long long)k_lo);
+  if (use_threshold) {
+    select_hist_kernel<0><<<grid, 512, 0, st>>>(conf, n, state, hist);
+    select_scan_kernel<0><<<1, 32, 0, st>>>(state, hist);
+    select_hist_kernel<1><<<grid, 512, 0, st>>>(conf, n, state, hist);
+    select_scan_kernel<1><<<1, 32, 0, st>>>(state, hist);
+    select_hist_kernel<2><<<grid, 512, 0, st>>>(conf, n, state, hist);
+    select_scan_kernel<2><<<1, 32, 0, st>>>(state, hist);
+    select_next_kernel<<<grid, 512, 0, st>>>(conf, n, state);
+  }
+  select_thr_kernel<<<1, 32, 0, st>>>(state, (long long)k_hi, gamma, use_threshold, out_thr);
+  compact_count_kernel<<<(unsigned)nb, kCompactThreads, 0, st>>>(conf, n, state, bcount);
+  compact_scan_kernel<<<1, 1024, 0, st>>>(bcount, (int)nb, boff, (long long*)out_count);
+  compact_scatter_kernel<<<(unsigned)nb, kCompactThreads, 0, st>>>(
+      conf, reinterpret_cast<const float4*>(pts4_in), n, state, boff,
+      reinterpret_cast<float4*>(pts4_out), (long long*)keep_idx);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+
+extern "C" int64_t evw_splat_workspace(int views_per_pass, int face_res) {
+  return (int64_t)views_per_pass * 6 * face_res * face_res * 8;
+}
+
+static int splat_pass(int G, const float4* pts, int64_t n_cap, const long long* n_dev,
+                      const float* w2c, int res, float focal, float z_near,
+                      unsigned long long* zbuf, cudaStream_t st) {
+  switch (G) {
+    case 1: return launch_splat<1>(pts, n_cap, n_dev, w2c, res, focal, z_near, zbuf, st);
+    case 2: return launch_splat<2>(pts, n_cap, n_dev, w2c, res, focal, z_near, zbuf, st);
+    case 3: return launch_splat<3>(pts, n_cap, n_dev, w2c, res, focal, z_near, zbuf, st);
+    case 4: return launch_splat<4>(pts, n_cap, n_dev, w2c, res, focal, z_near, zbuf, st);
+    case 6: return launch_splat<6>(pts, n_cap, n_dev, w2c, res, focal, z_near, zbuf, st);
+    case 8: return launch_splat<8>(pts, n_cap, n_dev, w2c, res, focal, z_near, zbuf, st);
+    default: return -1;
+  }
+}
+
+extern "C" int evw_splat_cubemap_equirect(const float* pts4, int64_t n_cap, const int64_t* n_dev,
+                                          const float* w2c, int V, int face_res, float focal,
+                                          float z_near, const uint32_t* lut, int outH, int outW,
+                                          uint8_t* out, void* zbuf_workspace, int64_t workspace_bytes,
+                                          int views_per_pass, void* stream) {
+  EVW_CHECK_ARG(pts4 && w2c && lut && out && zbuf_workspace, "evw_splat_cubemap_equirect: null pointer");
+  EVW_CHECK_ARG(n_cap >= 0 && n_cap < (1ll << 32), "evw_splat_cubemap_equirect: n out of range");
+  EVW_CHECK_ARG(V > 0 && face_res > 0 && face_res <= 16383 && outH > 0 && outW > 0,
+                "evw_splat_cubemap_equirect: bad shape");
+  int G = views_per_pass;
+  EVW_CHECK_ARG(G == 1 || G == 2 || G == 3 || G == 4 || G == 6 || G == 8,
+                "evw_splat_cubemap_equirect: views_per_pass must be one of 1,2,3,4,6,8");
+  if (workspace_bytes < evw_splat_workspace(G, face_res)) {
+    evw::set_error("evw_splat_cubemap_equirect: workspace too small");
+    return EVW_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* zbuf = (unsigned long long*)zbuf_workspace;
+  const size_t view_cells = (size_t)6 * face_res * face_res;
+  const int64_t npix = (int64_t)outH * outW;
+  for (int v0 = 0; v0 < V;) {
+    int g = (V - v0 < G) ? (V - v0) : G;
+    // a short tail uses the largest supported group size <= what is left
+    while (!(g == 1 || g == 2 || g == 3 || g == 4 || g == 6 || g == 8)) --g;
+    EVW_CUDA(cudaMemsetAsync(zbuf, 0xFF, (size_t)g * view_cells * 8, st));
+    if (n_cap > 0) {
+      if (splat_pass(g, reinterpret_cast<const float4*>(pts4), n_cap, (const long long*)n_dev,
+                     w2c + (size_t)v0 * 72, face_res, focal, z_near, zbuf, st) != 0) {
+        evw::set_error("evw_splat_cubemap_equirect: internal group size");
+        return EVW_ERR_INVALID;
+      }
+    }
+    for (int j = 0; j < g; ++j) {
+      int64_t quads = (npix + 3) / 4;
+      resolve_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(
+          zbuf + (size_t)j * view_cells, reinterpret_cast<const float4*>(pts4), lut, face_res, npix,
+          out + (size_t)(v0 + j) * npix * 3);
+    }
+    v0 += g;
+  }
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+
+extern "C" int evw_splat_faces_debug(const float* pts4, int64_t n, const float* w2c, int V,
+                                     int face_res, float focal, float z_near, int64_t* win_idx,
+                                     void* zbuf_workspace, int64_t workspace_bytes, void* stream) {
+  EVW_CHECK_ARG(pts4 && w2c && win_idx && zbuf_workspace, "evw_splat_faces_debug: null pointer");
+  EVW_CHECK_ARG(n >= 0 && n < (1ll << 32) && V > 0 && face_res > 0, "evw_splat_faces_debug: bad shape");
+  if (workspace_bytes < evw_splat_workspace(1, face_res)) {
+    evw::set_error("evw_splat_faces_debug: workspace too small");
+    return EVW_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* zbuf = (unsigned long long*)zbuf_workspace;
+  const int64_t view_cells = (int64_t)6 * face_res * face_res;
+  for (int v = 0; v < V; ++v) {
+    EVW_CUDA(cudaMemsetAsync(zbuf, 0xFF, (size_t)view_cells * 8, st));
+    if (n > 0)
+      launch_splat<1>(reinterpret_cast<const float4*>(pts4), n, nullptr, w2c + (size_t)v * 72,
+                      face_res, focal, z_near, zbuf, st);
+    zbuf_to_index_kernel<<<(unsigned)((view_cells + 255) / 256), 256, 0, st>>>(
+        zbuf, view_cells, (long long*)win_idx + (size_t)v * view_cells);
+  }
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+
+extern "C" int evw_splat_faces_u8(const float* pts4, int64_t n, const float* w2c, int V, int face_res,
+                                  float focal, float z_near, uint8_t* faces_out, void* zbuf_workspace,
+                                  int64_t workspace_bytes, void* stream) {
+  EVW_CHECK_ARG(pts4 && w2c && faces_out && zbuf_workspace, "evw_splat_faces_u8: null pointer");
+  EVW_CHECK_ARG(n >= 0 && n < (1ll << 32) && V > 0 && face_res > 0, "evw_splat_faces_u8: bad shape");
+  if (workspace_bytes < evw_splat_workspace(1, face_res)) {
+    evw::set_error("evw_splat_faces_u8: workspace too small");
+    return EVW_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* zbuf = (unsigned long long*)zbuf_workspace;
+  const int64_t view_cells = (int64_t)6 * face_res * face_res;
+  for (int v = 0; v < V; ++v) {
+    EVW_CUDA(cudaMemsetAsync(zbuf, 0xFF, (size_t)view_cells * 8, st));
+    if (n > 0)
+      launch_splat<1>(reinterpret_cast<const float4*>(pts4), n, nullptr, w2c + (size_t)v * 72,
+                      face_res, focal, z_near, zbuf, st);
+    zbuf_to_rgb_kernel<<<(unsigned)((view_cells + 255) / 256), 256, 0, st>>>(
+        zbuf, reinterpret_cast<const float4*>(pts4), view_cells, faces_out + (size_t)v * view_cells * 3);
+  }
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+
+extern "C" int evw_cube_to_equirect_u8(const uint8_t* faces, const uint32_t* lut, int B, int face_res,
+                                       int outH, int outW, uint8_t* out, void* stream) {
+  EVW_CHECK_ARG(faces && lut && out, "evw_cube_to_equirect_u8: null pointer");
+  EVW_CHECK_ARG(B > 0 && B <= 65535 && face_res > 0 && face_res <= 16383 && outH > 0 && outW > 0,
+                "evw_cube_to_equirect_u8: bad shape");
+  int64_t npix = (int64_t)outH * outW;
+  dim3 grd((unsigned)((npix + 255) / 256), B);
+  cube_gather_kernel<<<grd, 256, 0, (cudaStream_t)stream>>>(faces, lut, face_res, npix, out);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}

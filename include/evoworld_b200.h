@@ -1,0 +1,129 @@
+/*
+ * evoworld_b200 — C ABI of the B200-native (sm_100a) hot paths of EvoWorld.
+ *
+ * The reference (JiahaoPlus/EvoWorld) has no FFI and no native code; every entry point below is
+ * the boundary a maintainer would bind (ctypes) underneath the named reference function.  All
+ * citations are file:line relative to the reference checkout.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name starts with `h_`;
+ *   - the caller owns every buffer (torch allocates them; pass tensor.data_ptr());
+ *   - no hidden allocation, no host synchronisation inside, work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - return value: 0 = EVW_OK, negative = error; evw_last_error() gives the message
+ *     (thread-local).  The Python shims raise RuntimeError on non-zero.
+ */
+#ifndef EVOWORLD_B200_H_
+#define EVOWORLD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVW_OK 0
+#define EVW_ERR_INVALID (-1)   /* bad argument (shape, alignment, null pointer)          */
+#define EVW_ERR_CUDA (-2)      /* a CUDA runtime / driver call failed                     */
+#define EVW_ERR_WORKSPACE (-3) /* caller-provided workspace too small                     */
+#define EVW_ERR_STATE (-4)     /* handle used before it was fully set up                  */
+
+const char* evw_last_error(void);
+/* ABI version, bumped on any signature change. */
+int evw_abi_version(void);
+/* Fills SM count / L2 bytes / compute capability (major*10+minor) of the current device. */
+int evw_device_info(int* sm_count, int64_t* l2_bytes, int* cc);
+
+/* ------------------------------------------------------------------------------------------
+ * Hot path 2 — 3D-memory reprojection
+ * ---------------------------------------------------------------------------------------- */
+
+/* Plücker embedding.  Replaces utils/plucker_embedding.py:221-255 ray_c2w_to_plucker.
+ * ray [H,W,3] f32 (camera-frame unit rays), c2w [T,3,4] f32, out [T,6,H,W] f32 contiguous:
+ * out[n,0:3] = R_n d, out[n,3:6] = t_n x (R_n d). */
+int evw_plucker(const float* ray, const float* c2w, float* out, int T, int H, int W, void* stream);
+
+/* Equirectangular -> perspective bilinear warp of uint8 images.
+ * Replaces equilib.Equi2Pers.__call__ (pyequilib 0.5.8; call site
+ * unified_loop_consistency.py:178-183,329).  equi [B,C,He,We] u8, out [B,C,Hp,Wp] u8.
+ * pix2dir [B,9] f32 row-major: M = R * G * K^-1 mapping the homogeneous output pixel (x,y,1) to a
+ * direction in equilib's global frame (x fwd, y right, z down); composed by the host shim in
+ * float64 (evoworld_b200/equi2pers.py).  phi = asin(Mz/|M|), theta = atan2(My,Mx),
+ * ui = (theta-pi) We/2pi + .5 mod We, uj = (phi-pi/2) He/pi + .5 mod He, bilinear with wrap,
+ * result truncated to uint8. */
+int evw_equi2pers_u8(const uint8_t* equi, const float* pix2dir, uint8_t* out, int B, int C, int He,
+                     int We, int Hp, int Wp, void* stream);
+
+/* Depth lift.  Replaces third_party/vggt/vggt/utils/geometry.py:12-111
+ * unproject_depth_map_to_point_map.  depth [S,H,W] f32, extr [S,3,4] f32 (cam-from-world),
+ * intr [S,3,3] f32.  Exactly one of out_f64 [S,H,W,3] / out_f32 [S,H,W,3] may be NULL. */
+int evw_lift_depth(const float* depth, const float* extr, const float* intr, double* out_f64,
+                   float* out_f32, int S, int H, int W, void* stream);
+
+/* Pack a point cloud for splatting: xyz (f64 or f32, exactly one non-NULL) [N,3] and colours.
+ * Colour source is either rgb_u8 [N,3] or images_f32 NCHW [S,3,H,W] in [0,1] (then N=S*H*W and
+ * the byte is trunc(x*255) as reproject_vggt_open3d_utils.py:286-292 _extract_colors).
+ * out: float4 per point {x,y,z, bits(r | g<<8 | b<<16)} = 16 B/point. */
+int evw_pack_points(const double* xyz_f64, const float* xyz_f32, const uint8_t* rgb_u8,
+                    const float* images_f32, int S, int HW, float* out_pts4, int64_t N,
+                    void* stream);
+
+/* Workspace bytes for evw_conf_select on n values. */
+int64_t evw_conf_select_workspace(int64_t n);
+
+/* Confidence-percentile filter + order-preserving compaction.
+ * Replaces reproject_vggt_open3d_utils.py:294-310 _apply_confidence_filter:
+ *   thr = lerp(sorted[k_lo], sorted[k_hi], gamma) (numpy 'linear' percentile; k_lo/k_hi/gamma are
+ *   computed by the host shim with numpy's own scalar arithmetic), keep = conf >= thr.
+ * use_threshold=0 keeps everything >= 0.0 (the conf_thres == 0.0 branch).
+ * pts4_in [n] float4 -> pts4_out [<=n] float4 in original order; *out_count (device int64) = kept;
+ * *out_thr (device f32) = threshold; keep_idx (optional, may be NULL) [<=n] int64 original indices. */
+int evw_conf_select(const float* conf, const float* pts4_in, int64_t n, int64_t k_lo, int64_t k_hi,
+                    float gamma, int use_threshold, float* pts4_out, int64_t* keep_idx,
+                    int64_t* out_count, float* out_thr, void* workspace, int64_t workspace_bytes,
+                    void* stream);
+
+/* Cube->equirect lookup table entry: (face<<28) | (row<<14) | col, or 0xFFFFFFFF for "no face".
+ * Built on the host by the shim with the reference's own arithmetic
+ * (reproject_vggt_open3d_utils.py:542-614) so that indices are bit-identical; see
+ * evoworld_b200/reprojection.py:build_cube_lut. */
+
+/* Z-buffer bytes needed for `views_per_pass` views of six res x res faces. */
+int64_t evw_splat_workspace(int views_per_pass, int face_res);
+
+/* Point splat + cube->equirect resolve for V target views.
+ * Replaces CubemapRenderer.render_cubemaps_to_panoramas (reproject_vggt_open3d_utils.py:668-711):
+ * 6 x V Open3D point renders (:617-666) followed by cube_to_equirectangular_cuda (:542-614).
+ *   pts4   [n_cap] float4 {x,y,z,rgb-bits};  n_dev: device int64 count (<= n_cap) or NULL => n_cap
+ *   w2c    [V,6,3,4] f32 cam-from-world per (view, face), face order front,right,back,left,top,bottom
+ *   lut    [outH,outW] u32 cube->equirect table;  out [V,outH,outW,3] u8
+ *   pixel = floor(fx*x/z+cx), nearest z wins, ties -> lowest point index, empty = 0.
+ * zbuf workspace >= evw_splat_workspace(views_per_pass, face_res). */
+int evw_splat_cubemap_equirect(const float* pts4, int64_t n_cap, const int64_t* n_dev,
+                               const float* w2c, int V, int face_res, float focal, float z_near,
+                               const uint32_t* lut, int outH, int outW, uint8_t* out,
+                               void* zbuf_workspace, int64_t workspace_bytes, int views_per_pass,
+                               void* stream);
+
+/* Same splat, but returns the raw per-face winners for parity tests:
+ * win_idx [V,6,res,res] int64 (-1 = empty). */
+int evw_splat_faces_debug(const float* pts4, int64_t n, const float* w2c, int V, int face_res,
+                          float focal, float z_near, int64_t* win_idx, void* zbuf_workspace,
+                          int64_t workspace_bytes, void* stream);
+
+/* Per-face renders (API completeness for CubemapRenderer.render_face / render_cubemap,
+ * reproject_vggt_open3d_utils.py:617-666): faces_out [V,6,res,res,3] u8 (HWC per face). */
+int evw_splat_faces_u8(const float* pts4, int64_t n, const float* w2c, int V, int face_res,
+                       float focal, float z_near, uint8_t* faces_out, void* zbuf_workspace,
+                       int64_t workspace_bytes, void* stream);
+
+/* cube_to_equirectangular_cuda (reproject_vggt_open3d_utils.py:542-614) on already rendered faces:
+ * faces [B,6,3,res,res] u8 (CHW per face, face order as above), out [B,outH,outW,3] u8. */
+int evw_cube_to_equirect_u8(const uint8_t* faces, const uint32_t* lut, int B, int face_res,
+                            int outH, int outW, uint8_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVOWORLD_B200_H_ */
