@@ -31,6 +31,9 @@ SIGNATURES = {
     "evw_splat_faces_u8": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_float, c_float, c_void_p,
                                    c_void_p, c_i64, c_void_p]),
     "evw_cube_to_equirect_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "evw_gemm_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                             C.c_char_p, c_void_p, c_int, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_int, c_float,
+                             c_void_p, c_float, c_float, c_int, c_int, c_void_p]),
     "evw_splat_faces_debug": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_float, c_float, c_void_p,
                                       c_void_p, c_i64, c_void_p]),
 }

@@ -239,23 +239,46 @@ __global__ void select_hist_kernel(const float* __restrict__ conf, int64_t n,
 }
 
 template <int PASS>
-__global__ void select_scan_kernel(SelectState* st, const unsigned* __restrict__ hist) {
-  // single thread: 2048 bins, negligible
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(1024) select_scan_kernel(SelectState* st, const unsigned* __restrict__ hist) {
+  // one block of 1024 threads, two bins per thread: find the bin that holds rank k
   constexpr int nb = 1 << radix_bits(PASS);
-  unsigned long long k = st->k, run = 0;
-  int bin = nb - 1;
-  for (int i = 0; i < nb; ++i) {
-    unsigned long long c = hist[PASS * 2048 + i];
-    if (run + c > k) {
-      bin = i;
-      break;
-    }
-    run += c;
+  __shared__ unsigned long long s_warp[32];
+  __shared__ int s_found;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long k = st->k;
+  unsigned c0 = (2 * tid < nb) ? hist[PASS * 2048 + 2 * tid] : 0u;
+  unsigned c1 = (2 * tid + 1 < nb) ? hist[PASS * 2048 + 2 * tid + 1] : 0u;
+  unsigned long long incl = (unsigned long long)c0 + c1;
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
   }
-  st->k = k - run;
-  st->prefix |= ((unsigned)bin) << radix_shift(PASS);
-  st->mask |= ((1u << radix_bits(PASS)) - 1u) << radix_shift(PASS);
+  if (lane == 31) s_warp[warp] = incl;
+  if (tid == 0) s_found = 0;
+  __syncthreads();
+  unsigned long long base = 0;
+  for (int w = 0; w < warp; ++w) base += s_warp[w];
+  unsigned long long excl = base + incl - ((unsigned long long)c0 + c1);
+  int bin = -1;
+  unsigned long long run = 0;
+  if (excl <= k && k < excl + c0) {
+    bin = 2 * tid;
+    run = excl;
+  } else if (excl + c0 <= k && k < excl + c0 + c1) {
+    bin = 2 * tid + 1;
+    run = excl + c0;
+  }
+  if (bin >= 0) {
+    s_found = 1;
+    st->k = k - run;
+    st->prefix |= ((unsigned)bin) << radix_shift(PASS);
+    st->mask |= ((1u << radix_bits(PASS)) - 1u) << radix_shift(PASS);
+  }
+  __syncthreads();
+  if (tid == 0 && !s_found) {  // rank beyond the valid (non-NaN) count: threshold becomes NaN anyway
+    st->prefix |= ((unsigned)(nb - 1)) << radix_shift(PASS);
+    st->mask |= ((1u << radix_bits(PASS)) - 1u) << radix_shift(PASS);
+  }
 }
 
 __global__ void select_next_kernel(const float* __restrict__ conf, int64_t n, SelectState* st) {
@@ -615,11 +638,11 @@ extern "C" int evw_conf_select(const float* conf, const float* pts4_in, int64_t 
   select_init_kernel<<<1, 256, 0, st>>>(state, hist, (long long)k_lo);
   if (use_threshold) {
     select_hist_kernel<0><<<grid, 512, 0, st>>>(conf, n, state, hist);
-    select_scan_kernel<0><<<1, 32, 0, st>>>(state, hist);
+    select_scan_kernel<0><<<1, 1024, 0, st>>>(state, hist);
     select_hist_kernel<1><<<grid, 512, 0, st>>>(conf, n, state, hist);
-    select_scan_kernel<1><<<1, 32, 0, st>>>(state, hist);
+    select_scan_kernel<1><<<1, 1024, 0, st>>>(state, hist);
     select_hist_kernel<2><<<grid, 512, 0, st>>>(conf, n, state, hist);
-    select_scan_kernel<2><<<1, 32, 0, st>>>(state, hist);
+    select_scan_kernel<2><<<1, 1024, 0, st>>>(state, hist);
     select_next_kernel<<<grid, 512, 0, st>>>(conf, n, state);
   }
   select_thr_kernel<<<1, 32, 0, st>>>(state, (long long)k_hi, gamma, use_threshold, out_thr);
@@ -655,7 +678,8 @@ extern "C" int evw_splat_cubemap_equirect(const float* pts4, int64_t n_cap, cons
                                           float z_near, const uint32_t* lut, int outH, int outW,
                                           uint8_t* out, void* zbuf_workspace, int64_t workspace_bytes,
                                           int views_per_pass, void* stream) {
-  EVW_CHECK_ARG(pts4 && w2c && lut && out && zbuf_workspace, "evw_splat_cubemap_equirect: null pointer");
+  EVW_CHECK_ARG((pts4 || n_cap == 0) && w2c && lut && out && zbuf_workspace,
+                "evw_splat_cubemap_equirect: null pointer");
   EVW_CHECK_ARG(n_cap >= 0 && n_cap < (1ll << 32), "evw_splat_cubemap_equirect: n out of range");
   EVW_CHECK_ARG(V > 0 && face_res > 0 && face_res <= 16383 && outH > 0 && outW > 0,
                 "evw_splat_cubemap_equirect: bad shape");

@@ -1,0 +1,498 @@
+// tcgen05 implicit-GEMM for the UNet denoise step (hot path 1): one persistent, warp-specialised
+// kernel serves every contraction of the network —
+//   nn.Linear                       (1 tap)                   diffusers attention.py / embeddings.py
+//   Conv2d 3x3 pad 1 (+1x1 shortcut) (9 taps [+1 from a second tensor])  diffusers resnet.py ResnetBlock2D
+//   Conv3d (3,1,1) pad (1,0,0)       (3 taps along T)          diffusers resnet.py TemporalResnetBlock
+// as D[m,n] = sum_{tap,k} A[m shifted by tap, k] * W[n, tap*K + k] with fp16 operands and fp32
+// accumulation in tensor memory.
+//
+//   warp 0      TMA producer: 5-D tiled loads of the activation tile (zero fill outside the image =
+//               the convolution padding) + 2-D loads of the weight tile, 128B swizzle, mbarrier ring
+//   warp 1      MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N (<=256), K=16 per instr.
+//   warp 2      TMEM allocator (512 columns = two accumulator stages)
+//   warps 4..7  epilogue: tcgen05.ld -> bias / broadcast row vector / GEGLU / scaled residuals -> global
+// The accumulator is double-buffered so the epilogue of tile i overlaps the main loop of tile i+1.
+#include "common.h"
+#include "tc_common.cuh"
+#include "tc_gemm.h"
+
+namespace evw {
+
+using namespace tc;
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // fp16 elements = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
+constexpr int kThreads = 256;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
+
+struct KernelParams {
+  GemmEpilogue ep;
+  int tiles_x, tiles_y, T, B, X, Y, bx, by;
+  int n_tiles, block_n, N;
+  int num_taps;
+  int chunks[2];
+  int8_t tap_dx[kMaxTaps], tap_dy[kMaxTaps], tap_dt[kMaxTaps], tap_src[kMaxTaps];
+  int num_stages;
+  int total_tiles;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
+  uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+// residuals may alias the output buffer (in-place update): coherent loads
+__device__ __forceinline__ void load8_plain(const float* p, float (&v)[8]) {
+  float4 a = reinterpret_cast<const float4*>(p)[0];
+  float4 b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8_plain(const __half* p, float (&v)[8]) {
+  uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
+  uint4 raw;
+  __half2* h = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = raw;
+}
+
+// epilogue for 8 consecutive output columns starting at column `n` of output row `row`
+template <typename OutT>
+__device__ __forceinline__ void epilogue8(const GemmEpilogue& ep, float (&v)[8], long long row, int n, int ldo,
+                                          long long rv_row) {
+  if (ep.s0 != 1.0f) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= ep.s0;
+  }
+  if (ep.rowvec) {
+    float r[8];
+    load8(ep.rowvec + rv_row * ldo + n, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += r[i];
+  }
+  if (ep.res1) {
+    float r[8];
+    if (ep.res1_fp16) load8_plain(reinterpret_cast<const __half*>(ep.res1) + row * ldo + n, r);
+    else load8_plain(reinterpret_cast<const float*>(ep.res1) + row * ldo + n, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(ep.s1, r[i], v[i]);
+  }
+  if (ep.res2) {
+    float r[8];
+    load8_plain(reinterpret_cast<const float*>(ep.res2) + row * ldo + n, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(ep.s2, r[i], v[i]);
+  }
+  store8(reinterpret_cast<OutT*>(ep.out) + row * ldo + n, v);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
+               const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ KernelParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stages = P.num_stages;
+  const uint32_t b_tile_bytes = (uint32_t)P.block_n * kBlockK * 2;
+  const uint32_t stage_bytes = kATileBytes + b_tile_bytes;
+  const uint32_t bar_base = smem_base + stages * stage_bytes;  // 8-byte barriers
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * stages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a0);
+    tma_prefetch_desc(&tmap_a1);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  int total_chunks = 0;
+  for (int t = 0; t < P.num_taps; ++t) total_chunks += P.chunks[P.tap_src[t]];
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % P.n_tiles;
+      int m_tile = tile / P.n_tiles;
+      const int tx = m_tile % P.tiles_x; m_tile /= P.tiles_x;
+      const int ty = m_tile % P.tiles_y; m_tile /= P.tiles_y;
+      const int tt = m_tile % P.T;
+      const int tb = m_tile / P.T;
+      const int x0 = tx * P.bx, y0 = ty * P.by, n0 = n_tile * P.block_n;
+      int kglob = 0;
+      for (int tap = 0; tap < P.num_taps; ++tap) {
+        const int src = P.tap_src[tap];
+        const CUtensorMap* ma = src ? &tmap_a1 : &tmap_a0;
+        const int cx = x0 + P.tap_dx[tap], cy = y0 + P.tap_dy[tap], ct = tt + P.tap_dt[tap];
+        for (int kc = 0; kc < P.chunks[src]; ++kc, ++kglob) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (lane == 0) {
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+            tma_load_5d(ma, sa, full_bar(stage), kc * kBlockK, cx, cy, ct, tb);
+            tma_load_2d(&tmap_b, sa + kATileBytes, full_bar(stage), kglob * kBlockK, n0);
+          }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_f16(kBlockM, P.block_n);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kAccStride;
+      for (int kc = 0; kc < total_chunks; ++kc) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint64_t da = make_desc_k_sw128(sa);
+          const uint64_t db = make_desc_k_sw128(sa + kATileBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_f16_ss(d_tmem, da + 2ull * k, db + 2ull * k, idesc, (kc | k) != 0);
+          tc_commit(empty_bar(stage));
+          if (kc == total_chunks - 1) tc_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;     // row of the 128-row tile
+    const GemmEpilogue& ep = P.ep;
+    const int ldo = ep.geglu ? P.N / 2 : P.N;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int n_tile = tile % P.n_tiles;
+      int m_tile = tile / P.n_tiles;
+      const int tx = m_tile % P.tiles_x; m_tile /= P.tiles_x;
+      const int ty = m_tile % P.tiles_y; m_tile /= P.tiles_y;
+      const int tt = m_tile % P.T;
+      const int tb = m_tile / P.T;
+      const int mx = r % P.bx, my = r / P.bx;
+      const int gx = tx * P.bx + mx, gy = ty * P.by + my;
+      const bool row_ok = gx < P.X && gy < P.Y;
+      const long long row = (((long long)tb * P.T + tt) * P.Y + gy) * P.X + gx;
+      const long long rv_row = ep.rowvec ? (row / ep.rv_div) % ep.rv_mod : 0;
+      const int n0 = n_tile * P.block_n;
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
+      for (int c = 0; c < P.block_n; c += 32) {
+        uint32_t raw[32];
+        __syncwarp();
+        if (P.block_n - c >= 32) {
+          tmem_ld_32x32b_x32(t_addr + c, raw);
+        } else {
+          uint32_t lo[16];
+          tmem_ld_32x32b_x16(t_addr + c, lo);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { raw[i] = lo[i]; raw[16 + i] = 0; }
+        }
+        tmem_ld_wait();
+        const int ncols = min(32, P.block_n - c);
+        if (!row_ok) {
+          // rows outside the image: nothing to store
+        } else if (ep.geglu) {
+          // weight rows were interleaved [16 x value | 16 x gate] per 32 columns at pack time
+          const int nh = n0 + c;  // column in the interleaved 2x space
+          const int no = nh / 2;  // first of 16 output columns
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (nh >= P.N) break;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float hv = __uint_as_float(raw[g * 8 + i]);
+              float gv = __uint_as_float(raw[16 + g * 8 + i]);
+              if (ep.bias) {
+                hv += __ldg(ep.bias + nh + g * 8 + i);
+                gv += __ldg(ep.bias + nh + 16 + g * 8 + i);
+              }
+              v[i] = hv * gelu_erf(gv);
+            }
+            if (ep.out_fp16) epilogue8<__half>(ep, v, row, no + g * 8, ldo, rv_row);
+            else epilogue8<float>(ep, v, row, no + g * 8, ldo, rv_row);
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = n0 + c + g * 8;
+            if (g * 8 >= ncols || n >= P.N) break;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[g * 8 + i]);
+            if (ep.bias) {
+              float bv[8];
+              load8(ep.bias + n, bv);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += bv[i];
+            }
+            if (ep.out_fp16) epilogue8<__half>(ep, v, row, n, ldo, rv_row);
+            else epilogue8<float>(ep, v, row, n, ldo, rv_row);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+}  // namespace
+
+int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return EVW_ERR_CUDA;
+  }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu box %u %u %u base %p", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, base);
+    return EVW_ERR_CUDA;
+  }
+  return EVW_OK;
+}
+
+static int pow2_floor(int v) {
+  int p = 1;
+  while (p * 2 <= v) p *= 2;
+  return p;
+}
+
+int gemm_plan(GemmOp* op, const GemmProblem& pr) {
+  EVW_CHECK_ARG(pr.C0 > 0 && pr.C0 % kBlockK == 0, "gemm: C0=%d must be a positive multiple of 64", pr.C0);
+  EVW_CHECK_ARG(pr.C1 % kBlockK == 0, "gemm: C1=%d must be a multiple of 64", pr.C1);
+  EVW_CHECK_ARG(pr.N > 0 && pr.N % 8 == 0, "gemm: N=%d must be a multiple of 8", pr.N);
+  EVW_CHECK_ARG(pr.num_taps >= 1 && pr.num_taps <= kMaxTaps, "gemm: bad tap count %d", pr.num_taps);
+  EVW_CHECK_ARG(pr.X > 0 && pr.Y > 0 && pr.T > 0 && pr.B > 0, "gemm: bad extents");
+  EVW_CHECK_ARG(pr.a0 && pr.w && pr.ep.out, "gemm: null operand");
+  EVW_CHECK_ARG(((uintptr_t)pr.a0 & 15) == 0 && ((uintptr_t)pr.w & 15) == 0 && ((uintptr_t)pr.ep.out & 15) == 0,
+                "gemm: operands must be 16-byte aligned");
+  KernelParams P{};
+  P.ep = pr.ep;
+  P.X = pr.X; P.Y = pr.Y; P.T = pr.T; P.B = pr.B; P.N = pr.N;
+  P.bx = pr.X >= kBlockM ? kBlockM : pow2_floor(pr.X);
+  if (pr.Y == 1) P.bx = kBlockM;  // token rows: a single 128-row strip (rows past X are zero-filled)
+  P.by = kBlockM / P.bx;
+  P.tiles_x = (pr.X + P.bx - 1) / P.bx;
+  P.tiles_y = (pr.Y + P.by - 1) / P.by;
+  int bn = pr.block_n;
+  if (bn <= 0) {
+    // largest tile width that divides N evenly among {256,160,128,...}; GEGLU needs a multiple of 32
+    const int cands[] = {256, 160, 128, 192, 96, 64, 32, 16};
+    bn = 0;
+    for (int c : cands) {
+      if (pr.N % c == 0 && (!pr.ep.geglu || c % 32 == 0)) { bn = c; break; }
+    }
+    if (bn == 0) bn = pr.ep.geglu ? 128 : (pr.N < 128 ? ((pr.N + 15) / 16) * 16 : 128);
+  }
+  EVW_CHECK_ARG(bn % 16 == 0 && bn >= 16 && bn <= 256, "gemm: BLOCK_N=%d invalid", bn);
+  EVW_CHECK_ARG(!pr.ep.geglu || (bn % 32 == 0 && pr.N % 32 == 0), "gemm: GEGLU needs N and BLOCK_N multiples of 32");
+  P.block_n = bn;
+  P.n_tiles = (pr.N + bn - 1) / bn;
+  P.num_taps = pr.num_taps;
+  P.chunks[0] = pr.C0 / kBlockK;
+  P.chunks[1] = pr.C1 / kBlockK;
+  long long ktot = 0;
+  for (int t = 0; t < pr.num_taps; ++t) {
+    P.tap_dx[t] = pr.tap_dx[t]; P.tap_dy[t] = pr.tap_dy[t]; P.tap_dt[t] = pr.tap_dt[t]; P.tap_src[t] = pr.tap_src[t];
+    EVW_CHECK_ARG(pr.tap_src[t] == 0 || (pr.tap_src[t] == 1 && pr.a1 && pr.C1 > 0), "gemm: tap %d uses a missing source", t);
+    ktot += pr.tap_src[t] ? pr.C1 : pr.C0;
+  }
+  EVW_CHECK_ARG(ktot == pr.K_total, "gemm: K_total=%lld but taps cover %lld", (long long)pr.K_total, ktot);
+  const uint32_t stage_bytes = kATileBytes + bn * kBlockK * 2;
+  int stages = (int)((227 * 1024 - 2048) / stage_bytes);
+  if (stages > 8) stages = 8;
+  P.num_stages = stages;
+  P.total_tiles = P.tiles_x * P.tiles_y * P.T * P.B * P.n_tiles;
+  op->smem_bytes = stages * stage_bytes + 8 * (2 * stages + 4) + 16 + 1024;
+  int sms = sm_count();
+  op->grid = P.total_tiles < sms ? P.total_tiles : sms;
+  static_assert(sizeof(KernelParams) <= sizeof(op->params), "GemmOp::params too small");
+  memcpy(op->params, &P, sizeof(P));
+
+  uint64_t dims[5] = {(uint64_t)pr.C0, (uint64_t)pr.X, (uint64_t)pr.Y, (uint64_t)pr.T, (uint64_t)pr.B};
+  uint64_t str[4] = {(uint64_t)pr.C0 * 2, (uint64_t)pr.C0 * 2 * pr.X, (uint64_t)pr.C0 * 2 * pr.X * pr.Y,
+                     (uint64_t)pr.C0 * 2 * pr.X * pr.Y * pr.T};
+  uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)P.bx, (uint32_t)P.by, 1, 1};
+  int rc = encode_tmap_f16(reinterpret_cast<CUtensorMap*>(op->tmap_a0), pr.a0, 5, dims, str, box);
+  if (rc) return rc;
+  if (pr.a1 && pr.C1 > 0) {
+    EVW_CHECK_ARG(((uintptr_t)pr.a1 & 15) == 0, "gemm: a1 must be 16-byte aligned");
+    dims[0] = pr.C1;
+    str[0] = (uint64_t)pr.C1 * 2; str[1] = str[0] * pr.X; str[2] = str[1] * pr.Y; str[3] = str[2] * pr.T;
+    rc = encode_tmap_f16(reinterpret_cast<CUtensorMap*>(op->tmap_a1), pr.a1, 5, dims, str, box);
+    if (rc) return rc;
+  } else {
+    memcpy(op->tmap_a1, op->tmap_a0, sizeof(op->tmap_a0));
+  }
+  uint64_t bdims[2] = {(uint64_t)pr.K_total, (uint64_t)pr.N};
+  uint64_t bstr[1] = {(uint64_t)pr.K_total * 2};
+  uint32_t bbox[2] = {(uint32_t)kBlockK, (uint32_t)bn};
+  rc = encode_tmap_f16(reinterpret_cast<CUtensorMap*>(op->tmap_b), pr.w, 2, bdims, bstr, bbox);
+  if (rc) return rc;
+  op->flops = 2.0 * pr.X * pr.Y * pr.T * pr.B * (double)pr.N * (double)pr.K_total;
+  return EVW_OK;
+}
+
+int gemm_launch(const GemmOp& op, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(tc_gemm_kernel): %s", cudaGetErrorString(e));
+      return EVW_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  KernelParams P;
+  memcpy(&P, op.params, sizeof(P));
+  tc_gemm_kernel<<<op.grid, kThreads, op.smem_bytes, stream>>>(
+      *reinterpret_cast<const CUtensorMap*>(op.tmap_a0), *reinterpret_cast<const CUtensorMap*>(op.tmap_a1),
+      *reinterpret_cast<const CUtensorMap*>(op.tmap_b), P);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("tc_gemm_kernel launch: %s", cudaGetErrorString(e));
+    return EVW_ERR_CUDA;
+  }
+  return EVW_OK;
+}
+
+}  // namespace evw
+
+// ------------------------------------------------------------------------------------------
+// C ABI: one generic entry (used by the parity tests and by Python-side micro-benchmarks)
+// ------------------------------------------------------------------------------------------
+extern "C" int evw_gemm_f16(const void* a0, const void* a1, const void* w, int B, int T, int Y, int X, int C0, int C1,
+                            int N, int num_taps, const int8_t* h_taps /*[num_taps,4] dx,dy,dt,src*/, void* out,
+                            int out_fp16, const float* bias, const float* rowvec, int64_t rv_div, int64_t rv_mod,
+                            const void* res1, int res1_fp16, float s1, const float* res2, float s2, float s0, int geglu,
+                            int block_n, void* stream) {
+  evw::GemmProblem pr{};
+  pr.a0 = a0; pr.a1 = a1; pr.w = w;
+  pr.B = B; pr.T = T; pr.Y = Y; pr.X = X; pr.C0 = C0; pr.C1 = C1; pr.N = N;
+  pr.num_taps = num_taps;
+  EVW_CHECK_ARG(num_taps >= 1 && num_taps <= evw::kMaxTaps && h_taps, "evw_gemm_f16: bad taps");
+  long long ktot = 0;
+  for (int t = 0; t < num_taps; ++t) {
+    pr.tap_dx[t] = h_taps[4 * t]; pr.tap_dy[t] = h_taps[4 * t + 1]; pr.tap_dt[t] = h_taps[4 * t + 2];
+    pr.tap_src[t] = h_taps[4 * t + 3];
+    ktot += pr.tap_src[t] ? C1 : C0;
+  }
+  pr.K_total = ktot;
+  pr.block_n = block_n;
+  pr.ep.out = out; pr.ep.out_fp16 = out_fp16; pr.ep.bias = bias; pr.ep.rowvec = rowvec;
+  pr.ep.rv_div = rv_div > 0 ? rv_div : 1; pr.ep.rv_mod = rv_mod > 0 ? rv_mod : 1;
+  pr.ep.res1 = res1; pr.ep.res1_fp16 = res1_fp16; pr.ep.s1 = s1; pr.ep.res2 = res2; pr.ep.s2 = s2; pr.ep.s0 = s0;
+  pr.ep.geglu = geglu;
+  evw::GemmOp op;
+  int rc = evw::gemm_plan(&op, pr);
+  if (rc) return rc;
+  return evw::gemm_launch(op, (cudaStream_t)stream);
+}

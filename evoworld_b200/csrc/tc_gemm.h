@@ -1,0 +1,58 @@
+// Host-side interface of the tcgen05 implicit-GEMM (tc_gemm.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+namespace evw {
+
+constexpr int kMaxTaps = 12;
+
+// out[row, n] = s0 * (acc + bias[n]) + rowvec[(row / rv_div) % rv_mod, n] + s1 * res1[row, n] + s2 * res2[row, n]
+// geglu: acc columns come in interleaved [16 value | 16 gate] groups, out has N/2 columns:
+//        out = (value + bias_v) * gelu(gate + bias_g), then the same affine tail.
+struct GemmEpilogue {
+  void* out = nullptr;
+  int out_fp16 = 1;
+  const float* bias = nullptr;
+  const float* rowvec = nullptr;
+  long long rv_div = 1, rv_mod = 1;
+  const void* res1 = nullptr;
+  int res1_fp16 = 0;
+  float s1 = 1.f;
+  const float* res2 = nullptr;
+  float s2 = 1.f;
+  float s0 = 1.f;
+  int geglu = 0;
+};
+
+// Activations are fp16 [B, T, Y, X, C] (channels last); weights fp16 [N, K_total] with
+// K_total = sum over taps of the tap's channel count, tap-major.  Rows of the output are
+// (b, t, y, x) flattened.  A tap reads the activation shifted by (dx, dy, dt); reads outside
+// [0,X) x [0,Y) x [0,T) are zero (TMA out-of-bounds fill) — the convolution padding.
+struct GemmProblem {
+  const void* a0 = nullptr;  // source 0, C0 channels
+  const void* a1 = nullptr;  // optional source 1 (1x1 shortcut input), C1 channels
+  const void* w = nullptr;
+  int B = 1, T = 1, Y = 1, X = 1, C0 = 0, C1 = 0, N = 0;
+  long long K_total = 0;
+  int num_taps = 1;
+  int8_t tap_dx[kMaxTaps] = {0}, tap_dy[kMaxTaps] = {0}, tap_dt[kMaxTaps] = {0}, tap_src[kMaxTaps] = {0};
+  int block_n = 0;  // 0 = choose
+  GemmEpilogue ep;
+};
+
+struct alignas(64) GemmOp {
+  alignas(64) unsigned char tmap_a0[128];
+  alignas(64) unsigned char tmap_a1[128];
+  alignas(64) unsigned char tmap_b[128];
+  unsigned char params[256];
+  int grid = 0;
+  int smem_bytes = 0;
+  double flops = 0;
+};
+
+int gemm_plan(GemmOp* op, const GemmProblem& pr);
+int gemm_launch(const GemmOp& op, cudaStream_t stream);
+
+}  // namespace evw

@@ -1,0 +1,60 @@
+"""Thin Python wrappers over the tensor-core / elementwise C-ABI entry points of the UNet path.
+
+These exist for the parity tests and micro-benchmarks; the denoise step itself is orchestrated in
+C++ (csrc/unet_host.cu) behind evw_unet_forward so that one call enqueues the whole network.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+CONV3x3_TAPS = [(dx, dy, 0, 0) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]  # weight [N, ky, kx, C] tap-major
+TEMPORAL_TAPS = [(0, 0, dt, 0) for dt in (-1, 0, 1)]
+LINEAR_TAPS = [(0, 0, 0, 0)]
+
+
+def gemm_f16(a0: torch.Tensor, w: torch.Tensor, taps: Sequence[Tuple[int, int, int, int]] = LINEAR_TAPS,
+             a1: Optional[torch.Tensor] = None, bias=None, rowvec=None, rv_div: int = 1, rv_mod: int = 1, res1=None,
+             s1: float = 1.0, res2=None, s2: float = 1.0, s0: float = 1.0, geglu: bool = False,
+             out_dtype=torch.float16, block_n: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a0 fp16 [B,T,Y,X,C0] (or [M,C0] for a linear layer), w fp16 [N,K_total] -> [rows, N or N/2]."""
+    _lib.require_cuda(a0, "a0")
+    if a0.dim() == 2:
+        a0 = a0[None, None, None]
+        if a1 is not None:
+            a1 = a1[None, None, None]
+    B, T, Y, X, C0 = a0.shape
+    C1 = a1.shape[-1] if a1 is not None else 0
+    N = w.shape[0]
+    rows = B * T * Y * X
+    n_out = N // 2 if geglu else N
+    if out is None:
+        out = torch.empty((rows, n_out), dtype=out_dtype, device=a0.device)
+    taps_arr = np.asarray(taps, dtype=np.int8).reshape(-1, 4)
+    assert a0.dtype == torch.float16 and w.dtype == torch.float16
+    with torch.cuda.device(a0.device):
+        _lib.check(_lib.lib().evw_gemm_f16(
+            _lib.ptr(a0), _lib.ptr(a1), _lib.ptr(w), B, T, Y, X, C0, C1, N, taps_arr.shape[0], taps_arr.tobytes(),
+            _lib.ptr(out), 1 if out.dtype == torch.float16 else 0, _lib.ptr(bias), _lib.ptr(rowvec), rv_div, rv_mod,
+            _lib.ptr(res1), 1 if (res1 is not None and res1.dtype == torch.float16) else 0, s1, _lib.ptr(res2), s2, s0,
+            1 if geglu else 0, block_n, _lib.stream_ptr(a0.device)), "evw_gemm_f16")
+    return out
+
+
+def geglu_interleave(w: torch.Tensor, b: Optional[torch.Tensor] = None):
+    """Reorder a GEGLU projection [2F, K] (= [value; gate]) into 32-row groups [16 value | 16 gate]
+    so that value and gate of the same output column land in the same accumulator tile."""
+    F2, K = w.shape
+    F = F2 // 2
+    assert F % 16 == 0
+    v, g = w[:F].reshape(F // 16, 16, K), w[F:].reshape(F // 16, 16, K)
+    wi = torch.stack([v, g], dim=1).reshape(F2, K).contiguous()
+    bi = None
+    if b is not None:
+        bi = torch.stack([b[:F].reshape(F // 16, 16), b[F:].reshape(F // 16, 16)], dim=1).reshape(F2).contiguous()
+    return wi, bi

@@ -123,6 +123,23 @@ int evw_splat_faces_u8(const float* pts4, int64_t n, const float* w2c, int V, in
 int evw_cube_to_equirect_u8(const uint8_t* faces, const uint32_t* lut, int B, int face_res,
                             int outH, int outW, uint8_t* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Hot path 1 — UNet denoise step (tensor-core kernels)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Generic tcgen05 implicit GEMM (csrc/tc_gemm.cu); the contraction behind every nn.Linear,
+ * Conv2d 3x3 (+1x1 shortcut) and Conv3d (3,1,1) of the diffusers SpatioTemporal UNet blocks that
+ * evoworld/trainer/unet_plucker.py:163-244 instantiates.
+ *   a0 fp16 [B,T,Y,X,C0] channels-last, a1 optional fp16 [B,T,Y,X,C1], w fp16 [N, K_total] tap-major,
+ *   h_taps (HOST) int8 [num_taps,4] = (dx,dy,dt,src); reads outside the tensor are zero (padding).
+ *   out[row,n] = s0*(acc+bias[n]) + rowvec[(row/rv_div)%rv_mod, n] + s1*res1[row,n] + s2*res2[row,n];
+ *   geglu: columns interleaved [16 value|16 gate], out has N/2 columns = (v+b)*gelu(g+b).
+ *   out/res1 are fp16 or fp32 (flags), bias/rowvec/res2 fp32.  C0, C1 multiples of 64; N multiple of 8. */
+int evw_gemm_f16(const void* a0, const void* a1, const void* w, int B, int T, int Y, int X, int C0, int C1,
+                 int N, int num_taps, const int8_t* h_taps, void* out, int out_fp16, const float* bias,
+                 const float* rowvec, int64_t rv_div, int64_t rv_mod, const void* res1, int res1_fp16, float s1,
+                 const float* res2, float s2, float s0, int geglu, int block_n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,132 @@
+"""tcgen05 implicit-GEMM (csrc/tc_gemm.cu) against a plain PyTorch fp32 reference of the same op
+on the same fp16-rounded operands.  Tolerance: fp32 accumulation of fp16 products -> relative L2
+<= 2e-3 for fp16 outputs (one rounding of the result), <= 2e-5 for fp32 outputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from evoworld_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+@pytest.fixture(autouse=True)
+def _seed(cuda_device, built_lib):
+    torch.manual_seed(0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 64), (1000, 320, 320), (258, 640, 1280), (4096, 1280, 160), (2, 320, 1280),
+                                   (777, 64, 16), (300, 128, 960), (512, 2560, 256)])
+@pytest.mark.parametrize("out_dtype", [torch.float16, torch.float32])
+def test_linear(M, K, N, out_dtype, cuda_device):
+    a = torch.randn(M, K, device=cuda_device).half()
+    w = (torch.randn(N, K, device=cuda_device) / K ** 0.5).half()
+    b = torch.randn(N, device=cuda_device)
+    got = ops.gemm_f16(a, w, bias=b, out_dtype=out_dtype)
+    want = a.float() @ w.float().T + b
+    assert got.shape == (M, N) and got.dtype == out_dtype
+    assert rel_l2(got, want) < (2e-3 if out_dtype == torch.float16 else 2e-5)
+
+
+@pytest.mark.parametrize("block_n", [16, 32, 64, 128, 160, 256])
+def test_linear_block_n(block_n, cuda_device):
+    M, K, N = 1500, 320, 640
+    a = torch.randn(M, K, device=cuda_device).half()
+    w = (torch.randn(N, K, device=cuda_device) / K ** 0.5).half()
+    got = ops.gemm_f16(a, w, out_dtype=torch.float32, block_n=block_n)
+    assert rel_l2(got, a.float() @ w.float().T) < 2e-5
+
+
+def test_linear_full_epilogue(cuda_device):
+    M, K, N, T, S = 2 * 3 * 50, 320, 320, 3, 50
+    a = torch.randn(M, K, device=cuda_device).half()
+    w = (torch.randn(N, K, device=cuda_device) / K ** 0.5).half()
+    b = torch.randn(N, device=cuda_device)
+    rv = torch.randn(T, N, device=cuda_device)
+    r1 = torch.randn(M, N, device=cuda_device)
+    r2 = torch.randn(M, N, device=cuda_device)
+    got = ops.gemm_f16(a, w, bias=b, rowvec=rv, rv_div=S, rv_mod=T, res1=r1, s1=0.3, res2=r2, s2=0.7, s0=0.3,
+                       out_dtype=torch.float32)
+    t_idx = (torch.arange(M, device=cuda_device) // S) % T
+    want = 0.3 * (a.float() @ w.float().T + b) + rv[t_idx] + 0.3 * r1 + 0.7 * r2
+    assert rel_l2(got, want) < 2e-5
+    # fp16 residual, in-place accumulate into the residual buffer
+    r1h = r1.half()
+    want2 = a.float() @ w.float().T + b + r1h.float()
+    buf = r1h.clone()
+    ops.gemm_f16(a, w, bias=b, res1=buf, out=buf)
+    assert rel_l2(buf, want2) < 2e-3
+
+
+@pytest.mark.parametrize("M,K,F_", [(640, 320, 1280), (100, 640, 2560)])
+def test_geglu(M, K, F_, cuda_device):
+    a = torch.randn(M, K, device=cuda_device).half()
+    w = (torch.randn(2 * F_, K, device=cuda_device) / K ** 0.5).half()
+    b = torch.randn(2 * F_, device=cuda_device)
+    wi, bi = ops.geglu_interleave(w, b)
+    got = ops.gemm_f16(a, wi, bias=bi, geglu=True, out_dtype=torch.float16)
+    h = a.float() @ w.float().T + b
+    want = h[:, :F_] * F.gelu(h[:, F_:])
+    assert got.shape == (M, F_)
+    assert rel_l2(got, want) < 2e-3
+
+
+@pytest.mark.parametrize("B,T,Y,X,C,N", [(1, 1, 8, 16, 64, 64), (2, 3, 9, 16, 128, 64), (1, 2, 18, 32, 64, 128),
+                                         (1, 2, 36, 64, 64, 64), (1, 1, 72, 128, 64, 32), (1, 2, 5, 7, 64, 64),
+                                         (1, 1, 20, 72, 64, 64)])
+def test_conv3x3(B, T, Y, X, C, N, cuda_device):
+    x = torch.randn(B * T, C, Y, X, device=cuda_device).half()
+    w = (torch.randn(N, C, 3, 3, device=cuda_device) / (9 * C) ** 0.5).half()
+    b = torch.randn(N, device=cuda_device)
+    want = F.conv2d(x.float(), w.float(), b, padding=1).permute(0, 2, 3, 1).reshape(-1, N)
+    a = x.permute(0, 2, 3, 1).reshape(B, T, Y, X, C).contiguous()
+    wk = w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()  # [N, ky, kx, C]
+    got = ops.gemm_f16(a, wk, taps=ops.CONV3x3_TAPS, bias=b, out_dtype=torch.float32)
+    assert rel_l2(got, want) < 2e-5
+
+
+def test_conv3x3_with_shortcut_and_temb(cuda_device):
+    B, T, Y, X, C, C1, N = 2, 2, 9, 16, 128, 192, 64
+    x = torch.randn(B * T, C, Y, X, device=cuda_device).half()
+    xs = torch.randn(B * T, C1, Y, X, device=cuda_device).half()
+    w = (torch.randn(N, C, 3, 3, device=cuda_device) / (9 * C) ** 0.5).half()
+    ws = (torch.randn(N, C1, 1, 1, device=cuda_device) / C1 ** 0.5).half()
+    b = torch.randn(N, device=cuda_device)
+    temb = torch.randn(B * T, N, device=cuda_device)
+    want = F.conv2d(x.float(), w.float(), b, padding=1) + F.conv2d(xs.float(), ws.float()) + temb[:, :, None, None]
+    want = want.permute(0, 2, 3, 1).reshape(-1, N)
+    a0 = x.permute(0, 2, 3, 1).reshape(B, T, Y, X, C).contiguous()
+    a1 = xs.permute(0, 2, 3, 1).reshape(B, T, Y, X, C1).contiguous()
+    wk = torch.cat([w.permute(0, 2, 3, 1).reshape(N, 9 * C), ws.reshape(N, C1)], dim=1).contiguous()
+    got = ops.gemm_f16(a0, wk, taps=ops.CONV3x3_TAPS + [(0, 0, 0, 1)], a1=a1, bias=b, rowvec=temb, rv_div=Y * X,
+                       rv_mod=B * T, out_dtype=torch.float32)
+    assert rel_l2(got, want) < 2e-5
+
+
+def test_temporal_conv(cuda_device):
+    B, T, S, C, N = 2, 5, 200, 128, 64
+    x = torch.randn(B, C, T, S, 1, device=cuda_device).half()
+    w = (torch.randn(N, C, 3, 1, 1, device=cuda_device) / (3 * C) ** 0.5).half()
+    b = torch.randn(N, device=cuda_device)
+    want = F.conv3d(x.float(), w.float(), b, padding=(1, 0, 0))  # [B,N,T,S,1]
+    want = want[..., 0].permute(0, 2, 3, 1).reshape(-1, N)
+    a = x[..., 0].permute(0, 2, 3, 1).reshape(B, T, 1, S, C).contiguous()
+    wk = w[..., 0, 0].permute(0, 2, 1).reshape(N, 3 * C).contiguous()  # [N, kt, C]
+    got = ops.gemm_f16(a, wk, taps=ops.TEMPORAL_TAPS, bias=b, out_dtype=torch.float32)
+    assert rel_l2(got, want) < 2e-5
+
+
+def test_large_persistent(cuda_device):
+    """More tiles than SMs with a long K loop: exercises ring wrap-around and both accumulator stages."""
+    M, K, N = 148 * 128 * 3 + 77, 1280, 320
+    a = torch.randn(M, K, device=cuda_device).half()
+    w = (torch.randn(N, K, device=cuda_device) / K ** 0.5).half()
+    got = ops.gemm_f16(a, w, out_dtype=torch.float16)
+    want = (a @ w.T).float()
+    assert rel_l2(got, want) < 3e-3
