@@ -1,0 +1,550 @@
+// Memory-bound kernels of the UNet denoise step (hot path 1).  Activations are channels-last
+// ([rows, C], rows = (b, t, y, x) flattened); the residual stream is fp32, GEMM operands fp16.
+//
+//   group_norm (stats + apply[+SiLU])   nn.GroupNorm(32) in ResnetBlock2D / TemporalResnetBlock /
+//                                       TransformerSpatioTemporalModel.norm / conv_norm_out  (diffusers resnet.py)
+//   layer_norm                          BasicTransformerBlock / TemporalBasicTransformerBlock norms (attention.py)
+//   temporal_attention                  TemporalBasicTransformerBlock.attn1 over T frames (K9 in SURVEY §2.3)
+//   upsample2x / downsplit              Upsample2D nearest x2, Downsample2D stride-2 phase split
+//   pre / post                          pipeline_evoworld.py:691-695 (scale + concat) and :709-714 (CFG + Euler)
+//   timestep embedding                  diffusers embeddings.py Timesteps(flip_sin_to_cos=True, shift 0)
+#include "common.h"
+#include "unet_elem.h"
+#include <cuda_fp16.h>
+
+namespace evw {
+namespace {
+
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm statistics: sum / sum of squares per (instance, group) in double
+// ------------------------------------------------------------------------------------------
+constexpr int kGnThreads = 256;
+
+template <typename T0>
+__global__ void gn_stats_kernel(const T0* __restrict__ src0, int C0, const float* __restrict__ src1, int C1,
+                                long long rows_per_inst, int rows_per_block, int groups, double* __restrict__ stats) {
+  const int inst = blockIdx.y;
+  const int C = C0 + C1;
+  const int cg = C / groups;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(rows_per_inst, r0 + rows_per_block);
+  __shared__ double s_sum[64], s_sq[64];
+  for (int i = threadIdx.x; i < groups; i += blockDim.x) { s_sum[i] = 0; s_sq[i] = 0; }
+  __syncthreads();
+  // each thread owns channels c = tid + k*blockDim (coalesced over channels)
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    if (c < C0) {
+      const T0* p = src0 + ((long long)inst * rows_per_inst + r0) * C0 + c;
+      for (long long r = r0; r < r1; ++r, p += C0) {
+        float v = (float)*p;
+        s += v;
+        q = fmaf(v, v, q);
+      }
+    } else {
+      const float* p = src1 + ((long long)inst * rows_per_inst + r0) * C1 + (c - C0);
+      for (long long r = r0; r < r1; ++r, p += C1) {
+        float v = *p;
+        s += v;
+        q = fmaf(v, v, q);
+      }
+    }
+    atomicAdd(&s_sum[c / cg], (double)s);
+    atomicAdd(&s_sq[c / cg], (double)q);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups; i += blockDim.x) {
+    atomicAdd(&stats[((long long)inst * groups + i) * 2 + 0], s_sum[i]);
+    atomicAdd(&stats[((long long)inst * groups + i) * 2 + 1], s_sq[i]);
+  }
+}
+
+// apply: 8 channels per thread
+template <typename T0>
+__global__ void gn_apply_kernel(const T0* __restrict__ src0, int C0, const float* __restrict__ src1, int C1,
+                                long long rows_total, long long rows_per_inst, int groups, float eps,
+                                const double* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int do_silu, __half* __restrict__ out,
+                                __half* __restrict__ raw_out) {
+  const int C = C0 + C1;
+  const int cv = C / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows_total * cv) return;
+  const long long row = idx / cv;
+  const int c = (int)(idx - row * cv) * 8;
+  const long long inst = row / rows_per_inst;
+  const int cg = C / groups;
+  const double cnt = (double)rows_per_inst * cg;
+  float v[8];
+  if (c < C0) {
+    const T0* p = src0 + row * C0 + c;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (float)p[i];
+  } else {
+    const float* p = src1 + row * C1 + (c - C0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = p[i];
+  }
+  if (raw_out) {
+    uint4 raw;
+    __half2* h = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(raw_out + row * C + c) = raw;
+  }
+  float o[8];
+  int g_prev = -1;
+  float mean = 0.f, rstd = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int g = (c + i) / cg;
+    if (g != g_prev) {
+      const double s = stats[(inst * groups + g) * 2], q = stats[(inst * groups + g) * 2 + 1];
+      const double m = s / cnt;
+      double var = q / cnt - m * m;
+      if (var < 0) var = 0;
+      mean = (float)m;
+      rstd = (float)(1.0 / sqrt(var + (double)eps));
+      g_prev = g;
+    }
+    float y = (v[i] - mean) * rstd * __ldg(gamma + c + i) + __ldg(beta + c + i);
+    o[i] = do_silu ? silu(y) : y;
+  }
+  uint4 raw;
+  __half2* h = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
+  *reinterpret_cast<uint4*>(out + row * C + c) = raw;
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, optional broadcast row vector added first, fp16 output
+// ------------------------------------------------------------------------------------------
+template <int MAXV>  // MAXV float4 per lane: C <= 128 * MAXV
+__global__ void layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ rowvec, long long rv_div,
+                                  long long rv_mod, long long rows, int C, float eps, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, __half* __restrict__ out) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nv = C / 4;
+  const float4* xp = reinterpret_cast<const float4*>(x + row * C);
+  const float4* rp = rowvec ? reinterpret_cast<const float4*>(rowvec + ((row / rv_div) % rv_mod) * C) : nullptr;
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + i * 32;
+    if (j < nv) {
+      v[i] = xp[j];
+      if (rp) {
+        float4 r = __ldg(rp + j);
+        v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
+      }
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + i * 32;
+    if (j < nv) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)C + eps);
+  const float4* gp = reinterpret_cast<const float4*>(gamma);
+  const float4* bp = reinterpret_cast<const float4*>(beta);
+  uint2* op = reinterpret_cast<uint2*>(out + row * C);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + i * 32;
+    if (j < nv) {
+      float4 g = __ldg(gp + j), b = __ldg(bp + j);
+      __half2 h0 = __floats2half2_rn((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+      __half2 h1 = __floats2half2_rn((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+      uint2 o2;
+      o2.x = *reinterpret_cast<uint32_t*>(&h0);
+      o2.y = *reinterpret_cast<uint32_t*>(&h1);
+      op[j] = o2;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Temporal self-attention over T <= 32 frames, head dim 64.  qkv fp16 [B*T*S, 3C] rows (b,t,s),
+// columns [q | k | v], each [heads, 64].  One (b, s, head) problem per half-warp (T <= 16) or warp.
+// Lane i owns query frame i: q in registers, K/V staged in shared memory and read as broadcasts.
+// ------------------------------------------------------------------------------------------
+constexpr int kTaWarps = 4;
+
+template <int TP>  // lanes per problem: 16 or 32
+__global__ void __launch_bounds__(kTaWarps * 32)
+temporal_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int Bn, int T, long long S, int heads,
+                     float scale_log2e) {
+  constexpr int PPW = 32 / TP;  // problems per warp
+  __shared__ __align__(16) __half s_k[kTaWarps][PPW][TP][64];
+  __shared__ __align__(16) __half s_v[kTaWarps][PPW][TP][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / TP, li = lane % TP;
+  const long long nprob = (long long)Bn * S * heads;
+  const long long prob0 = ((long long)blockIdx.x * kTaWarps + warp) * PPW;
+  const int C = heads * 64;
+  const long long ld = 3LL * C;
+  // cooperative K/V load: for each problem of this warp, T rows x 128 B; 8 lanes per row
+  for (int pp = 0; pp < PPW; ++pp) {
+    const long long prob = prob0 + pp;
+    if (prob >= nprob) break;
+    const int h = (int)(prob % heads);
+    const long long bs = prob / heads;
+    const long long s = bs % S, b = bs / S;
+    for (int t = lane >> 3; t < T; t += 4) {
+      const long long row = ((long long)b * T + t) * S + s;
+      const uint4* kp = reinterpret_cast<const uint4*>(qkv + row * ld + C + h * 64) + (lane & 7);
+      const uint4* vp = reinterpret_cast<const uint4*>(qkv + row * ld + 2 * C + h * 64) + (lane & 7);
+      reinterpret_cast<uint4*>(&s_k[warp][pp][t][0])[lane & 7] = __ldg(kp);
+      reinterpret_cast<uint4*>(&s_v[warp][pp][t][0])[lane & 7] = __ldg(vp);
+    }
+  }
+  __syncwarp();
+  const long long prob = prob0 + sub;
+  if (prob >= nprob || li >= T) return;
+  const int h = (int)(prob % heads);
+  const long long bs = prob / heads;
+  const long long s = bs % S, b = bs / S;
+  const long long qrow = ((long long)b * T + li) * S + s;
+  __half2 q[32];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(qkv + qrow * ld + h * 64);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint4 r = __ldg(qp + i);
+      q[4 * i + 0] = *reinterpret_cast<__half2*>(&r.x);
+      q[4 * i + 1] = *reinterpret_cast<__half2*>(&r.y);
+      q[4 * i + 2] = *reinterpret_cast<__half2*>(&r.z);
+      q[4 * i + 3] = *reinterpret_cast<__half2*>(&r.w);
+    }
+  }
+  float sc[TP];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < TP; ++j) {
+    sc[j] = -INFINITY;
+    if (j < T) {
+      const __half2* kj = reinterpret_cast<const __half2*>(&s_k[warp][sub][j][0]);
+      float acc = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) {
+        float2 a = __half22float2(q[d]), kk = __half22float2(kj[d]);
+        acc = fmaf(a.x, kk.x, acc);
+        acc = fmaf(a.y, kk.y, acc);
+      }
+      sc[j] = acc * scale_log2e;
+      mx = fmaxf(mx, sc[j]);
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < TP; ++j) {
+    sc[j] = (j < T) ? exp2f(sc[j] - mx) : 0.f;
+    sum += sc[j];
+  }
+  const float inv = 1.0f / sum;
+  float o[64];
+#pragma unroll
+  for (int d = 0; d < 64; ++d) o[d] = 0.f;
+#pragma unroll
+  for (int j = 0; j < TP; ++j) {
+    if (j < T) {
+      const __half2* vj = reinterpret_cast<const __half2*>(&s_v[warp][sub][j][0]);
+      const float p = sc[j] * inv;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) {
+        float2 vv = __half22float2(vj[d]);
+        o[2 * d] = fmaf(p, vv.x, o[2 * d]);
+        o[2 * d + 1] = fmaf(p, vv.y, o[2 * d + 1]);
+      }
+    }
+  }
+  uint4* op = reinterpret_cast<uint4*>(out + qrow * C + h * 64);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint4 r;
+    __half2 h0 = __floats2half2_rn(o[8 * i + 0], o[8 * i + 1]), h1 = __floats2half2_rn(o[8 * i + 2], o[8 * i + 3]);
+    __half2 h2 = __floats2half2_rn(o[8 * i + 4], o[8 * i + 5]), h3 = __floats2half2_rn(o[8 * i + 6], o[8 * i + 7]);
+    r.x = *reinterpret_cast<uint32_t*>(&h0);
+    r.y = *reinterpret_cast<uint32_t*>(&h1);
+    r.z = *reinterpret_cast<uint32_t*>(&h2);
+    r.w = *reinterpret_cast<uint32_t*>(&h3);
+    op[i] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// nearest x2 upsample (fp32 [n,h,w,C] -> fp16 [n,2h,2w,C]) and stride-2 phase split
+// (fp32 [n,h,w,C] -> fp16 [n*4, h/2, w/2, C], image index n*4 + (y&1)*2 + (x&1))
+// ------------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const float* __restrict__ x, __half* __restrict__ out, long long n, int h, int w, int C) {
+  const int cv = C / 8;
+  const long long total = n * (2LL * h) * (2LL * w) * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % cv) * 8;
+  long long p = idx / cv;
+  const int ox = (int)(p % (2 * w)); p /= 2 * w;
+  const int oy = (int)(p % (2 * h));
+  const long long img = p / (2 * h);
+  const float* src = x + ((img * h + oy / 2) * w + ox / 2) * C + c;
+  float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+  uint4 r;
+  __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w), h2 = __floats2half2_rn(b.x, b.y),
+          h3 = __floats2half2_rn(b.z, b.w);
+  r.x = *reinterpret_cast<uint32_t*>(&h0); r.y = *reinterpret_cast<uint32_t*>(&h1);
+  r.z = *reinterpret_cast<uint32_t*>(&h2); r.w = *reinterpret_cast<uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(out + ((img * 2 * h + oy) * 2 * w + ox) * C + c) = r;
+}
+
+__global__ void downsplit_kernel(const float* __restrict__ x, __half* __restrict__ out, long long n, int h, int w, int C) {
+  const int cv = C / 8;
+  const int h2 = (h + 1) / 2, w2 = (w + 1) / 2;
+  const long long total = n * 4 * (long long)h2 * w2 * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % cv) * 8;
+  long long p = idx / cv;
+  const int x2 = (int)(p % w2); p /= w2;
+  const int y2 = (int)(p % h2); p /= h2;
+  const int ph = (int)(p % 4);
+  const long long img = p / 4;
+  const int iy = 2 * y2 + (ph >> 1), ix = 2 * x2 + (ph & 1);
+  uint4 r = make_uint4(0, 0, 0, 0);
+  if (iy < h && ix < w) {
+    const float* src = x + ((img * h + iy) * w + ix) * C + c;
+    float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+    __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w), h2_ = __floats2half2_rn(b.x, b.y),
+            h3 = __floats2half2_rn(b.z, b.w);
+    r.x = *reinterpret_cast<uint32_t*>(&h0); r.y = *reinterpret_cast<uint32_t*>(&h1);
+    r.z = *reinterpret_cast<uint32_t*>(&h2_); r.w = *reinterpret_cast<uint32_t*>(&h3);
+  }
+  *reinterpret_cast<uint4*>(out + idx * 8) = r;
+}
+
+// ------------------------------------------------------------------------------------------
+// pre: latents [1,T,4,h,w] fp32 (NCHW per frame) / sqrt(sigma^2+1), duplicated for CFG, concatenated
+// with cond [2,T,Cc,h,w] -> fp16 channels-last [2*T, h, w, Cpad] (zero padded to Cpad)
+// ------------------------------------------------------------------------------------------
+__global__ void pre_kernel(const float* __restrict__ latents, const float* __restrict__ cond, int Bc, int T, int Cl,
+                           int Cc, long long HW, float inv_scale, int Cpad, __half* __restrict__ out) {
+  const long long total = (long long)Bc * T * HW;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long p = idx % HW;
+  const long long f = idx / HW;  // frame in the CFG batch: b*T + t
+  const int t = (int)(f % T);
+  __half* o = out + idx * Cpad;
+  for (int c = 0; c < Cl; ++c) o[c] = __float2half_rn(latents[((long long)t * Cl + c) * HW + p] * inv_scale);
+  for (int c = 0; c < Cc; ++c) o[Cl + c] = __float2half_rn(cond[(f * Cc + c) * HW + p]);
+  for (int c = Cl + Cc; c < Cpad; ++c) o[c] = __float2half_rn(0.f);
+}
+
+// raw sample [B,T,Cin,h,w] fp32 -> fp16 channels-last padded (UNet.forward called on its own)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, long long frames, int Cin, long long HW, int Cpad,
+                                    __half* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= frames * HW) return;
+  const long long p = idx % HW, f = idx / HW;
+  __half* o = out + idx * Cpad;
+  for (int c = 0; c < Cin; ++c) o[c] = __float2half_rn(x[(f * Cin + c) * HW + p]);
+  for (int c = Cin; c < Cpad; ++c) o[c] = __float2half_rn(0.f);
+}
+
+// model output fp32 channels-last [2*T, h, w, Npad] -> NCHW [B,T,Co,h,w]
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ y, long long frames, int Co, long long HW, int Npad,
+                                    float* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= frames * HW) return;
+  const long long p = idx % HW, f = idx / HW;
+  for (int c = 0; c < Co; ++c) out[(f * Co + c) * HW + p] = y[idx * Npad + c];
+}
+
+// post: CFG combine + Euler (v-prediction) step on NCHW latents, reading the channels-last model output
+//   v = vu + g_t (vc - vu);  x0 = v * (-sigma / sqrt(sigma^2+1)) + x / (sigma^2+1);  d = (x - x0)/sigma;
+//   x' = x + d (sigma_next - sigma)
+__global__ void post_kernel(const float* __restrict__ y, int T, int Cl, long long HW, int Npad, float sigma,
+                            float sigma_next, float g_min, float g_max, float* __restrict__ latents) {
+  const long long total = (long long)T * HW;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long p = idx % HW;
+  const int t = (int)(idx / HW);
+  const float g = (T > 1) ? g_min + (g_max - g_min) * ((float)t / (float)(T - 1)) : g_min;
+  const float c_out = -sigma / sqrtf(sigma * sigma + 1.0f);
+  const float c_skip = 1.0f / (sigma * sigma + 1.0f);
+  const float* yu = y + idx * Npad;
+  const float* yc = y + ((long long)T * HW + idx) * Npad;
+  for (int c = 0; c < Cl; ++c) {
+    const float vu = yu[c], vc = yc[c];
+    const float v = vu + g * (vc - vu);
+    float* lp = latents + ((long long)t * Cl + c) * HW + p;
+    const float x = *lp;
+    const float x0 = v * c_out + x * c_skip;
+    const float d = (x - x0) / sigma;
+    *lp = x + d * (sigma_next - sigma);
+  }
+}
+
+// sinusoidal timestep embedding (flip_sin_to_cos=True, downscale_freq_shift=0): out [n, dim] fp16 = [cos | sin]
+__global__ void timestep_embed_kernel(const float* __restrict__ t, int n, int dim, __half* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (idx >= n * half) return;
+  const int i = idx / half, k = idx % half;
+  const float f = expf(-logf(10000.0f) * (float)k / (float)half);
+  const float a = t[i] * f;
+  out[(long long)i * dim + k] = __float2half_rn(cosf(a));
+  out[(long long)i * dim + half + k] = __float2half_rn(sinf(a));
+}
+
+// y = silu(x) (fp32 -> fp16), used on the time embedding before every time_emb_proj
+__global__ void silu_f16_kernel(const float* __restrict__ x, __half* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(silu(x[i]));
+}
+__global__ void cast_f16_kernel(const float* __restrict__ x, __half* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(x[i]);
+}
+__global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
+inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace
+
+// ==========================================================================================
+// host launchers
+// ==========================================================================================
+int group_norm(const void* src0, int src0_fp16, int C0, const float* src1, int C1, long long insts,
+               long long rows_per_inst, float eps, const float* gamma, const float* beta, int do_silu, double* stats,
+               __half* out, __half* raw_out, cudaStream_t st) {
+  const int C = C0 + C1, groups = 32;
+  EVW_CHECK_ARG(C % groups == 0 && C % 8 == 0 && C0 % 8 == 0, "group_norm: C=%d (C0=%d) not supported", C, C0);
+  EVW_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * insts, st));
+  // enough blocks per instance to fill the machine, >= 8 rows per block
+  long long want_blocks = (long long)sm_count() * 4 / (insts > 0 ? insts : 1) + 1;
+  int rpb = (int)((rows_per_inst + want_blocks - 1) / want_blocks);
+  if (rpb < 8) rpb = 8;
+  dim3 grid((unsigned)((rows_per_inst + rpb - 1) / rpb), (unsigned)insts);
+  if (src0_fp16)
+    gn_stats_kernel<__half><<<grid, kGnThreads, 0, st>>>((const __half*)src0, C0, src1, C1, rows_per_inst, rpb, groups, stats);
+  else
+    gn_stats_kernel<float><<<grid, kGnThreads, 0, st>>>((const float*)src0, C0, src1, C1, rows_per_inst, rpb, groups, stats);
+  const long long rows_total = insts * rows_per_inst;
+  const long long n = rows_total * (C / 8);
+  if (src0_fp16)
+    gn_apply_kernel<__half><<<blocks_for(n, 256), 256, 0, st>>>((const __half*)src0, C0, src1, C1, rows_total, rows_per_inst,
+                                                                 groups, eps, stats, gamma, beta, do_silu, out, raw_out);
+  else
+    gn_apply_kernel<float><<<blocks_for(n, 256), 256, 0, st>>>((const float*)src0, C0, src1, C1, rows_total, rows_per_inst,
+                                                                groups, eps, stats, gamma, beta, do_silu, out, raw_out);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+
+int layer_norm(const float* x, const float* rowvec, long long rv_div, long long rv_mod, long long rows, int C, float eps,
+               const float* gamma, const float* beta, __half* out, cudaStream_t st) {
+  EVW_CHECK_ARG(C % 4 == 0 && C <= 128 * 20, "layer_norm: C=%d not supported", C);
+  const int warps = 8;
+  const unsigned grid = (unsigned)((rows + warps - 1) / warps);
+  if (C <= 128 * 5)
+    layer_norm_kernel<5><<<grid, warps * 32, 0, st>>>(x, rowvec, rv_div, rv_mod, rows, C, eps, gamma, beta, out);
+  else if (C <= 128 * 10)
+    layer_norm_kernel<10><<<grid, warps * 32, 0, st>>>(x, rowvec, rv_div, rv_mod, rows, C, eps, gamma, beta, out);
+  else
+    layer_norm_kernel<20><<<grid, warps * 32, 0, st>>>(x, rowvec, rv_div, rv_mod, rows, C, eps, gamma, beta, out);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+
+int temporal_attention(const __half* qkv, __half* out, int B, int T, long long S, int heads, cudaStream_t st) {
+  EVW_CHECK_ARG(T >= 1 && T <= 32, "temporal_attention: T=%d must be in [1,32]", T);
+  const float scale_log2e = 0.125f * 1.4426950408889634f;  // head dim 64
+  const long long nprob = (long long)B * S * heads;
+  if (T <= 16) {
+    const long long per_block = kTaWarps * 2;
+    temporal_attn_kernel<16><<<(unsigned)((nprob + per_block - 1) / per_block), kTaWarps * 32, 0, st>>>(
+        qkv, out, B, T, S, heads, scale_log2e);
+  } else {
+    const long long per_block = kTaWarps;
+    temporal_attn_kernel<32><<<(unsigned)((nprob + per_block - 1) / per_block), kTaWarps * 32, 0, st>>>(
+        qkv, out, B, T, S, heads, scale_log2e);
+  }
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+
+int upsample2x(const float* x, __half* out, long long n, int h, int w, int C, cudaStream_t st) {
+  EVW_CHECK_ARG(C % 8 == 0, "upsample2x: C %% 8");
+  upsample2x_kernel<<<blocks_for(n * 4LL * h * w * (C / 8), 256), 256, 0, st>>>(x, out, n, h, w, C);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+int downsplit(const float* x, __half* out, long long n, int h, int w, int C, cudaStream_t st) {
+  EVW_CHECK_ARG(C % 8 == 0, "downsplit: C %% 8");
+  downsplit_kernel<<<blocks_for(n * 4LL * ((h + 1) / 2) * ((w + 1) / 2) * (C / 8), 256), 256, 0, st>>>(x, out, n, h, w, C);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+int pre_concat(const float* latents, const float* cond, int Bc, int T, int Cl, int Cc, long long HW, float sigma, int Cpad,
+               __half* out, cudaStream_t st) {
+  const float inv = 1.0f / sqrtf(sigma * sigma + 1.0f);
+  pre_kernel<<<blocks_for((long long)Bc * T * HW, 256), 256, 0, st>>>(latents, cond, Bc, T, Cl, Cc, HW, inv, Cpad, out);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+int nchw_to_nhwc_f16(const float* x, long long frames, int Cin, long long HW, int Cpad, __half* out, cudaStream_t st) {
+  nchw_to_nhwc_kernel<<<blocks_for(frames * HW, 256), 256, 0, st>>>(x, frames, Cin, HW, Cpad, out);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+int nhwc_to_nchw_f32(const float* y, long long frames, int Co, long long HW, int Npad, float* out, cudaStream_t st) {
+  nhwc_to_nchw_kernel<<<blocks_for(frames * HW, 256), 256, 0, st>>>(y, frames, Co, HW, Npad, out);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+int post_cfg_euler(const float* y, int T, int Cl, long long HW, int Npad, float sigma, float sigma_next, float g_min,
+                   float g_max, float* latents, cudaStream_t st) {
+  post_kernel<<<blocks_for((long long)T * HW, 256), 256, 0, st>>>(y, T, Cl, HW, Npad, sigma, sigma_next, g_min, g_max, latents);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+int timestep_embed(const float* t, int n, int dim, __half* out, cudaStream_t st) {
+  timestep_embed_kernel<<<blocks_for((long long)n * dim / 2, 128), 128, 0, st>>>(t, n, dim, out);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+int silu_f16(const float* x, __half* out, long long n, cudaStream_t st) {
+  silu_f16_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, out, n);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+int cast_f16(const float* x, __half* out, long long n, cudaStream_t st) {
+  cast_f16_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, out, n);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+int add_f32(const float* a, const float* b, float* out, long long n, cudaStream_t st) {
+  add_f32_kernel<<<blocks_for(n, 256), 256, 0, st>>>(a, b, out, n);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+
+}  // namespace evw

@@ -1,0 +1,34 @@
+// Host launchers of the memory-bound UNet kernels (unet_elem.cu) and the attention kernels.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace evw {
+
+// GroupNorm(32 groups) over `insts` instances of `rows_per_inst` rows; input = concat(src0[C0], src1[C1]) along
+// channels (src1 may be null); src0 is fp32 or fp16, src1 fp32.  out fp16 [rows, C]; raw_out (optional) = fp16 copy
+// of the un-normalised input.  stats: double [insts, 32, 2] scratch.
+int group_norm(const void* src0, int src0_fp16, int C0, const float* src1, int C1, long long insts,
+               long long rows_per_inst, float eps, const float* gamma, const float* beta, int do_silu, double* stats,
+               __half* out, __half* raw_out, cudaStream_t st);
+// LayerNorm over C of (x[row] + rowvec[(row / rv_div) % rv_mod]) -> fp16
+int layer_norm(const float* x, const float* rowvec, long long rv_div, long long rv_mod, long long rows, int C, float eps,
+               const float* gamma, const float* beta, __half* out, cudaStream_t st);
+// qkv fp16 [B*T*S, 3*heads*64] rows (b,t,s) -> out fp16 [B*T*S, heads*64], attention over t
+int temporal_attention(const __half* qkv, __half* out, int B, int T, long long S, int heads, cudaStream_t st);
+// qkv fp16 [F*S, 3*heads*64] rows (f,s) -> out fp16 [F*S, heads*64], attention over s (tcgen05 flash attention)
+int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, cudaStream_t st);
+int upsample2x(const float* x, __half* out, long long n, int h, int w, int C, cudaStream_t st);
+int downsplit(const float* x, __half* out, long long n, int h, int w, int C, cudaStream_t st);
+int pre_concat(const float* latents, const float* cond, int Bc, int T, int Cl, int Cc, long long HW, float sigma, int Cpad,
+               __half* out, cudaStream_t st);
+int nchw_to_nhwc_f16(const float* x, long long frames, int Cin, long long HW, int Cpad, __half* out, cudaStream_t st);
+int nhwc_to_nchw_f32(const float* y, long long frames, int Co, long long HW, int Npad, float* out, cudaStream_t st);
+int post_cfg_euler(const float* y, int T, int Cl, long long HW, int Npad, float sigma, float sigma_next, float g_min,
+                   float g_max, float* latents, cudaStream_t st);
+int timestep_embed(const float* t, int n, int dim, __half* out, cudaStream_t st);
+int silu_f16(const float* x, __half* out, long long n, cudaStream_t st);
+int cast_f16(const float* x, __half* out, long long n, cudaStream_t st);
+int add_f32(const float* a, const float* b, float* out, long long n, cudaStream_t st);
+
+}  // namespace evw
