@@ -34,6 +34,12 @@ SIGNATURES = {
     "evw_gemm_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              C.c_char_p, c_void_p, c_int, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_int, c_float,
                              c_void_p, c_float, c_float, c_int, c_int, c_void_p]),
+    "evw_spatial_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "evw_temporal_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_i64, c_int, c_void_p]),
+    "evw_group_norm_f16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_i64, c_i64, c_float, c_void_p, c_void_p,
+                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "evw_layer_norm_f16": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_float, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]),
     "evw_splat_faces_debug": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_float, c_float, c_void_p,
                                       c_void_p, c_i64, c_void_p]),
 }

@@ -1,0 +1,286 @@
+// Spatial self-attention of the UNet transformer blocks (K6 in SURVEY §2.3): flash-attention forward,
+// head dim 64, fp16 operands, on tcgen05 tensor cores with TMEM-resident score tiles.
+//   diffusers attention_processor.py AttnProcessor2_0 as used by BasicTransformerBlock.attn1:
+//   softmax(Q K^T / sqrt(64)) V per (frame, head) over S = h*w tokens.
+//
+// One CTA per (128-query tile, head, frame); 192 threads:
+//   warp 0      TMA producer   Q once, then a 3-stage ring of (K_j, V_j) 128x64 tiles (3-D tensor map over
+//                              the fused qkv buffer [F*S, 3C]; rows past S are zero-filled)
+//   warp 1      MMA issuer     S_j = Q K_j^T   (M128 N128 K64)  -> TMEM (double buffered)
+//                              O_j = P_j V_j   (M128 N64  K128) -> TMEM (double buffered), P_j from smem
+//   warps 2..5  softmax        one query row per thread: tcgen05.ld S_j -> running max / sum in the log2
+//                              domain -> P_j (fp16) written to smem in the 128B-swizzled K-major layout;
+//                              O_{j-1} is folded into register accumulators while PV_j runs
+#include "common.h"
+#include "tc_common.cuh"
+#include "unet_elem.h"
+
+namespace evw {
+using namespace tc;
+namespace {
+
+constexpr int kBQ = 128, kBKV = 128, kD = 64;
+constexpr int kKvStages = 3;
+constexpr int kTileBytes = 128 * 64 * 2;  // 16 KiB: Q, K_j, V_j tiles and each half of P
+constexpr int kAttnThreads = 192;
+// smem map (offsets from the 1024-aligned base)
+constexpr int kOffQ = 0;
+constexpr int kOffK = kOffQ + kTileBytes;
+constexpr int kOffV = kOffK + kKvStages * kTileBytes;
+constexpr int kOffP = kOffV + kKvStages * kTileBytes;
+constexpr int kOffBar = kOffP + 2 * 2 * kTileBytes;
+constexpr int kAttnSmem = kOffBar + 256 + 1024;
+// TMEM columns
+constexpr int kTmemS = 0, kTmemO = 256;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+spatial_attn_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ out, int S, int C, float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x, head = blockIdx.y, frame = blockIdx.z;
+  const int q0 = q_tile * kBQ;
+  const int n_kv = (S + kBKV - 1) / kBKV;
+
+  const uint32_t bar = base + kOffBar;
+  const uint32_t q_full = bar;
+  auto kv_full = [&](int s) { return bar + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bar + 8u * (1 + kKvStages + s); };
+  auto s_full = [&](int b) { return bar + 8u * (1 + 2 * kKvStages + b); };
+  auto s_empty = [&](int b) { return bar + 8u * (3 + 2 * kKvStages + b); };
+  auto p_full = [&](int b) { return bar + 8u * (5 + 2 * kKvStages + b); };
+  auto o_full = [&](int b) { return bar + 8u * (7 + 2 * kKvStages + b); };
+  const uint32_t tmem_slot = bar + 8u * (9 + 2 * kKvStages);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + kOffBar + 8 * (9 + 2 * kKvStages));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKvStages; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(s_full(b), 1);
+      mbar_init(s_empty(b), 4);
+      mbar_init(p_full(b), 4);
+      mbar_init(o_full(b), 1);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kTileBytes);
+      tma_load_3d(&tmap, base + kOffQ, q_full, head * kD, q0, frame);
+    }
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j % kKvStages;
+      mbar_wait(kv_empty(st), ((j / kKvStages) & 1) ^ 1u);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(kv_full(st), 2 * kTileBytes);
+        tma_load_3d(&tmap, base + kOffK + st * kTileBytes, kv_full(st), C + head * kD, j * kBKV, frame);
+        tma_load_3d(&tmap, base + kOffV + st * kTileBytes, kv_full(st), 2 * C + head * kD, j * kBKV, frame);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc_s = make_idesc_f16(kBQ, kBKV, 0, 0, 0);
+    const uint32_t idesc_o = make_idesc_f16(kBQ, kD, 0, 0, 1);  // B (= V) is MN-major
+    auto issue_s = [&](int i) {
+      const int st = i % kKvStages, b = i & 1;
+      mbar_wait(kv_full(st), (i / kKvStages) & 1);
+      mbar_wait(s_empty(b), ((i >> 1) & 1) ^ 1u);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t dq = make_desc_k_sw128(base + kOffQ);
+        const uint64_t dk = make_desc_k_sw128(base + kOffK + st * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) umma_f16_ss(tmem_base + kTmemS + b * kBKV, dq + 2ull * k, dk + 2ull * k, idesc_s, k != 0);
+        tc_commit(s_full(b));
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_s(0);
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) issue_s(j + 1);
+      const int st = j % kKvStages, b = j & 1;
+      mbar_wait(p_full(b), (j >> 1) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int ks = 0; ks < kBKV / 16; ++ks) {
+          const uint64_t dp = make_desc_k_sw128(base + kOffP + b * 2 * kTileBytes + (ks >> 2) * kTileBytes) + 2ull * (ks & 3);
+          const uint64_t dv = make_desc_mn_sw128(base + kOffV + st * kTileBytes + ks * 2048, 1024);
+          umma_f16_ss(tmem_base + kTmemO + b * kD, dp, dv, idesc_o, ks != 0);
+        }
+        tc_commit(o_full(b));
+        tc_commit(kv_empty(st));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== softmax / output (warps 2..5) =====================
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+    float o_acc[kD];
+#pragma unroll
+    for (int d = 0; d < kD; ++d) o_acc[d] = 0.f;
+
+    auto fold_o = [&](int i, float alpha) {
+      const int b = i & 1;
+      mbar_wait(o_full(b), (i >> 1) & 1);
+      tc_fence_after();
+      uint32_t lo[32], hi[32];
+      tmem_ld_32x32b_x32(lane_addr + kTmemO + b * kD, lo);
+      tmem_ld_32x32b_x32(lane_addr + kTmemO + b * kD + 32, hi);
+      tmem_ld_wait();
+#pragma unroll
+      for (int d = 0; d < 32; ++d) {
+        o_acc[d] = fmaf(o_acc[d], alpha, __uint_as_float(lo[d]));
+        o_acc[32 + d] = fmaf(o_acc[32 + d], alpha, __uint_as_float(hi[d]));
+      }
+    };
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int b = j & 1;
+      mbar_wait(s_full(b), (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t s[128];
+      {
+        uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+        uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+        uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
+        uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
+        tmem_ld_32x32b_x32(lane_addr + kTmemS + b * kBKV + 0, s0);
+        tmem_ld_32x32b_x32(lane_addr + kTmemS + b * kBKV + 32, s1);
+        tmem_ld_32x32b_x32(lane_addr + kTmemS + b * kBKV + 64, s2);
+        tmem_ld_32x32b_x32(lane_addr + kTmemS + b * kBKV + 96, s3);
+        tmem_ld_wait();
+      }
+      // the score tile now lives in registers: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty(b));
+
+      const int kv_valid = S - j * kBKV;  // >= 1; < 128 only in the last tile
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 128; ++c) {
+        float v = __uint_as_float(s[c]) * scale_log2e;
+        if (c >= kv_valid) v = -INFINITY;
+        s[c] = __float_as_uint(v);
+        mx = fmaxf(mx, v);
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = fast_exp2(m_run - m_new);  // first tile: exp2(-inf) = 0
+      float sum = 0.f;
+      uint8_t* prow = base_ptr + kOffP + b * 2 * kTileBytes + r * 128;
+#pragma unroll
+      for (int ch = 0; ch < 16; ++ch) {  // 16-byte chunks of 8 probabilities
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float p0 = fast_exp2(__uint_as_float(s[ch * 8 + 2 * i]) - m_new);
+          const float p1 = fast_exp2(__uint_as_float(s[ch * 8 + 2 * i + 1]) - m_new);
+          sum += p0 + p1;
+          __half2 h = __floats2half2_rn(p0, p1);
+          w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        const int atom = ch >> 3, cc = ch & 7;
+        *reinterpret_cast<uint4*>(prow + atom * kTileBytes + ((cc ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      l_run = l_run * alpha + sum;
+      m_run = m_new;
+      fence_proxy_async();  // make the generic-proxy smem writes visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(b));
+      if (j > 0) fold_o(j - 1, alpha_prev);
+      alpha_prev = alpha;
+    }
+    fold_o(n_kv - 1, alpha_prev);
+    const int qrow = q0 + r;
+    if (qrow < S) {
+      const float inv = 1.0f / l_run;
+      uint4* op = reinterpret_cast<uint4*>(out + ((long long)frame * S + qrow) * C + head * kD);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        __half2 h0 = __floats2half2_rn(o_acc[8 * i + 0] * inv, o_acc[8 * i + 1] * inv);
+        __half2 h1 = __floats2half2_rn(o_acc[8 * i + 2] * inv, o_acc[8 * i + 3] * inv);
+        __half2 h2 = __floats2half2_rn(o_acc[8 * i + 4] * inv, o_acc[8 * i + 5] * inv);
+        __half2 h3 = __floats2half2_rn(o_acc[8 * i + 6] * inv, o_acc[8 * i + 7] * inv);
+        uint4 v;
+        v.x = *reinterpret_cast<uint32_t*>(&h0); v.y = *reinterpret_cast<uint32_t*>(&h1);
+        v.z = *reinterpret_cast<uint32_t*>(&h2); v.w = *reinterpret_cast<uint32_t*>(&h3);
+        op[i] = v;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, cudaStream_t st) {
+  EVW_CHECK_ARG(qkv && out && F > 0 && S > 0 && heads > 0, "spatial_attention: bad arguments");
+  const int C = heads * kD;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EVW_CUDA(cudaFuncSetAttribute(spatial_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    attr_set = true;
+  }
+  alignas(64) CUtensorMap tmap;
+  uint64_t dims[3] = {(uint64_t)3 * C, (uint64_t)S, (uint64_t)F};
+  uint64_t str[2] = {(uint64_t)3 * C * 2, (uint64_t)3 * C * 2 * S};
+  uint32_t box[3] = {(uint32_t)kD, (uint32_t)kBQ, 1};
+  int rc = encode_tmap_f16(&tmap, qkv, 3, dims, str, box);
+  if (rc) return rc;
+  dim3 grid((S + kBQ - 1) / kBQ, heads, F);
+  spatial_attn_kernel<<<grid, kAttnThreads, kAttnSmem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+
+}  // namespace evw
+
+// C ABI for tests / micro-benchmarks
+extern "C" int evw_spatial_attention_f16(const void* qkv, void* out, int F, int S, int heads, void* stream) {
+  return evw::spatial_attention((const __half*)qkv, (__half*)out, F, S, heads, (cudaStream_t)stream);
+}
+extern "C" int evw_temporal_attention_f16(const void* qkv, void* out, int B, int T, int64_t S, int heads, void* stream) {
+  return evw::temporal_attention((const __half*)qkv, (__half*)out, B, T, S, heads, (cudaStream_t)stream);
+}
+extern "C" int evw_group_norm_f16(const void* src0, int src0_fp16, int C0, const float* src1, int C1, int64_t insts,
+                                  int64_t rows_per_inst, float eps, const float* gamma, const float* beta, int do_silu,
+                                  void* stats_ws, void* out, void* raw_out, void* stream) {
+  return evw::group_norm(src0, src0_fp16, C0, src1, C1, insts, rows_per_inst, eps, gamma, beta, do_silu, (double*)stats_ws,
+                         (__half*)out, (__half*)raw_out, (cudaStream_t)stream);
+}
+extern "C" int evw_layer_norm_f16(const float* x, const float* rowvec, int64_t rv_div, int64_t rv_mod, int64_t rows, int C,
+                                  float eps, const float* gamma, const float* beta, void* out, void* stream) {
+  return evw::layer_norm(x, rowvec, rv_div > 0 ? rv_div : 1, rv_mod > 0 ? rv_mod : 1, rows, C, eps, gamma, beta, (__half*)out,
+                         (cudaStream_t)stream);
+}

@@ -58,3 +58,50 @@ def geglu_interleave(w: torch.Tensor, b: Optional[torch.Tensor] = None):
     if b is not None:
         bi = torch.stack([b[:F].reshape(F // 16, 16), b[F:].reshape(F // 16, 16)], dim=1).reshape(F2).contiguous()
     return wi, bi
+
+
+def spatial_attention(qkv: torch.Tensor, frames: int, S: int, heads: int) -> torch.Tensor:
+    """qkv fp16 [frames*S, 3*heads*64] -> fp16 [frames*S, heads*64]."""
+    _lib.require_cuda(qkv, "qkv")
+    out = torch.empty((frames * S, heads * 64), dtype=torch.float16, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        _lib.check(_lib.lib().evw_spatial_attention_f16(_lib.ptr(qkv), _lib.ptr(out), frames, S, heads,
+                                                        _lib.stream_ptr(qkv.device)), "evw_spatial_attention_f16")
+    return out
+
+
+def temporal_attention(qkv: torch.Tensor, B: int, T: int, S: int, heads: int) -> torch.Tensor:
+    """qkv fp16 [B*T*S, 3*heads*64] rows (b,t,s) -> fp16 [B*T*S, heads*64], softmax over t."""
+    _lib.require_cuda(qkv, "qkv")
+    out = torch.empty((B * T * S, heads * 64), dtype=torch.float16, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        _lib.check(_lib.lib().evw_temporal_attention_f16(_lib.ptr(qkv), _lib.ptr(out), B, T, S, heads,
+                                                         _lib.stream_ptr(qkv.device)), "evw_temporal_attention_f16")
+    return out
+
+
+def group_norm(src0: torch.Tensor, gamma, beta, insts: int, eps: float, silu: bool, src1: Optional[torch.Tensor] = None,
+               want_raw: bool = False):
+    """src0 [rows, C0] fp32|fp16 (+ src1 [rows, C1] fp32) -> fp16 [rows, C0+C1] (and the raw fp16 copy)."""
+    _lib.require_cuda(src0, "src0")
+    rows, C0 = src0.shape
+    C1 = src1.shape[1] if src1 is not None else 0
+    out = torch.empty((rows, C0 + C1), dtype=torch.float16, device=src0.device)
+    raw = torch.empty_like(out) if want_raw else None
+    ws = torch.empty(insts * 64, dtype=torch.float64, device=src0.device)
+    with torch.cuda.device(src0.device):
+        _lib.check(_lib.lib().evw_group_norm_f16(_lib.ptr(src0), 1 if src0.dtype == torch.float16 else 0, C0, _lib.ptr(src1),
+                                                 C1, insts, rows // insts, eps, _lib.ptr(gamma), _lib.ptr(beta),
+                                                 1 if silu else 0, _lib.ptr(ws), _lib.ptr(out), _lib.ptr(raw),
+                                                 _lib.stream_ptr(src0.device)), "evw_group_norm_f16")
+    return (out, raw) if want_raw else out
+
+
+def layer_norm(x: torch.Tensor, gamma, beta, eps: float = 1e-5, rowvec=None, rv_div: int = 1, rv_mod: int = 1):
+    _lib.require_cuda(x, "x")
+    rows, C = x.shape
+    out = torch.empty((rows, C), dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().evw_layer_norm_f16(_lib.ptr(x), _lib.ptr(rowvec), rv_div, rv_mod, rows, C, eps, _lib.ptr(gamma),
+                                                 _lib.ptr(beta), _lib.ptr(out), _lib.stream_ptr(x.device)), "evw_layer_norm_f16")
+    return out

@@ -140,6 +140,26 @@ int evw_gemm_f16(const void* a0, const void* a1, const void* w, int B, int T, in
                  const float* rowvec, int64_t rv_div, int64_t rv_mod, const void* res1, int res1_fp16, float s1,
                  const float* res2, float s2, float s0, int geglu, int block_n, void* stream);
 
+/* Spatial self-attention (BasicTransformerBlock.attn1 -> F.scaled_dot_product_attention, head dim 64):
+ * qkv fp16 [F*S, 3*heads*64] (columns [q|k|v], each [heads,64]) -> out fp16 [F*S, heads*64]; softmax over
+ * the S tokens of each frame.  tcgen05 flash-attention forward (csrc/tc_attention.cu). */
+int evw_spatial_attention_f16(const void* qkv, void* out, int F, int S, int heads, void* stream);
+
+/* Temporal self-attention (TemporalBasicTransformerBlock.attn1): same qkv layout with rows ordered
+ * (b, t, s); softmax over the T <= 32 frames of each (b, s, head). */
+int evw_temporal_attention_f16(const void* qkv, void* out, int B, int T, int64_t S, int heads, void* stream);
+
+/* GroupNorm(32) [+SiLU] over `insts` instances of `rows_per_inst` channels-last rows; input is the channel
+ * concatenation of src0 (fp32 or fp16, C0 ch) and optional src1 (fp32, C1 ch); out fp16 [rows, C0+C1];
+ * raw_out (optional) receives the un-normalised fp16 copy; stats_ws >= insts*64 doubles. */
+int evw_group_norm_f16(const void* src0, int src0_fp16, int C0, const float* src1, int C1, int64_t insts,
+                       int64_t rows_per_inst, float eps, const float* gamma, const float* beta, int do_silu,
+                       void* stats_ws, void* out, void* raw_out, void* stream);
+
+/* LayerNorm over C of x[row] (+ rowvec[(row/rv_div)%rv_mod]) -> fp16 [rows, C]. */
+int evw_layer_norm_f16(const float* x, const float* rowvec, int64_t rv_div, int64_t rv_mod, int64_t rows, int C,
+                       float eps, const float* gamma, const float* beta, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
