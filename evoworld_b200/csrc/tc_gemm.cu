@@ -95,7 +95,7 @@ __device__ __forceinline__ void epilogue8(const GemmEpilogue& ep, float (&v)[8],
   }
   if (ep.rowvec) {
     float r[8];
-    load8(ep.rowvec + rv_row * ldo + n, r);
+    load8(ep.rowvec + rv_row * (ep.rv_ld ? ep.rv_ld : ldo) + n, r);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += r[i];
   }
@@ -417,16 +417,17 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   static_assert(sizeof(KernelParams) <= sizeof(op->params), "GemmOp::params too small");
   memcpy(op->params, &P, sizeof(P));
 
-  uint64_t dims[5] = {(uint64_t)pr.C0, (uint64_t)pr.X, (uint64_t)pr.Y, (uint64_t)pr.T, (uint64_t)pr.B};
+  const int Tm = pr.Tmap > 0 ? pr.Tmap : pr.T;
+  uint64_t dims[5] = {(uint64_t)pr.C0, (uint64_t)pr.X, (uint64_t)pr.Y, (uint64_t)Tm, (uint64_t)pr.B};
   uint64_t str[4] = {(uint64_t)pr.C0 * 2, (uint64_t)pr.C0 * 2 * pr.X, (uint64_t)pr.C0 * 2 * pr.X * pr.Y,
-                     (uint64_t)pr.C0 * 2 * pr.X * pr.Y * pr.T};
+                     (uint64_t)pr.C0 * 2 * pr.X * pr.Y * Tm};
   uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)P.bx, (uint32_t)P.by, 1, 1};
   int rc = encode_tmap_f16(reinterpret_cast<CUtensorMap*>(op->tmap_a0), pr.a0, 5, dims, str, box);
   if (rc) return rc;
   if (pr.a1 && pr.C1 > 0) {
     EVW_CHECK_ARG(((uintptr_t)pr.a1 & 15) == 0, "gemm: a1 must be 16-byte aligned");
     dims[0] = pr.C1;
-    str[0] = (uint64_t)pr.C1 * 2; str[1] = str[0] * pr.X; str[2] = str[1] * pr.Y; str[3] = str[2] * pr.T;
+    str[0] = (uint64_t)pr.C1 * 2; str[1] = str[0] * pr.X; str[2] = str[1] * pr.Y; str[3] = str[2] * Tm;
     rc = encode_tmap_f16(reinterpret_cast<CUtensorMap*>(op->tmap_a1), pr.a1, 5, dims, str, box);
     if (rc) return rc;
   } else {

@@ -8,7 +8,7 @@ namespace evw {
 
 constexpr int kMaxTaps = 12;
 
-// out[row, n] = s0 * (acc + bias[n]) + rowvec[(row / rv_div) % rv_mod, n] + s1 * res1[row, n] + s2 * res2[row, n]
+// out[row, n] = s0 * (acc + bias[n]) + rowvec[((row / rv_div) % rv_mod) * rv_ld + n] + s1 * res1[row, n] + s2 * res2[row, n]
 // geglu: acc columns come in interleaved [16 value | 16 gate] groups, out has N/2 columns:
 //        out = (value + bias_v) * gelu(gate + bias_g), then the same affine tail.
 struct GemmEpilogue {
@@ -17,6 +17,7 @@ struct GemmEpilogue {
   const float* bias = nullptr;
   const float* rowvec = nullptr;
   long long rv_div = 1, rv_mod = 1;
+  int rv_ld = 0;  // row stride of rowvec in floats (0 = output width)
   const void* res1 = nullptr;
   int res1_fp16 = 0;
   float s1 = 1.f;
@@ -35,6 +36,8 @@ struct GemmProblem {
   const void* a1 = nullptr;  // optional source 1 (1x1 shortcut input), C1 channels
   const void* w = nullptr;
   int B = 1, T = 1, Y = 1, X = 1, C0 = 0, C1 = 0, N = 0;
+  int Tmap = 0;  // extent of the T dimension of the tensor map when it differs from T (0 = T); used by the
+                 // stride-2 convolution, whose taps select one of 4 phase images through the T coordinate
   long long K_total = 0;
   int num_taps = 1;
   int8_t tap_dx[kMaxTaps] = {0}, tap_dy[kMaxTaps] = {0}, tap_dt[kMaxTaps] = {0}, tap_src[kMaxTaps] = {0};

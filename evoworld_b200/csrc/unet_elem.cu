@@ -420,6 +420,10 @@ __global__ void cast_f16_kernel(const float* __restrict__ x, __half* __restrict_
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = __float2half_rn(x[i]);
 }
+__global__ void fill_f32_kernel(float* __restrict__ out, float v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v;
+}
 __global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a[i] + b[i];
@@ -538,6 +542,11 @@ int silu_f16(const float* x, __half* out, long long n, cudaStream_t st) {
 }
 int cast_f16(const float* x, __half* out, long long n, cudaStream_t st) {
   cast_f16_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, out, n);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+int fill_f32(float* out, float v, int n, cudaStream_t st) {
+  fill_f32_kernel<<<blocks_for(n, 128), 128, 0, st>>>(out, v, n);
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }

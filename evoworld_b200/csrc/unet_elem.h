@@ -29,6 +29,7 @@ int post_cfg_euler(const float* y, int T, int Cl, long long HW, int Npad, float 
 int timestep_embed(const float* t, int n, int dim, __half* out, cudaStream_t st);
 int silu_f16(const float* x, __half* out, long long n, cudaStream_t st);
 int cast_f16(const float* x, __half* out, long long n, cudaStream_t st);
+int fill_f32(float* out, float v, int n, cudaStream_t st);
 int add_f32(const float* a, const float* b, float* out, long long n, cudaStream_t st);
 
 }  // namespace evw

@@ -160,6 +160,31 @@ int evw_group_norm_f16(const void* src0, int src0_fp16, int C0, const float* src
 int evw_layer_norm_f16(const float* x, const float* rowvec, int64_t rv_div, int64_t rv_mod, int64_t rows, int C,
                        float eps, const float* gamma, const float* beta, void* out, void* stream);
 
+/* UNetSpatioTemporalConditionModel on the device (evoworld/trainer/unet_plucker.py:30-488).
+ * evw_unet_create takes the packed parameters by name (see evoworld_b200/unet.py:pack_parameters for
+ * the naming and layouts; the caller keeps the tensors alive) plus named host scalars (AlphaBlender
+ * alphas, offsets into the batched time_emb_proj / cross-attention tables).
+ *   cfg_ints  = {in_ch, out_ch, boc[4], heads[4], down_attn[4], layers_per_block, cross_dim,
+ *                addition_time_embed_dim, temb_total, xattn_total};  cfg_floats = {eps_cross, eps_plain, eps_mid, eps_up} */
+int evw_unet_create(void** handle, const int* cfg_ints, int n_ints, const float* cfg_floats, int n_floats,
+                    const char* const* tensor_names, const void* const* tensor_ptrs, int n_tensors,
+                    const char* const* scalar_names, const double* scalar_values, int n_scalars);
+int evw_unet_destroy(void* handle);
+/* Bytes of caller-provided workspace needed for a [B,T,*,h,w] call (-1 on error). */
+int64_t evw_unet_workspace_bytes(void* handle, int B, int T, int h, int w);
+/* forward (unet_plucker.py:355-488): sample fp32 [B,T,Cin,h,w], timestep (= 0.25 ln sigma), encoder_hidden_states
+ * fp32 [B,1,cross_dim], added_time_ids fp32 [B,3] -> out fp32 [B,T,Cout,h,w].  workspace 1024-B aligned. */
+int evw_unet_forward(void* handle, const float* sample, float timestep, const float* ehs, const float* added_time_ids,
+                     float* out, int B, int T, int h, int w, void* workspace, int64_t workspace_bytes, void* stream);
+/* One iteration of the denoise loop (pipeline_evoworld.py:689-725), in place on `latents` fp32 [1,T,4,h,w]:
+ * cat([latents]*2)/sqrt(sigma^2+1) ++ cond_latents fp32 [2,T,Cin-4,h,w] -> UNet -> CFG with guidance
+ * linspace(g_min,g_max,T) -> Euler v-prediction step sigma -> sigma_next. */
+int evw_denoise_step(void* handle, float* latents, const float* cond_latents, float sigma, float sigma_next,
+                     const float* ehs, const float* added_time_ids, float g_min, float g_max, int T, int h, int w,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+/* Kernel launches and algorithmic FLOPs of the current plan (after the first forward / step). */
+int evw_unet_plan_info(void* handle, int64_t* launches, double* flops);
+
 #ifdef __cplusplus
 }
 #endif
