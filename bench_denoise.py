@@ -1,0 +1,168 @@
+"""Denoise-step arm of bench.py (imported by it): UNet forward on the CFG batch + CFG combine +
+Euler step (pipeline_evoworld.py:689-725) at 576x1024 (72x128 latents), T frames, random-init UNet."""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+
+UNET_CFG = dict(in_channels=18, block_out_channels=(320, 640, 1280, 1280), num_attention_heads=(5, 10, 20, 20),
+                cross_attention_dim=1024)
+LAT_H, LAT_W = 72, 128
+
+
+def make_inputs(T, h, w, dev, seed):
+    """SURVEY §8d synthetic inputs: latents ~ 700 N(0,1), cond = [first-frame latent | memory latent | Plücker]."""
+    import torch
+
+    from evoworld_b200 import synthetic
+    from evoworld_b200.plucker import equirectangular_to_ray, ray_c2w_to_plucker
+
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    lat = torch.randn(1, T, 4, h, w, generator=g) * 700.0007
+    cond = torch.randn(2, T, 14, h, w, generator=g)
+    cond[0, :, :8] = 0
+    ehs = torch.randn(2, 1, 1024, generator=g)
+    ehs[0] = 0
+    ids = torch.tensor([[6.0, 127.0, 0.02]] * 2)
+    if dev is not None:
+        ray = torch.from_numpy(equirectangular_to_ray(h, w)).to(dev)
+        poses = synthetic.curve_trajectory()[101:101 + T].copy()
+        poses[:, :3] *= 0.1
+        c2w = torch.from_numpy(synthetic.euler_c2w(poses)[:, :3, :4]).float().to(dev)
+        pl = ray_c2w_to_plucker(ray, c2w).cpu()
+        cond[:, :, 8:14] = pl[None]
+    return lat, cond, ehs, ids
+
+
+def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
+    import torch
+
+    from evoworld_b200.scheduler import EulerDiscreteScheduler
+    from evoworld_b200.unet import UNetSpatioTemporalConditionModel, algorithmic_flops, DEFAULT_CONFIG
+
+    T, h, w = args.frames, LAT_H, LAT_W
+    unet = UNetSpatioTemporalConditionModel(**UNET_CFG).init_random(seed=0, device=dev)
+    unet._ensure_handle()
+    unet.free_master_parameters()
+    lat_h, cond_h, ehs_h, ids_h = make_inputs(T, h, w, dev, seed=rank)
+    lat_p, cond_p = lat_h.pin_memory(), cond_h.pin_memory()
+    out_p = torch.empty_like(lat_h).pin_memory()
+    lat, cond, ehs, ids = lat_h.to(dev), cond_h.to(dev), ehs_h.to(dev), ids_h.to(dev)
+    sched = EulerDiscreteScheduler()
+    sched.set_timesteps(25)
+    sig = [float(s) for s in sched.sigmas]
+
+    def step(i, x):
+        unet.denoise_step(x, cond, sig[i % 25], sig[i % 25 + 1], ehs, ids, 1.0, 3.0)
+
+    x = lat.clone()
+    for i in range(args.warmup):
+        step(i, x)
+    torch.cuda.synchronize(dev)
+    launches, plan_flops = unet.plan_info()
+    x.copy_(lat)
+    barrier(world)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i, x)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    barrier(world)
+    ms = e0.elapsed_time(e1)
+    finite = bool(torch.isfinite(x).all())
+
+    # end to end: the step's inputs come from pinned host memory, the result goes back to the host
+    xd = torch.empty_like(lat)
+    cd = torch.empty_like(cond)
+    torch.cuda.synchronize(dev)
+    barrier(world)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        xd.copy_(lat_p, non_blocking=True)
+        cd.copy_(cond_p, non_blocking=True)
+        unet.denoise_step(xd, cd, sig[i % 25], sig[i % 25 + 1], ehs, ids, 1.0, 3.0)
+        out_p.copy_(xd, non_blocking=True)
+        torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+
+    ms = allreduce_max(ms, dev, world)
+    e2e_s = allreduce_max(e2e_s, dev, world)
+    fl = algorithmic_flops(dict(DEFAULT_CONFIG, **UNET_CFG), 2, T, h, w)
+    steps_per_s = world * args.steps / (ms * 1e-3)
+    achieved = fl["total"] * (args.steps / (ms * 1e-3))  # TFLOP/s per GPU
+    res = {
+        "metric": "denoise-steps/sec", "unit": "steps/s", "value": steps_per_s, "ms_per_step": ms / args.steps, "dtype": "fp16",
+        "e2e": {"value": world * args.steps / e2e_s, "unit": "steps/s",
+                "h2d_bytes_per_step": lat_p.numel() * 4 + cond_p.numel() * 4, "d2h_bytes_per_step": out_p.numel() * 4},
+        "roofline": {"bound": "tensor", "kernel": "whole denoise step (tc_gemm_kernel + spatial_attn_kernel dominate)",
+                     "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
+                     "traffic": None, "algorithmic_tflop_per_step": fl, "executed_tflop_per_step": plan_flops / 1e12,
+                     "peak_source": peaks["source"] + " (sustained bf16/fp16 dense)"},
+        "gpu_launches": launches * args.steps,
+        "config": {"workload": f"config 2: single 576x1024x{T}f clip, CFG batch 2, 72x128 latents, random-init 1.525B-param UNet, "
+                               f"Karras sigmas (25-step schedule)", "frames": T, "finite_output": finite,
+                   "l2": "working set (activations + 3 GB of fp16 weights) >> 126 MB L2; K steps in one CUDA-event pair"},
+    }
+    if rank == 0 and not args.no_cpu_baseline:
+        res["cpu_baseline"] = run_cpu(T, steps=1)
+    return res
+
+
+def run_cpu(T, steps=1, warmup=0):
+    """The reference's CPU path for one denoise step, restated by the fp32 PyTorch oracle (diffusers is not
+    installable here), on a bounded sample: the full-width UNet at 18x32 latents (1/16 of the pixels)."""
+    import torch
+
+    from evoworld_b200.unet import algorithmic_flops, DEFAULT_CONFIG
+    from oracle import unet_torch as O
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    h, w = 18, 32
+    with torch.device("meta"):
+        m = O.UNetSpatioTemporalConditionModel()
+    m = m.to_empty(device="cpu")
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "norm" in n and n.endswith("weight"):
+                p.fill_(1.0)
+            elif "norm" in n or n.endswith("bias"):
+                p.zero_()
+            elif n.endswith("mix_factor"):
+                p.fill_(0.5)
+            else:
+                p.uniform_(-0.02, 0.02, generator=g)
+    lat, cond, ehs, ids = make_inputs(T, h, w, None, 0)
+    sig = O.karras_sigmas(25)
+    guid = torch.linspace(1.0, 3.0, T).view(1, T, 1, 1, 1)
+    with torch.no_grad():
+        for i in range(warmup):
+            O.denoise_step(m, lat, cond, float(sig[0]), float(sig[1]), ehs, ids, guid)
+        t0 = time.perf_counter()
+        x = lat
+        for i in range(steps):
+            x = O.denoise_step(m, x, cond, float(sig[i]), float(sig[i + 1]), ehs, ids, guid)
+        dt = time.perf_counter() - t0
+    cfg = dict(DEFAULT_CONFIG, **UNET_CFG)
+    f_small = algorithmic_flops(cfg, 2, T, h, w)["total"]
+    f_full = algorithmic_flops(cfg, 2, T, LAT_H, LAT_W)["total"]
+    small_sps = steps / dt
+    return {"value": small_sps * f_small / f_full, "unit": "steps/s", "cores": threads, "kind": "port",
+            "sample": f"{steps} step(s) of the fp32 PyTorch oracle UNet (full 1.525B width) at {h}x{w} latents, T={T}: "
+                      f"{dt:.1f} s, {f_small:.2f} TFLOP/step; scaled to 72x128 by the FLOP ratio {f_full / f_small:.1f}",
+            "seconds": dt, "measured_small_steps_per_s": small_sps}
+
+
+def run_reference(args):
+    cpu = run_cpu(args.frames, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
+    return {"metric": "denoise-steps/sec", "value": cpu["value"], "unit": "steps/s", "n_gpus": 0, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 / cpu["value"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": f"config 1: single 576x1024x{args.frames}f clip, CPU fp32 oracle UNet (bounded sample, FLOP-scaled)"},
+            "impl": "reference", "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -9,6 +9,8 @@
 #include "tc_gemm.h"
 #include "unet_elem.h"
 
+#include <cmath>
+#include <cstdlib>
 #include <functional>
 #include <map>
 #include <memory>
@@ -48,7 +50,15 @@ struct CallArgs {  // per-call pointers/scalars referenced by the planned ops
   int mode = 0;  // 0 = forward, 1 = denoise step
 };
 
+struct OpMeta {
+  std::string label;
+  const void* out = nullptr;
+  long long n = 0;
+  int fp16 = 0;
+};
+
 struct Plan {
+  std::vector<OpMeta> meta;
   int B = 0, T = 0, h = 0, w = 0;
   void* ws = nullptr;
   long long ws_bytes = 0;
@@ -114,13 +124,16 @@ struct Builder {
     }
     return it->second;
   }
-  void push(Op op, int launches = 1) {
+  void push(Op op, int launches = 1, const std::string& label = "", const void* out = nullptr, long long n = 0, int fp16 = 0) {
     P.launches += launches;
-    if (!dry) P.ops.push_back(std::move(op));
+    if (!dry) {
+      P.ops.push_back(std::move(op));
+      P.meta.push_back(OpMeta{label, out, n, fp16});
+    }
   }
 
   // ---- planned GEMM
-  void gemm(GemmProblem pr) {
+  void gemm(GemmProblem pr, const std::string& label = "gemm") {
     if (dry) {
       P.launches += 1;
       return;
@@ -133,7 +146,9 @@ struct Builder {
       return;
     }
     P.flops += op->flops;
-    push([op](cudaStream_t st) { return gemm_launch(*op, st); });
+    const long long rows = (long long)pr.B * pr.T * pr.Y * pr.X;
+    push([op](cudaStream_t st) { return gemm_launch(*op, st); }, 1, label + " " + std::to_string(rows) + "x" + std::to_string(pr.N) + "x" + std::to_string(pr.K_total),
+         pr.ep.out, rows * (pr.ep.geglu ? pr.N / 2 : pr.N), pr.ep.out_fp16);
   }
   static void taps_conv3x3(GemmProblem& pr) {
     pr.num_taps = 9;
@@ -149,20 +164,21 @@ struct Builder {
     pr.X = (int)M; pr.C0 = K; pr.N = N; pr.K_total = K; pr.num_taps = 1;
     if (bias) ep.bias = Wf(wname + ".bias");
     pr.ep = ep;
-    gemm(pr);
+    gemm(pr, wname);
   }
   void gnorm(const void* src0, int src0_fp16, int C0, const float* src1, int C1, long long insts, long long rows, float eps,
              const std::string& name, int silu, __half* out, __half* raw) {
     const float* g = Wf(name + ".weight");
     const float* b = Wf(name + ".bias");
     double* st_ = stats;
-    push([=](cudaStream_t st) { return group_norm(src0, src0_fp16, C0, src1, C1, insts, rows, eps, g, b, silu, st_, out, raw, st); }, 3);
+    push([=](cudaStream_t st) { return group_norm(src0, src0_fp16, C0, src1, C1, insts, rows, eps, g, b, silu, st_, out, raw, st); }, 3,
+         name, out, insts * rows * (C0 + C1), 1);
   }
   void lnorm(const float* x, const float* rowvec, long long rv_div, long long rv_mod, long long rows, int C,
              const std::string& name, __half* out) {
     const float* g = Wf(name + ".weight");
     const float* b = Wf(name + ".bias");
-    push([=](cudaStream_t st) { return layer_norm(x, rowvec, rv_div, rv_mod, rows, C, 1e-5f, g, b, out, st); });
+    push([=](cudaStream_t st) { return layer_norm(x, rowvec, rv_div, rv_mod, rows, C, 1e-5f, g, b, out, st); }, 1, name, out, rows * C, 1);
   }
 
   // ---- SpatioTemporalResBlock (diffusers resnet.py): x = cat(x0, x1) -> out
@@ -182,7 +198,7 @@ struct Builder {
       pr.ep.out = h16; pr.ep.out_fp16 = 1; pr.ep.bias = Wf(sp + ".conv1.bias");
       pr.ep.rowvec = temb_all + (long long)Sc(sp + ".time_emb_proj.offset");
       pr.ep.rv_ld = U.cfg.temb_total; pr.ep.rv_div = (long long)T * S; pr.ep.rv_mod = B;
-      gemm(pr);
+      gemm(pr, sp + ".conv1");
     }
     gnorm(h16, 1, Cout, nullptr, 0, BF, S, eps, sp + ".norm2", 1, n16, nullptr);
     {
@@ -197,7 +213,7 @@ struct Builder {
         pr.ep.res1 = x0; pr.ep.res1_fp16 = 0; pr.ep.s1 = 1.f;
       }
       pr.ep.out = f2; pr.ep.out_fp16 = 0; pr.ep.bias = Wf(sp + ".conv2.bias");
-      gemm(pr);
+      gemm(pr, sp + ".conv2");
     }
     // temporal part: GroupNorm statistics over (T, h, w) per batch element
     gnorm(f2, 0, Cout, nullptr, 0, B, (long long)T * S, eps, tp + ".norm1", 1, n16, nullptr);
@@ -209,7 +225,7 @@ struct Builder {
       for (int i = 0; i < 3; ++i) { pr.tap_dx[i] = pr.tap_dy[i] = 0; pr.tap_dt[i] = (int8_t)(i - 1); pr.tap_src[i] = 0; }
       ep.bias = Wf(name + ".bias");
       pr.ep = ep;
-      gemm(pr);
+      gemm(pr, name);
     };
     {
       GemmEpilogue ep;
@@ -248,7 +264,7 @@ struct Builder {
     linear(n16, M, C, sb + ".attn1.qkv", 3 * C, ep_f16(qkv16), false);
     {
       const __half* q = qkv16; __half* o = attn16; int S_ = (int)S;
-      push([=](cudaStream_t st) { return spatial_attention(q, o, BF, S_, heads, st); });
+      push([=](cudaStream_t st) { return spatial_attention(q, o, BF, S_, heads, st); }, 1, sb + ".attn1.sdpa", o, M * C, 1);
       P.flops += 4.0 * BF * heads * (double)S * (double)S * 64.0;
     }
     {
@@ -284,7 +300,7 @@ struct Builder {
     linear(n16, M, C, tb + ".attn1.qkv", 3 * C, ep_f16(qkv16), false);
     {
       const __half* q = qkv16; __half* o = attn16; int B_ = B, T_ = T;
-      push([=](cudaStream_t st) { return temporal_attention(q, o, B_, T_, S, heads, st); });
+      push([=](cudaStream_t st) { return temporal_attention(q, o, B_, T_, S, heads, st); }, 1, tb + ".attn1.sdpa", o, M * C, 1);
       P.flops += 4.0 * B * S * heads * (double)T * (double)T * 64.0;
     }
     {
@@ -317,7 +333,7 @@ struct Builder {
     pr.B = 1; pr.T = frames; pr.Y = hh; pr.X = ww; pr.C0 = Cin; pr.N = N; pr.K_total = 9LL * Cin;
     taps_conv3x3(pr);
     pr.ep.out = outp; pr.ep.out_fp16 = 0; pr.ep.bias = Wf(name + ".bias");
-    gemm(pr);
+    gemm(pr, name);
   }
 
   int build() {
@@ -349,8 +365,11 @@ struct Builder {
     f0 = bump.take<float>(maxMC);
     f1 = bump.take<float>(maxMC);
     f2 = bump.take<float>(maxMC);
-    pp[0] = bump.take<float>(maxMC);
-    pp[1] = bump.take<float>(maxMC);
+    // the up-sampling convolutions write [M_{l-1}, boc[l]] (e.g. 640 channels at level 0)
+    long long maxPP = maxMC;
+    for (int l = 1; l < 4; ++l) maxPP = std::max(maxPP, lM[l - 1] * c.boc[l]);
+    pp[0] = bump.take<float>(maxPP);
+    pp[1] = bump.take<float>(maxPP);
     y32 = bump.take<float>(lM[0] * c.cout_pad);
     stats = bump.take<double>(64LL * std::max(BF, 1));
     small16 = bump.take<__half>(5LL * kSmall);
@@ -442,7 +461,7 @@ struct Builder {
             pr.tap_src[t] = 0;
           }
         pr.ep.out = o; pr.ep.out_fp16 = 0; pr.ep.bias = Wf(bp + ".downsamplers.0.conv.bias");
-        gemm(pr);
+        gemm(pr, bp + ".downsamplers.0.conv");
         skips.push_back({o, Cout});
         x = o; xC = Cout;
       }
@@ -524,15 +543,63 @@ int ensure_plan(UNet* U, int B, int T, int h, int w, void* ws, long long ws_byte
   return EVW_OK;
 }
 
+int debug_stats(const void* p, long long n, int fp16, cudaStream_t st, double* absmax, long long* bad) {
+  std::vector<char> host((size_t)n * (fp16 ? 2 : 4));
+  if (cudaMemcpyAsync(host.data(), p, host.size(), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+  cudaStreamSynchronize(st);
+  double am = 0;
+  long long b = 0;
+  for (long long i = 0; i < n; ++i) {
+    float v = fp16 ? __half2float(reinterpret_cast<const __half*>(host.data())[i]) : reinterpret_cast<const float*>(host.data())[i];
+    if (!(v == v) || v > 3.0e38f || v < -3.0e38f) ++b;
+    else if (fabs(v) > am) am = fabs(v);
+  }
+  *absmax = am;
+  *bad = b;
+  return 0;
+}
+
 int run_plan(UNet* U, cudaStream_t st) {
+  static const bool debug = getenv("EVW_UNET_DEBUG") != nullptr;
+  size_t i = 0;
   for (auto& op : U->plan->ops) {
     int rc = op(st);
     if (rc) return rc;
+    if (debug) {
+      const OpMeta& m = U->plan->meta[i];
+      cudaError_t e = cudaStreamSynchronize(st);
+      double amax = 0;
+      long long bad = 0;
+      if (e == cudaSuccess && m.out && m.n > 0) debug_stats(m.out, m.n, m.fp16, st, &amax, &bad);
+      fprintf(stderr, "[evw_unet] op %4zu %-70s %s absmax %.4g nonfinite %lld\n", i, m.label.c_str(),
+              e == cudaSuccess ? "ok" : cudaGetErrorString(e), amax, bad);
+      if (const char* dir = getenv("EVW_UNET_DUMP_DIR")) {
+        if (e == cudaSuccess && m.out && m.n > 0) {
+          std::vector<char> host((size_t)m.n * (m.fp16 ? 2 : 4));
+          cudaMemcpy(host.data(), m.out, host.size(), cudaMemcpyDeviceToHost);
+          std::string path = std::string(dir) + "/op" + std::to_string(i) + (m.fp16 ? ".f16" : ".f32");
+          if (FILE* f = fopen(path.c_str(), "wb")) {
+            fwrite(host.data(), 1, host.size(), f);
+            fclose(f);
+          }
+          if (FILE* f = fopen((std::string(dir) + "/index.txt").c_str(), "a")) {
+            fprintf(f, "%zu %s %lld %d\n", i, m.label.empty() ? "-" : m.label.c_str(), m.n, m.fp16);
+            fclose(f);
+          }
+        }
+      }
+      if (e != cudaSuccess) {
+        set_error("op %zu (%s): %s", i, m.label.c_str(), cudaGetErrorString(e));
+        return EVW_ERR_CUDA;
+      }
+    }
+    ++i;
   }
   return EVW_OK;
 }
 
 }  // namespace
+
 }  // namespace evw
 
 using evw::UNet;

@@ -515,3 +515,50 @@ class UNetSpatioTemporalConditionModel:
                                                    float(max_guidance), T_, h, w, _lib.ptr(ws), ws.numel(),
                                                    _lib.stream_ptr(self._device)), "evw_denoise_step")
         return latents
+
+
+def algorithmic_flops(cfg: dict, B: int, T: int, h: int, w: int) -> Dict[str, float]:
+    """2*MAC count of one UNet forward on a [B,T,*,h,w] batch, walking the architecture as the reference
+    executes it (every conv / linear / SDPA, including the full single-key cross-attention projections);
+    SURVEY Appendix C.  Returns TFLOP per bucket and the total."""
+    lay = block_layout(cfg)
+    boc = lay["boc"]
+    temb, cross = boc[0] * 4, cfg["cross_attention_dim"]
+    BF = B * T
+    hs, ws = [h], [w]
+    for _ in range(3):
+        hs.append((hs[-1] + 1) // 2); ws.append((ws[-1] + 1) // 2)
+    level_of = {}
+    for i in range(4):
+        level_of[f"down_blocks.{i}"] = i
+        level_of[f"up_blocks.{i}"] = 3 - i
+    level_of["mid_block"] = 3
+    conv = gemm = sdpa_s = sdpa_t = 0.0
+    conv += 2.0 * BF * hs[0] * ws[0] * 9 * cfg["in_channels"] * boc[0]
+    gemm += 2.0 * B * (boc[0] * temb + temb * temb + cfg["projection_class_embeddings_input_dim"] * temb + temb * temb)
+    for p, cin, cout in lay["res"]:
+        l = level_of[p.rsplit(".resnets", 1)[0]]
+        M = BF * hs[l] * ws[l]
+        conv += 2.0 * M * 9 * (cin * cout + cout * cout) + (2.0 * M * cin * cout if cin != cout else 0.0)
+        conv += 2.0 * M * 3 * 2 * cout * cout
+        gemm += 2.0 * BF * temb * cout * 2
+    for p, c, heads in lay["att"]:
+        l = level_of[p.rsplit(".attentions", 1)[0]]
+        S = hs[l] * ws[l]
+        M = BF * S
+        gemm += 2.0 * M * c * c * 2                      # proj_in, proj_out
+        gemm += 2.0 * T * (c * 4 * c + 4 * c * c) * B    # time_pos_embed MLP
+        for _blk in range(2):                            # spatial + temporal block
+            gemm += 2.0 * M * c * c * 4                  # attn1 q,k,v,out
+            gemm += 2.0 * M * c * c * 2 + 2.0 * M * cross * c * 2  # attn2 q,out on tokens; k,v on the 1-token context
+        gemm += 2.0 * M * (c * 8 * c + 4 * c * c) * 3    # ff, ff_in, ff
+        sdpa_s += 4.0 * BF * heads * S * S * 64 + 4.0 * BF * heads * S * 1 * 64
+        sdpa_t += 4.0 * B * S * heads * T * T * 64 + 4.0 * B * S * heads * T * 1 * 64
+    for p, c in lay["samplers"]:
+        i = int(p.split(".")[1])
+        l = i + 1 if p.startswith("down") else 3 - i - 1
+        conv += 2.0 * BF * hs[l] * ws[l] * 9 * c * c
+    conv += 2.0 * BF * hs[0] * ws[0] * 9 * boc[0] * cfg["out_channels"]
+    tot = conv + gemm + sdpa_s + sdpa_t
+    return {"conv": conv / 1e12, "gemm": gemm / 1e12, "sdpa_spatial": sdpa_s / 1e12, "sdpa_temporal": sdpa_t / 1e12,
+            "total": tot / 1e12}
