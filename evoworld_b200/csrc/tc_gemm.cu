@@ -26,7 +26,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // fp16 elements = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;        // 4 control warps + 8 epilogue warps
+constexpr int kEpiWarps = 8;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 
 struct KernelParams {
@@ -40,7 +41,19 @@ struct KernelParams {
   int total_tiles;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// exact-GELU 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below
+// the fp16 rounding of the result); ~3x cheaper than erff, which made the GEGLU epilogue the bottleneck.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = p * t * __expf(-z * z);  // erfc(|x| / sqrt 2)
+  const float h = 0.5f * x;
+  return x >= 0.f ? h * (2.0f - e) : h * e;
+}
 
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
   float4 a = __ldg(reinterpret_cast<const float4*>(p));
@@ -145,7 +158,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), kEpiWarps);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -222,6 +235,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
     // ===================== epilogue =====================
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;     // row of the 128-row tile
+    const int chalf = (warp - 4) >> 2;  // two warps share a lane quarter and alternate 32-column chunks
     const GemmEpilogue& ep = P.ep;
     const int ldo = ep.geglu ? P.N / 2 : P.N;
     int it = 0;
@@ -244,7 +258,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
-      for (int c = 0; c < P.block_n; c += 32) {
+      for (int c = chalf * 32; c < P.block_n; c += 64) {
         uint32_t raw[32];
         __syncwarp();
         if (P.block_n - c >= 32) {
@@ -266,15 +280,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             if (nh >= P.N) break;
-            float v[8];
+            float v[8], bh[8], bg[8];
+            if (ep.bias) {
+              load8(ep.bias + nh + g * 8, bh);
+              load8(ep.bias + nh + 16 + g * 8, bg);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { bh[i] = 0.f; bg[i] = 0.f; }
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              float hv = __uint_as_float(raw[g * 8 + i]);
-              float gv = __uint_as_float(raw[16 + g * 8 + i]);
-              if (ep.bias) {
-                hv += __ldg(ep.bias + nh + g * 8 + i);
-                gv += __ldg(ep.bias + nh + 16 + g * 8 + i);
-              }
+              const float hv = __uint_as_float(raw[g * 8 + i]) + bh[i];
+              const float gv = __uint_as_float(raw[16 + g * 8 + i]) + bg[i];
               v[i] = hv * gelu_erf(gv);
             }
             if (ep.out_fp16) epilogue8<__half>(ep, v, row, no + g * 8, ldo, rv_row);

@@ -18,13 +18,23 @@ namespace {
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
 // ------------------------------------------------------------------------------------------
-// GroupNorm statistics: sum / sum of squares per (instance, group) in double
+// GroupNorm: (1) per-channel partial sums in registers (each thread owns fixed channel quads, rows are
+// strided over thread rows -> coalesced 16-byte loads), reduced per group in shared memory and added
+// to double accumulators; (2) finalize -> (mean, rstd) per (instance, group); (3) apply [+SiLU] -> fp16.
 // ------------------------------------------------------------------------------------------
-constexpr int kGnThreads = 256;
+constexpr int kGnMaxNQ = 2;  // channel quads per thread: C <= 4 * 512 * kGnMaxNQ
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const __half* p) {
+  uint2 r = *reinterpret_cast<const uint2*>(p);
+  float2 a = __half22float2(*reinterpret_cast<__half2*>(&r.x)), b = __half22float2(*reinterpret_cast<__half2*>(&r.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
 
 template <typename T0>
-__global__ void gn_stats_kernel(const T0* __restrict__ src0, int C0, const float* __restrict__ src1, int C1,
-                                long long rows_per_inst, int rows_per_block, int groups, double* __restrict__ stats) {
+__global__ void __launch_bounds__(512)
+gn_stats_kernel(const T0* __restrict__ src0, int C0, const float* __restrict__ src1, int C1, long long rows_per_inst,
+                int rows_per_block, int groups, int TQ, int NQ, double* __restrict__ stats) {
   const int inst = blockIdx.y;
   const int C = C0 + C1;
   const int cg = C / groups;
@@ -33,26 +43,37 @@ __global__ void gn_stats_kernel(const T0* __restrict__ src0, int C0, const float
   __shared__ double s_sum[64], s_sq[64];
   for (int i = threadIdx.x; i < groups; i += blockDim.x) { s_sum[i] = 0; s_sq[i] = 0; }
   __syncthreads();
-  // each thread owns channels c = tid + k*blockDim (coalesced over channels)
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f, q = 0.f;
-    if (c < C0) {
-      const T0* p = src0 + ((long long)inst * rows_per_inst + r0) * C0 + c;
-      for (long long r = r0; r < r1; ++r, p += C0) {
-        float v = (float)*p;
-        s += v;
-        q = fmaf(v, v, q);
-      }
-    } else {
-      const float* p = src1 + ((long long)inst * rows_per_inst + r0) * C1 + (c - C0);
-      for (long long r = r0; r < r1; ++r, p += C1) {
-        float v = *p;
-        s += v;
-        q = fmaf(v, v, q);
+  const int tq = threadIdx.x % TQ, tr = threadIdx.x / TQ, R = blockDim.x / TQ;
+  float s[kGnMaxNQ][4], q[kGnMaxNQ][4];
+#pragma unroll
+  for (int j = 0; j < kGnMaxNQ; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { s[j][i] = 0.f; q[j][i] = 0.f; }
+  if (tr < R) {
+    for (long long r = r0 + tr; r < r1; r += R) {
+      const long long row = (long long)inst * rows_per_inst + r;
+#pragma unroll
+      for (int j = 0; j < kGnMaxNQ; ++j) {
+        if (j < NQ) {
+          const int c = 4 * (tq + j * TQ);
+          float4 v = (c < C0) ? ld4(src0 + row * C0 + c) : ld4(src1 + row * C1 + (c - C0));
+          s[j][0] += v.x; s[j][1] += v.y; s[j][2] += v.z; s[j][3] += v.w;
+          q[j][0] = fmaf(v.x, v.x, q[j][0]); q[j][1] = fmaf(v.y, v.y, q[j][1]);
+          q[j][2] = fmaf(v.z, v.z, q[j][2]); q[j][3] = fmaf(v.w, v.w, q[j][3]);
+        }
       }
     }
-    atomicAdd(&s_sum[c / cg], (double)s);
-    atomicAdd(&s_sq[c / cg], (double)q);
+#pragma unroll
+    for (int j = 0; j < kGnMaxNQ; ++j) {
+      if (j < NQ) {
+        const int c = 4 * (tq + j * TQ);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          atomicAdd(&s_sum[(c + i) / cg], (double)s[j][i]);
+          atomicAdd(&s_sq[(c + i) / cg], (double)q[j][i]);
+        }
+      }
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < groups; i += blockDim.x) {
@@ -61,13 +82,21 @@ __global__ void gn_stats_kernel(const T0* __restrict__ src0, int C0, const float
   }
 }
 
+__global__ void gn_finalize_kernel(const double* __restrict__ stats, int n, double cnt, float eps, float2* __restrict__ mr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double m = stats[2 * i] / cnt;
+  double var = stats[2 * i + 1] / cnt - m * m;
+  if (var < 0) var = 0;
+  mr[i] = make_float2((float)m, (float)(1.0 / sqrt(var + (double)eps)));
+}
+
 // apply: 8 channels per thread
 template <typename T0>
 __global__ void gn_apply_kernel(const T0* __restrict__ src0, int C0, const float* __restrict__ src1, int C1,
-                                long long rows_total, long long rows_per_inst, int groups, float eps,
-                                const double* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, int do_silu, __half* __restrict__ out,
-                                __half* __restrict__ raw_out) {
+                                long long rows_total, long long rows_per_inst, int groups, const float2* __restrict__ mr,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu,
+                                __half* __restrict__ out, __half* __restrict__ raw_out) {
   const int C = C0 + C1;
   const int cv = C / 8;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -76,16 +105,17 @@ __global__ void gn_apply_kernel(const T0* __restrict__ src0, int C0, const float
   const int c = (int)(idx - row * cv) * 8;
   const long long inst = row / rows_per_inst;
   const int cg = C / groups;
-  const double cnt = (double)rows_per_inst * cg;
   float v[8];
-  if (c < C0) {
-    const T0* p = src0 + row * C0 + c;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (float)p[i];
-  } else {
-    const float* p = src1 + row * C1 + (c - C0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = p[i];
+  {
+    float4 a, b;
+    if (c < C0) {
+      a = ld4(src0 + row * C0 + c);
+      b = ld4(src0 + row * C0 + c + 4);
+    } else {
+      a = ld4(src1 + row * C1 + (c - C0));
+      b = ld4(src1 + row * C1 + (c - C0) + 4);
+    }
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   }
   if (raw_out) {
     uint4 raw;
@@ -94,22 +124,21 @@ __global__ void gn_apply_kernel(const T0* __restrict__ src0, int C0, const float
     for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
     *reinterpret_cast<uint4*>(raw_out + row * C + c) = raw;
   }
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+  const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bet[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   float o[8];
   int g_prev = -1;
-  float mean = 0.f, rstd = 0.f;
+  float2 m = make_float2(0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int g = (c + i) / cg;
     if (g != g_prev) {
-      const double s = stats[(inst * groups + g) * 2], q = stats[(inst * groups + g) * 2 + 1];
-      const double m = s / cnt;
-      double var = q / cnt - m * m;
-      if (var < 0) var = 0;
-      mean = (float)m;
-      rstd = (float)(1.0 / sqrt(var + (double)eps));
+      m = __ldg(mr + inst * groups + g);
       g_prev = g;
     }
-    float y = (v[i] - mean) * rstd * __ldg(gamma + c + i) + __ldg(beta + c + i);
+    float y = (v[i] - m.x) * m.y * gam[i] + bet[i];
     o[i] = do_silu ? silu(y) : y;
   }
   uint4 raw;
@@ -441,24 +470,34 @@ int group_norm(const void* src0, int src0_fp16, int C0, const float* src1, int C
                __half* out, __half* raw_out, cudaStream_t st) {
   const int C = C0 + C1, groups = 32;
   EVW_CHECK_ARG(C % groups == 0 && C % 8 == 0 && C0 % 8 == 0, "group_norm: C=%d (C0=%d) not supported", C, C0);
+  const int Q = C / 4;
+  int NQ = (Q + 511) / 512;
+  while (NQ <= kGnMaxNQ && Q % NQ != 0) ++NQ;
+  EVW_CHECK_ARG(NQ <= kGnMaxNQ, "group_norm: C=%d too wide", C);
+  const int TQ = Q / NQ;
+  const int R = 512 / TQ > 0 ? 512 / TQ : 1;
+  const int threads = TQ * R;
+  // stats scratch: [insts,32,2] doubles followed by [insts,32] float2 (mean, rstd)
+  float2* mr = reinterpret_cast<float2*>(stats + 2 * groups * insts);
   EVW_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * insts, st));
-  // enough blocks per instance to fill the machine, >= 8 rows per block
   long long want_blocks = (long long)sm_count() * 4 / (insts > 0 ? insts : 1) + 1;
   int rpb = (int)((rows_per_inst + want_blocks - 1) / want_blocks);
-  if (rpb < 8) rpb = 8;
+  if (rpb < 4 * R) rpb = 4 * R;
   dim3 grid((unsigned)((rows_per_inst + rpb - 1) / rpb), (unsigned)insts);
   if (src0_fp16)
-    gn_stats_kernel<__half><<<grid, kGnThreads, 0, st>>>((const __half*)src0, C0, src1, C1, rows_per_inst, rpb, groups, stats);
+    gn_stats_kernel<__half><<<grid, threads, 0, st>>>((const __half*)src0, C0, src1, C1, rows_per_inst, rpb, groups, TQ, NQ, stats);
   else
-    gn_stats_kernel<float><<<grid, kGnThreads, 0, st>>>((const float*)src0, C0, src1, C1, rows_per_inst, rpb, groups, stats);
+    gn_stats_kernel<float><<<grid, threads, 0, st>>>((const float*)src0, C0, src1, C1, rows_per_inst, rpb, groups, TQ, NQ, stats);
+  const int ng = (int)(insts * groups);
+  gn_finalize_kernel<<<(ng + 127) / 128, 128, 0, st>>>(stats, ng, (double)rows_per_inst * (C / groups), eps, mr);
   const long long rows_total = insts * rows_per_inst;
   const long long n = rows_total * (C / 8);
   if (src0_fp16)
     gn_apply_kernel<__half><<<blocks_for(n, 256), 256, 0, st>>>((const __half*)src0, C0, src1, C1, rows_total, rows_per_inst,
-                                                                 groups, eps, stats, gamma, beta, do_silu, out, raw_out);
+                                                                 groups, mr, gamma, beta, do_silu, out, raw_out);
   else
     gn_apply_kernel<float><<<blocks_for(n, 256), 256, 0, st>>>((const float*)src0, C0, src1, C1, rows_total, rows_per_inst,
-                                                                groups, eps, stats, gamma, beta, do_silu, out, raw_out);
+                                                                groups, mr, gamma, beta, do_silu, out, raw_out);
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }

@@ -171,7 +171,7 @@ struct Builder {
     const float* g = Wf(name + ".weight");
     const float* b = Wf(name + ".bias");
     double* st_ = stats;
-    push([=](cudaStream_t st) { return group_norm(src0, src0_fp16, C0, src1, C1, insts, rows, eps, g, b, silu, st_, out, raw, st); }, 3,
+    push([=](cudaStream_t st) { return group_norm(src0, src0_fp16, C0, src1, C1, insts, rows, eps, g, b, silu, st_, out, raw, st); }, 4,
          name, out, insts * rows * (C0 + C1), 1);
   }
   void lnorm(const float* x, const float* rowvec, long long rv_div, long long rv_mod, long long rows, int C,
@@ -371,7 +371,7 @@ struct Builder {
     pp[0] = bump.take<float>(maxPP);
     pp[1] = bump.take<float>(maxPP);
     y32 = bump.take<float>(lM[0] * c.cout_pad);
-    stats = bump.take<double>(64LL * std::max(BF, 1));
+    stats = bump.take<double>(96LL * std::max(BF, 1));  // [insts,32,2] double sums + [insts,32] float2 (mean, rstd)
     small16 = bump.take<__half>(5LL * kSmall);
     emb = bump.take<float>(8LL * c.temb_dim);
     emb2 = bump.take<float>(8LL * c.temb_dim);
@@ -388,7 +388,7 @@ struct Builder {
         const CallArgs& a = u->args;
         if (a.mode == 1) return pre_concat(a.latents, a.cond, B_, T_, 4, Cin - 4, HW, a.sigma, Cpad, o, st);
         return nchw_to_nhwc_f16(a.sample, (long long)B_ * T_, Cin, HW, Cpad, o, st);
-      });
+      }, 1, "pre (scale+concat+layout)");
     }
     // ---- time / added-id embeddings (unet_plucker.py:384-414)
     {
@@ -400,27 +400,27 @@ struct Builder {
         int rc = timestep_embed(ts, B_, c0, s16, st);
         if (rc) return rc;
         return timestep_embed(a.added, B_ * 3, add_dim, s16 + kSmall, st);  // [B*3, 256] == [B, 768]
-      }, 3);
+      }, 3, "timestep embeddings");
       GemmEpilogue e1; e1.out = emb; e1.out_fp16 = 0;
       linear(small16, B, c.boc[0], "time_embedding.linear_1", c.temb_dim, e1);
       { float* x = emb; __half* o = small16 + 2 * kSmall; long long n = (long long)B * c.temb_dim;
-        push([=](cudaStream_t st) { return silu_f16(x, o, n, st); }); }
+        push([=](cudaStream_t st) { return silu_f16(x, o, n, st); }, 1, "silu"); }
       GemmEpilogue e2; e2.out = emb; e2.out_fp16 = 0;
       linear(small16 + 2 * kSmall, B, c.temb_dim, "time_embedding.linear_2", c.temb_dim, e2);
       GemmEpilogue e3; e3.out = emb2; e3.out_fp16 = 0;
       linear(small16 + kSmall, B, 3 * c.add_dim, "add_embedding.linear_1", c.temb_dim, e3);
       { float* x = emb2; __half* o = small16 + 2 * kSmall; long long n = (long long)B * c.temb_dim;
-        push([=](cudaStream_t st) { return silu_f16(x, o, n, st); }); }
+        push([=](cudaStream_t st) { return silu_f16(x, o, n, st); }, 1, "silu"); }
       GemmEpilogue e4; e4.out = emb; e4.out_fp16 = 0; e4.res1 = emb;  // emb = time_emb + add_emb
       linear(small16 + 2 * kSmall, B, c.temb_dim, "add_embedding.linear_2", c.temb_dim, e4);
       // every time_emb_proj(SiLU(emb)) of the 44 res blocks in one GEMM
       { float* x = emb; __half* o = small16 + 3 * kSmall; long long n = (long long)B * c.temb_dim;
-        push([=](cudaStream_t st) { return silu_f16(x, o, n, st); }); }
+        push([=](cudaStream_t st) { return silu_f16(x, o, n, st); }, 1, "silu"); }
       GemmEpilogue e5; e5.out = temb_all; e5.out_fp16 = 0;
       linear(small16 + 3 * kSmall, B, c.temb_dim, "temb_proj_all", c.temb_total, e5);
       // every single-key cross attention: to_out(to_v(ehs_b)) + bias, folded weights, one GEMM
       { __half* o = small16 + 4 * kSmall; long long n = (long long)B * c.cross_dim;
-        push([=](cudaStream_t st) { return cast_f16(u->args.ehs, o, n, st); }); }
+        push([=](cudaStream_t st) { return cast_f16(u->args.ehs, o, n, st); }, 1, "cast"); }
       GemmEpilogue e6; e6.out = xattn_all; e6.out_fp16 = 0;
       linear(small16 + 4 * kSmall, B, c.cross_dim, "xattn_all", c.xattn_total, e6);
     }
@@ -446,7 +446,7 @@ struct Builder {
       if (i < 3) {
         // Downsample2D: conv 3x3 stride 2 pad 1 on the 4 phase images
         { const float* xi = x; __half* o = resamp16; long long n = BF; int hh = lh[i], ww = lw[i], C = xC;
-          push([=](cudaStream_t st) { return downsplit(xi, o, n, hh, ww, C, st); }); }
+          push([=](cudaStream_t st) { return downsplit(xi, o, n, hh, ww, C, st); }, 1, "downsplit"); }
         float* o = bump.take<float>(lM[i + 1] * Cout);
         GemmProblem pr;
         pr.a0 = resamp16; pr.w = W(bp + ".downsamplers.0.conv.weight");
@@ -492,7 +492,7 @@ struct Builder {
       if (i < 3) {
         // Upsample2D: nearest x2 then conv 3x3
         { const float* xi = x; __half* o = resamp16; long long n = BF; int hh = lh[lvl], ww = lw[lvl], C = xC;
-          push([=](cudaStream_t st) { return upsample2x(xi, o, n, hh, ww, C, st); }); }
+          push([=](cudaStream_t st) { return upsample2x(xi, o, n, hh, ww, C, st); }, 1, "upsample2x"); }
         EVW_CHECK_ARG(lh[lvl - 1] == 2 * lh[lvl] && lw[lvl - 1] == 2 * lw[lvl],
                       "latent size %dx%d must be divisible by 8 (three x2 resampling stages)", P.h, P.w);
         float* o = pp[cur ^ 1];
@@ -510,7 +510,7 @@ struct Builder {
         const CallArgs& a = u->args;
         if (a.mode == 1) return post_cfg_euler(y, T_, Co, HW, Np, a.sigma, a.sigma_next, a.g_min, a.g_max, a.latents_out, st);
         return nhwc_to_nchw_f32(y, (long long)B_ * T_, Co, HW, Np, a.out, st);
-      });
+      }, 1, "post (CFG+Euler / layout)");
     }
     if (!fail.empty()) {
       set_error("evw_unet plan: %s", fail.c_str());
@@ -559,8 +559,36 @@ int debug_stats(const void* p, long long n, int fp16, cudaStream_t st, double* a
   return 0;
 }
 
+// EVW_UNET_PROFILE=<path>: time every op with CUDA events (serialised) and append "index ms label" lines
+int run_plan_profiled(UNet* U, cudaStream_t st, const char* path) {
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  FILE* f = fopen(path, "a");
+  size_t i = 0;
+  for (auto& op : U->plan->ops) {
+    cudaEventRecord(e0, st);
+    int rc = op(st);
+    if (rc) return rc;
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (f) fprintf(f, "%zu %.6f %s\n", i, ms, U->plan->meta[i].label.empty() ? "-" : U->plan->meta[i].label.c_str());
+    ++i;
+  }
+  if (f) {
+    fprintf(f, "END\n");
+    fclose(f);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return EVW_OK;
+}
+
 int run_plan(UNet* U, cudaStream_t st) {
   static const bool debug = getenv("EVW_UNET_DEBUG") != nullptr;
+  if (const char* prof = getenv("EVW_UNET_PROFILE")) return run_plan_profiled(U, st, prof);
   size_t i = 0;
   for (auto& op : U->plan->ops) {
     int rc = op(st);

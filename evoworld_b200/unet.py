@@ -550,7 +550,9 @@ def algorithmic_flops(cfg: dict, B: int, T: int, h: int, w: int) -> Dict[str, fl
         gemm += 2.0 * T * (c * 4 * c + 4 * c * c) * B    # time_pos_embed MLP
         for _blk in range(2):                            # spatial + temporal block
             gemm += 2.0 * M * c * c * 4                  # attn1 q,k,v,out
-            gemm += 2.0 * M * c * c * 2 + 2.0 * M * cross * c * 2  # attn2 q,out on tokens; k,v on the 1-token context
+            gemm += 2.0 * M * c * c * 2                  # attn2 to_q, to_out on every token
+        gemm += 2.0 * BF * cross * c * 2                 # spatial attn2 to_k, to_v: one context token per frame
+        gemm += 2.0 * (M // T) * cross * c * 2           # temporal attn2 to_k, to_v: one context token per (b, s)
         gemm += 2.0 * M * (c * 8 * c + 4 * c * c) * 3    # ff, ff_in, ff
         sdpa_s += 4.0 * BF * heads * S * S * 64 + 4.0 * BF * heads * S * 1 * 64
         sdpa_t += 4.0 * B * S * heads * T * T * 64 + 4.0 * B * S * heads * T * 1 * 64
