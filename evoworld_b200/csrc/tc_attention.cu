@@ -14,6 +14,7 @@
 #include "common.h"
 #include "tc_common.cuh"
 #include "unet_elem.h"
+#include <cstdlib>
 
 namespace evw {
 using namespace tc;
@@ -242,14 +243,281 @@ spatial_attn_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict
   }
 }
 
+
+// ==========================================================================================
+// v2: two 128-query tiles per CTA (two softmax warpgroups ping-pong on the MUFU pipe and share every
+// K/V tile), single-buffered S/O in TMEM, P through shared memory, event-driven MMA issue.
+//   warp 0 TMA | warp 1 MMA | warps 4..7 softmax group A (rows q0..q0+127) | warps 8..11 group B (+128)
+// Registers are rebalanced with setmaxnreg: the control warpgroup drops to 40, the softmax warpgroups grow to 232.
+// ==========================================================================================
+constexpr int kA2Threads = 384;  // warpgroup 0: TMA + MMA (+2 idle warps), warpgroups 1, 2: softmax groups A, B
+constexpr int kA2OffQ = 0;                                   // 2 x 16 KiB
+constexpr int kA2OffK = kA2OffQ + 2 * kTileBytes;            // 3 x 16 KiB
+constexpr int kA2OffV = kA2OffK + kKvStages * kTileBytes;    // 3 x 16 KiB
+constexpr int kA2OffP = kA2OffV + kKvStages * kTileBytes;    // 2 groups x 32 KiB
+constexpr int kA2OffBar = kA2OffP + 2 * 2 * kTileBytes;
+constexpr int kA2Smem = kA2OffBar + 256 + 1024;
+constexpr int kPolyEvery = 4;  // every 4th exponential is evaluated on the FMA pipe instead of MUFU
+
+// 2^x for x <= 0 on the FMA/ALU pipes: round-to-nearest split x = n + r, |r| <= 0.5, degree-4 polynomial for 2^r
+// (relative error < 5e-5, below the fp16 rounding of P), exponent patched in with an integer add.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;  // 1.5 * 2^23: the low mantissa bits now hold round(x)
+  const float n = t - 12582912.0f;
+  const float r = x - n;
+  float p = fmaf(9.618129e-3f, r, 5.550411e-2f);
+  p = fmaf(p, r, 2.402265e-1f);
+  p = fmaf(p, r, 6.931472e-1f);
+  p = fmaf(p, r, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+__global__ void __launch_bounds__(kA2Threads, 1)
+spatial_attn2_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ out, int S, int C, float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, frame = blockIdx.z;
+  const int q0 = blockIdx.x * 2 * kBQ;
+  const int n_kv = (S + kBKV - 1) / kBKV;
+  const bool b_active = q0 + kBQ < S;
+
+  const uint32_t bar = base + kA2OffBar;
+  const uint32_t q_full = bar;
+  auto kv_full = [&](int s) { return bar + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bar + 8u * (1 + kKvStages + s); };
+  auto s_full = [&](int g) { return bar + 8u * (1 + 2 * kKvStages + g); };
+  auto s_empty = [&](int g) { return bar + 8u * (3 + 2 * kKvStages + g); };
+  auto p_full = [&](int g) { return bar + 8u * (5 + 2 * kKvStages + g); };
+  auto o_full = [&](int g) { return bar + 8u * (7 + 2 * kKvStages + g); };
+  const uint32_t tmem_slot = bar + 8u * (9 + 2 * kKvStages);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + kA2OffBar + 8 * (9 + 2 * kKvStages));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKvStages; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(s_full(g), 1);
+      mbar_init(s_empty(g), 4);
+      mbar_init(p_full(g), 4);
+      mbar_init(o_full(g), 1);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  }
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+      tma_load_3d(&tmap, base + kA2OffQ, q_full, head * kD, q0, frame);
+      tma_load_3d(&tmap, base + kA2OffQ + kTileBytes, q_full, head * kD, q0 + kBQ, frame);
+    }
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j % kKvStages;
+      mbar_wait(kv_empty(st), ((j / kKvStages) & 1) ^ 1u);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(kv_full(st), 2 * kTileBytes);
+        tma_load_3d(&tmap, base + kA2OffK + st * kTileBytes, kv_full(st), C + head * kD, j * kBKV, frame);
+        tma_load_3d(&tmap, base + kA2OffV + st * kTileBytes, kv_full(st), 2 * C + head * kD, j * kBKV, frame);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (event driven) =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(kBQ, kBKV, 0, 0, 0);
+      const uint32_t idesc_o = make_idesc_f16(kBQ, kD, 0, 0, 1);
+      mbar_wait(q_full, 0);
+      int s_next[2] = {0, 0}, pv_next[2] = {0, 0};
+      const int n_g[2] = {n_kv, b_active ? n_kv : 0};
+      long long t0 = clock64();
+      while (pv_next[0] < n_g[0] || pv_next[1] < n_g[1]) {
+        bool progress = false;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          // ---- S_g(i) = Q_g K_i^T : needs K_i in smem and the previous S_g read out by the softmax group
+          int i = s_next[g];
+          if (i < n_g[g] && mbar_test(kv_full(i % kKvStages), (i / kKvStages) & 1) &&
+              (i == 0 || mbar_test(s_empty(g), (i - 1) & 1))) {
+            tc_fence_after();
+            const uint64_t dq = make_desc_k_sw128(base + kA2OffQ + g * kTileBytes);
+            const uint64_t dk = make_desc_k_sw128(base + kA2OffK + (i % kKvStages) * kTileBytes);
+#pragma unroll
+            for (int k = 0; k < kD / 16; ++k)
+              umma_f16_ss(tmem_base + g * kBKV, dq + 2ull * k, dk + 2ull * k, idesc_s, k != 0);
+            tc_commit(s_full(g));
+            s_next[g] = i + 1;
+            progress = true;
+          }
+          // ---- O_g(i) = P_g(i) V_i : needs P_g(i) in smem (which also implies O_g(i-1) was folded)
+          i = pv_next[g];
+          if (i < n_g[g] && i < s_next[g] && mbar_test(p_full(g), i & 1)) {
+            tc_fence_after();
+            const int st = i % kKvStages;
+#pragma unroll
+            for (int ks = 0; ks < kBKV / 16; ++ks) {
+              const uint64_t dp = make_desc_k_sw128(base + kA2OffP + g * 2 * kTileBytes + (ks >> 2) * kTileBytes) + 2ull * (ks & 3);
+              const uint64_t dv = make_desc_mn_sw128(base + kA2OffV + st * kTileBytes + ks * 2048, 1024);
+              umma_f16_ss(tmem_base + 256 + g * kD, dp, dv, idesc_o, ks != 0);
+            }
+            tc_commit(o_full(g));
+            pv_next[g] = i + 1;
+            // K_i / V_i are free once both groups have issued their PV for tile i
+            const int other = g ^ 1;
+            if (n_g[other] == 0 || pv_next[other] > i) tc_commit(kv_empty(st));
+            progress = true;
+          }
+        }
+        if (progress) t0 = clock64();
+        else if (clock64() - t0 > 8000000000ll) __trap();
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== softmax groups =====================
+    const int g = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int qrow = q0 + g * kBQ + r;
+    if (g == 0 || b_active) {
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t s_addr = lane_addr + g * kBKV, o_addr = lane_addr + 256 + g * kD;
+      float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+      float o_acc[kD];
+#pragma unroll
+      for (int d = 0; d < kD; ++d) o_acc[d] = 0.f;
+      uint8_t* prow = base_ptr + kA2OffP + g * 2 * kTileBytes + r * 128;
+
+      auto fold_o = [&](int i, float alpha) {
+        mbar_wait(o_full(g), i & 1);
+        tc_fence_after();
+        uint32_t lo[32], hi[32];
+        tmem_ld_32x32b_x32(o_addr, lo);
+        tmem_ld_32x32b_x32(o_addr + 32, hi);
+        tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < 32; ++d) {
+          o_acc[d] = fmaf(o_acc[d], alpha, __uint_as_float(lo[d]));
+          o_acc[32 + d] = fmaf(o_acc[32 + d], alpha, __uint_as_float(hi[d]));
+        }
+      };
+
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(s_full(g), j & 1);
+        tc_fence_after();
+        uint32_t s[128];
+        {
+          uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+          uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+          uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
+          uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
+          tmem_ld_32x32b_x32(s_addr + 0, s0);
+          tmem_ld_32x32b_x32(s_addr + 32, s1);
+          tmem_ld_32x32b_x32(s_addr + 64, s2);
+          tmem_ld_32x32b_x32(s_addr + 96, s3);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty(g));  // S_g(j+1) may now overwrite the TMEM tile
+        // fold the previous PV result: also proves PV_g(j-1) is done, i.e. the P buffer is free again
+        if (j > 0) fold_o(j - 1, alpha_prev);
+
+        const int kv_valid = S - j * kBKV;
+        float mx = -INFINITY;
+        if (kv_valid >= kBKV) {
+#pragma unroll
+          for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(s[c]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 128; ++c) {
+            if (c >= kv_valid) s[c] = 0xff800000u;  // -inf
+            mx = fmaxf(mx, __uint_as_float(s[c]));
+          }
+        }
+        const float m_new = fmaxf(m_run, mx * scale_log2e);
+        const float alpha = fast_exp2(m_run - m_new);
+        const float neg_m = -m_new;
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c0 = ch * 8 + 2 * i;
+            const float x0 = fmaf(__uint_as_float(s[c0]), scale_log2e, neg_m);
+            const float x1 = fmaf(__uint_as_float(s[c0 + 1]), scale_log2e, neg_m);
+            const float p0 = fast_exp2(x0);
+            const float p1 = ((c0 + 1) % kPolyEvery == kPolyEvery - 1) ? exp2_poly(x1) : fast_exp2(x1);
+            sum0 += p0;
+            sum1 += p1;
+            __half2 h = __floats2half2_rn(p0, p1);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          const int atom = ch >> 3, cc = ch & 7;
+          *reinterpret_cast<uint4*>(prow + atom * kTileBytes + ((cc ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        l_run = l_run * alpha + (sum0 + sum1);
+        m_run = m_new;
+        alpha_prev = alpha;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(g));
+      }
+      fold_o(n_kv - 1, alpha_prev);
+      if (qrow < S) {
+        const float inv = 1.0f / l_run;
+        uint4* op = reinterpret_cast<uint4*>(out + ((long long)frame * S + qrow) * C + head * kD);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          __half2 h0 = __floats2half2_rn(o_acc[8 * i + 0] * inv, o_acc[8 * i + 1] * inv);
+          __half2 h1 = __floats2half2_rn(o_acc[8 * i + 2] * inv, o_acc[8 * i + 3] * inv);
+          __half2 h2 = __floats2half2_rn(o_acc[8 * i + 4] * inv, o_acc[8 * i + 5] * inv);
+          __half2 h3 = __floats2half2_rn(o_acc[8 * i + 6] * inv, o_acc[8 * i + 7] * inv);
+          uint4 v;
+          v.x = *reinterpret_cast<uint32_t*>(&h0); v.y = *reinterpret_cast<uint32_t*>(&h1);
+          v.z = *reinterpret_cast<uint32_t*>(&h2); v.w = *reinterpret_cast<uint32_t*>(&h3);
+          op[i] = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace
 
 int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, cudaStream_t st) {
   EVW_CHECK_ARG(qkv && out && F > 0 && S > 0 && heads > 0, "spatial_attention: bad arguments");
   const int C = heads * kD;
   static bool attr_set = false;
+  static bool use_v1 = false;
   if (!attr_set) {
     EVW_CUDA(cudaFuncSetAttribute(spatial_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    EVW_CUDA(cudaFuncSetAttribute(spatial_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2Smem));
+    use_v1 = getenv("EVW_ATTN_V1") != nullptr;
     attr_set = true;
   }
   alignas(64) CUtensorMap tmap;
@@ -258,8 +526,13 @@ int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, c
   uint32_t box[3] = {(uint32_t)kD, (uint32_t)kBQ, 1};
   int rc = encode_tmap_f16(&tmap, qkv, 3, dims, str, box);
   if (rc) return rc;
-  dim3 grid((S + kBQ - 1) / kBQ, heads, F);
-  spatial_attn_kernel<<<grid, kAttnThreads, kAttnSmem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
+  if (use_v1) {
+    dim3 grid((S + kBQ - 1) / kBQ, heads, F);
+    spatial_attn_kernel<<<grid, kAttnThreads, kAttnSmem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
+  } else {
+    dim3 grid((S + 2 * kBQ - 1) / (2 * kBQ), heads, F);
+    spatial_attn2_kernel<<<grid, kA2Threads, kA2Smem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
+  }
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }

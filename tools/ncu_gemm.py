@@ -1,0 +1,27 @@
+"""Small driver for ncu captures of single kernels: python tools/ncu_gemm.py <case>"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from evoworld_b200 import ops
+dev = torch.device("cuda:0")
+case = sys.argv[1] if len(sys.argv) > 1 else "geglu"
+M = 28 * 9216
+if case == "geglu":
+    a = torch.randn(M, 320, device=dev).half(); w = torch.randn(2560, 320, device=dev).half() * 0.05
+    f = lambda: ops.gemm_f16(a, w, geglu=True)
+elif case == "linear":
+    a = torch.randn(M, 320, device=dev).half(); w = torch.randn(320, 320, device=dev).half() * 0.05
+    f = lambda: ops.gemm_f16(a, w)
+elif case == "ff2":
+    a = torch.randn(M, 1280, device=dev).half(); w = torch.randn(320, 1280, device=dev).half() * 0.03
+    r = torch.randn(M, 320, device=dev)
+    f = lambda: ops.gemm_f16(a, w, res1=r, out_dtype=torch.float32)
+elif case == "attn":
+    qkv = torch.randn(28 * 9216, 960, device=dev).half()
+    f = lambda: ops.spatial_attention(qkv, 28, 9216, 5)
+elif case == "gn":
+    x = torch.randn(M, 320, device=dev); g = torch.ones(320, device=dev); b = torch.zeros(320, device=dev)
+    f = lambda: ops.group_norm(x, g, b, 28, 1e-6, True)
+for _ in range(4):
+    f()
+torch.cuda.synchronize()
