@@ -318,10 +318,9 @@ spatial_attn2_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp < 4) {
+    // control warpgroup: give registers back, the softmax warpgroups take them (register budgets are per branch,
+    // so the setmaxnreg has to dominate the whole role body)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-  }
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -390,7 +389,9 @@ spatial_attn2_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     // ===================== softmax groups =====================
     const int g = (warp - 4) >> 2;
     const int quarter = warp & 3;

@@ -98,34 +98,62 @@ __device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = raw;
 }
 
-// epilogue for 8 consecutive output columns starting at column `n` of output row `row`
-template <typename OutT>
-__device__ __forceinline__ void epilogue8(const GemmEpilogue& ep, float (&v)[8], long long row, int n, int ldo,
-                                          long long rv_row) {
-  if (ep.s0 != 1.0f) {
+// 16 consecutive values of a residual / row-vector operand (fp32 or fp16) at element offset `off`;
+// when only 8 remain (N tail) the upper half is zero.  Coherent loads: residuals may alias the output.
+__device__ __forceinline__ void load16(const void* base, int is_fp16, long long off, bool full, float (&v)[16]) {
+  float lo[8], hi[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] *= ep.s0;
+  for (int i = 0; i < 8; ++i) hi[i] = 0.f;
+  if (is_fp16) {
+    const __half* p = reinterpret_cast<const __half*>(base) + off;
+    load8_plain(p, lo);
+    if (full) load8_plain(p + 8, hi);
+  } else {
+    const float* p = reinterpret_cast<const float*>(base) + off;
+    load8_plain(p, lo);
+    if (full) load8_plain(p + 8, hi);
   }
-  if (ep.rowvec) {
-    float r[8];
-    load8(ep.rowvec + rv_row * (ep.rv_ld ? ep.rv_ld : ldo) + n, r);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += r[i];
-  }
-  if (ep.res1) {
-    float r[8];
-    if (ep.res1_fp16) load8_plain(reinterpret_cast<const __half*>(ep.res1) + row * ldo + n, r);
-    else load8_plain(reinterpret_cast<const float*>(ep.res1) + row * ldo + n, r);
+  for (int i = 0; i < 8; ++i) { v[i] = lo[i]; v[8 + i] = hi[i]; }
+}
+
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+
+// store 16 consecutive outputs at element offset `off`: one 32-byte sector (fp16) or two (fp32) per row
+__device__ __forceinline__ void store16(const GemmEpilogue& ep, const float (&v)[16], long long off, bool wide_ok) {
+  if (ep.out_fp16) {
+    uint32_t w[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaf(ep.s1, r[i], v[i]);
-  }
-  if (ep.res2) {
-    float r[8];
-    load8_plain(reinterpret_cast<const float*>(ep.res2) + row * ldo + n, r);
+    for (int i = 0; i < 8; ++i) {
+      __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    __half* p = reinterpret_cast<__half*>(ep.out) + off;
+    if (wide_ok) {
+      st_global_256(p, w);
+    } else {
+      *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(p + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+  } else {
+    float* p = reinterpret_cast<float*>(ep.out) + off;
+    if (wide_ok) {
+      uint32_t w[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaf(ep.s2, r[i], v[i]);
+      for (int i = 0; i < 8; ++i) w[i] = __float_as_uint(v[i]);
+      st_global_256(p, w);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = __float_as_uint(v[8 + i]);
+      st_global_256(p + 8, w);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
   }
-  store8(reinterpret_cast<OutT*>(ep.out) + row * ldo + n, v);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -233,11 +261,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int q = warp & 3;          // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;     // row of the 128-row tile
-    const int chalf = (warp - 4) >> 2;  // two warps share a lane quarter and alternate 32-column chunks
+    // Two warps share each TMEM lane quarter and alternate column steps.  Per step: issue the TMEM load, issue the
+    // global loads of the NEXT step's residual / row-vector operands (software pipeline: their latency overlaps this
+    // step's work), wait for TMEM, apply the epilogue, store one full 32-byte sector per row where alignment allows.
+    // The bias slice of the tile is staged in shared memory once per tile.
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;         // row of the 128-row tile
+    const int cgrp = (warp - 4) >> 2;    // column group of this warp
+    constexpr int NG = kEpiWarps / 4;
     const GemmEpilogue& ep = P.ep;
     const int ldo = ep.geglu ? P.N / 2 : P.N;
+    const int rv_ld = ep.rv_ld ? ep.rv_ld : ldo;
+    const int esz = ep.out_fp16 ? 2 : 4;
+    const bool wide_ok = (((long long)ldo * esz) % 32 == 0) && ((reinterpret_cast<uintptr_t>(ep.out) & 31) == 0);
+    float* bias_s = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 8 * (2 * stages + 4) + 16);
+    const int et = threadIdx.x - 128;    // 0 .. 32*kEpiWarps-1
     int it = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -254,65 +292,87 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
       const long long row = (((long long)tb * P.T + tt) * P.Y + gy) * P.X + gx;
       const long long rv_row = ep.rowvec ? (row / ep.rv_div) % ep.rv_mod : 0;
       const int n0 = n_tile * P.block_n;
+      float* bs = bias_s + acc * 256;
+      if (et < P.block_n) bs[et] = (ep.bias && n0 + et < P.N) ? __ldg(ep.bias + n0 + et) : 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
 
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
-      for (int c = chalf * 32; c < P.block_n; c += 64) {
-        uint32_t raw[32];
-        __syncwarp();
-        if (P.block_n - c >= 32) {
-          tmem_ld_32x32b_x32(t_addr + c, raw);
-        } else {
-          uint32_t lo[16];
-          tmem_ld_32x32b_x16(t_addr + c, lo);
+      if (ep.geglu) {
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        // 32 accumulator columns = [16 value | 16 gate] -> 16 outputs
+        for (int k = cgrp; k * 32 < P.block_n; k += NG) {
+          uint32_t raw[32];
+          __syncwarp();
+          tmem_ld_32x32b_x32(t_addr + k * 32, raw);
+          tmem_ld_wait();
+          const int nh = n0 + k * 32;
+          if (row_ok && nh < P.N) {
+            float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { raw[i] = lo[i]; raw[16 + i] = 0; }
-        }
-        tmem_ld_wait();
-        const int ncols = min(32, P.block_n - c);
-        if (!row_ok) {
-          // rows outside the image: nothing to store
-        } else if (ep.geglu) {
-          // weight rows were interleaved [16 x value | 16 x gate] per 32 columns at pack time
-          const int nh = n0 + c;  // column in the interleaved 2x space
-          const int no = nh / 2;  // first of 16 output columns
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            if (nh >= P.N) break;
-            float v[8], bh[8], bg[8];
-            if (ep.bias) {
-              load8(ep.bias + nh + g * 8, bh);
-              load8(ep.bias + nh + 16 + g * 8, bg);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { bh[i] = 0.f; bg[i] = 0.f; }
+            for (int i = 0; i < 16; ++i) {
+              const float hv = __uint_as_float(raw[i]) + bs[k * 32 + i];
+              const float gv = __uint_as_float(raw[16 + i]) + bs[k * 32 + 16 + i];
+              v[i] = hv * gelu_erf(gv) * ep.s0;
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float hv = __uint_as_float(raw[g * 8 + i]) + bh[i];
-              const float gv = __uint_as_float(raw[16 + g * 8 + i]) + bg[i];
-              v[i] = hv * gelu_erf(gv);
-            }
-            if (ep.out_fp16) epilogue8<__half>(ep, v, row, no + g * 8, ldo, rv_row);
-            else epilogue8<float>(ep, v, row, no + g * 8, ldo, rv_row);
+            store16(ep, v, row * ldo + nh / 2, wide_ok);
           }
-        } else {
+        }
+      } else {
+        const int nsteps = P.block_n / 16;
+        float r1n[16], rvn[16];
+        auto prefetch = [&](int k) {
+          const int n = n0 + k * 16;
+          const bool ok = row_ok && k < nsteps && n < P.N;
+          const bool full = n + 16 <= P.N;
+          if (ep.res1) {
+            if (ok) load16(ep.res1, ep.res1_fp16, row * ldo + n, full, r1n);
+          }
+          if (ep.rowvec) {
+            if (ok) load16(ep.rowvec, 0, rv_row * rv_ld + n, full, rvn);
+          }
+        };
+        prefetch(cgrp);
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        for (int k = cgrp; k < nsteps; k += NG) {
+          uint32_t raw[16];
+          float r1[16], rv[16];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = n0 + c + g * 8;
-            if (g * 8 >= ncols || n >= P.N) break;
-            float v[8];
+          for (int i = 0; i < 16; ++i) { r1[i] = r1n[i]; rv[i] = rvn[i]; }
+          __syncwarp();
+          tmem_ld_32x32b_x16(t_addr + k * 16, raw);
+          prefetch(k + NG);
+          tmem_ld_wait();
+          const int n = n0 + k * 16;
+          if (row_ok && n < P.N) {
+            const bool full = n + 16 <= P.N;
+            float v[16];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[g * 8 + i]);
-            if (ep.bias) {
-              float bv[8];
-              load8(ep.bias + n, bv);
+            for (int i = 0; i < 16; ++i) v[i] = (__uint_as_float(raw[i]) + bs[k * 16 + i]) * ep.s0;
+            if (ep.rowvec) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] += bv[i];
+              for (int i = 0; i < 16; ++i) v[i] += rv[i];
             }
-            if (ep.out_fp16) epilogue8<__half>(ep, v, row, n, ldo, rv_row);
-            else epilogue8<float>(ep, v, row, n, ldo, rv_row);
+            if (ep.res1) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaf(ep.s1, r1[i], v[i]);
+            }
+            if (ep.res2) {
+              float r2[16];
+              load16(ep.res2, 0, row * ldo + n, full, r2);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaf(ep.s2, r2[i], v[i]);
+            }
+            if (full) {
+              store16(ep, v, row * ldo + n, wide_ok);
+            } else {  // N tail: only the first 8 columns exist (N is a multiple of 8)
+              float v8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v8[i] = v[i];
+              if (ep.out_fp16) store8(reinterpret_cast<__half*>(ep.out) + row * ldo + n, v8);
+              else store8(reinterpret_cast<float*>(ep.out) + row * ldo + n, v8);
+            }
           }
         }
       }
@@ -424,11 +484,11 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   }
   EVW_CHECK_ARG(ktot == pr.K_total, "gemm: K_total=%lld but taps cover %lld", (long long)pr.K_total, ktot);
   const uint32_t stage_bytes = kATileBytes + bn * kBlockK * 2;
-  int stages = (int)((227 * 1024 - 2048) / stage_bytes);
+  int stages = (int)((227 * 1024 - 4096) / stage_bytes);
   if (stages > 8) stages = 8;
   P.num_stages = stages;
   P.total_tiles = P.tiles_x * P.tiles_y * P.T * P.B * P.n_tiles;
-  op->smem_bytes = stages * stage_bytes + 8 * (2 * stages + 4) + 16 + 1024;
+  op->smem_bytes = stages * stage_bytes + 8 * (2 * stages + 4) + 16 + 2 * 256 * 4 + 1024;
   int sms = sm_count();
   op->grid = P.total_tiles < sms ? P.total_tiles : sms;
   static_assert(sizeof(KernelParams) <= sizeof(op->params), "GemmOp::params too small");
