@@ -66,9 +66,12 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
     barrier(world)
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    from evoworld_b200.distributed import gather_latents
+
     e0.record()
     for i in range(args.steps):
         step(i, x)
+    gathered = gather_latents(x)  # clip boundary: the only collective of the path (no-op at world == 1)
     e1.record()
     torch.cuda.synchronize(dev)
     barrier(world)
@@ -105,6 +108,7 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
         "gpu_launches": launches * args.steps,
         "config": {"workload": f"config 2: single 576x1024x{T}f clip, CFG batch 2, 72x128 latents, random-init 1.525B-param UNet, "
                                f"Karras sigmas (25-step schedule)", "frames": T, "finite_output": finite,
+                   "collective": f"all-gather of latents {tuple(gathered.shape)} at the clip boundary",
                    "l2": "working set (activations + 3 GB of fp16 weights) >> 126 MB L2; K steps in one CUDA-event pair"},
     }
     if rank == 0 and not args.no_cpu_baseline:
