@@ -47,6 +47,7 @@ def gather_latents(latents: torch.Tensor) -> torch.Tensor:
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return latents.unsqueeze(0)
     x = latents.contiguous()
-    out = torch.empty((dist.get_world_size(),) + tuple(x.shape), dtype=x.dtype, device=x.device)
-    dist.all_gather_into_tensor(out, x)
-    return out
+    world = dist.get_world_size()
+    out = torch.empty(world * x.numel(), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.view(-1))
+    return out.view((world,) + tuple(x.shape))

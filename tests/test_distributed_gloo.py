@@ -18,6 +18,7 @@ def _free_port():
 
 def _worker(rank, world, port, q):
     os.environ.update(WORLD_SIZE=str(world), RANK=str(rank), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")  # the container hostname may not resolve
     r, _, w = D.init_from_env("gloo")
     clips = list(D.shard_range(5, r, w, start_idx=10))
     lat = torch.full((1, 3, 4, 2, 4), float(r + 1))
