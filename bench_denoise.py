@@ -118,7 +118,7 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
 
 def run_cpu(T, steps=1, warmup=0):
     """The reference's CPU path for one denoise step, restated by the fp32 PyTorch oracle (diffusers is not
-    installable here), on a bounded sample: the full-width UNet at 18x32 latents (1/16 of the pixels)."""
+    installable here), on a bounded sample: the full-width UNet at 24x32 latents (1/12 of the pixels)."""
     import torch
 
     from evoworld_b200.unet import algorithmic_flops, DEFAULT_CONFIG
@@ -126,7 +126,7 @@ def run_cpu(T, steps=1, warmup=0):
 
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    h, w = 18, 32
+    h, w = 24, 32  # divisible by 8: three stride-2 stages must round-trip
     with torch.device("meta"):
         m = O.UNetSpatioTemporalConditionModel()
     m = m.to_empty(device="cpu")

@@ -508,17 +508,282 @@ spatial_attn2_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
   }
 }
 
+// ==========================================================================================
+// v3: as v2, plus (a) O and the softmax denominator accumulate in TENSOR MEMORY across all K/V tiles — the
+// denominator comes from a second tiny MMA of P against an all-ones [16 x 128] operand, so the CUDA cores neither
+// sum probabilities nor fold partial outputs; (b) lazy rescaling: the exponent reference m_ref of a row only moves
+// when the tile maximum exceeds it by more than 2^8, and only then are O and L rescaled in place (tcgen05.ld/st);
+// P = exp2(s c - m_ref) <= 256 stays well inside fp16.  Per score element the softmax warps issue ~3 instructions
+// (FMNMX3/2, FFMA, MUFU|poly, F2FP/2) instead of ~10.
+// ==========================================================================================
+constexpr int kA3OffOnes = kA2OffBar + 256;                  // 4 KiB of fp16 1.0 (K-major [16 x 128], swizzle-invariant)
+constexpr int kA3Smem = kA3OffOnes + 4096 + 1024;
+constexpr int kTmemO3 = 256, kTmemL3 = 384;                  // O_g at 256 + 64 g, L_g at 384 + 16 g
+constexpr float kLazyTau = 8.0f;
+
+__global__ void __launch_bounds__(kA2Threads, 1)
+spatial_attn3_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ out, int S, int C, float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, frame = blockIdx.z;
+  const int q0 = blockIdx.x * 2 * kBQ;
+  const int n_kv = (S + kBKV - 1) / kBKV;
+  const bool b_active = q0 + kBQ < S;
+
+  const uint32_t bar = base + kA2OffBar;
+  const uint32_t q_full = bar;
+  auto kv_full = [&](int s) { return bar + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bar + 8u * (1 + kKvStages + s); };
+  auto s_full = [&](int g) { return bar + 8u * (1 + 2 * kKvStages + g); };
+  auto s_empty = [&](int g) { return bar + 8u * (3 + 2 * kKvStages + g); };
+  auto p_full = [&](int g) { return bar + 8u * (5 + 2 * kKvStages + g); };
+  auto o_full = [&](int g) { return bar + 8u * (7 + 2 * kKvStages + g); };
+  const uint32_t tmem_slot = bar + 8u * (9 + 2 * kKvStages);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + kA2OffBar + 8 * (9 + 2 * kKvStages));
+
+  // all-ones operand for the row-sum MMA
+  for (int i = threadIdx.x; i < 4096 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(base_ptr + kA3OffOnes)[i] = 0x3C003C00u;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKvStages; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(s_full(g), 1);
+      mbar_init(s_empty(g), 4);
+      mbar_init(p_full(g), 4);
+      mbar_init(o_full(g), 1);
+    }
+    fence_barrier_init();
+  }
+  fence_proxy_async();  // ones tile + barrier inits visible to the async proxy
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+        tma_load_3d(&tmap, base + kA2OffQ, q_full, head * kD, q0, frame);
+        tma_load_3d(&tmap, base + kA2OffQ + kTileBytes, q_full, head * kD, q0 + kBQ, frame);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % kKvStages;
+        mbar_wait(kv_empty(st), ((j / kKvStages) & 1) ^ 1u);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(kv_full(st), 2 * kTileBytes);
+          tma_load_3d(&tmap, base + kA2OffK + st * kTileBytes, kv_full(st), C + head * kD, j * kBKV, frame);
+          tma_load_3d(&tmap, base + kA2OffV + st * kTileBytes, kv_full(st), 2 * C + head * kD, j * kBKV, frame);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer (event driven) =====================
+      if (lane == 0) {
+        const uint32_t idesc_s = make_idesc_f16(kBQ, kBKV, 0, 0, 0);
+        const uint32_t idesc_o = make_idesc_f16(kBQ, kD, 0, 0, 1);
+        const uint32_t idesc_l = make_idesc_f16(kBQ, 16, 0, 0, 0);
+        mbar_wait(q_full, 0);
+        int s_next[2] = {0, 0}, pv_next[2] = {0, 0};
+        const int n_g[2] = {n_kv, b_active ? n_kv : 0};
+        long long t0 = clock64();
+        while (pv_next[0] < n_g[0] || pv_next[1] < n_g[1]) {
+          bool progress = false;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            int i = s_next[g];
+            if (i < n_g[g] && mbar_test(kv_full(i % kKvStages), (i / kKvStages) & 1) &&
+                (i == 0 || mbar_test(s_empty(g), (i - 1) & 1))) {
+              tc_fence_after();
+              const uint64_t dq = make_desc_k_sw128(base + kA2OffQ + g * kTileBytes);
+              const uint64_t dk = make_desc_k_sw128(base + kA2OffK + (i % kKvStages) * kTileBytes);
+#pragma unroll
+              for (int k = 0; k < kD / 16; ++k)
+                umma_f16_ss(tmem_base + g * kBKV, dq + 2ull * k, dk + 2ull * k, idesc_s, k != 0);
+              tc_commit(s_full(g));
+              s_next[g] = i + 1;
+              progress = true;
+            }
+            i = pv_next[g];
+            if (i < n_g[g] && i < s_next[g] && mbar_test(p_full(g), i & 1)) {
+              tc_fence_after();
+              const int st = i % kKvStages;
+#pragma unroll
+              for (int ks = 0; ks < kBKV / 16; ++ks) {
+                const uint64_t dp = make_desc_k_sw128(base + kA2OffP + g * 2 * kTileBytes + (ks >> 2) * kTileBytes) + 2ull * (ks & 3);
+                const uint64_t dv = make_desc_mn_sw128(base + kA2OffV + st * kTileBytes + ks * 2048, 1024);
+                const uint64_t d1 = make_desc_k_sw128(base + kA3OffOnes + (ks >> 2) * 2048) + 2ull * (ks & 3);
+                umma_f16_ss(tmem_base + kTmemO3 + g * kD, dp, dv, idesc_o, (i | ks) != 0);   // O_g += P V
+                umma_f16_ss(tmem_base + kTmemL3 + g * 16, dp, d1, idesc_l, (i | ks) != 0);   // L_g += P 1
+              }
+              tc_commit(o_full(g));
+              pv_next[g] = i + 1;
+              const int other = g ^ 1;
+              if (n_g[other] == 0 || pv_next[other] > i) tc_commit(kv_empty(st));
+              progress = true;
+            }
+          }
+          if (progress) t0 = clock64();
+          else if (clock64() - t0 > 8000000000ll) __trap();
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // ===================== softmax groups =====================
+    const int g = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int qrow = q0 + g * kBQ + r;
+    if (g == 0 || b_active) {
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t s_addr = lane_addr + g * kBKV, o_addr = lane_addr + kTmemO3 + g * kD, l_addr = lane_addr + kTmemL3 + g * 16;
+      float m_ref = -INFINITY;
+      uint8_t* prow = base_ptr + kA2OffP + g * 2 * kTileBytes + r * 128;
+
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(s_full(g), j & 1);
+        tc_fence_after();
+        uint32_t s[128];
+        {
+          uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+          uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+          uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
+          uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
+          tmem_ld_32x32b_x32(s_addr + 0, s0);
+          tmem_ld_32x32b_x32(s_addr + 32, s1);
+          tmem_ld_32x32b_x32(s_addr + 64, s2);
+          tmem_ld_32x32b_x32(s_addr + 96, s3);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty(g));
+
+        const int kv_valid = S - j * kBKV;
+        float mx = -INFINITY;
+        if (kv_valid >= kBKV) {
+#pragma unroll
+          for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(s[c]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 128; ++c) {
+            if (c >= kv_valid) s[c] = 0xff800000u;
+            mx = fmaxf(mx, __uint_as_float(s[c]));
+          }
+        }
+        const float m_tile = mx * scale_log2e;
+        // P buffer / O accumulator of this group are free once PV_g(j-1) has completed
+        if (j > 0) {
+          mbar_wait(o_full(g), (j - 1) & 1);
+          tc_fence_after();
+        }
+        const bool need = m_tile > m_ref + kLazyTau;  // first tile: m_ref = -inf -> true
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = need ? m_tile : m_ref;
+          if (j > 0) {
+            const float f = need ? fast_exp2(m_ref - m_new) : 1.0f;
+            // rescale O (64 columns) and L (16 columns) of this row in tensor memory
+#pragma unroll
+            for (int part = 0; part < 4; ++part) {
+              uint32_t v[16];
+              tmem_ld_32x32b_x16(o_addr + part * 16, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+              tmem_st_32x32b_x16(o_addr + part * 16, v);
+            }
+            {
+              uint32_t v[16];
+              tmem_ld_32x32b_x16(l_addr, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+              tmem_st_32x32b_x16(l_addr, v);
+            }
+            tmem_st_wait();
+          }
+          m_ref = m_new;
+        }
+        const float neg_m = -m_ref;
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c0 = ch * 8 + 2 * i;
+            const float x0 = fmaf(__uint_as_float(s[c0]), scale_log2e, neg_m);
+            const float x1 = fmaf(__uint_as_float(s[c0 + 1]), scale_log2e, neg_m);
+            const float p0 = fast_exp2(x0);
+            const float p1 = ((c0 + 1) % kPolyEvery == kPolyEvery - 1) ? exp2_poly(x1) : fast_exp2(x1);
+            __half2 h = __floats2half2_rn(p0, p1);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          const int atom = ch >> 3, cc = ch & 7;
+          *reinterpret_cast<uint4*>(prow + atom * kTileBytes + ((cc ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(g));
+      }
+      // final: O / L
+      mbar_wait(o_full(g), (n_kv - 1) & 1);
+      tc_fence_after();
+      uint32_t lo[32], hi[32], lv[16];
+      tmem_ld_32x32b_x32(o_addr, lo);
+      tmem_ld_32x32b_x32(o_addr + 32, hi);
+      tmem_ld_32x32b_x16(l_addr, lv);
+      tmem_ld_wait();
+      if (qrow < S) {
+        const float inv = 1.0f / __uint_as_float(lv[0]);
+        uint4* op = reinterpret_cast<uint4*>(out + ((long long)frame * S + qrow) * C + head * kD);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t* src = (i < 4) ? &lo[8 * i] : &hi[8 * (i - 4)];
+          __half2 h0 = __floats2half2_rn(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
+          __half2 h1 = __floats2half2_rn(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
+          __half2 h2 = __floats2half2_rn(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
+          __half2 h3 = __floats2half2_rn(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
+          uint4 v;
+          v.x = *reinterpret_cast<uint32_t*>(&h0); v.y = *reinterpret_cast<uint32_t*>(&h1);
+          v.z = *reinterpret_cast<uint32_t*>(&h2); v.w = *reinterpret_cast<uint32_t*>(&h3);
+          op[i] = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace
 
 int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, cudaStream_t st) {
   EVW_CHECK_ARG(qkv && out && F > 0 && S > 0 && heads > 0, "spatial_attention: bad arguments");
   const int C = heads * kD;
   static bool attr_set = false;
-  static bool use_v1 = false;
+  static bool use_v1 = false, use_v2 = false;
   if (!attr_set) {
     EVW_CUDA(cudaFuncSetAttribute(spatial_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     EVW_CUDA(cudaFuncSetAttribute(spatial_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2Smem));
+    EVW_CUDA(cudaFuncSetAttribute(spatial_attn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3Smem));
     use_v1 = getenv("EVW_ATTN_V1") != nullptr;
+    use_v2 = getenv("EVW_ATTN_V2") != nullptr;
     attr_set = true;
   }
   alignas(64) CUtensorMap tmap;
@@ -530,9 +795,12 @@ int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, c
   if (use_v1) {
     dim3 grid((S + kBQ - 1) / kBQ, heads, F);
     spatial_attn_kernel<<<grid, kAttnThreads, kAttnSmem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
-  } else {
+  } else if (use_v2) {
     dim3 grid((S + 2 * kBQ - 1) / (2 * kBQ), heads, F);
     spatial_attn2_kernel<<<grid, kA2Threads, kA2Smem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
+  } else {
+    dim3 grid((S + 2 * kBQ - 1) / (2 * kBQ), heads, F);
+    spatial_attn3_kernel<<<grid, kA2Threads, kA3Smem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
   }
   EVW_LAUNCH_CHECK();
   return EVW_OK;
