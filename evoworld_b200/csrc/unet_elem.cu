@@ -50,18 +50,30 @@ gn_stats_kernel(const T0* __restrict__ src0, int C0, const float* __restrict__ s
 #pragma unroll
     for (int i = 0; i < 4; ++i) { s[j][i] = 0.f; q[j][i] = 0.f; }
   if (tr < R) {
-    for (long long r = r0 + tr; r < r1; r += R) {
-      const long long row = (long long)inst * rows_per_inst + r;
+    // 4 rows in flight per thread (independent 16-byte loads) to cover DRAM latency
+    for (long long rb = r0 + tr; rb < r1; rb += 4LL * R) {
+      float4 v[4][kGnMaxNQ];
 #pragma unroll
-      for (int j = 0; j < kGnMaxNQ; ++j) {
-        if (j < NQ) {
-          const int c = 4 * (tq + j * TQ);
-          float4 v = (c < C0) ? ld4(src0 + row * C0 + c) : ld4(src1 + row * C1 + (c - C0));
-          s[j][0] += v.x; s[j][1] += v.y; s[j][2] += v.z; s[j][3] += v.w;
-          q[j][0] = fmaf(v.x, v.x, q[j][0]); q[j][1] = fmaf(v.y, v.y, q[j][1]);
-          q[j][2] = fmaf(v.z, v.z, q[j][2]); q[j][3] = fmaf(v.w, v.w, q[j][3]);
+      for (int u = 0; u < 4; ++u) {
+        const long long r = rb + (long long)u * R;
+        const long long row = (long long)inst * rows_per_inst + r;
+#pragma unroll
+        for (int j = 0; j < kGnMaxNQ; ++j) {
+          v[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j < NQ && r < r1) {
+            const int c = 4 * (tq + j * TQ);
+            v[u][j] = (c < C0) ? ld4(src0 + row * C0 + c) : ld4(src1 + row * C1 + (c - C0));
+          }
         }
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < kGnMaxNQ; ++j) {
+          s[j][0] += v[u][j].x; s[j][1] += v[u][j].y; s[j][2] += v[u][j].z; s[j][3] += v[u][j].w;
+          q[j][0] = fmaf(v[u][j].x, v[u][j].x, q[j][0]); q[j][1] = fmaf(v[u][j].y, v[u][j].y, q[j][1]);
+          q[j][2] = fmaf(v[u][j].z, v[u][j].z, q[j][2]); q[j][3] = fmaf(v[u][j].w, v[u][j].w, q[j][3]);
+        }
     }
 #pragma unroll
     for (int j = 0; j < kGnMaxNQ; ++j) {
@@ -82,20 +94,32 @@ gn_stats_kernel(const T0* __restrict__ src0, int C0, const float* __restrict__ s
   }
 }
 
-__global__ void gn_finalize_kernel(const double* __restrict__ stats, int n, double cnt, float eps, float2* __restrict__ mr) {
+// finalize: per (instance, channel) affine y = a x + b with a = rstd * gamma, b = beta - mean * rstd * gamma
+__global__ void gn_finalize_kernel(const double* __restrict__ stats, int insts, int C, int groups, double cnt, float eps,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float2* __restrict__ ab) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double m = stats[2 * i] / cnt;
-  double var = stats[2 * i + 1] / cnt - m * m;
+  if (i >= insts * C) return;
+  const int inst = i / C, c = i - inst * C;
+  const int g = c / (C / groups);
+  const double m = stats[(inst * groups + g) * 2] / cnt;
+  double var = stats[(inst * groups + g) * 2 + 1] / cnt - m * m;
   if (var < 0) var = 0;
-  mr[i] = make_float2((float)m, (float)(1.0 / sqrt(var + (double)eps)));
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float a = rstd * gamma[c];
+  ab[i] = make_float2(a, beta[c] - (float)m * a);
 }
 
-// apply: 8 channels per thread
+__device__ __forceinline__ float silu_fast(float y) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return y * r;
+}
+
+// apply: 8 channels per thread, y = a x + b [-> SiLU] -> fp16
 template <typename T0>
 __global__ void gn_apply_kernel(const T0* __restrict__ src0, int C0, const float* __restrict__ src1, int C1,
-                                long long rows_total, long long rows_per_inst, int groups, const float2* __restrict__ mr,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu,
+                                long long rows_total, long long rows_per_inst, const float2* __restrict__ ab, int do_silu,
                                 __half* __restrict__ out, __half* __restrict__ raw_out) {
   const int C = C0 + C1;
   const int cv = C / 8;
@@ -104,7 +128,6 @@ __global__ void gn_apply_kernel(const T0* __restrict__ src0, int C0, const float
   const long long row = idx / cv;
   const int c = (int)(idx - row * cv) * 8;
   const long long inst = row / rows_per_inst;
-  const int cg = C / groups;
   float v[8];
   {
     float4 a, b;
@@ -124,22 +147,14 @@ __global__ void gn_apply_kernel(const T0* __restrict__ src0, int C0, const float
     for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
     *reinterpret_cast<uint4*>(raw_out + row * C + c) = raw;
   }
-  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
-  const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
-  const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-  const float bet[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const float4* abp = reinterpret_cast<const float4*>(ab + inst * C + c);  // 8 x (a, b)
   float o[8];
-  int g_prev = -1;
-  float2 m = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int g = (c + i) / cg;
-    if (g != g_prev) {
-      m = __ldg(mr + inst * groups + g);
-      g_prev = g;
-    }
-    float y = (v[i] - m.x) * m.y * gam[i] + bet[i];
-    o[i] = do_silu ? silu(y) : y;
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = __ldg(abp + i);
+    const float y0 = fmaf(v[2 * i], t.x, t.y), y1 = fmaf(v[2 * i + 1], t.z, t.w);
+    o[2 * i] = do_silu ? silu_fast(y0) : y0;
+    o[2 * i + 1] = do_silu ? silu_fast(y1) : y1;
   }
   uint4 raw;
   __half2* h = reinterpret_cast<__half2*>(&raw);
@@ -477,8 +492,8 @@ int group_norm(const void* src0, int src0_fp16, int C0, const float* src1, int C
   const int TQ = Q / NQ;
   const int R = 512 / TQ > 0 ? 512 / TQ : 1;
   const int threads = TQ * R;
-  // stats scratch: [insts,32,2] doubles followed by [insts,32] float2 (mean, rstd)
-  float2* mr = reinterpret_cast<float2*>(stats + 2 * groups * insts);
+  // stats scratch: [insts,32,2] doubles followed by the [insts, C] float2 (scale, shift) table
+  float2* ab = reinterpret_cast<float2*>(stats + 2 * groups * insts);
   EVW_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * insts, st));
   long long want_blocks = (long long)sm_count() * 4 / (insts > 0 ? insts : 1) + 1;
   int rpb = (int)((rows_per_inst + want_blocks - 1) / want_blocks);
@@ -488,16 +503,17 @@ int group_norm(const void* src0, int src0_fp16, int C0, const float* src1, int C
     gn_stats_kernel<__half><<<grid, threads, 0, st>>>((const __half*)src0, C0, src1, C1, rows_per_inst, rpb, groups, TQ, NQ, stats);
   else
     gn_stats_kernel<float><<<grid, threads, 0, st>>>((const float*)src0, C0, src1, C1, rows_per_inst, rpb, groups, TQ, NQ, stats);
-  const int ng = (int)(insts * groups);
-  gn_finalize_kernel<<<(ng + 127) / 128, 128, 0, st>>>(stats, ng, (double)rows_per_inst * (C / groups), eps, mr);
+  const int nc = (int)(insts * C);
+  gn_finalize_kernel<<<(nc + 255) / 256, 256, 0, st>>>(stats, (int)insts, C, groups, (double)rows_per_inst * (C / groups), eps,
+                                                        gamma, beta, ab);
   const long long rows_total = insts * rows_per_inst;
   const long long n = rows_total * (C / 8);
   if (src0_fp16)
-    gn_apply_kernel<__half><<<blocks_for(n, 256), 256, 0, st>>>((const __half*)src0, C0, src1, C1, rows_total, rows_per_inst,
-                                                                 groups, mr, gamma, beta, do_silu, out, raw_out);
+    gn_apply_kernel<__half><<<blocks_for(n, 256), 256, 0, st>>>((const __half*)src0, C0, src1, C1, rows_total, rows_per_inst, ab,
+                                                                 do_silu, out, raw_out);
   else
-    gn_apply_kernel<float><<<blocks_for(n, 256), 256, 0, st>>>((const float*)src0, C0, src1, C1, rows_total, rows_per_inst,
-                                                                groups, mr, gamma, beta, do_silu, out, raw_out);
+    gn_apply_kernel<float><<<blocks_for(n, 256), 256, 0, st>>>((const float*)src0, C0, src1, C1, rows_total, rows_per_inst, ab,
+                                                                do_silu, out, raw_out);
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }

@@ -371,7 +371,7 @@ struct Builder {
     pp[0] = bump.take<float>(maxPP);
     pp[1] = bump.take<float>(maxPP);
     y32 = bump.take<float>(lM[0] * c.cout_pad);
-    stats = bump.take<double>(96LL * std::max(BF, 1));  // [insts,32,2] double sums + [insts,32] float2 (mean, rstd)
+    stats = bump.take<double>((64LL + 4 * 1280) * std::max(BF, 1));  // [insts,32,2] double sums + [insts,C<=5120] float2 (scale, shift)
     small16 = bump.take<__half>(5LL * kSmall);
     emb = bump.take<float>(8LL * c.temb_dim);
     emb2 = bump.take<float>(8LL * c.temb_dim);
