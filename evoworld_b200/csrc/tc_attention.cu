@@ -521,6 +521,10 @@ constexpr int kA3Smem = kA3OffOnes + 4096 + 1024;
 constexpr int kTmemO3 = 256, kTmemL3 = 384;                  // O_g at 256 + 64 g, L_g at 384 + 16 g
 constexpr float kLazyTau = 8.0f;
 
+__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t units16) {  // advance the 14-bit start address field
+  return d + units16;  // never carries out of the address field for in-range tiles
+}
+
 __global__ void __launch_bounds__(kA2Threads, 1)
 spatial_attn3_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ out, int S, int C, float scale_log2e) {
   extern __shared__ uint8_t smem_raw[];
@@ -550,7 +554,7 @@ spatial_attn3_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
     mbar_init(q_full, 1);
     for (int s = 0; s < kKvStages; ++s) {
       mbar_init(kv_full(s), 1);
-      mbar_init(kv_empty(s), 1);
+      mbar_init(kv_empty(s), b_active ? 2 : 1);  // one tcgen05.commit per active group
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(s_full(g), 1);
@@ -568,7 +572,7 @@ spatial_attn3_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
       // ===================== TMA producer =====================
       if (lane == 0) {
@@ -586,51 +590,50 @@ spatial_attn3_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
         }
         __syncwarp();
       }
-    } else if (warp == 1) {
-      // ===================== MMA issuer (event driven) =====================
-      if (lane == 0) {
+    } else if (warp == 1 || warp == 2) {
+      // ===================== MMA issuers: warp 1 drives group A, warp 2 drives group B (event driven) =====================
+      const int g = warp - 1;
+      if (lane == 0 && (g == 0 || b_active)) {
         const uint32_t idesc_s = make_idesc_f16(kBQ, kBKV, 0, 0, 0);
         const uint32_t idesc_o = make_idesc_f16(kBQ, kD, 0, 0, 1);
         const uint32_t idesc_l = make_idesc_f16(kBQ, 16, 0, 0, 0);
+        // loop-invariant descriptors; per-k-step offsets are compile-time constants added to the address field
+        const uint64_t dq = make_desc_k_sw128(base + kA2OffQ + g * kTileBytes);
+        const uint64_t dp = make_desc_k_sw128(base + kA2OffP + g * 2 * kTileBytes);
+        const uint64_t d1 = make_desc_k_sw128(base + kA3OffOnes);
+        const uint64_t dk0 = make_desc_k_sw128(base + kA2OffK);
+        const uint64_t dv0 = make_desc_mn_sw128(base + kA2OffV, 1024);
+        const uint32_t t_s = tmem_base + g * kBKV, t_o = tmem_base + kTmemO3 + g * kD, t_l = tmem_base + kTmemL3 + g * 16;
         mbar_wait(q_full, 0);
-        int s_next[2] = {0, 0}, pv_next[2] = {0, 0};
-        const int n_g[2] = {n_kv, b_active ? n_kv : 0};
+        int s_next = 0, pv_next = 0;
         long long t0 = clock64();
-        while (pv_next[0] < n_g[0] || pv_next[1] < n_g[1]) {
+        while (pv_next < n_kv) {
           bool progress = false;
+          if (s_next < n_kv && mbar_test(kv_full(s_next % kKvStages), (s_next / kKvStages) & 1) &&
+              (s_next == 0 || mbar_test(s_empty(g), (s_next - 1) & 1))) {
+            tc_fence_after();
+            const uint64_t dk = desc_add(dk0, (s_next % kKvStages) * (kTileBytes >> 4));
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            int i = s_next[g];
-            if (i < n_g[g] && mbar_test(kv_full(i % kKvStages), (i / kKvStages) & 1) &&
-                (i == 0 || mbar_test(s_empty(g), (i - 1) & 1))) {
-              tc_fence_after();
-              const uint64_t dq = make_desc_k_sw128(base + kA2OffQ + g * kTileBytes);
-              const uint64_t dk = make_desc_k_sw128(base + kA2OffK + (i % kKvStages) * kTileBytes);
+            for (int k = 0; k < kD / 16; ++k) umma_f16_ss(t_s, desc_add(dq, 2 * k), desc_add(dk, 2 * k), idesc_s, k != 0);
+            tc_commit(s_full(g));
+            ++s_next;
+            progress = true;
+          }
+          if (pv_next < s_next && mbar_test(p_full(g), pv_next & 1)) {
+            tc_fence_after();
+            const int st = pv_next % kKvStages;
+            const uint64_t dv = desc_add(dv0, st * (kTileBytes >> 4));
+            const uint32_t acc = pv_next != 0;
 #pragma unroll
-              for (int k = 0; k < kD / 16; ++k)
-                umma_f16_ss(tmem_base + g * kBKV, dq + 2ull * k, dk + 2ull * k, idesc_s, k != 0);
-              tc_commit(s_full(g));
-              s_next[g] = i + 1;
-              progress = true;
+            for (int ks = 0; ks < kBKV / 16; ++ks) {
+              const uint64_t a = desc_add(dp, (ks >> 2) * (kTileBytes >> 4) + 2 * (ks & 3));
+              umma_f16_ss(t_o, a, desc_add(dv, ks * (2048 >> 4)), idesc_o, acc | (ks != 0));                         // O += P V
+              umma_f16_ss(t_l, a, desc_add(d1, (ks >> 2) * (2048 >> 4) + 2 * (ks & 3)), idesc_l, acc | (ks != 0));   // L += P 1
             }
-            i = pv_next[g];
-            if (i < n_g[g] && i < s_next[g] && mbar_test(p_full(g), i & 1)) {
-              tc_fence_after();
-              const int st = i % kKvStages;
-#pragma unroll
-              for (int ks = 0; ks < kBKV / 16; ++ks) {
-                const uint64_t dp = make_desc_k_sw128(base + kA2OffP + g * 2 * kTileBytes + (ks >> 2) * kTileBytes) + 2ull * (ks & 3);
-                const uint64_t dv = make_desc_mn_sw128(base + kA2OffV + st * kTileBytes + ks * 2048, 1024);
-                const uint64_t d1 = make_desc_k_sw128(base + kA3OffOnes + (ks >> 2) * 2048) + 2ull * (ks & 3);
-                umma_f16_ss(tmem_base + kTmemO3 + g * kD, dp, dv, idesc_o, (i | ks) != 0);   // O_g += P V
-                umma_f16_ss(tmem_base + kTmemL3 + g * 16, dp, d1, idesc_l, (i | ks) != 0);   // L_g += P 1
-              }
-              tc_commit(o_full(g));
-              pv_next[g] = i + 1;
-              const int other = g ^ 1;
-              if (n_g[other] == 0 || pv_next[other] > i) tc_commit(kv_empty(st));
-              progress = true;
-            }
+            tc_commit(o_full(g));
+            tc_commit(kv_empty(st));
+            ++pv_next;
+            progress = true;
           }
           if (progress) t0 = clock64();
           else if (clock64() - t0 > 8000000000ll) __trap();
@@ -639,7 +642,7 @@ spatial_attn3_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
       __syncwarp();
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ===================== softmax groups =====================
     const int g = (warp - 4) >> 2;
     const int quarter = warp & 3;
@@ -668,7 +671,7 @@ spatial_attn3_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(s_empty(g));
+        if (lane == 0) mbar_arrive(s_empty(g));  // S_g(j+1) may now overwrite the TMEM tile
 
         const int kv_valid = S - j * kBKV;
         float mx = -INFINITY;
@@ -683,17 +686,27 @@ spatial_attn3_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
           }
         }
         const float m_tile = mx * scale_log2e;
-        // P buffer / O accumulator of this group are free once PV_g(j-1) has completed
+        const bool need = m_tile > m_ref + kLazyTau;  // first tile: m_ref = -inf -> true
+        const float m_old = m_ref;
+        if (need) m_ref = m_tile;
+        const float neg_m = -m_ref;
+        // probabilities first (registers only): this phase overlaps the PV MMA of the previous tile
+        uint32_t w[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          const float x0 = fmaf(__uint_as_float(s[2 * i]), scale_log2e, neg_m);
+          const float x1 = fmaf(__uint_as_float(s[2 * i + 1]), scale_log2e, neg_m);
+          const float p0 = fast_exp2(x0);
+          const float p1 = ((2 * i + 1) % kPolyEvery == kPolyEvery - 1) ? exp2_poly(x1) : fast_exp2(x1);
+          __half2 h = __floats2half2_rn(p0, p1);
+          w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        // P buffer / O, L accumulators of this group are free once PV_g(j-1) has completed
         if (j > 0) {
           mbar_wait(o_full(g), (j - 1) & 1);
           tc_fence_after();
-        }
-        const bool need = m_tile > m_ref + kLazyTau;  // first tile: m_ref = -inf -> true
-        if (__any_sync(0xffffffffu, need)) {
-          const float m_new = need ? m_tile : m_ref;
-          if (j > 0) {
-            const float f = need ? fast_exp2(m_ref - m_new) : 1.0f;
-            // rescale O (64 columns) and L (16 columns) of this row in tensor memory
+          if (__any_sync(0xffffffffu, need)) {
+            const float f = need ? fast_exp2(m_old - m_ref) : 1.0f;
 #pragma unroll
             for (int part = 0; part < 4; ++part) {
               uint32_t v[16];
@@ -713,24 +726,12 @@ spatial_attn3_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
             }
             tmem_st_wait();
           }
-          m_ref = m_new;
         }
-        const float neg_m = -m_ref;
 #pragma unroll
         for (int ch = 0; ch < 16; ++ch) {
-          uint32_t w[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int c0 = ch * 8 + 2 * i;
-            const float x0 = fmaf(__uint_as_float(s[c0]), scale_log2e, neg_m);
-            const float x1 = fmaf(__uint_as_float(s[c0 + 1]), scale_log2e, neg_m);
-            const float p0 = fast_exp2(x0);
-            const float p1 = ((c0 + 1) % kPolyEvery == kPolyEvery - 1) ? exp2_poly(x1) : fast_exp2(x1);
-            __half2 h = __floats2half2_rn(p0, p1);
-            w[i] = *reinterpret_cast<uint32_t*>(&h);
-          }
           const int atom = ch >> 3, cc = ch & 7;
-          *reinterpret_cast<uint4*>(prow + atom * kTileBytes + ((cc ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(prow + atom * kTileBytes + ((cc ^ (r & 7)) << 4)) =
+              make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
         }
         fence_proxy_async();
         tc_fence_before();
