@@ -772,19 +772,253 @@ spatial_attn3_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
   }
 }
 
+// ==========================================================================================
+// v4: as v3, but the probability tile P never touches shared memory: the softmax warps write it (fp16, two per
+// 32-bit column) over the first 64 columns of their S tile with tcgen05.st and the PV / row-sum MMAs take their A
+// operand from TENSOR MEMORY.  Shared memory then only carries Q, K, V (v3 was bound by smem bandwidth: P written,
+// read by the PV MMA and read again by the row-sum MMA).  S_g(j+1) is issued right behind PV_g(j) in the same
+// in-order MMA stream, so it may overwrite the aliased S/P columns; the two query groups keep the tensor pipe busy.
+// ==========================================================================================
+constexpr int kA4Stages = 4;
+constexpr int kA4OffQ = 0;
+constexpr int kA4OffK = kA4OffQ + 2 * kTileBytes;
+constexpr int kA4OffV = kA4OffK + kA4Stages * kTileBytes;
+constexpr int kA4OffOnes = kA4OffV + kA4Stages * kTileBytes;
+constexpr int kA4OffBar = kA4OffOnes + 4096;
+constexpr int kA4Smem = kA4OffBar + 256 + 1024;
+
+__global__ void __launch_bounds__(kA2Threads, 1)
+spatial_attn4_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ out, int S, int C, float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, frame = blockIdx.z;
+  const int q0 = blockIdx.x * 2 * kBQ;
+  const int n_kv = (S + kBKV - 1) / kBKV;
+  const bool b_active = q0 + kBQ < S;
+
+  const uint32_t bar = base + kA4OffBar;
+  const uint32_t q_full = bar;
+  auto kv_full = [&](int s) { return bar + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bar + 8u * (1 + kA4Stages + s); };
+  auto s_full = [&](int g) { return bar + 8u * (1 + 2 * kA4Stages + g); };
+  auto p_full = [&](int g) { return bar + 8u * (3 + 2 * kA4Stages + g); };
+  auto o_full = [&](int g) { return bar + 8u * (5 + 2 * kA4Stages + g); };
+  const uint32_t tmem_slot = bar + 8u * (7 + 2 * kA4Stages);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + kA4OffBar + 8 * (7 + 2 * kA4Stages));
+
+  for (int i = threadIdx.x; i < 4096 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(base_ptr + kA4OffOnes)[i] = 0x3C003C00u;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kA4Stages; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), b_active ? 2 : 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(s_full(g), 1);
+      mbar_init(p_full(g), 4);
+      mbar_init(o_full(g), 1);
+    }
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+        tma_load_3d(&tmap, base + kA4OffQ, q_full, head * kD, q0, frame);
+        tma_load_3d(&tmap, base + kA4OffQ + kTileBytes, q_full, head * kD, q0 + kBQ, frame);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % kA4Stages;
+        mbar_wait(kv_empty(st), ((j / kA4Stages) & 1) ^ 1u);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(kv_full(st), 2 * kTileBytes);
+          tma_load_3d(&tmap, base + kA4OffK + st * kTileBytes, kv_full(st), C + head * kD, j * kBKV, frame);
+          tma_load_3d(&tmap, base + kA4OffV + st * kTileBytes, kv_full(st), 2 * C + head * kD, j * kBKV, frame);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1 || warp == 2) {
+      // ===================== MMA issuers: one thread per query group =====================
+      const int g = warp - 1;
+      if (lane == 0 && (g == 0 || b_active)) {
+        const uint32_t idesc_s = make_idesc_f16(kBQ, kBKV, 0, 0, 0);
+        const uint32_t idesc_o = make_idesc_f16(kBQ, kD, 0, 0, 1);
+        const uint32_t idesc_l = make_idesc_f16(kBQ, 16, 0, 0, 0);
+        const uint64_t dq = make_desc_k_sw128(base + kA4OffQ + g * kTileBytes);
+        const uint64_t d1 = make_desc_k_sw128(base + kA4OffOnes);
+        const uint64_t dk0 = make_desc_k_sw128(base + kA4OffK);
+        const uint64_t dv0 = make_desc_mn_sw128(base + kA4OffV, 1024);
+        const uint32_t t_s = tmem_base + g * kBKV;  // S tile; P aliases its first 64 columns
+        const uint32_t t_o = tmem_base + kTmemO3 + g * kD, t_l = tmem_base + kTmemL3 + g * 16;
+        mbar_wait(q_full, 0);
+        for (int i = 0; i < n_kv; ++i) {
+          const int st = i % kA4Stages;
+          mbar_wait(kv_full(st), (i / kA4Stages) & 1);
+          tc_fence_after();
+          const uint64_t dk = desc_add(dk0, st * (kTileBytes >> 4));
+#pragma unroll
+          for (int k = 0; k < kD / 16; ++k) umma_f16_ss(t_s, desc_add(dq, 2 * k), desc_add(dk, 2 * k), idesc_s, k != 0);
+          tc_commit(s_full(g));
+          mbar_wait(p_full(g), i & 1);
+          tc_fence_after();
+          const uint64_t dv = desc_add(dv0, st * (kTileBytes >> 4));
+          const uint32_t acc = i != 0;
+#pragma unroll
+          for (int ks = 0; ks < kBKV / 16; ++ks) {
+            umma_f16_ts(t_o, t_s + ks * 8, desc_add(dv, ks * (2048 >> 4)), idesc_o, acc | (ks != 0));                       // O += P V
+            umma_f16_ts(t_l, t_s + ks * 8, desc_add(d1, (ks >> 2) * (2048 >> 4) + 2 * (ks & 3)), idesc_l, acc | (ks != 0)); // L += P 1
+          }
+          tc_commit(kv_empty(st));
+          if (i == n_kv - 1) tc_commit(o_full(g));
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // ===================== softmax groups =====================
+    const int g = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int qrow = q0 + g * kBQ + r;
+    if (g == 0 || b_active) {
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t s_addr = lane_addr + g * kBKV, o_addr = lane_addr + kTmemO3 + g * kD, l_addr = lane_addr + kTmemL3 + g * 16;
+      float m_ref = -INFINITY;
+
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(s_full(g), j & 1);  // also implies PV_g(j-1) and L_g(j-1) completed (in-order MMA stream)
+        tc_fence_after();
+        uint32_t s[128];
+        {
+          uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+          uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+          uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
+          uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
+          tmem_ld_32x32b_x32(s_addr + 0, s0);
+          tmem_ld_32x32b_x32(s_addr + 32, s1);
+          tmem_ld_32x32b_x32(s_addr + 64, s2);
+          tmem_ld_32x32b_x32(s_addr + 96, s3);
+          tmem_ld_wait();
+        }
+        const int kv_valid = S - j * kBKV;
+        float mx = -INFINITY;
+        if (kv_valid >= kBKV) {
+#pragma unroll
+          for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(s[c]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 128; ++c) {
+            if (c >= kv_valid) s[c] = 0xff800000u;
+            mx = fmaxf(mx, __uint_as_float(s[c]));
+          }
+        }
+        const float m_tile = mx * scale_log2e;
+        const bool need = m_tile > m_ref + kLazyTau;
+        const float m_old = m_ref;
+        if (need) m_ref = m_tile;
+        const float neg_m = -m_ref;
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          const float f = need ? fast_exp2(m_old - m_ref) : 1.0f;
+#pragma unroll
+          for (int part = 0; part < 4; ++part) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(o_addr + part * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+            tmem_st_32x32b_x16(o_addr + part * 16, v);
+          }
+          {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(l_addr, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+            tmem_st_32x32b_x16(l_addr, v);
+          }
+        }
+        // probabilities, packed two per 32-bit TMEM column (even kv index in the low half), written over S columns 0..63
+#pragma unroll
+        for (int part = 0; part < 4; ++part) {
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c0 = part * 32 + 2 * i;
+            const float x0 = fmaf(__uint_as_float(s[c0]), scale_log2e, neg_m);
+            const float x1 = fmaf(__uint_as_float(s[c0 + 1]), scale_log2e, neg_m);
+            const float p0 = fast_exp2(x0);
+            const float p1 = ((c0 + 1) % kPolyEvery == kPolyEvery - 1) ? exp2_poly(x1) : fast_exp2(x1);
+            __half2 h = __floats2half2_rn(p0, p1);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          tmem_st_32x32b_x16(s_addr + part * 16, w);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(g));
+      }
+      mbar_wait(o_full(g), 0);
+      tc_fence_after();
+      uint32_t lo[32], hi[32], lv[16];
+      tmem_ld_32x32b_x32(o_addr, lo);
+      tmem_ld_32x32b_x32(o_addr + 32, hi);
+      tmem_ld_32x32b_x16(l_addr, lv);
+      tmem_ld_wait();
+      if (qrow < S) {
+        const float inv = 1.0f / __uint_as_float(lv[0]);
+        uint4* op = reinterpret_cast<uint4*>(out + ((long long)frame * S + qrow) * C + head * kD);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t* src = (i < 4) ? &lo[8 * i] : &hi[8 * (i - 4)];
+          __half2 h0 = __floats2half2_rn(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
+          __half2 h1 = __floats2half2_rn(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
+          __half2 h2 = __floats2half2_rn(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
+          __half2 h3 = __floats2half2_rn(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
+          uint4 v;
+          v.x = *reinterpret_cast<uint32_t*>(&h0); v.y = *reinterpret_cast<uint32_t*>(&h1);
+          v.z = *reinterpret_cast<uint32_t*>(&h2); v.w = *reinterpret_cast<uint32_t*>(&h3);
+          op[i] = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace
 
 int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, cudaStream_t st) {
   EVW_CHECK_ARG(qkv && out && F > 0 && S > 0 && heads > 0, "spatial_attention: bad arguments");
   const int C = heads * kD;
   static bool attr_set = false;
-  static bool use_v1 = false, use_v2 = false;
+  static bool use_v1 = false, use_v2 = false, use_v3 = false;
   if (!attr_set) {
     EVW_CUDA(cudaFuncSetAttribute(spatial_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     EVW_CUDA(cudaFuncSetAttribute(spatial_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2Smem));
     EVW_CUDA(cudaFuncSetAttribute(spatial_attn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3Smem));
     use_v1 = getenv("EVW_ATTN_V1") != nullptr;
+    EVW_CUDA(cudaFuncSetAttribute(spatial_attn4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA4Smem));
     use_v2 = getenv("EVW_ATTN_V2") != nullptr;
+    use_v3 = getenv("EVW_ATTN_V3") != nullptr;
     attr_set = true;
   }
   alignas(64) CUtensorMap tmap;
@@ -799,9 +1033,12 @@ int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, c
   } else if (use_v2) {
     dim3 grid((S + 2 * kBQ - 1) / (2 * kBQ), heads, F);
     spatial_attn2_kernel<<<grid, kA2Threads, kA2Smem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
-  } else {
+  } else if (use_v3) {
     dim3 grid((S + 2 * kBQ - 1) / (2 * kBQ), heads, F);
     spatial_attn3_kernel<<<grid, kA2Threads, kA3Smem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
+  } else {
+    dim3 grid((S + 2 * kBQ - 1) / (2 * kBQ), heads, F);
+    spatial_attn4_kernel<<<grid, kA2Threads, kA4Smem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
   }
   EVW_LAUNCH_CHECK();
   return EVW_OK;
