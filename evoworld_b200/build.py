@@ -45,6 +45,7 @@ def _stamp(srcs: list[Path]) -> str:
         h.update(p.name.encode())
         h.update(p.read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(os.environ.get("EVW_NVCC_EXTRA", "").encode())
     return h.hexdigest()
 
 
@@ -57,11 +58,12 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     if not force and LIB_PATH.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
         return LIB_PATH
     nvcc = _nvcc()
+    extra = os.environ.get("EVW_NVCC_EXTRA", "").split()  # experiments only (e.g. -DEVW_POLY_EVERY=2)
     objs = []
     procs = []
     for src in srcs:
         obj = OUT_DIR / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-I", str(ROOT / "include"), "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", str(ROOT / "include"), "-c", str(src), "-o", str(obj)]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     log = []

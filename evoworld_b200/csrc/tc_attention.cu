@@ -257,7 +257,10 @@ constexpr int kA2OffV = kA2OffK + kKvStages * kTileBytes;    // 3 x 16 KiB
 constexpr int kA2OffP = kA2OffV + kKvStages * kTileBytes;    // 2 groups x 32 KiB
 constexpr int kA2OffBar = kA2OffP + 2 * 2 * kTileBytes;
 constexpr int kA2Smem = kA2OffBar + 256 + 1024;
-constexpr int kPolyEvery = 4;  // every 4th exponential is evaluated on the FMA pipe instead of MUFU
+#ifndef EVW_POLY_EVERY
+#define EVW_POLY_EVERY 4
+#endif
+constexpr int kPolyEvery = EVW_POLY_EVERY;  // every n-th exponential is evaluated on the FMA pipe instead of MUFU
 
 // 2^x for x <= 0 on the FMA/ALU pipes: round-to-nearest split x = n + r, |r| <= 0.5, degree-4 polynomial for 2^r
 // (relative error < 5e-5, below the fp16 rounding of P), exponent patched in with an integer add.
@@ -1010,7 +1013,7 @@ int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, c
   EVW_CHECK_ARG(qkv && out && F > 0 && S > 0 && heads > 0, "spatial_attention: bad arguments");
   const int C = heads * kD;
   static bool attr_set = false;
-  static bool use_v1 = false, use_v2 = false, use_v3 = false;
+  static bool use_v1 = false, use_v2 = false, use_v4 = false;
   if (!attr_set) {
     EVW_CUDA(cudaFuncSetAttribute(spatial_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     EVW_CUDA(cudaFuncSetAttribute(spatial_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2Smem));
@@ -1018,7 +1021,7 @@ int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, c
     use_v1 = getenv("EVW_ATTN_V1") != nullptr;
     EVW_CUDA(cudaFuncSetAttribute(spatial_attn4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA4Smem));
     use_v2 = getenv("EVW_ATTN_V2") != nullptr;
-    use_v3 = getenv("EVW_ATTN_V3") != nullptr;
+    use_v4 = getenv("EVW_ATTN_V4") != nullptr;
     attr_set = true;
   }
   alignas(64) CUtensorMap tmap;
@@ -1033,12 +1036,12 @@ int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, c
   } else if (use_v2) {
     dim3 grid((S + 2 * kBQ - 1) / (2 * kBQ), heads, F);
     spatial_attn2_kernel<<<grid, kA2Threads, kA2Smem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
-  } else if (use_v3) {
-    dim3 grid((S + 2 * kBQ - 1) / (2 * kBQ), heads, F);
-    spatial_attn3_kernel<<<grid, kA2Threads, kA3Smem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
-  } else {
+  } else if (use_v4) {  // P in tensor memory: correct, but the serialised S/PV chain makes it slower than v3 (5.9 vs 5.0 ms)
     dim3 grid((S + 2 * kBQ - 1) / (2 * kBQ), heads, F);
     spatial_attn4_kernel<<<grid, kA2Threads, kA4Smem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
+  } else {
+    dim3 grid((S + 2 * kBQ - 1) / (2 * kBQ), heads, F);
+    spatial_attn3_kernel<<<grid, kA2Threads, kA3Smem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
   }
   EVW_LAUNCH_CHECK();
   return EVW_OK;
