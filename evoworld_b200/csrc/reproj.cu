@@ -25,6 +25,12 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   return r;
 }
 
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------
 // Plücker
 // ------------------------------------------------------------------------------------------
@@ -434,7 +440,7 @@ __device__ __forceinline__ void splat_one(const float* __restrict__ m, float x, 
   unsigned long long key = ((unsigned long long)__float_as_uint(zc) << 32) | idx;
   unsigned long long* cell = zface + (size_t)py * res + px;
   // cheap pre-test (plain L2 read) saves most of the losing atomics
-  if (key < *((volatile unsigned long long*)cell)) atomicMin(cell, key);
+  if (key < ld_relaxed_u64(cell)) atomicMin(cell, key);
 }
 
 template <int G>
@@ -543,6 +549,120 @@ __global__ void cube_gather_kernel(const uint8_t* __restrict__ faces, const uint
   o[0] = r;
   o[1] = g;
   o[2] = bl;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Cube splat: one camera-space transform per (point, view); the face is the major axis of X_c and the face-local
+// coordinates are the exact signed permutations inv(T_face [Rz180]) of the reference's CUBEMAP_TRANSFORMS
+// (reproject_vggt_open3d_utils.py:29-36,619-622,652-658), so six 90-degree pinhole renders cost one mat-vec.
+//   front (x, y, z) | right (-z, y, x) | back (-x, y, -z) | left (z, y, -x) | top (-x, -z, -y) | bottom (-x, z, y)
+// Specification (mirrored by oracle_splat_keys_cube): X_c by fmaf chains; face = argmax(|x|,|y|,|z|) with ties
+// resolved x over y over z... exactly as coded below; keep z' > z_near; u = fmaf(f, x'/z', c) etc. as splat_one.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cube_splat_one(const float* __restrict__ m, float x, float y, float z, float focal, float c,
+                                               float z_near, int res, unsigned long long* __restrict__ zview, unsigned idx,
+                                               int pretest) {
+  const float xc = fmaf(m[0], x, fmaf(m[1], y, fmaf(m[2], z, m[3])));
+  const float yc = fmaf(m[4], x, fmaf(m[5], y, fmaf(m[6], z, m[7])));
+  const float zc = fmaf(m[8], x, fmaf(m[9], y, fmaf(m[10], z, m[11])));
+  const float ax = fabsf(xc), ay = fabsf(yc), az = fabsf(zc);
+  int face;
+  float fx, fy, fz;
+  if (az >= ax && az >= ay) {
+    if (zc > 0.f) { face = 0; fx = xc; fy = yc; fz = zc; }        // front
+    else          { face = 2; fx = -xc; fy = yc; fz = -zc; }      // back
+  } else if (ax >= ay) {
+    if (xc > 0.f) { face = 1; fx = -zc; fy = yc; fz = xc; }       // right
+    else          { face = 3; fx = zc; fy = yc; fz = -xc; }       // left
+  } else {
+    if (yc > 0.f) { face = 5; fx = -xc; fy = zc; fz = yc; }       // bottom
+    else          { face = 4; fx = -xc; fy = -zc; fz = -yc; }     // top
+  }
+  if (!(fz > z_near)) return;
+  const float u = fmaf(focal, __fdiv_rn(fx, fz), c);
+  const float v = fmaf(focal, __fdiv_rn(fy, fz), c);
+  const float fres = (float)res;
+  if (!(u >= 0.f && u < fres && v >= 0.f && v < fres)) return;
+  const int px = (int)floorf(u), py = (int)floorf(v);
+  const unsigned long long key = ((unsigned long long)__float_as_uint(fz) << 32) | idx;
+  unsigned long long* cell = zview + ((size_t)face * res + py) * res + px;
+  if (!pretest || key < ld_relaxed_u64(cell)) atomicMin(cell, key);
+}
+
+template <int G>
+__global__ void __launch_bounds__(256)
+cube_splat_kernel(const float4* __restrict__ pts, int64_t n_cap, const long long* __restrict__ n_dev,
+                  const float* __restrict__ w2c /*[G,12]*/, int res, float focal, float z_near, int pretest,
+                  unsigned long long* __restrict__ zbuf /*[G,6,res,res]*/) {
+  __shared__ float s_m[G * 12];
+  for (int i = threadIdx.x; i < G * 12; i += blockDim.x) s_m[i] = w2c[i];
+  __syncthreads();
+  int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
+  const float c = 0.5f * (float)res;
+  const size_t view_sz = (size_t)6 * res * res;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 p = ld_stream_f4(pts + i);
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      cube_splat_one(s_m + g * 12, p.x, p.y, p.z, focal, c, z_near, res, zbuf + (size_t)g * view_sz, (unsigned)i, pretest);
+  }
+}
+
+// resolve G views at once: the lookup-table entry of a pixel quad is read once for all views of the pass
+template <int G>
+__global__ void resolve_multi_kernel(const unsigned long long* __restrict__ zbuf /*[G,6,res,res]*/,
+                                     const float4* __restrict__ pts, const uint32_t* __restrict__ lut, int res,
+                                     int64_t npix, int g_count, uint8_t* __restrict__ out /*[G,npix,3]*/) {
+  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t p0 = q * 4;
+  if (p0 >= npix) return;
+  uint32_t e[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) e[j] = (p0 + j < npix) ? lut[p0 + j] : 0xFFFFFFFFu;
+  const size_t view_sz = (size_t)6 * res * res;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    if (g >= g_count) break;
+    unsigned rgb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      rgb[j] = 0;
+      if (e[j] != 0xFFFFFFFFu) {
+        const unsigned face = e[j] >> 28, row = (e[j] >> 14) & 0x3FFFu, col = e[j] & 0x3FFFu;
+        const unsigned long long key = zbuf[(size_t)g * view_sz + ((size_t)face * res + row) * res + col];
+        if (key != kEmptyKey) rgb[j] = __float_as_uint(__ldg(&pts[(unsigned)(key & 0xFFFFFFFFull)].w)) & 0xFFFFFFu;
+      }
+    }
+    uint8_t* o8 = out + ((size_t)g * npix + p0) * 3;
+    if (p0 + 3 < npix) {
+      uint32_t* o = reinterpret_cast<uint32_t*>(o8);  // (g*npix + p0)*3 is a multiple of 4 when npix % 4 == 0
+      o[0] = rgb[0] | (rgb[1] << 24);
+      o[1] = (rgb[1] >> 8) | (rgb[2] << 16);
+      o[2] = (rgb[2] >> 16) | (rgb[3] << 8);
+    } else {
+      for (int j = 0; j < 4 && p0 + j < npix; ++j) {
+        o8[j * 3 + 0] = rgb[j] & 0xFF;
+        o8[j * 3 + 1] = (rgb[j] >> 8) & 0xFF;
+        o8[j * 3 + 2] = (rgb[j] >> 16) & 0xFF;
+      }
+    }
+  }
+}
+
+template <int G>
+int launch_cube_pass(const float4* pts, int64_t n_cap, const long long* n_dev, const float* w2c, int res, float focal,
+                     float z_near, int pretest, unsigned long long* zbuf, const uint32_t* lut, int64_t npix, int g_count,
+                     uint8_t* out, cudaStream_t st) {
+  if (n_cap > 0) {
+    int64_t want = (n_cap + 255) / 256;
+    int64_t cap = (int64_t)evw::sm_count() * 8;
+    cube_splat_kernel<G><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(pts, n_cap, n_dev, w2c, res, focal, z_near,
+                                                                                pretest, zbuf);
+  }
+  const int64_t quads = (npix + 3) / 4;
+  resolve_multi_kernel<G><<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(zbuf, pts, lut, res, npix, g_count, out);
+  return 0;
 }
 
 template <int G>
@@ -774,6 +894,77 @@ extern "C" int evw_cube_to_equirect_u8(const uint8_t* faces, const uint32_t* lut
   int64_t npix = (int64_t)outH * outW;
   dim3 grd((unsigned)((npix + 255) / 256), B);
   cube_gather_kernel<<<grd, 256, 0, (cudaStream_t)stream>>>(faces, lut, face_res, npix, out);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+
+extern "C" int evw_splat_cube_equirect(const float* pts4, int64_t n_cap, const int64_t* n_dev, const float* w2c_front,
+                                       int V, int face_res, float focal, float z_near, const uint32_t* lut, int outH,
+                                       int outW, uint8_t* out, void* zbuf_workspace, int64_t workspace_bytes,
+                                       int views_per_pass, int pretest, void* stream) {
+  EVW_CHECK_ARG((pts4 || n_cap == 0) && w2c_front && lut && out && zbuf_workspace, "evw_splat_cube_equirect: null pointer");
+  EVW_CHECK_ARG(n_cap >= 0 && n_cap < (1ll << 32), "evw_splat_cube_equirect: n out of range");
+  EVW_CHECK_ARG(V > 0 && face_res > 0 && face_res <= 16383 && outH > 0 && outW > 0, "evw_splat_cube_equirect: bad shape");
+  EVW_CHECK_ARG(((int64_t)outH * outW) % 4 == 0, "evw_splat_cube_equirect: outH*outW must be a multiple of 4");
+  const int G = views_per_pass;
+  EVW_CHECK_ARG(G == 1 || G == 2 || G == 4 || G == 8, "evw_splat_cube_equirect: views_per_pass must be 1, 2, 4 or 8");
+  if (workspace_bytes < evw_splat_workspace(G, face_res)) {
+    evw::set_error("evw_splat_cube_equirect: workspace too small");
+    return EVW_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* zbuf = (unsigned long long*)zbuf_workspace;
+  const size_t view_cells = (size_t)6 * face_res * face_res;
+  const int64_t npix = (int64_t)outH * outW;
+  const float4* p4 = reinterpret_cast<const float4*>(pts4);
+  for (int v0 = 0; v0 < V; v0 += G) {
+    const int g = (V - v0 < G) ? (V - v0) : G;
+    EVW_CUDA(cudaMemsetAsync(zbuf, 0xFF, (size_t)G * view_cells * 8, st));
+    // a short tail still runs the G-view kernel: the surplus matrices are copies of the last view, results dropped
+    const float* m = w2c_front + (size_t)v0 * 12;
+    uint8_t* o = out + (size_t)v0 * npix * 3;
+    float* tail = nullptr;
+    if (g < G) {
+      // tail matrices live at the end of the z-buffer workspace? no: keep it simple — run single-view passes
+      for (int j = 0; j < g; ++j)
+        launch_cube_pass<1>(p4, n_cap, (const long long*)n_dev, m + (size_t)j * 12, face_res, focal, z_near, pretest,
+                            zbuf + (size_t)j * view_cells, lut, npix, 1, o + (size_t)j * npix * 3, st);
+      (void)tail;
+      continue;
+    }
+    switch (G) {
+      case 1: launch_cube_pass<1>(p4, n_cap, (const long long*)n_dev, m, face_res, focal, z_near, pretest, zbuf, lut, npix, g, o, st); break;
+      case 2: launch_cube_pass<2>(p4, n_cap, (const long long*)n_dev, m, face_res, focal, z_near, pretest, zbuf, lut, npix, g, o, st); break;
+      case 4: launch_cube_pass<4>(p4, n_cap, (const long long*)n_dev, m, face_res, focal, z_near, pretest, zbuf, lut, npix, g, o, st); break;
+      default: launch_cube_pass<8>(p4, n_cap, (const long long*)n_dev, m, face_res, focal, z_near, pretest, zbuf, lut, npix, g, o, st); break;
+    }
+  }
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+
+extern "C" int evw_splat_cube_faces_debug(const float* pts4, int64_t n, const float* w2c_front, int V, int face_res,
+                                          float focal, float z_near, int64_t* win_idx, void* zbuf_workspace,
+                                          int64_t workspace_bytes, void* stream) {
+  EVW_CHECK_ARG(pts4 && w2c_front && win_idx && zbuf_workspace, "evw_splat_cube_faces_debug: null pointer");
+  EVW_CHECK_ARG(n >= 0 && n < (1ll << 32) && V > 0 && face_res > 0, "evw_splat_cube_faces_debug: bad shape");
+  if (workspace_bytes < evw_splat_workspace(1, face_res)) {
+    evw::set_error("evw_splat_cube_faces_debug: workspace too small");
+    return EVW_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* zbuf = (unsigned long long*)zbuf_workspace;
+  const int64_t view_cells = (int64_t)6 * face_res * face_res;
+  for (int v = 0; v < V; ++v) {
+    EVW_CUDA(cudaMemsetAsync(zbuf, 0xFF, (size_t)view_cells * 8, st));
+    if (n > 0) {
+      int64_t want = (n + 255) / 256, cap = (int64_t)evw::sm_count() * 8;
+      cube_splat_kernel<1><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(
+          reinterpret_cast<const float4*>(pts4), n, nullptr, w2c_front + (size_t)v * 12, face_res, focal, z_near, 1, zbuf);
+    }
+    zbuf_to_index_kernel<<<(unsigned)((view_cells + 255) / 256), 256, 0, st>>>(zbuf, view_cells,
+                                                                               (long long*)win_idx + (size_t)v * view_cells);
+  }
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }

@@ -44,6 +44,7 @@ FACE_RES = 512          # reproject_vggt_open3d_utils.py:617,636
 PANO_W, PANO_H = 2000, 1000  # :705
 Z_NEAR = 1e-6           # near plane of the point pass
 DEFAULT_VIEWS_PER_PASS = 4
+DEFAULT_PRETEST = os.environ.get("EVW_SPLAT_PRETEST", "1") != "0"  # read the cell before the 64-bit atomic min
 
 
 # ---------------------------------------------------------------------------------------------
@@ -135,6 +136,13 @@ def face_w2c_matrices(target_c2w: np.ndarray) -> np.ndarray:
                 cam = cam @ Fz
             out[v, fi] = np.linalg.inv(cam)[:3, :4]
     return out.astype(np.float32)
+
+
+def front_w2c_matrices(target_c2w: np.ndarray) -> np.ndarray:
+    """[V,4,4] target camera-to-world -> [V,3,4] float32 cam-from-world of the front cube face; the other five
+    faces are exact signed axis permutations of it (cube formulation of the splat, csrc/reproj.cu)."""
+    target_c2w = np.asarray(target_c2w, dtype=np.float64)
+    return np.stack([np.linalg.inv(c)[:3, :4] for c in target_c2w]).astype(np.float32)
 
 
 def rotation_from_vectors(u, v):
@@ -244,10 +252,13 @@ def conf_select_device(conf: torch.Tensor, pts4: Optional[torch.Tensor], conf_th
 def splat_to_panoramas_device(scene: PointScene, w2c: torch.Tensor, width: int = PANO_W, height: int = PANO_H,
                               face_res: int = FACE_RES, views_per_pass: int = DEFAULT_VIEWS_PER_PASS,
                               z_near: float = Z_NEAR, out: Optional[torch.Tensor] = None,
-                              zbuf: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Fused splat + resolve: w2c [V,6,3,4] f32 (CUDA) -> uint8 [V,height,width,3] (CUDA)."""
+                              zbuf: Optional[torch.Tensor] = None, pretest: Optional[bool] = None) -> torch.Tensor:
+    """Fused splat + resolve -> uint8 [V,height,width,3] (CUDA).
+    w2c [V,3,4]: cube formulation (front-face camera, one transform per point-view; the fast path);
+    w2c [V,6,3,4]: six independent per-face cameras (the literal restatement of render_cubemap)."""
     dev = scene.device
     V = w2c.shape[0]
+    pretest = DEFAULT_PRETEST if pretest is None else pretest
     w2c = w2c.to(dev, torch.float32).contiguous()
     lut = cube_lut_device(width, height, face_res, dev)
     L = _lib.lib()
@@ -257,10 +268,17 @@ def splat_to_panoramas_device(scene: PointScene, w2c: torch.Tensor, width: int =
     if out is None:
         out = torch.empty((V, height, width, 3), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(L.evw_splat_cubemap_equirect(
-            _lib.ptr(scene.pts4), scene.pts4.shape[0], _lib.ptr(scene.count), _lib.ptr(w2c), V, face_res,
-            face_res / 2.0, z_near, _lib.ptr(lut), height, width, _lib.ptr(out), _lib.ptr(zbuf),
-            zbuf.numel() * zbuf.element_size(), views_per_pass, _lib.stream_ptr(dev)), "evw_splat_cubemap_equirect")
+        if w2c.dim() == 3:
+            _lib.check(L.evw_splat_cube_equirect(
+                _lib.ptr(scene.pts4), scene.pts4.shape[0], _lib.ptr(scene.count), _lib.ptr(w2c), V, face_res,
+                face_res / 2.0, z_near, _lib.ptr(lut), height, width, _lib.ptr(out), _lib.ptr(zbuf),
+                zbuf.numel() * zbuf.element_size(), views_per_pass, 1 if pretest else 0, _lib.stream_ptr(dev)),
+                "evw_splat_cube_equirect")
+        else:
+            _lib.check(L.evw_splat_cubemap_equirect(
+                _lib.ptr(scene.pts4), scene.pts4.shape[0], _lib.ptr(scene.count), _lib.ptr(w2c), V, face_res,
+                face_res / 2.0, z_near, _lib.ptr(lut), height, width, _lib.ptr(out), _lib.ptr(zbuf),
+                zbuf.numel() * zbuf.element_size(), views_per_pass, _lib.stream_ptr(dev)), "evw_splat_cubemap_equirect")
     return out
 
 
@@ -487,7 +505,7 @@ class CubemapRenderer:
 
     def render_cubemaps_to_panoramas_device(self, scene_3d: PointScene, target_extrinsic: np.ndarray,
                                             width: int = PANO_W, height: int = PANO_H) -> torch.Tensor:
-        w2c = torch.from_numpy(face_w2c_matrices(target_extrinsic)).to(scene_3d.device)
+        w2c = torch.from_numpy(front_w2c_matrices(target_extrinsic)).to(scene_3d.device)
         return splat_to_panoramas_device(scene_3d, w2c, width, height, FACE_RES, self.views_per_pass)
 
     def render_cubemaps_to_panoramas(self, scene_3d: PointScene, target_extrinsic: np.ndarray, orig_extrinsic=None,

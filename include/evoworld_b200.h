@@ -106,6 +106,19 @@ int evw_splat_cubemap_equirect(const float* pts4, int64_t n_cap, const int64_t* 
                                void* zbuf_workspace, int64_t workspace_bytes, int views_per_pass,
                                void* stream);
 
+/* Cube formulation of the same render (the fast path behind render_cubemaps_to_panoramas): w2c_front [V,3,4] f32 is
+ * the cam-from-world of the FRONT face only (= inv(target_c2w)); the other five faces are the exact signed axis
+ * permutations of the reference's CUBEMAP_TRANSFORMS, so each (point, view) costs one transform and the point lands
+ * in the face of its major axis.  Otherwise the contract of evw_splat_cubemap_equirect; views_per_pass in {1,2,4,8},
+ * outH*outW % 4 == 0; pretest != 0 reads the cell before issuing the 64-bit atomic min. */
+int evw_splat_cube_equirect(const float* pts4, int64_t n_cap, const int64_t* n_dev, const float* w2c_front, int V,
+                            int face_res, float focal, float z_near, const uint32_t* lut, int outH, int outW,
+                            uint8_t* out, void* zbuf_workspace, int64_t workspace_bytes, int views_per_pass,
+                            int pretest, void* stream);
+int evw_splat_cube_faces_debug(const float* pts4, int64_t n, const float* w2c_front, int V, int face_res, float focal,
+                               float z_near, int64_t* win_idx, void* zbuf_workspace, int64_t workspace_bytes,
+                               void* stream);
+
 /* Same splat, but returns the raw per-face winners for parity tests:
  * win_idx [V,6,res,res] int64 (-1 = empty). */
 int evw_splat_faces_debug(const float* pts4, int64_t n, const float* w2c, int V, int face_res,

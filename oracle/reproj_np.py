@@ -381,6 +381,23 @@ def splat_keys(pts4: np.ndarray, w2c: np.ndarray, res: int, focal: float, z_near
     return keys
 
 
+def front_w2c(target_c2w: np.ndarray) -> np.ndarray:
+    """[V,4,4] target camera-to-world -> [V,3,4] float32 cam-from-world of the FRONT cube face (T_front = I)."""
+    return np.stack([np.linalg.inv(c)[:3, :4] for c in np.asarray(target_c2w, dtype=np.float64)]).astype(np.float32)
+
+
+def splat_keys_cube(pts4: np.ndarray, w2c_front: np.ndarray, res: int, focal: float, z_near: float) -> np.ndarray:
+    """Cube formulation (oracle_splat_keys_cube): one transform per (point, view), face = major axis."""
+    pts4 = np.ascontiguousarray(pts4, dtype=np.float32)
+    w2c_front = np.ascontiguousarray(w2c_front, dtype=np.float32)
+    V = w2c_front.shape[0]
+    keys = np.empty((V, 6, res, res), dtype=np.uint64)
+    _clib().oracle_splat_keys_cube(
+        pts4.ctypes.data_as(C.c_void_p), C.c_int64(pts4.shape[0]), w2c_front.ctypes.data_as(C.c_void_p), C.c_int(V),
+        C.c_int(res), C.c_float(focal), C.c_float(z_near), keys.ctypes.data_as(C.c_void_p))
+    return keys
+
+
 def keys_to_index(keys: np.ndarray) -> np.ndarray:
     idx = (keys & np.uint64(0xFFFFFFFF)).astype(np.int64)
     idx[keys == np.uint64(0xFFFFFFFFFFFFFFFF)] = -1
@@ -405,4 +422,12 @@ def render_panoramas(xyz: np.ndarray, rgb: np.ndarray, target_c2w: np.ndarray, r
     pts4 = pack_points(xyz, rgb)
     w2c = face_w2c(target_c2w).astype(np.float32)
     keys = splat_keys(pts4, w2c, res, res / 2.0, z_near)
+    return resolve(keys, pts4, cube_to_equirect_lut(width, height, res))
+
+
+def render_panoramas_cube(xyz: np.ndarray, rgb: np.ndarray, target_c2w: np.ndarray, res: int = 512, width: int = 2000,
+                          height: int = 1000, z_near: float = 1e-6) -> np.ndarray:
+    """render_cubemaps_to_panoramas on the oracle, cube formulation (what the product's fast path computes)."""
+    pts4 = pack_points(xyz, rgb)
+    keys = splat_keys_cube(pts4, front_w2c(target_c2w), res, res / 2.0, z_near)
     return resolve(keys, pts4, cube_to_equirect_lut(width, height, res))

@@ -48,6 +48,46 @@ void oracle_splat_keys(const float* pts4, int64_t n, const float* w2c, int V, in
   }
 }
 
+/* Cube formulation (evoworld_b200/csrc/reproj.cu:cube_splat_one): one camera-space transform per (point, view) with
+ * the FRONT camera's w2c [V,12]; face = major axis, face-local coordinates = inv(T_face [Rz180]) applied exactly:
+ *   front (x,y,z) | right (-z,y,x) | back (-x,y,-z) | left (z,y,-x) | top (-x,-z,-y) | bottom (-x,z,y)
+ * (CUBEMAP_TRANSFORMS, reproject_vggt_open3d_utils.py:29-36; do_flip Rz(180) for top/bottom :619-622,652-655). */
+void oracle_splat_keys_cube(const float* pts4, int64_t n, const float* w2c_front, int V, int res, float focal,
+                            float z_near, uint64_t* keys) {
+  const float c = 0.5f * (float)res;
+  const float fres = (float)res;
+  const int64_t face_sz = (int64_t)res * res;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int v = 0; v < V; ++v) {
+    const float* m = w2c_front + (int64_t)v * 12;
+    uint64_t* zv = keys + (int64_t)v * 6 * face_sz;
+    for (int64_t i = 0; i < 6 * face_sz; ++i) zv[i] = UINT64_MAX;
+    for (int64_t i = 0; i < n; ++i) {
+      const float x = pts4[i * 4], y = pts4[i * 4 + 1], z = pts4[i * 4 + 2];
+      const float xc = fmaf(m[0], x, fmaf(m[1], y, fmaf(m[2], z, m[3])));
+      const float yc = fmaf(m[4], x, fmaf(m[5], y, fmaf(m[6], z, m[7])));
+      const float zc = fmaf(m[8], x, fmaf(m[9], y, fmaf(m[10], z, m[11])));
+      const float ax = fabsf(xc), ay = fabsf(yc), az = fabsf(zc);
+      int face; float fx, fy, fz;
+      if (az >= ax && az >= ay) {
+        if (zc > 0.f) { face = 0; fx = xc; fy = yc; fz = zc; } else { face = 2; fx = -xc; fy = yc; fz = -zc; }
+      } else if (ax >= ay) {
+        if (xc > 0.f) { face = 1; fx = -zc; fy = yc; fz = xc; } else { face = 3; fx = zc; fy = yc; fz = -xc; }
+      } else {
+        if (yc > 0.f) { face = 5; fx = -xc; fy = zc; fz = yc; } else { face = 4; fx = -xc; fy = -zc; fz = -yc; }
+      }
+      if (!(fz > z_near)) continue;
+      float u = fmaf(focal, fx / fz, c);
+      float vv = fmaf(focal, fy / fz, c);
+      if (!(u >= 0.f && u < fres && vv >= 0.f && vv < fres)) continue;
+      int px = (int)floorf(u), py = (int)floorf(vv);
+      uint64_t key = ((uint64_t)f2u(fz) << 32) | (uint32_t)i;
+      uint64_t* cell = zv + ((int64_t)face * res + py) * res + px;
+      if (key < *cell) *cell = key;
+    }
+  }
+}
+
 /* cube->equirect gather through the lookup table (reproject_vggt_open3d_utils.py:603-612):
  * lut [npix] = face<<28 | row<<14 | col, 0xFFFFFFFF = none; out [V,npix,3] */
 void oracle_resolve(const uint64_t* keys, const float* pts4, const uint32_t* lut, int V, int res,

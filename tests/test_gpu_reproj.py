@@ -213,7 +213,7 @@ def test_predictions_to_target_view_end_to_end(tmp_path, cuda_device, built_lib)
     cols = O.extract_colors(p["images"])
     v, c = O.apply_confidence_filter(p["world_points_from_depth"], p["depth_conf"], cols, 50.0)
     tgt = O.align_extrinsics(p["camera_pose"], p["extrinsic"], 24, outdir)
-    want = O.render_panoramas(v, c, tgt, z_near=R.Z_NEAR)
+    want = O.render_panoramas_cube(v, c, tgt, z_near=R.Z_NEAR)
     np.testing.assert_array_equal(panos, want)
     import cv2
 
@@ -240,15 +240,60 @@ def test_full_size_properties(cuda_device, built_lib):
     assert abs(n - 25 * 392 * 518 // 2) <= 2
     assert bool((keep[1:n] > keep[: n - 1]).all())  # order-preserving compaction
     tgt = R.SceneBuilder().align_extrinsics(p["camera_pose"], p["extrinsic"], 24, "x_0", False)
-    w2c = torch.from_numpy(R.face_w2c_matrices(tgt)).to(dev)
+    w2c = torch.from_numpy(R.front_w2c_matrices(tgt)).to(dev)
     scene = R.PointScene(out, count)
     a = R.splat_to_panoramas_device(scene, w2c, views_per_pass=4)
     b = R.splat_to_panoramas_device(scene, w2c, views_per_pass=8)
-    c = R.splat_to_panoramas_device(R.PointScene(out[:n].clone()), w2c, views_per_pass=1)
+    c = R.splat_to_panoramas_device(R.PointScene(out[:n].clone()), w2c, views_per_pass=1, pretest=False)
     assert torch.equal(a, b) and torch.equal(a, c)
     assert torch.equal(a, R.splat_to_panoramas_device(scene, w2c, views_per_pass=4))
     assert float((a.sum(dim=-1) > 0).float().mean()) > 0.2  # panoramas are populated
     sel = [0, 23]
-    want = O.resolve(O.splat_keys(out[:n].cpu().numpy(), w2c[sel].cpu().numpy(), 512, 256.0, R.Z_NEAR),
+    want = O.resolve(O.splat_keys_cube(out[:n].cpu().numpy(), w2c[sel].cpu().numpy(), 512, 256.0, R.Z_NEAR),
                      out[:n].cpu().numpy(), O.cube_to_equirect_lut(2000, 1000, 512))
     np.testing.assert_array_equal(a[sel].cpu().numpy(), want)
+    # the six-independent-cameras formulation agrees except on face-boundary / rounding pixels
+    w6 = torch.from_numpy(R.face_w2c_matrices(tgt[sel])).to(dev)
+    d = R.splat_to_panoramas_device(scene, w6, views_per_pass=2)
+    assert float((d != a[sel]).any(dim=-1).float().mean()) < 2e-3
+
+
+@pytest.mark.parametrize("n,res,V", [(1, 16, 1), (5000, 32, 3), (200_000, 128, 2), (1_000_000, 512, 2)])
+def test_cube_splat_winner_index_bit_exact(n, res, V, cuda_device, built_lib):
+    xyz, rgb = synthetic.random_cloud(n, seed=n + 1)
+    if n > 10:
+        xyz[n // 2:n // 2 + n // 10] = xyz[: n // 10]  # z ties -> lowest index wins
+    if n >= 5000:  # points exactly on face boundaries and on the axes
+        xyz[:6] = np.array([[1, 1, 1], [-1, 1, 1], [1, -1, 0], [0, 0, 2], [0, 3, 0], [-2, 0, 0]], dtype=np.float64)
+    pts4 = O.pack_points(xyz, rgb)
+    cam = synthetic.euler_c2w(synthetic.curve_trajectory())[30:30 + V]
+    cam[:, :3, :3] *= 1.3
+    if n >= 5000:
+        cam[0] = np.eye(4)
+    w2c = O.front_w2c(cam)
+    want = O.keys_to_index(O.splat_keys_cube(pts4, w2c, res, res / 2.0, R.Z_NEAR))
+    L = R._lib.lib()
+    p = torch.from_numpy(pts4).to(cuda_device)
+    w = torch.from_numpy(w2c).to(cuda_device)
+    ws = torch.empty(L.evw_splat_workspace(1, res), dtype=torch.uint8, device=cuda_device)
+    win = torch.empty((V, 6, res, res), dtype=torch.int64, device=cuda_device)
+    R._lib.check(L.evw_splat_cube_faces_debug(p.data_ptr(), n, w.data_ptr(), V, res, res / 2.0, R.Z_NEAR, win.data_ptr(),
+                                              ws.data_ptr(), ws.numel(), R._lib.stream_ptr(cuda_device)))
+    np.testing.assert_array_equal(win.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("G", [1, 2, 4, 8])
+def test_cube_fused_panoramas_bit_exact(G, cuda_device, built_lib):
+    n, res, V = 300_000, 128, 7
+    xyz, rgb = synthetic.random_cloud(n, seed=12)
+    cam = synthetic.euler_c2w(synthetic.curve_trajectory())[40:40 + V]
+    want = O.render_panoramas_cube(xyz, rgb, cam, res=res, width=400, height=200, z_near=R.Z_NEAR)
+    scene = R.SceneBuilder().build_open3d_scene(xyz, rgb)
+    w2c = torch.from_numpy(R.front_w2c_matrices(cam)).to(cuda_device)
+    for pretest in (True, False):
+        got = R.splat_to_panoramas_device(scene, w2c, 400, 200, res, G, pretest=pretest)
+        np.testing.assert_array_equal(got.cpu().numpy(), want)
+    scene2 = R.PointScene(scene.pts4, torch.tensor([n // 3], dtype=torch.int64, device=cuda_device))
+    got2 = R.splat_to_panoramas_device(scene2, w2c, 400, 200, res, G)
+    want2 = O.render_panoramas_cube(xyz[: n // 3], rgb[: n // 3], cam, res=res, width=400, height=200, z_near=R.Z_NEAR)
+    np.testing.assert_array_equal(got2.cpu().numpy(), want2)
