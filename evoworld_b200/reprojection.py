@@ -44,7 +44,7 @@ FACE_RES = 512          # reproject_vggt_open3d_utils.py:617,636
 PANO_W, PANO_H = 2000, 1000  # :705
 Z_NEAR = 1e-6           # near plane of the point pass
 DEFAULT_VIEWS_PER_PASS = 4
-DEFAULT_PRETEST = os.environ.get("EVW_SPLAT_PRETEST", "1") != "0"  # read the cell before the 64-bit atomic min
+DEFAULT_PRETEST = os.environ.get("EVW_SPLAT_PRETEST", "0") != "0"  # read the cell before the 64-bit atomic min (slower on B200)
 
 
 # ---------------------------------------------------------------------------------------------

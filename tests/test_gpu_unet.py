@@ -105,3 +105,38 @@ def test_unet_forward_full_width(cuda_device, built_lib):
     assert err < 3e-3
     launches, flops = ours.plan_info()
     assert launches > 500 and flops > 0
+
+
+def test_full_size_properties(cuda_device, built_lib):
+    """BASELINE config 2 size (576x1024x14f -> 72x128 latents, CFG batch 2, full-width UNet): size-independent
+    properties instead of the (minutes-long) fp32 oracle —
+      determinism; identical batch rows give identical outputs; a zero-length Euler step (sigma_next == sigma) is the
+      identity; the fused step equals pre -> forward -> CFG -> Euler assembled from the public forward()."""
+    import bench_denoise as bd
+
+    dev = cuda_device
+    unet = UNetSpatioTemporalConditionModel(**bd.UNET_CFG).init_random(seed=0, device=dev)
+    T, h, w = 14, 72, 128
+    lat, cond, ehs, ids = [t.to(dev) for t in bd.make_inputs(T, h, w, dev, seed=0)]
+    sigma, sigma_next = 700.0, 545.73
+    x_in = torch.cat([torch.cat([lat] * 2) / (sigma ** 2 + 1) ** 0.5, cond], dim=2)
+    t = 0.25 * math.log(sigma)
+    v1 = unet(x_in, t, ehs, ids).sample
+    v2 = unet(x_in, t, ehs, ids).sample
+    assert torch.isfinite(v1).all() and torch.equal(v1, v2)
+    # identical batch rows -> identical outputs
+    same = unet(torch.cat([x_in[1:2]] * 2), t, torch.cat([ehs[1:2]] * 2), ids).sample
+    assert torch.equal(same[0], same[1])
+    assert rel_l2(same[1], v1[1]) < 1e-6
+    # fused step == public forward + CFG + Euler in torch
+    g = torch.linspace(1.0, 3.0, T, device=dev).view(1, T, 1, 1, 1)
+    v = v1[0:1] + g * (v1[1:2] - v1[0:1])
+    x0 = v * (-sigma / (sigma ** 2 + 1) ** 0.5) + lat / (sigma ** 2 + 1)
+    want = lat + (lat - x0) / sigma * (sigma_next - sigma)
+    got = unet.denoise_step(lat.clone(), cond, sigma, sigma_next, ehs, ids, 1.0, 3.0)
+    assert rel_l2(got, want) < 1e-6
+    # zero-length step leaves the latents untouched (x + d * 0)
+    same_lat = unet.denoise_step(lat.clone(), cond, sigma, sigma, ehs, ids, 1.0, 3.0)
+    assert torch.equal(same_lat, lat)
+    launches, flops = unet.plan_info()
+    assert 700 < launches < 1200 and 80e12 < flops < 95e12
