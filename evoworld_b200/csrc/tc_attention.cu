@@ -528,6 +528,9 @@ __device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t units16) {  //
   return d + units16;  // never carries out of the address field for in-range tiles
 }
 
+#ifndef EVW_ATTN_ONES_MMA
+#define EVW_ATTN_ONES_MMA 1
+#endif
 #ifndef EVW_EXP_F16X2
 #define EVW_EXP_F16X2 0
 #endif
@@ -643,7 +646,9 @@ spatial_attn3_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
             for (int ks = 0; ks < kBKV / 16; ++ks) {
               const uint64_t a = desc_add(dp, (ks >> 2) * (kTileBytes >> 4) + 2 * (ks & 3));
               umma_f16_ss(t_o, a, desc_add(dv, ks * (2048 >> 4)), idesc_o, acc | (ks != 0));                         // O += P V
+#if EVW_ATTN_ONES_MMA
               umma_f16_ss(t_l, a, desc_add(d1, (ks >> 2) * (2048 >> 4) + 2 * (ks & 3)), idesc_l, acc | (ks != 0));   // L += P 1
+#endif
             }
             tc_commit(o_full(g));
             tc_commit(kv_empty(st));
@@ -667,6 +672,7 @@ spatial_attn3_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
       const uint32_t s_addr = lane_addr + g * kBKV, o_addr = lane_addr + kTmemO3 + g * kD, l_addr = lane_addr + kTmemL3 + g * 16;
       float m_ref = -INFINITY;
+      float l_run = 0.f;
       uint8_t* prow = base_ptr + kA2OffP + g * 2 * kTileBytes + r * 128;
 
       for (int j = 0; j < n_kv; ++j) {
@@ -707,6 +713,9 @@ spatial_attn3_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
         const float neg_m = -m_ref;
         // probabilities first (registers only): this phase overlaps the PV MMA of the previous tile
         uint32_t w[64];
+#if !EVW_ATTN_ONES_MMA
+        float sum0 = 0.f, sum1 = 0.f;
+#endif
 #pragma unroll
         for (int i = 0; i < 64; ++i) {
           const float x0 = fmaf(__uint_as_float(s[2 * i]), scale_log2e, neg_m);
@@ -718,8 +727,15 @@ spatial_attn3_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
           const float p1 = ((2 * i + 1) % kPolyEvery == kPolyEvery - 1) ? exp2_poly(x1) : fast_exp2(x1);
           __half2 h = __floats2half2_rn(p0, p1);
           w[i] = *reinterpret_cast<uint32_t*>(&h);
+#if !EVW_ATTN_ONES_MMA
+          sum0 += p0;
+          sum1 += p1;
+#endif
 #endif
         }
+#if !EVW_ATTN_ONES_MMA
+        l_run = l_run * (need ? fast_exp2(m_old - m_ref) : 1.0f) + (sum0 + sum1);
+#endif
         // P buffer / O, L accumulators of this group are free once PV_g(j-1) has completed
         if (j > 0) {
           mbar_wait(o_full(g), (j - 1) & 1);
@@ -735,6 +751,7 @@ spatial_attn3_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
               for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
               tmem_st_32x32b_x16(o_addr + part * 16, v);
             }
+#if EVW_ATTN_ONES_MMA
             {
               uint32_t v[16];
               tmem_ld_32x32b_x16(l_addr, v);
@@ -743,6 +760,7 @@ spatial_attn3_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
               for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
               tmem_st_32x32b_x16(l_addr, v);
             }
+#endif
             tmem_st_wait();
           }
         }
@@ -765,6 +783,9 @@ spatial_attn3_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
       tmem_ld_32x32b_x32(o_addr + 32, hi);
       tmem_ld_32x32b_x16(l_addr, lv);
       tmem_ld_wait();
+#if !EVW_ATTN_ONES_MMA
+      lv[0] = __float_as_uint(l_run);
+#endif
       if (qrow < S) {
         const float inv = 1.0f / __uint_as_float(lv[0]);
         uint4* op = reinterpret_cast<uint4*>(out + ((long long)frame * S + qrow) * C + head * kD);
