@@ -113,7 +113,7 @@ def run_reproj_ours(args, dev, rank, world):
     tgt = R.SceneBuilder(dev).align_extrinsics(p["camera_pose"], p["extrinsic"], c["V"], "bench_0", False)
     w2c = torch.from_numpy(R.front_w2c_matrices(tgt)).to(dev)  # cube formulation: one transform per point-view
     G = args.views_per_pass
-    zbuf = torch.empty(R._lib.lib().evw_splat_workspace(G, c["face_res"]), dtype=torch.uint8, device=dev)
+    zbuf = torch.empty(R.splat_workspace_bytes(G, c["face_res"]), dtype=torch.uint8, device=dev)
     out = torch.empty((c["V"], c["pano"][0], c["pano"][1], 3), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 

@@ -26,6 +26,7 @@ SIGNATURES = {
     "evw_conf_select": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_float, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
     "evw_splat_workspace": (c_i64, [c_int, c_int]),
+    "evw_splat_workspace_flags": (c_i64, [c_int, c_int, c_int]),
     "evw_splat_cubemap_equirect": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_int, c_int, c_float, c_float,
                                            c_void_p, c_int, c_int, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "evw_splat_faces_u8": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_float, c_float, c_void_p,
@@ -35,6 +36,7 @@ SIGNATURES = {
                              C.c_char_p, c_void_p, c_int, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_int, c_float,
                              c_void_p, c_float, c_float, c_int, c_int, c_void_p]),
     "evw_spatial_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "evw_set_attention_variant": (None, [c_int]),
     "evw_temporal_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_i64, c_int, c_void_p]),
     "evw_group_norm_f16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_i64, c_i64, c_float, c_void_p, c_void_p,
                                    c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -650,18 +650,114 @@ __global__ void resolve_multi_kernel(const unsigned long long* __restrict__ zbuf
   }
 }
 
+
+// v2 of the cube splat: P points per thread per trip (P independent 16-byte loads in flight) and each view's matrix is
+// fetched from shared memory once per trip (3 x LDS.128) for all P points.  Same arithmetic, same keys.
+template <int G, int P>
+__global__ void __launch_bounds__(256)
+cube_splat2_kernel(const float4* __restrict__ pts, int64_t n_cap, const long long* __restrict__ n_dev,
+                   const float* __restrict__ w2c /*[G,12]*/, int res, float focal, float z_near, int pretest,
+                   unsigned long long* __restrict__ zbuf /*[G,6,res,res]*/) {
+  __shared__ __align__(16) float s_m[G * 12];
+  for (int i = threadIdx.x; i < G * 12; i += blockDim.x) s_m[i] = w2c[i];
+  __syncthreads();
+  const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
+  const float c = 0.5f * (float)res;
+  const size_t view_sz = (size_t)6 * res * res;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * P) {
+    float4 p[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      const int64_t i = i0 + k * stride;
+      p[k] = ld_stream_f4(pts + (i < n ? i : i0));
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float m[12];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4 row = *reinterpret_cast<const float4*>(s_m + g * 12 + q * 4);
+        m[q * 4 + 0] = row.x; m[q * 4 + 1] = row.y; m[q * 4 + 2] = row.z; m[q * 4 + 3] = row.w;
+      }
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+        const int64_t i = i0 + k * stride;
+        if (i < n) cube_splat_one(m, p[k].x, p[k].y, p[k].z, focal, c, z_near, res, zbuf + (size_t)g * view_sz, (unsigned)i, pretest);
+      }
+    }
+  }
+}
+
+// v2 of the resolve: the 4 x G dependent gather chains of a thread (lookup entry -> z-buffer key -> point colour) are
+// issued level by level — all keys, then all colours — so 16 loads are in flight instead of one (v1 was
+// long-scoreboard bound: 48 of 54 stall cycles per issue).
+template <int G>
+__global__ void __launch_bounds__(256)
+resolve_multi2_kernel(const unsigned long long* __restrict__ zbuf /*[G,6,res,res]*/, const float4* __restrict__ pts,
+                      const uint32_t* __restrict__ lut, int res, int64_t npix, int g_count,
+                      uint8_t* __restrict__ out /*[G,npix,3]*/) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t p0 = q * 4;
+  if (p0 >= npix) return;  // npix % 4 == 0 (checked by the caller): a quad is never ragged
+  const uint4 e4 = *reinterpret_cast<const uint4*>(lut + p0);
+  const uint32_t e[4] = {e4.x, e4.y, e4.z, e4.w};
+  const size_t view_sz = (size_t)6 * res * res;
+  uint32_t cell[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const unsigned face = e[j] >> 28, row = (e[j] >> 14) & 0x3FFFu, col = e[j] & 0x3FFFu;
+    cell[j] = (e[j] != 0xFFFFFFFFu) ? (face * res + row) * res + col : 0u;
+  }
+  unsigned long long key[G][4];
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) key[g][j] = (g < g_count) ? zbuf[(size_t)g * view_sz + cell[j]] : kEmptyKey;
+  uint32_t rgb[G][4];
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool hit = key[g][j] != kEmptyKey && e[j] != 0xFFFFFFFFu;
+      const unsigned idx = hit ? (unsigned)(key[g][j] & 0xFFFFFFFFull) : 0u;
+      const uint32_t w = __float_as_uint(__ldg(&pts[idx].w));
+      rgb[g][j] = hit ? (w & 0xFFFFFFu) : 0u;
+    }
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    if (g >= g_count) break;
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + ((size_t)g * npix + p0) * 3);  // 12-byte aligned quad
+    o[0] = rgb[g][0] | (rgb[g][1] << 24);
+    o[1] = (rgb[g][1] >> 8) | (rgb[g][2] << 16);
+    o[2] = (rgb[g][2] >> 16) | (rgb[g][3] << 8);
+  }
+}
+
 template <int G>
 int launch_cube_pass(const float4* pts, int64_t n_cap, const long long* n_dev, const float* w2c, int res, float focal,
-                     float z_near, int pretest, unsigned long long* zbuf, const uint32_t* lut, int64_t npix, int g_count,
+                     float z_near, int flags, unsigned long long* zbuf, const uint32_t* lut, int64_t npix, int g_count,
                      uint8_t* out, cudaStream_t st) {
+  const int pretest = flags & EVW_SPLAT_PRETEST;
   if (n_cap > 0) {
-    int64_t want = (n_cap + 255) / 256;
-    int64_t cap = (int64_t)evw::sm_count() * 8;
-    cube_splat_kernel<G><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(pts, n_cap, n_dev, w2c, res, focal, z_near,
-                                                                                pretest, zbuf);
+    if (flags & EVW_SPLAT_V1_KERNELS) {
+      int64_t want = (n_cap + 255) / 256;
+      int64_t cap = (int64_t)evw::sm_count() * 8;
+      cube_splat_kernel<G><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(pts, n_cap, n_dev, w2c, res, focal, z_near,
+                                                                                  pretest, zbuf);
+    } else {
+      constexpr int P = 2;
+      int64_t want = (n_cap + 256 * P - 1) / (256 * P);
+      int64_t cap = (int64_t)evw::sm_count() * 8;
+      cube_splat2_kernel<G, P><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(pts, n_cap, n_dev, w2c, res, focal,
+                                                                                      z_near, pretest, zbuf);
+    }
   }
   const int64_t quads = (npix + 3) / 4;
-  resolve_multi_kernel<G><<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(zbuf, pts, lut, res, npix, g_count, out);
+  if (flags & EVW_SPLAT_V1_KERNELS)
+    resolve_multi_kernel<G><<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(zbuf, pts, lut, res, npix, g_count, out);
+  else
+    resolve_multi2_kernel<G><<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(zbuf, pts, lut, res, npix, g_count, out);
   return 0;
 }
 
@@ -898,17 +994,65 @@ extern "C" int evw_cube_to_equirect_u8(const uint8_t* faces, const uint32_t* lut
   return EVW_OK;
 }
 
+extern "C" int64_t evw_splat_workspace_flags(int views_per_pass, int face_res, int flags) {
+  return evw_splat_workspace(views_per_pass, face_res) * ((flags & EVW_SPLAT_OVERLAP) ? 2 : 1);
+}
+
+namespace {
+// Two internal streams for the pass pipeline (fork/join around the caller's stream with events; capturable).
+struct SplatStreams {
+  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+  int device = -1;
+};
+int splat_streams(SplatStreams** out) {
+  static SplatStreams per_dev[16];
+  int dev = 0;
+  EVW_CUDA(cudaGetDevice(&dev));
+  EVW_CHECK_ARG(dev >= 0 && dev < 16, "evw_splat_cube_equirect: device index %d out of range", dev);
+  SplatStreams& s = per_dev[dev];
+  if (s.device != dev) {
+    for (int i = 0; i < 2; ++i) {
+      EVW_CUDA(cudaStreamCreateWithFlags(&s.s[i], cudaStreamNonBlocking));
+      EVW_CUDA(cudaEventCreateWithFlags(&s.join[i], cudaEventDisableTiming));
+    }
+    EVW_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    s.device = dev;
+  }
+  *out = &s;
+  return EVW_OK;
+}
+
+int cube_pass_dispatch(int G, const float4* p4, int64_t n_cap, const long long* n_dev, const float* m, int res, float focal,
+                       float z_near, int flags, unsigned long long* zbuf, const uint32_t* lut, int64_t npix, int g,
+                       uint8_t* o, cudaStream_t st) {
+  const size_t view_cells = (size_t)6 * res * res;
+  if (g < G) {  // short tail: single-view passes
+    for (int j = 0; j < g; ++j)
+      launch_cube_pass<1>(p4, n_cap, n_dev, m + (size_t)j * 12, res, focal, z_near, flags, zbuf + (size_t)j * view_cells, lut,
+                          npix, 1, o + (size_t)j * npix * 3, st);
+    return 0;
+  }
+  switch (G) {
+    case 1: return launch_cube_pass<1>(p4, n_cap, n_dev, m, res, focal, z_near, flags, zbuf, lut, npix, g, o, st);
+    case 2: return launch_cube_pass<2>(p4, n_cap, n_dev, m, res, focal, z_near, flags, zbuf, lut, npix, g, o, st);
+    case 4: return launch_cube_pass<4>(p4, n_cap, n_dev, m, res, focal, z_near, flags, zbuf, lut, npix, g, o, st);
+    default: return launch_cube_pass<8>(p4, n_cap, n_dev, m, res, focal, z_near, flags, zbuf, lut, npix, g, o, st);
+  }
+}
+}  // namespace
+
 extern "C" int evw_splat_cube_equirect(const float* pts4, int64_t n_cap, const int64_t* n_dev, const float* w2c_front,
                                        int V, int face_res, float focal, float z_near, const uint32_t* lut, int outH,
                                        int outW, uint8_t* out, void* zbuf_workspace, int64_t workspace_bytes,
-                                       int views_per_pass, int pretest, void* stream) {
+                                       int views_per_pass, int flags, void* stream) {
   EVW_CHECK_ARG((pts4 || n_cap == 0) && w2c_front && lut && out && zbuf_workspace, "evw_splat_cube_equirect: null pointer");
   EVW_CHECK_ARG(n_cap >= 0 && n_cap < (1ll << 32), "evw_splat_cube_equirect: n out of range");
   EVW_CHECK_ARG(V > 0 && face_res > 0 && face_res <= 16383 && outH > 0 && outW > 0, "evw_splat_cube_equirect: bad shape");
   EVW_CHECK_ARG(((int64_t)outH * outW) % 4 == 0, "evw_splat_cube_equirect: outH*outW must be a multiple of 4");
   const int G = views_per_pass;
   EVW_CHECK_ARG(G == 1 || G == 2 || G == 4 || G == 8, "evw_splat_cube_equirect: views_per_pass must be 1, 2, 4 or 8");
-  if (workspace_bytes < evw_splat_workspace(G, face_res)) {
+  if (workspace_bytes < evw_splat_workspace_flags(G, face_res, flags)) {
     evw::set_error("evw_splat_cube_equirect: workspace too small");
     return EVW_ERR_WORKSPACE;
   }
@@ -917,26 +1061,30 @@ extern "C" int evw_splat_cube_equirect(const float* pts4, int64_t n_cap, const i
   const size_t view_cells = (size_t)6 * face_res * face_res;
   const int64_t npix = (int64_t)outH * outW;
   const float4* p4 = reinterpret_cast<const float4*>(pts4);
-  for (int v0 = 0; v0 < V; v0 += G) {
+  const int passes = (V + G - 1) / G;
+  const bool overlap = (flags & EVW_SPLAT_OVERLAP) && passes > 1;
+  SplatStreams* ss = nullptr;
+  if (overlap) {
+    // pass p runs clear -> splat -> resolve on internal stream p % 2 with its own half of the workspace, so the
+    // (L2-atomic bound) splat of one pass overlaps the (gather-latency bound) resolve and the clear of its neighbours
+    int rc = splat_streams(&ss);
+    if (rc) return rc;
+    EVW_CUDA(cudaEventRecord(ss->fork, st));
+    EVW_CUDA(cudaStreamWaitEvent(ss->s[0], ss->fork, 0));
+    EVW_CUDA(cudaStreamWaitEvent(ss->s[1], ss->fork, 0));
+  }
+  for (int v0 = 0, pass = 0; v0 < V; v0 += G, ++pass) {
     const int g = (V - v0 < G) ? (V - v0) : G;
-    EVW_CUDA(cudaMemsetAsync(zbuf, 0xFF, (size_t)G * view_cells * 8, st));
-    // a short tail still runs the G-view kernel: the surplus matrices are copies of the last view, results dropped
-    const float* m = w2c_front + (size_t)v0 * 12;
-    uint8_t* o = out + (size_t)v0 * npix * 3;
-    float* tail = nullptr;
-    if (g < G) {
-      // tail matrices live at the end of the z-buffer workspace? no: keep it simple — run single-view passes
-      for (int j = 0; j < g; ++j)
-        launch_cube_pass<1>(p4, n_cap, (const long long*)n_dev, m + (size_t)j * 12, face_res, focal, z_near, pretest,
-                            zbuf + (size_t)j * view_cells, lut, npix, 1, o + (size_t)j * npix * 3, st);
-      (void)tail;
-      continue;
-    }
-    switch (G) {
-      case 1: launch_cube_pass<1>(p4, n_cap, (const long long*)n_dev, m, face_res, focal, z_near, pretest, zbuf, lut, npix, g, o, st); break;
-      case 2: launch_cube_pass<2>(p4, n_cap, (const long long*)n_dev, m, face_res, focal, z_near, pretest, zbuf, lut, npix, g, o, st); break;
-      case 4: launch_cube_pass<4>(p4, n_cap, (const long long*)n_dev, m, face_res, focal, z_near, pretest, zbuf, lut, npix, g, o, st); break;
-      default: launch_cube_pass<8>(p4, n_cap, (const long long*)n_dev, m, face_res, focal, z_near, pretest, zbuf, lut, npix, g, o, st); break;
+    cudaStream_t ps = overlap ? ss->s[pass & 1] : st;
+    unsigned long long* zb = zbuf + (overlap ? (size_t)(pass & 1) * G * view_cells : 0);
+    EVW_CUDA(cudaMemsetAsync(zb, 0xFF, (size_t)G * view_cells * 8, ps));
+    cube_pass_dispatch(G, p4, n_cap, (const long long*)n_dev, w2c_front + (size_t)v0 * 12, face_res, focal, z_near, flags, zb,
+                       lut, npix, g, out + (size_t)v0 * npix * 3, ps);
+  }
+  if (overlap) {
+    for (int i = 0; i < 2; ++i) {
+      EVW_CUDA(cudaEventRecord(ss->join[i], ss->s[i]));
+      EVW_CUDA(cudaStreamWaitEvent(st, ss->join[i], 0));
     }
   }
   EVW_LAUNCH_CHECK();

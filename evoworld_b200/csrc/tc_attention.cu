@@ -1044,23 +1044,345 @@ spatial_attn4_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
   }
 }
 
+// ==========================================================================================
+// v5: v3 with the two softmax groups explicitly out of phase.  ncu (profiles/r01_attn3_stalls.txt) showed v3's groups
+// running in lockstep: both hit their 96 MUFU.EX2 per tile at the same time (pipe saturated, mio throttle) and then both
+// did their FMA / TMEM / smem work with the MUFU pipe idle — xu 42 %, tensor 31 %, issue 46 % busy, nothing saturated.
+// Here a token (two named barriers) serialises only the MUFU-dense phase between the groups, and the exponent
+// arguments + polynomial exponentials are computed before the token is taken.
+// ==========================================================================================
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_volatile(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_shared_volatile(uint32_t addr, uint32_t v) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+constexpr int kA5OffToken = kA3OffOnes + 4096;  // 256 words: one per softmax thread
+constexpr int kA5Smem = kA5OffToken + 1024 + 1024;
+
+template <int kPolyN, bool kStagger>
+__global__ void __launch_bounds__(kA2Threads, 1)
+spatial_attn5_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ out, int S, int C, float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, frame = blockIdx.z;
+  const int q0 = blockIdx.x * 2 * kBQ;
+  const int n_kv = (S + kBKV - 1) / kBKV;
+  const bool b_active = q0 + kBQ < S;
+
+  const uint32_t bar = base + kA2OffBar;
+  const uint32_t q_full = bar;
+  auto kv_full = [&](int s) { return bar + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bar + 8u * (1 + kKvStages + s); };
+  auto s_full = [&](int g) { return bar + 8u * (1 + 2 * kKvStages + g); };
+  auto s_empty = [&](int g) { return bar + 8u * (3 + 2 * kKvStages + g); };
+  auto p_full = [&](int g) { return bar + 8u * (5 + 2 * kKvStages + g); };
+  auto o_full = [&](int g) { return bar + 8u * (7 + 2 * kKvStages + g); };
+  const uint32_t tmem_slot = bar + 8u * (9 + 2 * kKvStages);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + kA2OffBar + 8 * (9 + 2 * kKvStages));
+
+  // all-ones operand for the row-sum MMA
+  for (int i = threadIdx.x; i < 4096 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(base_ptr + kA3OffOnes)[i] = 0x3C003C00u;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKvStages; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), b_active ? 2 : 1);  // one tcgen05.commit per active group
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(s_full(g), 1);
+      mbar_init(s_empty(g), 4);
+      mbar_init(p_full(g), 4);
+      mbar_init(o_full(g), 1);
+    }
+    fence_barrier_init();
+  }
+  fence_proxy_async();  // ones tile + barrier inits visible to the async proxy
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+        tma_load_3d(&tmap, base + kA2OffQ, q_full, head * kD, q0, frame);
+        tma_load_3d(&tmap, base + kA2OffQ + kTileBytes, q_full, head * kD, q0 + kBQ, frame);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % kKvStages;
+        mbar_wait(kv_empty(st), ((j / kKvStages) & 1) ^ 1u);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(kv_full(st), 2 * kTileBytes);
+          tma_load_3d(&tmap, base + kA2OffK + st * kTileBytes, kv_full(st), C + head * kD, j * kBKV, frame);
+          tma_load_3d(&tmap, base + kA2OffV + st * kTileBytes, kv_full(st), 2 * C + head * kD, j * kBKV, frame);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1 || warp == 2) {
+      // ===================== MMA issuers: warp 1 drives group A, warp 2 drives group B (event driven) =====================
+      const int g = warp - 1;
+      if (lane == 0 && (g == 0 || b_active)) {
+        const uint32_t idesc_s = make_idesc_f16(kBQ, kBKV, 0, 0, 0);
+        const uint32_t idesc_o = make_idesc_f16(kBQ, kD, 0, 0, 1);
+        const uint32_t idesc_l = make_idesc_f16(kBQ, 16, 0, 0, 0);
+        // loop-invariant descriptors; per-k-step offsets are compile-time constants added to the address field
+        const uint64_t dq = make_desc_k_sw128(base + kA2OffQ + g * kTileBytes);
+        const uint64_t dp = make_desc_k_sw128(base + kA2OffP + g * 2 * kTileBytes);
+        const uint64_t d1 = make_desc_k_sw128(base + kA3OffOnes);
+        const uint64_t dk0 = make_desc_k_sw128(base + kA2OffK);
+        const uint64_t dv0 = make_desc_mn_sw128(base + kA2OffV, 1024);
+        const uint32_t t_s = tmem_base + g * kBKV, t_o = tmem_base + kTmemO3 + g * kD, t_l = tmem_base + kTmemL3 + g * 16;
+        mbar_wait(q_full, 0);
+        int s_next = 0, pv_next = 0;
+        long long t0 = clock64();
+        while (pv_next < n_kv) {
+          bool progress = false;
+          if (s_next < n_kv && mbar_test(kv_full(s_next % kKvStages), (s_next / kKvStages) & 1) &&
+              (s_next == 0 || mbar_test(s_empty(g), (s_next - 1) & 1))) {
+            tc_fence_after();
+            const uint64_t dk = desc_add(dk0, (s_next % kKvStages) * (kTileBytes >> 4));
+#pragma unroll
+            for (int k = 0; k < kD / 16; ++k) umma_f16_ss(t_s, desc_add(dq, 2 * k), desc_add(dk, 2 * k), idesc_s, k != 0);
+            tc_commit(s_full(g));
+            ++s_next;
+            progress = true;
+          }
+          if (pv_next < s_next && mbar_test(p_full(g), pv_next & 1)) {
+            tc_fence_after();
+            const int st = pv_next % kKvStages;
+            const uint64_t dv = desc_add(dv0, st * (kTileBytes >> 4));
+            const uint32_t acc = pv_next != 0;
+#pragma unroll
+            for (int ks = 0; ks < kBKV / 16; ++ks) {
+              const uint64_t a = desc_add(dp, (ks >> 2) * (kTileBytes >> 4) + 2 * (ks & 3));
+              umma_f16_ss(t_o, a, desc_add(dv, ks * (2048 >> 4)), idesc_o, acc | (ks != 0));                         // O += P V
+#if EVW_ATTN_ONES_MMA
+              umma_f16_ss(t_l, a, desc_add(d1, (ks >> 2) * (2048 >> 4) + 2 * (ks & 3)), idesc_l, acc | (ks != 0));   // L += P 1
+#endif
+            }
+            tc_commit(o_full(g));
+            tc_commit(kv_empty(st));
+            ++pv_next;
+            progress = true;
+          }
+          if (progress) t0 = clock64();
+          else if (clock64() - t0 > 8000000000ll) __trap();
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // ===================== softmax groups =====================
+    const int g = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int qrow = q0 + g * kBQ + r;
+    if (g == 0 || b_active) {
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t s_addr = lane_addr + g * kBKV, o_addr = lane_addr + kTmemO3 + g * kD, l_addr = lane_addr + kTmemL3 + g * 16;
+      float m_ref = -INFINITY;
+      float l_run = 0.f;
+      const uint32_t token_word = base + kA5OffToken + 4u * (threadIdx.x - 128);
+      if (kStagger) st_shared_volatile(token_word, 0u);
+      if (kStagger && b_active && g == 1) named_bar_arrive(1, 256);  // group A goes first
+      uint8_t* prow = base_ptr + kA2OffP + g * 2 * kTileBytes + r * 128;
+
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(s_full(g), j & 1);
+        tc_fence_after();
+        uint32_t s[128];
+        {
+          uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+          uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+          uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
+          uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
+          tmem_ld_32x32b_x32(s_addr + 0, s0);
+          tmem_ld_32x32b_x32(s_addr + 32, s1);
+          tmem_ld_32x32b_x32(s_addr + 64, s2);
+          tmem_ld_32x32b_x32(s_addr + 96, s3);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty(g));  // S_g(j+1) may now overwrite the TMEM tile
+
+        const int kv_valid = S - j * kBKV;
+        float mx = -INFINITY;
+        if (kv_valid >= kBKV) {
+#pragma unroll
+          for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(s[c]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 128; ++c) {
+            if (c >= kv_valid) s[c] = 0xff800000u;
+            mx = fmaxf(mx, __uint_as_float(s[c]));
+          }
+        }
+        const float m_tile = mx * scale_log2e;
+        const bool need = m_tile > m_ref + kLazyTau;  // first tile: m_ref = -inf -> true
+        const float m_old = m_ref;
+        if (need) m_ref = m_tile;
+        const float neg_m = -m_ref;
+        // (1) FMA-pipe phase, outside the MUFU token: the polynomial share of the exponentials.  It overlaps the other
+        // group's MUFU phase on the same SM sub-partitions.
+        if (kPolyN > 0) {
+#pragma unroll
+          for (int c = kPolyN - 1; c < 128; c += (kPolyN > 0 ? kPolyN : 128))
+            s[c] = __float_as_uint(exp2_poly(fmaf(__uint_as_float(s[c]), scale_log2e, neg_m)));
+        }
+        // (2) MUFU phase: the two query groups take turns (named barriers 1 / 2), so one group's exponentials run while
+        // the other group loads, scales, stores and waits — instead of both saturating the MUFU pipe in lockstep and
+        // both leaving it idle afterwards.  ptxas only honours data dependencies, so the phase is pinned between the
+        // barriers by one: its exponent arguments depend on a shared-memory word read after the acquire (always 0), and a
+        // word derived from its results is stored before the release.
+        float neg_m_dep = neg_m;
+        if (kStagger && b_active) {
+          named_bar_sync(1 + g, 256);
+          neg_m_dep = neg_m + __uint_as_float(ld_shared_volatile(token_word));
+        }
+        uint32_t w[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          const bool poly0 = kPolyN > 0 && ((2 * i) % (kPolyN > 0 ? kPolyN : 1)) == kPolyN - 1;
+          const bool poly1 = kPolyN > 0 && ((2 * i + 1) % (kPolyN > 0 ? kPolyN : 1)) == kPolyN - 1;
+          const float p0 = poly0 ? __uint_as_float(s[2 * i]) : fast_exp2(fmaf(__uint_as_float(s[2 * i]), scale_log2e, neg_m_dep));
+          const float p1 = poly1 ? __uint_as_float(s[2 * i + 1])
+                                 : fast_exp2(fmaf(__uint_as_float(s[2 * i + 1]), scale_log2e, neg_m_dep));
+          __half2 h = __floats2half2_rn(p0, p1);
+          w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        if (kStagger && b_active) {
+          // probabilities are >= 0: the two fp16 sign bits are 0 at run time, which the compiler cannot know
+          st_shared_volatile(token_word, (w[15] | w[31] | w[47] | w[63]) & 0x80008000u);
+          if (!(g == 1 && j + 1 == n_kv)) named_bar_arrive(2 - g, 256);
+        }
+        // P buffer / O, L accumulators of this group are free once PV_g(j-1) has completed
+        if (j > 0) {
+          mbar_wait(o_full(g), (j - 1) & 1);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, need)) {
+            const float f = need ? fast_exp2(m_old - m_ref) : 1.0f;
+#pragma unroll
+            for (int part = 0; part < 4; ++part) {
+              uint32_t v[16];
+              tmem_ld_32x32b_x16(o_addr + part * 16, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+              tmem_st_32x32b_x16(o_addr + part * 16, v);
+            }
+#if EVW_ATTN_ONES_MMA
+            {
+              uint32_t v[16];
+              tmem_ld_32x32b_x16(l_addr, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+              tmem_st_32x32b_x16(l_addr, v);
+            }
+#endif
+            tmem_st_wait();
+          }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) {
+          const int atom = ch >> 3, cc = ch & 7;
+          *reinterpret_cast<uint4*>(prow + atom * kTileBytes + ((cc ^ (r & 7)) << 4)) =
+              make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(g));
+      }
+      // final: O / L
+      mbar_wait(o_full(g), (n_kv - 1) & 1);
+      tc_fence_after();
+      uint32_t lo[32], hi[32], lv[16];
+      tmem_ld_32x32b_x32(o_addr, lo);
+      tmem_ld_32x32b_x32(o_addr + 32, hi);
+      tmem_ld_32x32b_x16(l_addr, lv);
+      tmem_ld_wait();
+#if !EVW_ATTN_ONES_MMA
+      lv[0] = __float_as_uint(l_run);
+#endif
+      if (qrow < S) {
+        const float inv = 1.0f / __uint_as_float(lv[0]);
+        uint4* op = reinterpret_cast<uint4*>(out + ((long long)frame * S + qrow) * C + head * kD);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t* src = (i < 4) ? &lo[8 * i] : &hi[8 * (i - 4)];
+          __half2 h0 = __floats2half2_rn(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
+          __half2 h1 = __floats2half2_rn(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
+          __half2 h2 = __floats2half2_rn(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
+          __half2 h3 = __floats2half2_rn(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
+          uint4 v;
+          v.x = *reinterpret_cast<uint32_t*>(&h0); v.y = *reinterpret_cast<uint32_t*>(&h1);
+          v.z = *reinterpret_cast<uint32_t*>(&h2); v.w = *reinterpret_cast<uint32_t*>(&h3);
+          op[i] = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace
+
+static int g_attn_variant_override = -2;
+void set_attention_variant(int v) { g_attn_variant_override = v; }
 
 int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, cudaStream_t st) {
   EVW_CHECK_ARG(qkv && out && F > 0 && S > 0 && heads > 0, "spatial_attention: bad arguments");
   const int C = heads * kD;
   static bool attr_set = false;
-  static bool use_v1 = false, use_v2 = false, use_v4 = false;
+  static bool use_v1 = false, use_v2 = false, use_v3 = false, use_v4 = false;
+  static int v5_variant = 0;
+  typedef void (*attn5_fn)(const CUtensorMap, __half*, int, int, float);
+  // v5 variants: {polynomial share, stagger}.  EVW_ATTN_V5=<index> selects one (micro-benchmarks); default = 0.
+  static const attn5_fn v5_table[] = {spatial_attn5_kernel<4, true>, spatial_attn5_kernel<8, true>, spatial_attn5_kernel<0, true>,
+                                      spatial_attn5_kernel<2, true>, spatial_attn5_kernel<4, false>};
   if (!attr_set) {
     EVW_CUDA(cudaFuncSetAttribute(spatial_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     EVW_CUDA(cudaFuncSetAttribute(spatial_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2Smem));
     EVW_CUDA(cudaFuncSetAttribute(spatial_attn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3Smem));
-    use_v1 = getenv("EVW_ATTN_V1") != nullptr;
     EVW_CUDA(cudaFuncSetAttribute(spatial_attn4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA4Smem));
+    for (attn5_fn f : v5_table) EVW_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kA5Smem));
+    use_v1 = getenv("EVW_ATTN_V1") != nullptr;
     use_v2 = getenv("EVW_ATTN_V2") != nullptr;
+    use_v3 = getenv("EVW_ATTN_V3") != nullptr;
     use_v4 = getenv("EVW_ATTN_V4") != nullptr;
+    if (const char* e = getenv("EVW_ATTN_V5")) v5_variant = atoi(e);
     attr_set = true;
   }
+  if (g_attn_variant_override >= -1) {  // evw_set_attention_variant (micro-benchmarks): -1 = v3, >= 0 = v5 table index
+    use_v3 = g_attn_variant_override == -1;
+    if (g_attn_variant_override >= 0) v5_variant = g_attn_variant_override;
+    use_v1 = use_v2 = use_v4 = false;
+  }
+  if (v5_variant < 0 || v5_variant >= (int)(sizeof(v5_table) / sizeof(v5_table[0]))) v5_variant = 0;
   alignas(64) CUtensorMap tmap;
   uint64_t dims[3] = {(uint64_t)3 * C, (uint64_t)S, (uint64_t)F};
   uint64_t str[2] = {(uint64_t)3 * C * 2, (uint64_t)3 * C * 2 * S};
@@ -1076,9 +1398,12 @@ int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, c
   } else if (use_v4) {  // P in tensor memory: correct, but the serialised S/PV chain makes it slower than v3 (5.9 vs 5.0 ms)
     dim3 grid((S + 2 * kBQ - 1) / (2 * kBQ), heads, F);
     spatial_attn4_kernel<<<grid, kA2Threads, kA4Smem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
-  } else {
+  } else if (use_v3) {
     dim3 grid((S + 2 * kBQ - 1) / (2 * kBQ), heads, F);
     spatial_attn3_kernel<<<grid, kA2Threads, kA3Smem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
+  } else {
+    dim3 grid((S + 2 * kBQ - 1) / (2 * kBQ), heads, F);
+    v5_table[v5_variant]<<<grid, kA2Threads, kA5Smem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
   }
   EVW_LAUNCH_CHECK();
   return EVW_OK;
@@ -1090,6 +1415,7 @@ int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, c
 extern "C" int evw_spatial_attention_f16(const void* qkv, void* out, int F, int S, int heads, void* stream) {
   return evw::spatial_attention((const __half*)qkv, (__half*)out, F, S, heads, (cudaStream_t)stream);
 }
+extern "C" void evw_set_attention_variant(int variant) { evw::set_attention_variant(variant); }
 extern "C" int evw_temporal_attention_f16(const void* qkv, void* out, int B, int T, int64_t S, int heads, void* stream) {
   return evw::temporal_attention((const __half*)qkv, (__half*)out, B, T, S, heads, (cudaStream_t)stream);
 }

@@ -31,10 +31,10 @@ __device__ __forceinline__ float4 ld4(const __half* p) {
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
-template <typename T0>
-__global__ void __launch_bounds__(512)
+template <typename T0, int NQ, int U>  // NQ channel quads per thread, U rows in flight per thread
+__global__ void __launch_bounds__(512, 2)
 gn_stats_kernel(const T0* __restrict__ src0, int C0, const float* __restrict__ src1, int C1, long long rows_per_inst,
-                int rows_per_block, int groups, int TQ, int NQ, double* __restrict__ stats) {
+                int rows_per_block, int groups, int TQ, double* __restrict__ stats) {
   const int inst = blockIdx.y;
   const int C = C0 + C1;
   const int cg = C / groups;
@@ -44,47 +44,43 @@ gn_stats_kernel(const T0* __restrict__ src0, int C0, const float* __restrict__ s
   for (int i = threadIdx.x; i < groups; i += blockDim.x) { s_sum[i] = 0; s_sq[i] = 0; }
   __syncthreads();
   const int tq = threadIdx.x % TQ, tr = threadIdx.x / TQ, R = blockDim.x / TQ;
-  float s[kGnMaxNQ][4], q[kGnMaxNQ][4];
+  float s[NQ][4], q[NQ][4];
 #pragma unroll
-  for (int j = 0; j < kGnMaxNQ; ++j)
+  for (int j = 0; j < NQ; ++j)
 #pragma unroll
     for (int i = 0; i < 4; ++i) { s[j][i] = 0.f; q[j][i] = 0.f; }
-  if (tr < R) {
-    // 4 rows in flight per thread (independent 16-byte loads) to cover DRAM latency
-    for (long long rb = r0 + tr; rb < r1; rb += 4LL * R) {
-      float4 v[4][kGnMaxNQ];
+  // U rows in flight per thread (independent 16-byte loads) to cover DRAM latency
+  for (long long rb = r0 + tr; rb < r1; rb += (long long)U * R) {
+    float4 v[U][NQ];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long r = rb + (long long)u * R;
-        const long long row = (long long)inst * rows_per_inst + r;
+    for (int u = 0; u < U; ++u) {
+      const long long r = rb + (long long)u * R;
+      const long long row = (long long)inst * rows_per_inst + r;
 #pragma unroll
-        for (int j = 0; j < kGnMaxNQ; ++j) {
-          v[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (j < NQ && r < r1) {
-            const int c = 4 * (tq + j * TQ);
-            v[u][j] = (c < C0) ? ld4(src0 + row * C0 + c) : ld4(src1 + row * C1 + (c - C0));
-          }
+      for (int j = 0; j < NQ; ++j) {
+        v[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < r1) {
+          const int c = 4 * (tq + j * TQ);
+          v[u][j] = (c < C0) ? ld4(src0 + row * C0 + c) : ld4(src1 + row * C1 + (c - C0));
         }
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int j = 0; j < kGnMaxNQ; ++j) {
-          s[j][0] += v[u][j].x; s[j][1] += v[u][j].y; s[j][2] += v[u][j].z; s[j][3] += v[u][j].w;
-          q[j][0] = fmaf(v[u][j].x, v[u][j].x, q[j][0]); q[j][1] = fmaf(v[u][j].y, v[u][j].y, q[j][1]);
-          q[j][2] = fmaf(v[u][j].z, v[u][j].z, q[j][2]); q[j][3] = fmaf(v[u][j].w, v[u][j].w, q[j][3]);
-        }
     }
 #pragma unroll
-    for (int j = 0; j < kGnMaxNQ; ++j) {
-      if (j < NQ) {
-        const int c = 4 * (tq + j * TQ);
+    for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          atomicAdd(&s_sum[(c + i) / cg], (double)s[j][i]);
-          atomicAdd(&s_sq[(c + i) / cg], (double)q[j][i]);
-        }
+      for (int j = 0; j < NQ; ++j) {
+        s[j][0] += v[u][j].x; s[j][1] += v[u][j].y; s[j][2] += v[u][j].z; s[j][3] += v[u][j].w;
+        q[j][0] = fmaf(v[u][j].x, v[u][j].x, q[j][0]); q[j][1] = fmaf(v[u][j].y, v[u][j].y, q[j][1]);
+        q[j][2] = fmaf(v[u][j].z, v[u][j].z, q[j][2]); q[j][3] = fmaf(v[u][j].w, v[u][j].w, q[j][3]);
       }
+  }
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) {
+    const int c = 4 * (tq + j * TQ);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      atomicAdd(&s_sum[(c + i) / cg], (double)s[j][i]);
+      atomicAdd(&s_sq[(c + i) / cg], (double)q[j][i]);
     }
   }
   __syncthreads();
@@ -116,51 +112,73 @@ __device__ __forceinline__ float silu_fast(float y) {
   return y * r;
 }
 
-// apply: 8 channels per thread, y = a x + b [-> SiLU] -> fp16
-template <typename T0>
-__global__ void gn_apply_kernel(const T0* __restrict__ src0, int C0, const float* __restrict__ src1, int C1,
-                                long long rows_total, long long rows_per_inst, const float2* __restrict__ ab, int do_silu,
-                                __half* __restrict__ out, __half* __restrict__ raw_out) {
+// apply: each thread owns one channel octet of one instance — its 8 (scale, shift) pairs stay in registers — and walks
+// rows with U loads in flight; y = a x + b [-> SiLU] -> fp16.  (v1 re-read the 64-byte table slice per 32 input bytes
+// and was L1-bound at 88 %.)
+template <typename T0, int U>
+__global__ void __launch_bounds__(320)
+gn_apply_kernel(const T0* __restrict__ src0, int C0, const float* __restrict__ src1, int C1, long long rows_per_inst,
+                int rows_per_block, const float2* __restrict__ ab, int do_silu, __half* __restrict__ out,
+                __half* __restrict__ raw_out) {
   const int C = C0 + C1;
   const int cv = C / 8;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows_total * cv) return;
-  const long long row = idx / cv;
-  const int c = (int)(idx - row * cv) * 8;
-  const long long inst = row / rows_per_inst;
-  float v[8];
+  const int tc = threadIdx.x % cv, tr = threadIdx.x / cv, R = blockDim.x / cv;
+  const int c = tc * 8;
+  const long long inst = blockIdx.y;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(rows_per_inst, r0 + rows_per_block);
+  float sa[8], sb[8];
   {
-    float4 a, b;
-    if (c < C0) {
-      a = ld4(src0 + row * C0 + c);
-      b = ld4(src0 + row * C0 + c + 4);
-    } else {
-      a = ld4(src1 + row * C1 + (c - C0));
-      b = ld4(src1 + row * C1 + (c - C0) + 4);
+    const float4* abp = reinterpret_cast<const float4*>(ab + inst * C + c);  // 8 x (a, b)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = __ldg(abp + i);
+      sa[2 * i] = t.x; sb[2 * i] = t.y; sa[2 * i + 1] = t.z; sb[2 * i + 1] = t.w;
     }
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   }
-  if (raw_out) {
-    uint4 raw;
-    __half2* h = reinterpret_cast<__half2*>(&raw);
+  const bool from0 = c < C0;
+  for (long long rb = r0 + tr; rb < r1; rb += (long long)U * R) {
+    float4 va[U], vb[U];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-    *reinterpret_cast<uint4*>(raw_out + row * C + c) = raw;
+    for (int u = 0; u < U; ++u) {
+      const long long r = rb + (long long)u * R;
+      if (r < r1) {
+        const long long row = inst * rows_per_inst + r;
+        if (from0) {
+          va[u] = ld4(src0 + row * C0 + c);
+          vb[u] = ld4(src0 + row * C0 + c + 4);
+        } else {
+          va[u] = ld4(src1 + row * C1 + (c - C0));
+          vb[u] = ld4(src1 + row * C1 + (c - C0) + 4);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = rb + (long long)u * R;
+      if (r >= r1) break;
+      const long long row = inst * rows_per_inst + r;
+      const float v[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+      if (raw_out) {
+        uint4 raw;
+        __half2* h = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4*>(raw_out + row * C + c) = raw;
+      }
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float y = fmaf(v[i], sa[i], sb[i]);
+        o[i] = do_silu ? silu_fast(y) : y;
+      }
+      uint4 raw;
+      __half2* h = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
+      *reinterpret_cast<uint4*>(out + row * C + c) = raw;
+    }
   }
-  const float4* abp = reinterpret_cast<const float4*>(ab + inst * C + c);  // 8 x (a, b)
-  float o[8];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float4 t = __ldg(abp + i);
-    const float y0 = fmaf(v[2 * i], t.x, t.y), y1 = fmaf(v[2 * i + 1], t.z, t.w);
-    o[2 * i] = do_silu ? silu_fast(y0) : y0;
-    o[2 * i + 1] = do_silu ? silu_fast(y1) : y1;
-  }
-  uint4 raw;
-  __half2* h = reinterpret_cast<__half2*>(&raw);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
-  *reinterpret_cast<uint4*>(out + row * C + c) = raw;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -496,24 +514,36 @@ int group_norm(const void* src0, int src0_fp16, int C0, const float* src1, int C
   float2* ab = reinterpret_cast<float2*>(stats + 2 * groups * insts);
   EVW_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * insts, st));
   long long want_blocks = (long long)sm_count() * 4 / (insts > 0 ? insts : 1) + 1;
+  constexpr int U1 = 8, U2 = 2;  // rows in flight per thread for NQ = 1 / 2
+  const int U = NQ == 1 ? U1 : U2;
   int rpb = (int)((rows_per_inst + want_blocks - 1) / want_blocks);
-  if (rpb < 4 * R) rpb = 4 * R;
+  if (rpb < U * R) rpb = U * R;
   dim3 grid((unsigned)((rows_per_inst + rpb - 1) / rpb), (unsigned)insts);
-  if (src0_fp16)
-    gn_stats_kernel<__half><<<grid, threads, 0, st>>>((const __half*)src0, C0, src1, C1, rows_per_inst, rpb, groups, TQ, NQ, stats);
-  else
-    gn_stats_kernel<float><<<grid, threads, 0, st>>>((const float*)src0, C0, src1, C1, rows_per_inst, rpb, groups, TQ, NQ, stats);
+#define EVW_GN_STATS(T0, NQv, Uv) \
+  gn_stats_kernel<T0, NQv, Uv><<<grid, threads, 0, st>>>((const T0*)src0, C0, src1, C1, rows_per_inst, rpb, groups, TQ, stats)
+  if (src0_fp16) { if (NQ == 1) EVW_GN_STATS(__half, 1, U1); else EVW_GN_STATS(__half, 2, U2); }
+  else           { if (NQ == 1) EVW_GN_STATS(float, 1, U1); else EVW_GN_STATS(float, 2, U2); }
+#undef EVW_GN_STATS
   const int nc = (int)(insts * C);
   gn_finalize_kernel<<<(nc + 255) / 256, 256, 0, st>>>(stats, (int)insts, C, groups, (double)rows_per_inst * (C / groups), eps,
                                                         gamma, beta, ab);
-  const long long rows_total = insts * rows_per_inst;
-  const long long n = rows_total * (C / 8);
-  if (src0_fp16)
-    gn_apply_kernel<__half><<<blocks_for(n, 256), 256, 0, st>>>((const __half*)src0, C0, src1, C1, rows_total, rows_per_inst, ab,
-                                                                 do_silu, out, raw_out);
-  else
-    gn_apply_kernel<float><<<blocks_for(n, 256), 256, 0, st>>>((const float*)src0, C0, src1, C1, rows_total, rows_per_inst, ab,
-                                                                do_silu, out, raw_out);
+  {
+    const int cv = C / 8;
+    EVW_CHECK_ARG(cv <= 320, "group_norm: C=%d too wide for the apply kernel", C);
+    const int Ra = 320 / cv > 0 ? 320 / cv : 1;
+    const int athreads = cv * Ra;
+    constexpr int UA = 4;
+    long long awant = (long long)sm_count() * 8 / (insts > 0 ? insts : 1) + 1;
+    int arpb = (int)((rows_per_inst + awant - 1) / awant);
+    if (arpb < UA * Ra) arpb = UA * Ra;
+    dim3 agrid((unsigned)((rows_per_inst + arpb - 1) / arpb), (unsigned)insts);
+    if (src0_fp16)
+      gn_apply_kernel<__half, UA><<<agrid, athreads, 0, st>>>((const __half*)src0, C0, src1, C1, rows_per_inst, arpb, ab, do_silu,
+                                                               out, raw_out);
+    else
+      gn_apply_kernel<float, UA><<<agrid, athreads, 0, st>>>((const float*)src0, C0, src1, C1, rows_per_inst, arpb, ab, do_silu,
+                                                              out, raw_out);
+  }
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }

@@ -45,6 +45,16 @@ PANO_W, PANO_H = 2000, 1000  # :705
 Z_NEAR = 1e-6           # near plane of the point pass
 DEFAULT_VIEWS_PER_PASS = 4
 DEFAULT_PRETEST = os.environ.get("EVW_SPLAT_PRETEST", "0") != "0"  # read the cell before the 64-bit atomic min (slower on B200)
+DEFAULT_OVERLAP = os.environ.get("EVW_SPLAT_OVERLAP", "1") != "0"  # two-stream pass pipeline (include/evoworld_b200.h)
+DEFAULT_V1_KERNELS = os.environ.get("EVW_SPLAT_V1", "0") != "0"    # first-generation kernels, A/B timing only
+SPLAT_PRETEST, SPLAT_OVERLAP, SPLAT_V1_KERNELS = 1, 2, 4
+
+
+def splat_flags(pretest: Optional[bool] = None, overlap: Optional[bool] = None, v1: Optional[bool] = None) -> int:
+    f = SPLAT_PRETEST if (DEFAULT_PRETEST if pretest is None else pretest) else 0
+    f |= SPLAT_OVERLAP if (DEFAULT_OVERLAP if overlap is None else overlap) else 0
+    f |= SPLAT_V1_KERNELS if (DEFAULT_V1_KERNELS if v1 is None else v1) else 0
+    return f
 
 
 # ---------------------------------------------------------------------------------------------
@@ -249,20 +259,25 @@ def conf_select_device(conf: torch.Tensor, pts4: Optional[torch.Tensor], conf_th
     return out, keep, count, thr
 
 
+def splat_workspace_bytes(views_per_pass: int = DEFAULT_VIEWS_PER_PASS, face_res: int = FACE_RES, flags: Optional[int] = None) -> int:
+    return int(_lib.lib().evw_splat_workspace_flags(views_per_pass, face_res, splat_flags() if flags is None else flags))
+
+
 def splat_to_panoramas_device(scene: PointScene, w2c: torch.Tensor, width: int = PANO_W, height: int = PANO_H,
                               face_res: int = FACE_RES, views_per_pass: int = DEFAULT_VIEWS_PER_PASS,
                               z_near: float = Z_NEAR, out: Optional[torch.Tensor] = None,
-                              zbuf: Optional[torch.Tensor] = None, pretest: Optional[bool] = None) -> torch.Tensor:
+                              zbuf: Optional[torch.Tensor] = None, pretest: Optional[bool] = None,
+                              overlap: Optional[bool] = None, v1_kernels: Optional[bool] = None) -> torch.Tensor:
     """Fused splat + resolve -> uint8 [V,height,width,3] (CUDA).
     w2c [V,3,4]: cube formulation (front-face camera, one transform per point-view; the fast path);
     w2c [V,6,3,4]: six independent per-face cameras (the literal restatement of render_cubemap)."""
     dev = scene.device
     V = w2c.shape[0]
-    pretest = DEFAULT_PRETEST if pretest is None else pretest
+    flags = splat_flags(pretest, overlap, v1_kernels)
     w2c = w2c.to(dev, torch.float32).contiguous()
     lut = cube_lut_device(width, height, face_res, dev)
     L = _lib.lib()
-    ws_bytes = L.evw_splat_workspace(views_per_pass, face_res)
+    ws_bytes = L.evw_splat_workspace_flags(views_per_pass, face_res, flags if w2c.dim() == 3 else 0)
     if zbuf is None or zbuf.numel() * zbuf.element_size() < ws_bytes:
         zbuf = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     if out is None:
@@ -272,7 +287,7 @@ def splat_to_panoramas_device(scene: PointScene, w2c: torch.Tensor, width: int =
             _lib.check(L.evw_splat_cube_equirect(
                 _lib.ptr(scene.pts4), scene.pts4.shape[0], _lib.ptr(scene.count), _lib.ptr(w2c), V, face_res,
                 face_res / 2.0, z_near, _lib.ptr(lut), height, width, _lib.ptr(out), _lib.ptr(zbuf),
-                zbuf.numel() * zbuf.element_size(), views_per_pass, 1 if pretest else 0, _lib.stream_ptr(dev)),
+                zbuf.numel() * zbuf.element_size(), views_per_pass, flags, _lib.stream_ptr(dev)),
                 "evw_splat_cube_equirect")
         else:
             _lib.check(L.evw_splat_cubemap_equirect(

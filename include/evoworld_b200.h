@@ -110,11 +110,21 @@ int evw_splat_cubemap_equirect(const float* pts4, int64_t n_cap, const int64_t* 
  * the cam-from-world of the FRONT face only (= inv(target_c2w)); the other five faces are the exact signed axis
  * permutations of the reference's CUBEMAP_TRANSFORMS, so each (point, view) costs one transform and the point lands
  * in the face of its major axis.  Otherwise the contract of evw_splat_cubemap_equirect; views_per_pass in {1,2,4,8},
- * outH*outW % 4 == 0; pretest != 0 reads the cell before issuing the 64-bit atomic min. */
+ * outH*outW % 4 == 0.  flags (bit set):
+ *   EVW_SPLAT_PRETEST     read the cell before issuing the 64-bit atomic min;
+ *   EVW_SPLAT_OVERLAP     run consecutive passes on two internal streams (forked from / joined to `stream` with events)
+ *                         so one pass's splat overlaps its neighbour's clear and resolve; the workspace must then hold
+ *                         two passes: evw_splat_workspace_flags(views_per_pass, face_res, flags);
+ *   EVW_SPLAT_V1_KERNELS  the first-generation kernels (one point per thread, dependent gathers) for A/B timing.
+ * All flag combinations produce identical bytes. */
+#define EVW_SPLAT_PRETEST 1
+#define EVW_SPLAT_OVERLAP 2
+#define EVW_SPLAT_V1_KERNELS 4
+int64_t evw_splat_workspace_flags(int views_per_pass, int face_res, int flags);
 int evw_splat_cube_equirect(const float* pts4, int64_t n_cap, const int64_t* n_dev, const float* w2c_front, int V,
                             int face_res, float focal, float z_near, const uint32_t* lut, int outH, int outW,
                             uint8_t* out, void* zbuf_workspace, int64_t workspace_bytes, int views_per_pass,
-                            int pretest, void* stream);
+                            int flags, void* stream);
 int evw_splat_cube_faces_debug(const float* pts4, int64_t n, const float* w2c_front, int V, int face_res, float focal,
                                float z_near, int64_t* win_idx, void* zbuf_workspace, int64_t workspace_bytes,
                                void* stream);
@@ -157,6 +167,9 @@ int evw_gemm_f16(const void* a0, const void* a1, const void* w, int B, int T, in
  * qkv fp16 [F*S, 3*heads*64] (columns [q|k|v], each [heads,64]) -> out fp16 [F*S, heads*64]; softmax over
  * the S tokens of each frame.  tcgen05 flash-attention forward (csrc/tc_attention.cu). */
 int evw_spatial_attention_f16(const void* qkv, void* out, int F, int S, int heads, void* stream);
+/* Micro-benchmark hook: pick the spatial-attention kernel generation at run time.  -2 = default (environment),
+ * -1 = v3 (groups in lockstep), k >= 0 = v5 variant k (csrc/tc_attention.cu: polynomial share / stagger table). */
+void evw_set_attention_variant(int variant);
 
 /* Temporal self-attention (TemporalBasicTransformerBlock.attn1): same qkv layout with rows ordered
  * (b, t, s); softmax over the T <= 32 frames of each (b, s, head). */

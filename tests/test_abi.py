@@ -25,6 +25,8 @@ def test_header_symbols_exported(built_lib):
 def test_version_and_sizes(built_lib):
     assert built_lib.evw_abi_version() >= 1
     assert built_lib.evw_splat_workspace(4, 512) == 4 * 6 * 512 * 512 * 8
+    assert built_lib.evw_splat_workspace_flags(4, 512, 2) == 2 * 4 * 6 * 512 * 512 * 8
+    assert built_lib.evw_splat_workspace_flags(4, 512, 1) == 4 * 6 * 512 * 512 * 8
     assert built_lib.evw_conf_select_workspace(5_076_400) > 0
     assert built_lib.evw_last_error() is not None
 

@@ -290,8 +290,15 @@ def test_cube_fused_panoramas_bit_exact(G, cuda_device, built_lib):
     want = O.render_panoramas_cube(xyz, rgb, cam, res=res, width=400, height=200, z_near=R.Z_NEAR)
     scene = R.SceneBuilder().build_open3d_scene(xyz, rgb)
     w2c = torch.from_numpy(R.front_w2c_matrices(cam)).to(cuda_device)
-    for pretest in (True, False):
-        got = R.splat_to_panoramas_device(scene, w2c, 400, 200, res, G, pretest=pretest)
+    # every flag combination (pre-test, two-stream pass pipeline, first-generation kernels) must give the same bytes
+    for pretest, overlap, v1 in [(True, False, True), (False, False, True), (False, True, False), (True, True, False),
+                                 (False, False, False), (False, True, True)]:
+        got = R.splat_to_panoramas_device(scene, w2c, 400, 200, res, G, pretest=pretest, overlap=overlap, v1_kernels=v1)
+        np.testing.assert_array_equal(got.cpu().numpy(), want)
+    # a caller-provided workspace is reused across calls and passes: stale keys must never leak into a later view
+    zb = torch.empty(R.splat_workspace_bytes(G, res, R.SPLAT_OVERLAP), dtype=torch.uint8, device=cuda_device)
+    for _ in range(2):
+        got = R.splat_to_panoramas_device(scene, w2c, 400, 200, res, G, zbuf=zb, overlap=True)
         np.testing.assert_array_equal(got.cpu().numpy(), want)
     scene2 = R.PointScene(scene.pts4, torch.tensor([n // 3], dtype=torch.int64, device=cuda_device))
     got2 = R.splat_to_panoramas_device(scene2, w2c, 400, 200, res, G)
