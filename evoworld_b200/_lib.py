@@ -27,6 +27,7 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
     "evw_splat_workspace": (c_i64, [c_int, c_int]),
     "evw_splat_workspace_flags": (c_i64, [c_int, c_int, c_int]),
+    "evw_set_splat_ctas_per_sm": (None, [c_int]),
     "evw_splat_cubemap_equirect": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_int, c_int, c_float, c_float,
                                            c_void_p, c_int, c_int, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "evw_splat_faces_u8": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_float, c_float, c_void_p,

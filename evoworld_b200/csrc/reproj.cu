@@ -12,6 +12,7 @@
 // IEEE division in a fixed order and is mirrored instruction-for-instruction by oracle/reproj_oracle.c.
 #include "common.h"
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace {
 
@@ -651,6 +652,16 @@ __global__ void resolve_multi_kernel(const unsigned long long* __restrict__ zbuf
 }
 
 
+int g_splat_ctas_per_sm = 0;  // 0 = EVW_SPLAT_CTAS_PER_SM or the default
+int splat_ctas_per_sm() {
+  if (g_splat_ctas_per_sm == 0) {
+    const char* e = getenv("EVW_SPLAT_CTAS_PER_SM");
+    const int v = e ? atoi(e) : 0;
+    g_splat_ctas_per_sm = (v >= 1 && v <= 8) ? v : 6;
+  }
+  return g_splat_ctas_per_sm;
+}
+
 // v2 of the cube splat: P points per thread per trip (P independent 16-byte loads in flight) and each view's matrix is
 // fetched from shared memory once per trip (3 x LDS.128) for all P points.  Same arithmetic, same keys.
 template <int G, int P>
@@ -737,9 +748,9 @@ resolve_multi2_kernel(const unsigned long long* __restrict__ zbuf /*[G,6,res,res
 template <int G>
 int launch_cube_pass(const float4* pts, int64_t n_cap, const long long* n_dev, const float* w2c, int res, float focal,
                      float z_near, int flags, unsigned long long* zbuf, const uint32_t* lut, int64_t npix, int g_count,
-                     uint8_t* out, cudaStream_t st) {
+                     uint8_t* out, cudaStream_t st, int what = 3 /* bit 0: splat, bit 1: resolve */) {
   const int pretest = flags & EVW_SPLAT_PRETEST;
-  if (n_cap > 0) {
+  if (n_cap > 0 && (what & 1)) {
     if (flags & EVW_SPLAT_V1_KERNELS) {
       int64_t want = (n_cap + 255) / 256;
       int64_t cap = (int64_t)evw::sm_count() * 8;
@@ -748,11 +759,13 @@ int launch_cube_pass(const float4* pts, int64_t n_cap, const long long* n_dev, c
     } else {
       constexpr int P = 2;
       int64_t want = (n_cap + 256 * P - 1) / (256 * P);
-      int64_t cap = (int64_t)evw::sm_count() * 8;
+      // resident CTAs per SM: < 8 leaves room for the neighbouring pass's resolve / clear to co-run (two-stream pipeline)
+      int64_t cap = (int64_t)evw::sm_count() * ((flags & EVW_SPLAT_OVERLAP) ? splat_ctas_per_sm() : 8);
       cube_splat2_kernel<G, P><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(pts, n_cap, n_dev, w2c, res, focal,
                                                                                       z_near, pretest, zbuf);
     }
   }
+  if (!(what & 2)) return 0;
   const int64_t quads = (npix + 3) / 4;
   if (flags & EVW_SPLAT_V1_KERNELS)
     resolve_multi_kernel<G><<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(zbuf, pts, lut, res, npix, g_count, out);
@@ -994,15 +1007,19 @@ extern "C" int evw_cube_to_equirect_u8(const uint8_t* faces, const uint32_t* lut
   return EVW_OK;
 }
 
+extern "C" void evw_set_splat_ctas_per_sm(int v) { g_splat_ctas_per_sm = (v >= 1 && v <= 8) ? v : 0; }
+
 extern "C" int64_t evw_splat_workspace_flags(int views_per_pass, int face_res, int flags) {
   return evw_splat_workspace(views_per_pass, face_res) * ((flags & EVW_SPLAT_OVERLAP) ? 2 : 1);
 }
 
 namespace {
 // Two internal streams for the pass pipeline (fork/join around the caller's stream with events; capturable).
+constexpr int kMaxPassEvents = 64;
 struct SplatStreams {
   cudaStream_t s[2] = {nullptr, nullptr};
   cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+  cudaEvent_t cleared[kMaxPassEvents] = {}, splatted[kMaxPassEvents] = {};
   int device = -1;
 };
 int splat_streams(SplatStreams** out) {
@@ -1017,6 +1034,10 @@ int splat_streams(SplatStreams** out) {
       EVW_CUDA(cudaEventCreateWithFlags(&s.join[i], cudaEventDisableTiming));
     }
     EVW_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    for (int i = 0; i < kMaxPassEvents; ++i) {
+      EVW_CUDA(cudaEventCreateWithFlags(&s.cleared[i], cudaEventDisableTiming));
+      EVW_CUDA(cudaEventCreateWithFlags(&s.splatted[i], cudaEventDisableTiming));
+    }
     s.device = dev;
   }
   *out = &s;
@@ -1025,19 +1046,19 @@ int splat_streams(SplatStreams** out) {
 
 int cube_pass_dispatch(int G, const float4* p4, int64_t n_cap, const long long* n_dev, const float* m, int res, float focal,
                        float z_near, int flags, unsigned long long* zbuf, const uint32_t* lut, int64_t npix, int g,
-                       uint8_t* o, cudaStream_t st) {
+                       uint8_t* o, cudaStream_t st, int what = 3) {
   const size_t view_cells = (size_t)6 * res * res;
   if (g < G) {  // short tail: single-view passes
     for (int j = 0; j < g; ++j)
       launch_cube_pass<1>(p4, n_cap, n_dev, m + (size_t)j * 12, res, focal, z_near, flags, zbuf + (size_t)j * view_cells, lut,
-                          npix, 1, o + (size_t)j * npix * 3, st);
+                          npix, 1, o + (size_t)j * npix * 3, st, what);
     return 0;
   }
   switch (G) {
-    case 1: return launch_cube_pass<1>(p4, n_cap, n_dev, m, res, focal, z_near, flags, zbuf, lut, npix, g, o, st);
-    case 2: return launch_cube_pass<2>(p4, n_cap, n_dev, m, res, focal, z_near, flags, zbuf, lut, npix, g, o, st);
-    case 4: return launch_cube_pass<4>(p4, n_cap, n_dev, m, res, focal, z_near, flags, zbuf, lut, npix, g, o, st);
-    default: return launch_cube_pass<8>(p4, n_cap, n_dev, m, res, focal, z_near, flags, zbuf, lut, npix, g, o, st);
+    case 1: return launch_cube_pass<1>(p4, n_cap, n_dev, m, res, focal, z_near, flags, zbuf, lut, npix, g, o, st, what);
+    case 2: return launch_cube_pass<2>(p4, n_cap, n_dev, m, res, focal, z_near, flags, zbuf, lut, npix, g, o, st, what);
+    case 4: return launch_cube_pass<4>(p4, n_cap, n_dev, m, res, focal, z_near, flags, zbuf, lut, npix, g, o, st, what);
+    default: return launch_cube_pass<8>(p4, n_cap, n_dev, m, res, focal, z_near, flags, zbuf, lut, npix, g, o, st, what);
   }
 }
 }  // namespace
@@ -1063,23 +1084,50 @@ extern "C" int evw_splat_cube_equirect(const float* pts4, int64_t n_cap, const i
   const float4* p4 = reinterpret_cast<const float4*>(pts4);
   const int passes = (V + G - 1) / G;
   const bool overlap = (flags & EVW_SPLAT_OVERLAP) && passes > 1;
+  const bool by_role = overlap && !(flags & EVW_SPLAT_OVERLAP_BY_PASS) && passes <= kMaxPassEvents;
   SplatStreams* ss = nullptr;
   if (overlap) {
-    // pass p runs clear -> splat -> resolve on internal stream p % 2 with its own half of the workspace, so the
-    // (L2-atomic bound) splat of one pass overlaps the (gather-latency bound) resolve and the clear of its neighbours
     int rc = splat_streams(&ss);
     if (rc) return rc;
     EVW_CUDA(cudaEventRecord(ss->fork, st));
     EVW_CUDA(cudaStreamWaitEvent(ss->s[0], ss->fork, 0));
     EVW_CUDA(cudaStreamWaitEvent(ss->s[1], ss->fork, 0));
   }
-  for (int v0 = 0, pass = 0; v0 < V; v0 += G, ++pass) {
-    const int g = (V - v0 < G) ? (V - v0) : G;
-    cudaStream_t ps = overlap ? ss->s[pass & 1] : st;
-    unsigned long long* zb = zbuf + (overlap ? (size_t)(pass & 1) * G * view_cells : 0);
-    EVW_CUDA(cudaMemsetAsync(zb, 0xFF, (size_t)G * view_cells * 8, ps));
-    cube_pass_dispatch(G, p4, n_cap, (const long long*)n_dev, w2c_front + (size_t)v0 * 12, face_res, focal, z_near, flags, zb,
-                       lut, npix, g, out + (size_t)v0 * npix * 3, ps);
+  if (by_role) {
+    // stream 0 runs the splats back to back (they are L2-atomic bound and gain nothing from overlapping each other);
+    // stream 1 clears the z-buffer halves and resolves: resolve(p) and clear(p + 2) overlap splat(p + 1).
+    cudaStream_t sa = ss->s[0], sb = ss->s[1];
+    auto zb_of = [&](int pass) { return zbuf + (size_t)(pass & 1) * G * view_cells; };
+    auto clear = [&](int pass) -> int {
+      EVW_CUDA(cudaMemsetAsync(zb_of(pass), 0xFF, (size_t)G * view_cells * 8, sb));
+      EVW_CUDA(cudaEventRecord(ss->cleared[pass], sb));
+      return EVW_OK;
+    };
+    int rc = clear(0);
+    if (rc) return rc;
+    if (passes > 1 && (rc = clear(1))) return rc;
+    for (int pass = 0; pass < passes; ++pass) {
+      const int v0 = pass * G;
+      const int g = (V - v0 < G) ? (V - v0) : G;
+      const float* m = w2c_front + (size_t)v0 * 12;
+      uint8_t* o = out + (size_t)v0 * npix * 3;
+      EVW_CUDA(cudaStreamWaitEvent(sa, ss->cleared[pass], 0));
+      cube_pass_dispatch(G, p4, n_cap, (const long long*)n_dev, m, face_res, focal, z_near, flags, zb_of(pass), lut, npix, g, o, sa, 1);
+      EVW_CUDA(cudaEventRecord(ss->splatted[pass], sa));
+      EVW_CUDA(cudaStreamWaitEvent(sb, ss->splatted[pass], 0));
+      cube_pass_dispatch(G, p4, n_cap, (const long long*)n_dev, m, face_res, focal, z_near, flags, zb_of(pass), lut, npix, g, o, sb, 2);
+      if (pass + 2 < passes && (rc = clear(pass + 2))) return rc;
+    }
+  } else {
+    // pass p runs clear -> splat -> resolve on internal stream p % 2 (or on the caller's stream) with its own half of the workspace
+    for (int v0 = 0, pass = 0; v0 < V; v0 += G, ++pass) {
+      const int g = (V - v0 < G) ? (V - v0) : G;
+      cudaStream_t ps = overlap ? ss->s[pass & 1] : st;
+      unsigned long long* zb = zbuf + (overlap ? (size_t)(pass & 1) * G * view_cells : 0);
+      EVW_CUDA(cudaMemsetAsync(zb, 0xFF, (size_t)G * view_cells * 8, ps));
+      cube_pass_dispatch(G, p4, n_cap, (const long long*)n_dev, w2c_front + (size_t)v0 * 12, face_res, focal, z_near, flags, zb,
+                         lut, npix, g, out + (size_t)v0 * npix * 3, ps);
+    }
   }
   if (overlap) {
     for (int i = 0; i < 2; ++i) {

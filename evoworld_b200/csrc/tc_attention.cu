@@ -1225,15 +1225,16 @@ spatial_attn5_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
 
         const int kv_valid = S - j * kBKV;
         float mx = -INFINITY;
-        if (kv_valid >= kBKV) {
+        if (kv_valid < kBKV) {
 #pragma unroll
-          for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(s[c]));
-        } else {
-#pragma unroll
-          for (int c = 0; c < 128; ++c) {
+          for (int c = 0; c < 128; ++c)
             if (c >= kv_valid) s[c] = 0xff800000u;
-            mx = fmaxf(mx, __uint_as_float(s[c]));
-          }
+        }
+        {  // four independent maxima: the serial FMNMX chain of v3 cost ~400 cycles per tile
+          float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int c = 0; c < 128; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], __uint_as_float(s[c]));
+          mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         }
         const float m_tile = mx * scale_log2e;
         const bool need = m_tile > m_ref + kLazyTau;  // first tile: m_ref = -inf -> true
@@ -1349,6 +1350,285 @@ spatial_attn5_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
   }
 }
 
+
+// ==========================================================================================
+// v6: two threads per query row.  ncu on v5 (profiles/r01c_attn5_*.txt) shows each softmax warp's per-tile chain —
+// wait S, tcgen05.ld, max, 128 exponentials, wait PV, store P, fence — is ~3300 cycles long with only 2 softmax warps
+// per SM sub-partition to overlap it (issue 54 %, MUFU 48 %, tensor 36 % busy).  Here a 128-row group is served by EIGHT
+// warps: warp (quarter, half) owns TMEM lanes 32 quarter .. +31 and score columns 64 half .. +63, so every sub-partition
+// holds 4 softmax warps (two per group) with half the per-thread work and registers (setmaxnreg 112 instead of 224).
+// The two halves of a row exchange their partial maxima through shared memory (one 256-thread named barrier per tile);
+// everything else — lazy rescale, TMEM-resident O and row sums, P through swizzled shared memory — is v3/v5.
+//   warp 0 TMA | warp 1 MMA group A | warp 2 MMA group B | warp 3 idle | warps 4..11 group A | warps 12..19 group B
+// ==========================================================================================
+constexpr int kA6Threads = 640;
+constexpr int kA6OffToken = kA3OffOnes + 4096;       // 512 words: one per softmax thread (stagger token dependency)
+constexpr int kA6OffMax = kA6OffToken + 2048;        // [2 parities][2 groups][2 halves][128 rows] fp32 partial maxima
+constexpr int kA6Smem = kA6OffMax + 4096 + 1024;
+
+template <int kPolyN, bool kStagger>
+__global__ void __launch_bounds__(kA6Threads, 1)
+spatial_attn6_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ out, int S, int C, float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, frame = blockIdx.z;
+  const int q0 = blockIdx.x * 2 * kBQ;
+  const int n_kv = (S + kBKV - 1) / kBKV;
+  const bool b_active = q0 + kBQ < S;
+
+  const uint32_t bar = base + kA2OffBar;
+  const uint32_t q_full = bar;
+  auto kv_full = [&](int s) { return bar + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bar + 8u * (1 + kKvStages + s); };
+  auto s_full = [&](int g) { return bar + 8u * (1 + 2 * kKvStages + g); };
+  auto s_empty = [&](int g) { return bar + 8u * (3 + 2 * kKvStages + g); };
+  auto p_full = [&](int g) { return bar + 8u * (5 + 2 * kKvStages + g); };
+  auto o_full = [&](int g) { return bar + 8u * (7 + 2 * kKvStages + g); };
+  const uint32_t tmem_slot = bar + 8u * (9 + 2 * kKvStages);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + kA2OffBar + 8 * (9 + 2 * kKvStages));
+
+  for (int i = threadIdx.x; i < 4096 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(base_ptr + kA3OffOnes)[i] = 0x3C003C00u;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKvStages; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), b_active ? 2 : 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(s_full(g), 1);
+      mbar_init(s_empty(g), 8);  // one arrival per softmax warp of the group
+      mbar_init(p_full(g), 8);
+      mbar_init(o_full(g), 1);
+    }
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+        tma_load_3d(&tmap, base + kA2OffQ, q_full, head * kD, q0, frame);
+        tma_load_3d(&tmap, base + kA2OffQ + kTileBytes, q_full, head * kD, q0 + kBQ, frame);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % kKvStages;
+        mbar_wait(kv_empty(st), ((j / kKvStages) & 1) ^ 1u);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(kv_full(st), 2 * kTileBytes);
+          tma_load_3d(&tmap, base + kA2OffK + st * kTileBytes, kv_full(st), C + head * kD, j * kBKV, frame);
+          tma_load_3d(&tmap, base + kA2OffV + st * kTileBytes, kv_full(st), 2 * C + head * kD, j * kBKV, frame);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1 || warp == 2) {
+      const int g = warp - 1;
+      if (lane == 0 && (g == 0 || b_active)) {
+        const uint32_t idesc_s = make_idesc_f16(kBQ, kBKV, 0, 0, 0);
+        const uint32_t idesc_o = make_idesc_f16(kBQ, kD, 0, 0, 1);
+        const uint32_t idesc_l = make_idesc_f16(kBQ, 16, 0, 0, 0);
+        const uint64_t dq = make_desc_k_sw128(base + kA2OffQ + g * kTileBytes);
+        const uint64_t dp = make_desc_k_sw128(base + kA2OffP + g * 2 * kTileBytes);
+        const uint64_t d1 = make_desc_k_sw128(base + kA3OffOnes);
+        const uint64_t dk0 = make_desc_k_sw128(base + kA2OffK);
+        const uint64_t dv0 = make_desc_mn_sw128(base + kA2OffV, 1024);
+        const uint32_t t_s = tmem_base + g * kBKV, t_o = tmem_base + kTmemO3 + g * kD, t_l = tmem_base + kTmemL3 + g * 16;
+        mbar_wait(q_full, 0);
+        int s_next = 0, pv_next = 0;
+        long long t0 = clock64();
+        while (pv_next < n_kv) {
+          bool progress = false;
+          if (s_next < n_kv && mbar_test(kv_full(s_next % kKvStages), (s_next / kKvStages) & 1) &&
+              (s_next == 0 || mbar_test(s_empty(g), (s_next - 1) & 1))) {
+            tc_fence_after();
+            const uint64_t dk = desc_add(dk0, (s_next % kKvStages) * (kTileBytes >> 4));
+#pragma unroll
+            for (int k = 0; k < kD / 16; ++k) umma_f16_ss(t_s, desc_add(dq, 2 * k), desc_add(dk, 2 * k), idesc_s, k != 0);
+            tc_commit(s_full(g));
+            ++s_next;
+            progress = true;
+          }
+          if (pv_next < s_next && mbar_test(p_full(g), pv_next & 1)) {
+            tc_fence_after();
+            const int st = pv_next % kKvStages;
+            const uint64_t dv = desc_add(dv0, st * (kTileBytes >> 4));
+            const uint32_t acc = pv_next != 0;
+#pragma unroll
+            for (int ks = 0; ks < kBKV / 16; ++ks) {
+              const uint64_t a = desc_add(dp, (ks >> 2) * (kTileBytes >> 4) + 2 * (ks & 3));
+              umma_f16_ss(t_o, a, desc_add(dv, ks * (2048 >> 4)), idesc_o, acc | (ks != 0));                         // O += P V
+              umma_f16_ss(t_l, a, desc_add(d1, (ks >> 2) * (2048 >> 4) + 2 * (ks & 3)), idesc_l, acc | (ks != 0));   // L += P 1
+            }
+            tc_commit(o_full(g));
+            tc_commit(kv_empty(st));
+            ++pv_next;
+            progress = true;
+          }
+          if (progress) t0 = clock64();
+          else if (clock64() - t0 > 8000000000ll) __trap();
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    // ===================== softmax: 8 warps per 128-row group =====================
+    const int sw = warp - 4;
+    const int g = sw >> 3;
+    const int half = (sw >> 2) & 1;
+    const int quarter = warp & 3;  // = sw & 3: the TMEM lane quarter this warp may address
+    const int r = quarter * 32 + lane;
+    const int qrow = q0 + g * kBQ + r;
+    if (g == 0 || b_active) {
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t s_addr = lane_addr + g * kBKV + half * 64;
+      const uint32_t o_addr = lane_addr + kTmemO3 + g * kD + half * 32;
+      const uint32_t l_addr = lane_addr + kTmemL3 + g * 16;
+      float m_ref = -INFINITY;
+      const uint32_t token_word = base + kA6OffToken + 4u * (threadIdx.x - 128);
+      if (kStagger) st_shared_volatile(token_word, 0u);
+      if (kStagger && b_active && g == 1) named_bar_arrive(1, 512);  // group A goes first
+      uint8_t* prow = base_ptr + kA2OffP + g * 2 * kTileBytes + half * kTileBytes + r * 128;
+      float* mxbuf = reinterpret_cast<float*>(base_ptr + kA6OffMax);
+
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(s_full(g), j & 1);
+        tc_fence_after();
+        uint32_t s[64];
+        {
+          uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+          uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+          tmem_ld_32x32b_x32(s_addr + 0, s0);
+          tmem_ld_32x32b_x32(s_addr + 32, s1);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty(g));  // 8 arrivals: S_g(j+1) may now overwrite the TMEM tile
+
+        const int kv_valid = S - j * kBKV - half * 64;  // valid columns of this half
+        if (kv_valid < 64) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            if (c >= kv_valid) s[c] = 0xff800000u;
+        }
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 64; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], __uint_as_float(s[c]));
+        float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        // exchange the half-row maxima (double-buffered by tile parity: a slot is rewritten two barriers later)
+        {
+          float* slot = mxbuf + (((j & 1) * 2 + g) * 2) * 128;
+          slot[half * 128 + r] = mx;
+          named_bar_sync(3 + g, 256);
+          mx = fmaxf(mx, slot[(half ^ 1) * 128 + r]);
+        }
+        const float m_tile = mx * scale_log2e;
+        const bool need = m_tile > m_ref + kLazyTau;  // identical in both threads of the row
+        const float m_old = m_ref;
+        if (need) m_ref = m_tile;
+        const float neg_m = -m_ref;
+        if (kPolyN > 0) {
+#pragma unroll
+          for (int c = kPolyN - 1; c < 64; c += (kPolyN > 0 ? kPolyN : 64))
+            s[c] = __float_as_uint(exp2_poly(fmaf(__uint_as_float(s[c]), scale_log2e, neg_m)));
+        }
+        float neg_m_dep = neg_m;
+        if (kStagger && b_active) {
+          named_bar_sync(1 + g, 512);
+          neg_m_dep = neg_m + __uint_as_float(ld_shared_volatile(token_word));
+        }
+        uint32_t w[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const bool poly0 = kPolyN > 0 && ((2 * i) % (kPolyN > 0 ? kPolyN : 1)) == kPolyN - 1;
+          const bool poly1 = kPolyN > 0 && ((2 * i + 1) % (kPolyN > 0 ? kPolyN : 1)) == kPolyN - 1;
+          const float p0 = poly0 ? __uint_as_float(s[2 * i]) : fast_exp2(fmaf(__uint_as_float(s[2 * i]), scale_log2e, neg_m_dep));
+          const float p1 = poly1 ? __uint_as_float(s[2 * i + 1])
+                                 : fast_exp2(fmaf(__uint_as_float(s[2 * i + 1]), scale_log2e, neg_m_dep));
+          __half2 h = __floats2half2_rn(p0, p1);
+          w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        if (kStagger && b_active) {
+          st_shared_volatile(token_word, (w[7] | w[15] | w[23] | w[31]) & 0x80008000u);
+          if (!(g == 1 && j + 1 == n_kv)) named_bar_arrive(2 - g, 512);
+        }
+        // P buffer / O, L accumulators of this group are free once PV_g(j-1) has completed
+        if (j > 0) {
+          mbar_wait(o_full(g), (j - 1) & 1);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, need)) {  // same rows, same decision in both warps of the quarter
+            const float f = need ? fast_exp2(m_old - m_ref) : 1.0f;
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {  // this warp's 32 of the 64 output columns
+              uint32_t v[16];
+              tmem_ld_32x32b_x16(o_addr + part * 16, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+              tmem_st_32x32b_x16(o_addr + part * 16, v);
+            }
+            if (half == 0) {
+              uint32_t v[16];
+              tmem_ld_32x32b_x16(l_addr, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+              tmem_st_32x32b_x16(l_addr, v);
+            }
+            tmem_st_wait();
+          }
+        }
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc)
+          *reinterpret_cast<uint4*>(prow + ((cc ^ (r & 7)) << 4)) = make_uint4(w[4 * cc], w[4 * cc + 1], w[4 * cc + 2], w[4 * cc + 3]);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(g));
+      }
+      // final: this warp's 32 output columns, normalised by the row sum
+      mbar_wait(o_full(g), (n_kv - 1) & 1);
+      tc_fence_after();
+      uint32_t ov[32], lv[16];
+      tmem_ld_32x32b_x32(o_addr, ov);
+      tmem_ld_32x32b_x16(l_addr, lv);
+      tmem_ld_wait();
+      if (qrow < S) {
+        const float inv = 1.0f / __uint_as_float(lv[0]);
+        uint4* op = reinterpret_cast<uint4*>(out + ((long long)frame * S + qrow) * C + head * kD + half * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t* src = &ov[8 * i];
+          __half2 h0 = __floats2half2_rn(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
+          __half2 h1 = __floats2half2_rn(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
+          __half2 h2 = __floats2half2_rn(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
+          __half2 h3 = __floats2half2_rn(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
+          uint4 v;
+          v.x = *reinterpret_cast<uint32_t*>(&h0); v.y = *reinterpret_cast<uint32_t*>(&h1);
+          v.z = *reinterpret_cast<uint32_t*>(&h2); v.w = *reinterpret_cast<uint32_t*>(&h3);
+          op[i] = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace
 
 static int g_attn_variant_override = -2;
@@ -1361,15 +1641,20 @@ int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, c
   static bool use_v1 = false, use_v2 = false, use_v3 = false, use_v4 = false;
   static int v5_variant = 0;
   typedef void (*attn5_fn)(const CUtensorMap, __half*, int, int, float);
-  // v5 variants: {polynomial share, stagger}.  EVW_ATTN_V5=<index> selects one (micro-benchmarks); default = 0.
-  static const attn5_fn v5_table[] = {spatial_attn5_kernel<4, true>, spatial_attn5_kernel<8, true>, spatial_attn5_kernel<0, true>,
-                                      spatial_attn5_kernel<2, true>, spatial_attn5_kernel<4, false>};
+  struct Variant { attn5_fn fn; int threads, smem; };
+  // v5 / v6 variants: {polynomial share, stagger}.  EVW_ATTN_V5=<index> or evw_set_attention_variant selects one.
+  static const Variant v5_table[] = {
+      {spatial_attn5_kernel<4, true>, kA2Threads, kA5Smem},  {spatial_attn5_kernel<8, true>, kA2Threads, kA5Smem},
+      {spatial_attn5_kernel<0, true>, kA2Threads, kA5Smem},  {spatial_attn5_kernel<2, true>, kA2Threads, kA5Smem},
+      {spatial_attn5_kernel<4, false>, kA2Threads, kA5Smem}, {spatial_attn6_kernel<4, false>, kA6Threads, kA6Smem},
+      {spatial_attn6_kernel<4, true>, kA6Threads, kA6Smem},  {spatial_attn6_kernel<0, false>, kA6Threads, kA6Smem},
+      {spatial_attn6_kernel<8, false>, kA6Threads, kA6Smem}};
   if (!attr_set) {
     EVW_CUDA(cudaFuncSetAttribute(spatial_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     EVW_CUDA(cudaFuncSetAttribute(spatial_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2Smem));
     EVW_CUDA(cudaFuncSetAttribute(spatial_attn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3Smem));
     EVW_CUDA(cudaFuncSetAttribute(spatial_attn4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA4Smem));
-    for (attn5_fn f : v5_table) EVW_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kA5Smem));
+    for (const Variant& v : v5_table) EVW_CUDA(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem));
     use_v1 = getenv("EVW_ATTN_V1") != nullptr;
     use_v2 = getenv("EVW_ATTN_V2") != nullptr;
     use_v3 = getenv("EVW_ATTN_V3") != nullptr;
@@ -1403,7 +1688,8 @@ int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, c
     spatial_attn3_kernel<<<grid, kA2Threads, kA3Smem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
   } else {
     dim3 grid((S + 2 * kBQ - 1) / (2 * kBQ), heads, F);
-    v5_table[v5_variant]<<<grid, kA2Threads, kA5Smem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
+    const Variant& v = v5_table[v5_variant];
+    v.fn<<<grid, v.threads, v.smem, st>>>(tmap, out, S, C, 0.125f * 1.4426950408889634f);
   }
   EVW_LAUNCH_CHECK();
   return EVW_OK;

@@ -184,57 +184,85 @@ gn_apply_kernel(const T0* __restrict__ src0, int C0, const float* __restrict__ s
 // ------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, optional broadcast row vector added first, fp16 output
 // ------------------------------------------------------------------------------------------
-template <int MAXV>  // MAXV float4 per lane: C <= 128 * MAXV
+template <int MAXV, int ROWS>  // MAXV float4 per lane: C <= 128 * MAXV; ROWS rows per warp, loaded together (DRAM latency)
 __global__ void layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ rowvec, long long rv_div,
                                   long long rv_mod, long long rows, int C, float eps, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, __half* __restrict__ out) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
+  if (row0 >= rows) return;
   const int lane = threadIdx.x & 31;
   const int nv = C / 4;
-  const float4* xp = reinterpret_cast<const float4*>(x + row * C);
-  const float4* rp = rowvec ? reinterpret_cast<const float4*>(rowvec + ((row / rv_div) % rv_mod) * C) : nullptr;
-  float4 v[MAXV];
-  float s = 0.f;
+  float4 v[ROWS][MAXV];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int j = lane + i * 32;
-    if (j < nv) {
-      v[i] = xp[j];
-      if (rp) {
-        float4 r = __ldg(rp + j);
-        v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
+  for (int r = 0; r < ROWS; ++r) {
+    const long long row = min(row0 + r, rows - 1);
+    const float4* xp = reinterpret_cast<const float4*>(x + row * C);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int j = lane + i * 32;
+      if (j < nv) v[r][i] = xp[j];
+    }
+  }
+  float mean[ROWS], rstd[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const long long row = min(row0 + r, rows - 1);
+    const float4* rp = rowvec ? reinterpret_cast<const float4*>(rowvec + ((row / rv_div) % rv_mod) * C) : nullptr;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int j = lane + i * 32;
+      if (j < nv) {
+        if (rp) {
+          float4 t = __ldg(rp + j);
+          v[r][i].x += t.x; v[r][i].y += t.y; v[r][i].z += t.z; v[r][i].w += t.w;
+        }
+        s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
       }
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
+    mean[r] = s;
   }
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)C;
-  float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int j = lane + i * 32;
-    if (j < nv) {
-      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      q += (a * a + b * b) + (c * c + d * d);
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    mean[r] = mean[r] / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int j = lane + i * 32;
+      if (j < nv) {
+        float a = v[r][i].x - mean[r], b = v[r][i].y - mean[r], c = v[r][i].z - mean[r], d = v[r][i].w - mean[r];
+        q += (a * a + b * b) + (c * c + d * d);
+      }
     }
+    rstd[r] = q;
   }
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / (float)C + eps);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
   const float4* gp = reinterpret_cast<const float4*>(gamma);
   const float4* bp = reinterpret_cast<const float4*>(beta);
-  uint2* op = reinterpret_cast<uint2*>(out + row * C);
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int j = lane + i * 32;
-    if (j < nv) {
-      float4 g = __ldg(gp + j), b = __ldg(bp + j);
-      __half2 h0 = __floats2half2_rn((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
-      __half2 h1 = __floats2half2_rn((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
-      uint2 o2;
-      o2.x = *reinterpret_cast<uint32_t*>(&h0);
-      o2.y = *reinterpret_cast<uint32_t*>(&h1);
-      op[j] = o2;
+  for (int r = 0; r < ROWS; ++r) {
+    if (row0 + r >= rows) break;
+    const float rs = rsqrtf(rstd[r] / (float)C + eps), mu = mean[r];
+    uint2* op = reinterpret_cast<uint2*>(out + (row0 + r) * C);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int j = lane + i * 32;
+      if (j < nv) {
+        float4 g = __ldg(gp + j), b = __ldg(bp + j);
+        __half2 h0 = __floats2half2_rn((v[r][i].x - mu) * rs * g.x + b.x, (v[r][i].y - mu) * rs * g.y + b.y);
+        __half2 h1 = __floats2half2_rn((v[r][i].z - mu) * rs * g.z + b.z, (v[r][i].w - mu) * rs * g.w + b.w);
+        uint2 o2;
+        o2.x = *reinterpret_cast<uint32_t*>(&h0);
+        o2.y = *reinterpret_cast<uint32_t*>(&h1);
+        op[j] = o2;
+      }
     }
   }
 }
@@ -552,13 +580,15 @@ int layer_norm(const float* x, const float* rowvec, long long rv_div, long long 
                const float* gamma, const float* beta, __half* out, cudaStream_t st) {
   EVW_CHECK_ARG(C % 4 == 0 && C <= 128 * 20, "layer_norm: C=%d not supported", C);
   const int warps = 8;
-  const unsigned grid = (unsigned)((rows + warps - 1) / warps);
-  if (C <= 128 * 5)
-    layer_norm_kernel<5><<<grid, warps * 32, 0, st>>>(x, rowvec, rv_div, rv_mod, rows, C, eps, gamma, beta, out);
+  auto grid = [&](int rows_per_warp) { return (unsigned)((rows + (long long)warps * rows_per_warp - 1) / ((long long)warps * rows_per_warp)); };
+  if (C <= 128 * 3)
+    layer_norm_kernel<3, 4><<<grid(4), warps * 32, 0, st>>>(x, rowvec, rv_div, rv_mod, rows, C, eps, gamma, beta, out);
+  else if (C <= 128 * 5)
+    layer_norm_kernel<5, 4><<<grid(4), warps * 32, 0, st>>>(x, rowvec, rv_div, rv_mod, rows, C, eps, gamma, beta, out);
   else if (C <= 128 * 10)
-    layer_norm_kernel<10><<<grid, warps * 32, 0, st>>>(x, rowvec, rv_div, rv_mod, rows, C, eps, gamma, beta, out);
+    layer_norm_kernel<10, 2><<<grid(2), warps * 32, 0, st>>>(x, rowvec, rv_div, rv_mod, rows, C, eps, gamma, beta, out);
   else
-    layer_norm_kernel<20><<<grid, warps * 32, 0, st>>>(x, rowvec, rv_div, rv_mod, rows, C, eps, gamma, beta, out);
+    layer_norm_kernel<20, 1><<<grid(1), warps * 32, 0, st>>>(x, rowvec, rv_div, rv_mod, rows, C, eps, gamma, beta, out);
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }

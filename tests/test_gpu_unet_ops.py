@@ -39,6 +39,28 @@ def test_spatial_attention(frames, S, heads, scale, cuda_device):
     assert rel_l2(got, want) < 3e-3
 
 
+@pytest.mark.parametrize("variant", [-1, 0, 2, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("frames,S,heads", [(2, 576, 3), (1, 129, 2), (1, 2304, 2), (3, 144, 5), (1, 300, 1)])
+def test_spatial_attention_variants(variant, frames, S, heads, cuda_device):
+    """Every kernel generation / variant behind evw_set_attention_variant (v3 lockstep, v5 staggered groups,
+    v6 two threads per row) against the same fp32 reference."""
+    from evoworld_b200 import _lib
+
+    C = heads * 64
+    qkv = (torch.randn(frames * S, 3 * C, device=cuda_device) * 2.0).half()
+    x = qkv.float().view(frames, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    want = ref_attention(x[0], x[1], x[2]).permute(0, 2, 1, 3).reshape(frames * S, C)
+    L = _lib.lib()
+    L.evw_set_attention_variant(variant)
+    try:
+        got = ops.spatial_attention(qkv, frames, S, heads)
+        torch.cuda.synchronize()
+    finally:
+        L.evw_set_attention_variant(-2)
+    assert torch.isfinite(got.float()).all()
+    assert rel_l2(got, want) < 3e-3
+
+
 @pytest.mark.parametrize("B,T,S,heads", [(1, 14, 64, 1), (2, 14, 200, 5), (2, 25, 144, 2), (1, 1, 10, 1), (1, 3, 33, 2),
                                          (2, 16, 37, 1), (1, 32, 20, 1), (2, 17, 5, 3)])
 def test_temporal_attention(B, T, S, heads, cuda_device):
