@@ -164,9 +164,11 @@ def run_cpu(T, steps=1, warmup=0):
 
 def run_reference(args):
     cpu = run_cpu(args.frames, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
-    return {"metric": "denoise-steps/sec", "value": cpu["value"], "unit": "steps/s", "n_gpus": 0, "steps": args.steps,
+    return {"metric": "denoise-steps/sec", "value": cpu["value"], "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 / cpu["value"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": f"config 1: single 576x1024x{args.frames}f clip, CPU fp32 oracle UNet (bounded sample, FLOP-scaled)"},
+            "config": {"workload": f"config 2: single 576x1024x{args.frames}f clip, CFG batch 2, 72x128 latents, random-init 1.525B-param UNet, "
+                                   f"Karras sigmas (25-step schedule)", "frames": args.frames,
+                       "arm": "reference CPU path (fp32 PyTorch oracle UNet on the host cores; bounded sample, FLOP-scaled — see cpu_baseline.sample)"},
             "impl": "reference", "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

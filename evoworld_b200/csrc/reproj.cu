@@ -657,7 +657,7 @@ int splat_ctas_per_sm() {
   if (g_splat_ctas_per_sm == 0) {
     const char* e = getenv("EVW_SPLAT_CTAS_PER_SM");
     const int v = e ? atoi(e) : 0;
-    g_splat_ctas_per_sm = (v >= 1 && v <= 8) ? v : 6;
+    g_splat_ctas_per_sm = (v >= 1 && v <= 8) ? v : 8;
   }
   return g_splat_ctas_per_sm;
 }
@@ -1084,7 +1084,7 @@ extern "C" int evw_splat_cube_equirect(const float* pts4, int64_t n_cap, const i
   const float4* p4 = reinterpret_cast<const float4*>(pts4);
   const int passes = (V + G - 1) / G;
   const bool overlap = (flags & EVW_SPLAT_OVERLAP) && passes > 1;
-  const bool by_role = overlap && !(flags & EVW_SPLAT_OVERLAP_BY_PASS) && passes <= kMaxPassEvents;
+  const bool by_role = overlap && (flags & EVW_SPLAT_OVERLAP_BY_ROLE) && passes <= kMaxPassEvents;
   SplatStreams* ss = nullptr;
   if (overlap) {
     int rc = splat_streams(&ss);

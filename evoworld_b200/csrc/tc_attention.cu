@@ -1480,7 +1480,7 @@ spatial_attn6_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
       __syncwarp();
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ===================== softmax: 8 warps per 128-row group =====================
     const int sw = warp - 4;
     const int g = sw >> 3;

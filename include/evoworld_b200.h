@@ -112,19 +112,19 @@ int evw_splat_cubemap_equirect(const float* pts4, int64_t n_cap, const int64_t* 
  * in the face of its major axis.  Otherwise the contract of evw_splat_cubemap_equirect; views_per_pass in {1,2,4,8},
  * outH*outW % 4 == 0.  flags (bit set):
  *   EVW_SPLAT_PRETEST     read the cell before issuing the 64-bit atomic min;
- *   EVW_SPLAT_OVERLAP     two internal streams (forked from / joined to `stream` with events): one runs the splats back
- *                         to back, the other the z-buffer clears and resolves, so resolve(p) and clear(p+2) overlap
- *                         splat(p+1); the workspace must then hold
+ *   EVW_SPLAT_OVERLAP     two internal streams (forked from / joined to `stream` with events): pass p runs its clear,
+ *                         splat and resolve on stream p % 2, so one pass's L2-atomic-bound splat overlaps its neighbour's
+ *                         gather-latency-bound resolve and its clear; the workspace must then hold
  *                         two passes: evw_splat_workspace_flags(views_per_pass, face_res, flags);
  *   EVW_SPLAT_V1_KERNELS  the first-generation kernels (one point per thread, dependent gathers) for A/B timing.
  * All flag combinations produce identical bytes. */
 #define EVW_SPLAT_PRETEST 1
 #define EVW_SPLAT_OVERLAP 2
 #define EVW_SPLAT_V1_KERNELS 4
-#define EVW_SPLAT_OVERLAP_BY_PASS 8 /* with OVERLAP: whole passes alternate between the two streams (first scheme, A/B timing) */
+#define EVW_SPLAT_OVERLAP_BY_ROLE 8 /* with OVERLAP: one stream runs every splat, the other every clear + resolve (measured slower) */
 int64_t evw_splat_workspace_flags(int views_per_pass, int face_res, int flags);
 /* Tuning hook: resident splat CTAs per SM (1..8) while EVW_SPLAT_OVERLAP is set; fewer leaves SM slots for the
- * neighbouring pass's resolve and clear.  0 restores the default (EVW_SPLAT_CTAS_PER_SM or 6). */
+ * neighbouring pass's resolve and clear.  0 restores the default (EVW_SPLAT_CTAS_PER_SM or 8). */
 void evw_set_splat_ctas_per_sm(int ctas);
 int evw_splat_cube_equirect(const float* pts4, int64_t n_cap, const int64_t* n_dev, const float* w2c_front, int V,
                             int face_res, float focal, float z_near, const uint32_t* lut, int outH, int outW,

@@ -291,11 +291,11 @@ def test_cube_fused_panoramas_bit_exact(G, cuda_device, built_lib):
     scene = R.SceneBuilder().build_open3d_scene(xyz, rgb)
     w2c = torch.from_numpy(R.front_w2c_matrices(cam)).to(cuda_device)
     # every flag combination (pre-test, two-stream pass pipeline, first-generation kernels) must give the same bytes
-    for pretest, overlap, v1, by_pass in [(True, False, True, False), (False, False, True, False), (False, True, False, False),
+    for pretest, overlap, v1, by_role in [(True, False, True, False), (False, False, True, False), (False, True, False, False),
                                           (True, True, False, False), (False, False, False, False), (False, True, True, False),
                                           (False, True, False, True), (True, True, True, True)]:
         got = R.splat_to_panoramas_device(scene, w2c, 400, 200, res, G, pretest=pretest, overlap=overlap, v1_kernels=v1,
-                                          by_pass=by_pass)
+                                          by_role=by_role)
         np.testing.assert_array_equal(got.cpu().numpy(), want)
     # a caller-provided workspace is reused across calls and passes: stale keys must never leak into a later view
     zb = torch.empty(R.splat_workspace_bytes(G, res, R.SPLAT_OVERLAP), dtype=torch.uint8, device=cuda_device)

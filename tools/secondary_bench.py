@@ -44,7 +44,15 @@ B = 49
 equi = torch.randint(0, 256, (B, 3, 576, 1024), dtype=torch.uint8, device=dev)
 e2p = Equi2Pers(384, 512, 90.0, mode="bilinear", device=dev)
 rots = [{"yaw": 0.1 * i, "pitch": 0.0, "roll": 0.0} for i in range(B)]
-report(f"equi2pers B={B} 576x1024->384x512", B * 3 * (576 * 1024 + 384 * 512), timed(lambda: e2p(equi, rots)))
+report(f"equi2pers B={B} via Equi2Pers() (host matrices + H2D)", B * 3 * (576 * 1024 + 384 * 512), timed(lambda: e2p(equi, rots)))
+from evoworld_b200.equi2pers import pix2dir_matrix
+from evoworld_b200 import _lib
+mats = torch.from_numpy(np.stack([pix2dir_matrix(r["yaw"], 0.0, 0.0, 384, 512, 90.0) for r in rots]).astype(np.float32).reshape(B, 9)).to(dev)
+e2p_out = torch.empty((B, 3, 384, 512), dtype=torch.uint8, device=dev)
+L = _lib.lib()
+report(f"equi2pers B={B} kernel only (evw_equi2pers_u8)", B * 3 * (576 * 1024 + 384 * 512),
+       timed(lambda: _lib.check(L.evw_equi2pers_u8(equi.data_ptr(), mats.data_ptr(), e2p_out.data_ptr(), B, 3, 576, 1024, 384, 512,
+                                                   _lib.stream_ptr(dev)))))
 
 # depth lift + pack + select at S=25 and S=49
 for S in (25, 49):
