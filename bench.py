@@ -160,12 +160,13 @@ def run_reproj_ours(args, dev, rank, world):
     torch.cuda.synchronize(dev)
     ms_splat = sum(s.elapsed_time(e) for s, e in ev2) / args.steps
 
-    # -- end to end through the reference-facing API with pinned host buffers
+    # -- end to end through the reference-facing API: the predictions live in page-locked host memory (torch tensors, which
+    # the API accepts next to numpy arrays), the panoramas come back into the renderer's page-locked buffer
     host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in
             {"world_points_from_depth": pts64.cpu().numpy(), "depth_conf": p["depth_conf"], "images": p["images"]}.items()}
-    preds = {k: v.numpy() for k, v in host.items()}
+    preds = dict(host)
     preds["extrinsic"] = p["extrinsic"]
-    pp, sb, cr = R.PointCloudProcessor(dev), R.SceneBuilder(dev), R.CubemapRenderer(G)
+    pp, sb, cr = R.PointCloudProcessor(dev), R.SceneBuilder(dev), R.CubemapRenderer(G, pinned_output=True)
 
     def e2e_step():
         scene_, _ = pp.filter_predictions_device(preds, c["conf_thres"], prediction_mode="depth_unproject")

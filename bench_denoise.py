@@ -95,6 +95,7 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
     ms = allreduce_max(ms, dev, world)
     e2e_s = allreduce_max(e2e_s, dev, world)
     fl = algorithmic_flops(dict(DEFAULT_CONFIG, **UNET_CFG), 2, T, h, w)
+    kernels = per_kernel_roofline(unet, lambda: step(0, xd), fl, peaks, dev) if rank == 0 else None
     steps_per_s = world * args.steps / (ms * 1e-3)
     achieved = fl["total"] * (args.steps / (ms * 1e-3))  # TFLOP/s per GPU
     res = {
@@ -104,6 +105,7 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
         "roofline": {"bound": "tensor", "kernel": "whole denoise step (tc_gemm_kernel + spatial_attn_kernel dominate)",
                      "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
                      "traffic": None, "algorithmic_tflop_per_step": fl, "executed_tflop_per_step": plan_flops / 1e12,
+                     "kernels": kernels,
                      "peak_source": peaks["source"] + " (sustained bf16/fp16 dense)"},
         "gpu_launches": launches * args.steps,
         "config": {"workload": f"config 2: single 576x1024x{T}f clip, CFG batch 2, 72x128 latents, random-init 1.525B-param UNet, "
@@ -114,6 +116,58 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
     if rank == 0 and not args.no_cpu_baseline:
         res["cpu_baseline"] = run_cpu(T, steps=1)
     return res
+
+
+def per_kernel_roofline(unet, run_step, fl, peaks, dev):
+    """Live per-kernel figures: one extra step replayed with a CUDA-event pair around every planned op
+    (EVW_UNET_PROFILE, csrc/unet_host.cu) — serialised, so the sum is a little above the pipelined step time."""
+    import re
+    import tempfile
+
+    import torch
+
+    path = os.path.join(tempfile.gettempdir(), f"evw_unet_profile_{os.getpid()}.txt")
+    if os.path.exists(path):
+        os.remove(path)
+    os.environ["EVW_UNET_PROFILE"] = path
+    try:
+        run_step()
+        torch.cuda.synchronize(dev)
+    finally:
+        del os.environ["EVW_UNET_PROFILE"]
+    gemm_ms = gemm_fl = attn_ms = tattn_ms = norm_ms = other_ms = 0.0
+    try:
+        for line in open(path):
+            if line.startswith("END"):
+                break
+            _, t, label = line.split(" ", 2)
+            t = float(t)
+            m = re.search(r"(\d+)x(\d+)x(\d+)\s*$", label)
+            name = label.split(" ")[0]
+            if m:
+                M, N, K = map(int, m.groups())
+                gemm_ms += t
+                gemm_fl += 2.0 * M * N * K
+            elif "sdpa" in name:
+                if "temporal_transformer" in name:
+                    tattn_ms += t
+                else:
+                    attn_ms += t
+            elif "norm" in name:
+                norm_ms += t
+            else:
+                other_ms += t
+        os.remove(path)
+    except OSError:
+        return None
+    if gemm_ms <= 0 or attn_ms <= 0:
+        return None
+    pk = peaks["tf_sustained"]
+    return {"how": "one step replayed with CUDA events around every op (serialised)",
+            "tc_gemm_kernel": {"ms": gemm_ms, "tflops": gemm_fl / gemm_ms / 1e9, "frac": gemm_fl / gemm_ms / 1e9 / pk},
+            "spatial_attn_kernel": {"ms": attn_ms, "tflops": fl["sdpa_spatial"] * 1e3 / attn_ms,
+                                    "frac": fl["sdpa_spatial"] * 1e3 / attn_ms / pk},
+            "temporal_attn_ms": tattn_ms, "group_layer_norm_ms": norm_ms, "other_ms": other_ms}
 
 
 def run_cpu(T, steps=1, warmup=0):

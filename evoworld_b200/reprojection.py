@@ -366,14 +366,20 @@ class PointCloudProcessor:
         return PointScene(out, count), keep
 
     def _extract_point_data(self, predictions: Dict, prediction_mode: str):
+        def conf_or_ones(key, pts):  # the default is only materialised when the key is missing
+            if key in predictions:
+                return predictions[key]
+            shape = tuple(pts.shape[:-1])
+            return torch.ones(shape, dtype=torch.float32) if isinstance(pts, torch.Tensor) else np.ones(shape, dtype=np.float32)
+
         if "Pointmap" in prediction_mode and "world_points" in predictions:
             pts = predictions["world_points"]
-            conf = predictions.get("world_points_conf", np.ones_like(np.asarray(pts)[..., 0]))
+            conf = conf_or_ones("world_points_conf", pts)
         else:
             if "Pointmap" in prediction_mode:
                 self.logger.info("Warning: world_points not found, falling back to depth-based points")
             pts = predictions["world_points_from_depth"]
-            conf = predictions.get("depth_conf", np.ones_like(np.asarray(pts)[..., 0]))
+            conf = conf_or_ones("depth_conf", pts)
         return pts, conf
 
     def _parse_frame_filter(self, filter_by_frames: str) -> Optional[int]:
@@ -448,10 +454,15 @@ class SceneBuilder:
 class CubemapRenderer:
     """Handles cubemap rendering and equirectangular conversion."""
 
-    def __init__(self, views_per_pass: int = DEFAULT_VIEWS_PER_PASS):
+    def __init__(self, views_per_pass: int = DEFAULT_VIEWS_PER_PASS, pinned_output: bool = False):
+        """pinned_output: return the panoramas as a numpy view of a page-locked buffer owned by this renderer (one
+        asynchronous device-to-host copy at PCIe rate; the array is overwritten by the next call).  The default
+        returns a fresh array like the reference does."""
         self.logger = logging.getLogger(self.__class__.__name__)
         self.start = True
         self.views_per_pass = views_per_pass
+        self.pinned_output = pinned_output
+        self._pinned: Optional[torch.Tensor] = None
 
     def cube_to_equirectangular_cuda(self, cube_faces_batch, width, height, device="cuda"):
         """dict face -> uint8 [B,3,res,res]  ->  numpy uint8 [B,height,width,3]."""
@@ -532,7 +543,15 @@ class CubemapRenderer:
                                      only_render_last_24_frame: bool = False, write_png: bool = True):
         """Render every target view to a 2000x1000 panorama; returns numpy uint8 [V,1000,2000,3] and
         writes outdir/{idx:02}.png (RGB->BGR for cv2, as the reference :707-710)."""
-        panos = self.render_cubemaps_to_panoramas_device(scene_3d, target_extrinsic).cpu().numpy()
+        dev_panos = self.render_cubemaps_to_panoramas_device(scene_3d, target_extrinsic)
+        if self.pinned_output:
+            if self._pinned is None or self._pinned.shape != dev_panos.shape:
+                self._pinned = torch.empty(dev_panos.shape, dtype=torch.uint8, pin_memory=True)
+            self._pinned.copy_(dev_panos, non_blocking=True)
+            torch.cuda.current_stream(dev_panos.device).synchronize()
+            panos = self._pinned.numpy()
+        else:
+            panos = dev_panos.cpu().numpy()
         if write_png:
             import cv2
 
