@@ -80,14 +80,21 @@ __global__ void equi2pers_kernel(const uint8_t* __restrict__ equi, const float* 
   const float PI = 3.14159265358979323846f;
   float ui = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(theta, PI), (float)We), __fmul_rn(2.0f, PI)), 0.5f);
   float uj = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(phi, __fmul_rn(0.5f, PI)), (float)He), PI), 0.5f);
-  ui = fmodf(ui, (float)We);
+  // theta in [-pi, pi] and phi in [-pi/2, pi/2] put ui in [-We + 0.5, 0.5] and uj in [-He + 0.5, 0.5]: |u| < extent, where
+  // fmod is the identity.  libdevice's fmodf and the integer '%' were ~3/4 of this kernel's instructions; the general
+  // path stays behind a never-taken branch so the result is the same expression in every case.
+  if (!(fabsf(ui) < (float)We)) ui = fmodf(ui, (float)We);
   if (ui < 0.f) ui = __fadd_rn(ui, (float)We);
-  uj = fmodf(uj, (float)He);
+  if (!(fabsf(uj) < (float)He)) uj = fmodf(uj, (float)He);
   if (uj < 0.f) uj = __fadd_rn(uj, (float)He);
   float x0f = floorf(ui), y0f = floorf(uj);
   float dx = __fsub_rn(ui, x0f), dy = __fsub_rn(uj, y0f);
-  int x0 = ((int)x0f) % We, y0 = ((int)y0f) % He;
-  int x1 = (x0 + 1) % We, y1 = (y0 + 1) % He;
+  int x0 = (int)x0f, y0 = (int)y0f;  // in [0, extent]: one conditional subtraction is the modulo
+  if (x0 >= We) x0 -= We;
+  if (y0 >= He) y0 -= He;
+  int x1 = x0 + 1, y1 = y0 + 1;
+  if (x1 >= We) x1 -= We;
+  if (y1 >= He) y1 -= He;
   float wx0 = __fsub_rn(1.0f, dx), wy0 = __fsub_rn(1.0f, dy);
   for (int c = 0; c < C; ++c) {
     const uint8_t* img = equi + ((size_t)b * C + c) * He * We;

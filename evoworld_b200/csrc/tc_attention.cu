@@ -1900,8 +1900,277 @@ spatial_attn7_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
   }
 }
 
+// ==========================================================================================
+// v8: v7 (P in its own tensor-memory columns, CUDA-core row sums) with v6's two threads per query row: 16 softmax
+// warps per CTA, four per SM sub-partition, to overlap the per-tile chain that v7 still leaves exposed.
+// ==========================================================================================
+constexpr int kA8OffToken = kA7OffBar + 256;          // 512 words
+constexpr int kA8OffMax = kA8OffToken + 2048;         // [2 parities][2 groups][2 halves][128 rows] fp32
+constexpr int kA8Smem = kA8OffMax + 4096 + 1024;
+
+template <int kPolyN, bool kStagger>
+__global__ void __launch_bounds__(kA6Threads, 1)
+spatial_attn8_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ out, int S, int C, float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, frame = blockIdx.z;
+  const int q0 = blockIdx.x * 2 * kBQ;
+  const int n_kv = (S + kBKV - 1) / kBKV;
+  const bool b_active = q0 + kBQ < S;
+
+  const uint32_t bar = base + kA7OffBar;
+  const uint32_t q_full = bar;
+  auto kv_full = [&](int s) { return bar + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bar + 8u * (1 + kA7Stages + s); };
+  auto s_full = [&](int g) { return bar + 8u * (1 + 2 * kA7Stages + g); };
+  auto s_empty = [&](int g) { return bar + 8u * (3 + 2 * kA7Stages + g); };
+  auto p_full = [&](int g) { return bar + 8u * (5 + 2 * kA7Stages + g); };
+  auto o_full = [&](int g) { return bar + 8u * (7 + 2 * kA7Stages + g); };
+  const uint32_t tmem_slot = bar + 8u * (9 + 2 * kA7Stages);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + kA7OffBar + 8 * (9 + 2 * kA7Stages));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kA7Stages; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), b_active ? 2 : 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(s_full(g), 1);
+      mbar_init(s_empty(g), 8);  // one arrival per softmax warp of the group
+      mbar_init(p_full(g), 8);
+      mbar_init(o_full(g), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+        tma_load_3d(&tmap, base + kA7OffQ, q_full, head * kD, q0, frame);
+        tma_load_3d(&tmap, base + kA7OffQ + kTileBytes, q_full, head * kD, q0 + kBQ, frame);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % kA7Stages;
+        mbar_wait(kv_empty(st), ((j / kA7Stages) & 1) ^ 1u);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(kv_full(st), 2 * kTileBytes);
+          tma_load_3d(&tmap, base + kA7OffK + st * kTileBytes, kv_full(st), C + head * kD, j * kBKV, frame);
+          tma_load_3d(&tmap, base + kA7OffV + st * kTileBytes, kv_full(st), 2 * C + head * kD, j * kBKV, frame);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1 || warp == 2) {
+      const int g = warp - 1;
+      if (lane == 0 && (g == 0 || b_active)) {
+        const uint32_t idesc_s = make_idesc_f16(kBQ, kBKV, 0, 0, 0);
+        const uint32_t idesc_o = make_idesc_f16(kBQ, kD, 0, 0, 1);
+        const uint64_t dq = make_desc_k_sw128(base + kA7OffQ + g * kTileBytes);
+        const uint64_t dk0 = make_desc_k_sw128(base + kA7OffK);
+        const uint64_t dv0 = make_desc_mn_sw128(base + kA7OffV, 1024);
+        const uint32_t t_s = tmem_base + g * kBKV, t_o = tmem_base + kTmemO7 + g * kD, t_p = tmem_base + kTmemP7 + g * 64;
+        mbar_wait(q_full, 0);
+        int s_next = 0, pv_next = 0;
+        long long t0 = clock64();
+        while (pv_next < n_kv) {
+          bool progress = false;
+          if (s_next < n_kv && mbar_test(kv_full(s_next % kA7Stages), (s_next / kA7Stages) & 1) &&
+              (s_next == 0 || mbar_test(s_empty(g), (s_next - 1) & 1))) {
+            tc_fence_after();
+            const uint64_t dk = desc_add(dk0, (s_next % kA7Stages) * (kTileBytes >> 4));
+#pragma unroll
+            for (int k = 0; k < kD / 16; ++k) umma_f16_ss(t_s, desc_add(dq, 2 * k), desc_add(dk, 2 * k), idesc_s, k != 0);
+            tc_commit(s_full(g));
+            ++s_next;
+            progress = true;
+          }
+          if (pv_next < s_next && mbar_test(p_full(g), pv_next & 1)) {
+            tc_fence_after();
+            const int st = pv_next % kA7Stages;
+            const uint64_t dv = desc_add(dv0, st * (kTileBytes >> 4));
+            const uint32_t acc = pv_next != 0;
+#pragma unroll
+            for (int ks = 0; ks < kBKV / 16; ++ks)  // O += P V, A operand from tensor memory
+              umma_f16_ts(t_o, t_p + ks * 8, desc_add(dv, ks * (2048 >> 4)), idesc_o, acc | (ks != 0));
+            tc_commit(o_full(g));
+            tc_commit(kv_empty(st));
+            ++pv_next;
+            progress = true;
+          }
+          if (progress) t0 = clock64();
+          else if (clock64() - t0 > 8000000000ll) __trap();
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // ===================== softmax: 8 warps per 128-row group =====================
+    const int sw = warp - 4;
+    const int g = sw >> 3;
+    const int half = (sw >> 2) & 1;
+    const int quarter = warp & 3;  // = sw & 3: the TMEM lane quarter this warp may address
+    const int r = quarter * 32 + lane;
+    const int qrow = q0 + g * kBQ + r;
+    if (g == 0 || b_active) {
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t s_addr = lane_addr + g * kBKV + half * 64;
+      const uint32_t o_addr = lane_addr + kTmemO7 + g * kD + half * 32;
+      const uint32_t p_addr = lane_addr + kTmemP7 + g * 64 + half * 32;
+      float m_ref = -INFINITY;
+      float l_run = 0.f;  // this thread's half of the row sum
+      const uint32_t token_word = base + kA8OffToken + 4u * (threadIdx.x - 128);
+      if (kStagger) st_shared_volatile(token_word, 0u);
+      if (kStagger && b_active && g == 1) named_bar_arrive(1, 512);  // group A goes first
+      float* mxbuf = reinterpret_cast<float*>(base_ptr + kA8OffMax);
+
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(s_full(g), j & 1);
+        tc_fence_after();
+        uint32_t s[64];
+        {
+          uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+          uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+          tmem_ld_32x32b_x32(s_addr + 0, s0);
+          tmem_ld_32x32b_x32(s_addr + 32, s1);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty(g));  // 8 arrivals: S_g(j+1) may now overwrite the TMEM tile
+
+        const int kv_valid = S - j * kBKV - half * 64;  // valid columns of this half
+        if (kv_valid < 64) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            if (c >= kv_valid) s[c] = 0xff800000u;
+        }
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 64; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], __uint_as_float(s[c]));
+        float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        // exchange the half-row maxima (double-buffered by tile parity: a slot is rewritten two barriers later)
+        {
+          float* slot = mxbuf + (((j & 1) * 2 + g) * 2) * 128;
+          slot[half * 128 + r] = mx;
+          named_bar_sync(3 + g, 256);
+          mx = fmaxf(mx, slot[(half ^ 1) * 128 + r]);
+        }
+        const float m_tile = mx * scale_log2e;
+        const bool need = m_tile > m_ref + kLazyTau;  // identical in both threads of the row
+        const float m_old = m_ref;
+        if (need) m_ref = m_tile;
+        const float neg_m = -m_ref;
+        if (kPolyN > 0) {
+#pragma unroll
+          for (int c = kPolyN - 1; c < 64; c += (kPolyN > 0 ? kPolyN : 64))
+            s[c] = __float_as_uint(exp2_poly(fmaf(__uint_as_float(s[c]), scale_log2e, neg_m)));
+        }
+        float neg_m_dep = neg_m;
+        if (kStagger && b_active) {
+          named_bar_sync(1 + g, 512);
+          neg_m_dep = neg_m + __uint_as_float(ld_shared_volatile(token_word));
+        }
+        uint32_t w[32];
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const bool poly0 = kPolyN > 0 && ((2 * i) % (kPolyN > 0 ? kPolyN : 1)) == kPolyN - 1;
+          const bool poly1 = kPolyN > 0 && ((2 * i + 1) % (kPolyN > 0 ? kPolyN : 1)) == kPolyN - 1;
+          const float p0 = poly0 ? __uint_as_float(s[2 * i]) : fast_exp2(fmaf(__uint_as_float(s[2 * i]), scale_log2e, neg_m_dep));
+          const float p1 = poly1 ? __uint_as_float(s[2 * i + 1])
+                                 : fast_exp2(fmaf(__uint_as_float(s[2 * i + 1]), scale_log2e, neg_m_dep));
+          sum4[(2 * i) & 3] += p0;
+          sum4[(2 * i + 1) & 3] += p1;
+          __half2 h = __floats2half2_rn(p0, p1);
+          w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        if (kStagger && b_active) {
+          st_shared_volatile(token_word, (w[7] | w[15] | w[23] | w[31]) & 0x80008000u);
+          if (!(g == 1 && j + 1 == n_kv)) named_bar_arrive(2 - g, 512);
+        }
+        const float f_resc = need ? fast_exp2(m_old - m_ref) : 1.0f;  // exp2(-inf) = 0 on the first tile
+        l_run = fmaf(l_run, f_resc, (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+        // the P columns and the O accumulator of this group are free once PV_g(j-1) has completed
+        if (j > 0) {
+          mbar_wait(o_full(g), (j - 1) & 1);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, need)) {  // same rows, same decision in both warps of the quarter
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {  // this warp's 32 of the 64 output columns
+              uint32_t v[16];
+              tmem_ld_32x32b_x16(o_addr + part * 16, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f_resc);
+              tmem_st_32x32b_x16(o_addr + part * 16, v);
+            }
+          }
+        }
+        // P: this warp's 64 keys = 32 packed columns
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          uint32_t(&wp)[16] = *reinterpret_cast<uint32_t(*)[16]>(&w[16 * part]);
+          tmem_st_32x32b_x16(p_addr + part * 16, wp);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(g));
+      }
+      // final: the two halves add their partial row sums, then each normalises its 32 output columns
+      {
+        float* slot = mxbuf + (((n_kv & 1) * 2 + g) * 2) * 128;  // the parity the last tile did not use
+        slot[half * 128 + r] = l_run;
+        named_bar_sync(3 + g, 256);
+        l_run += slot[(half ^ 1) * 128 + r];
+      }
+      mbar_wait(o_full(g), (n_kv - 1) & 1);
+      tc_fence_after();
+      uint32_t ov[32];
+      tmem_ld_32x32b_x32(o_addr, ov);
+      tmem_ld_wait();
+      if (qrow < S) {
+        const float inv = 1.0f / l_run;
+        uint4* op = reinterpret_cast<uint4*>(out + ((long long)frame * S + qrow) * C + head * kD + half * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t* src = &ov[8 * i];
+          __half2 h0 = __floats2half2_rn(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
+          __half2 h1 = __floats2half2_rn(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
+          __half2 h2 = __floats2half2_rn(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
+          __half2 h3 = __floats2half2_rn(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
+          uint4 v;
+          v.x = *reinterpret_cast<uint32_t*>(&h0); v.y = *reinterpret_cast<uint32_t*>(&h1);
+          v.z = *reinterpret_cast<uint32_t*>(&h2); v.w = *reinterpret_cast<uint32_t*>(&h3);
+          op[i] = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+
 }  // namespace
 
+// default kernel: v7, all exponentials on MUFU, no stagger (tools/attn_bench.py: 3.95 ms at 28 x 9216 x 5 heads vs 4.99 ms for v3)
+constexpr int kDefaultAttnVariant = 13;
 static int g_attn_variant_override = -2;
 void set_attention_variant(int v) { g_attn_variant_override = v; }
 
@@ -1910,7 +2179,7 @@ int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, c
   const int C = heads * kD;
   static bool attr_set = false;
   static bool use_v1 = false, use_v2 = false, use_v3 = false, use_v4 = false;
-  static int v5_variant = 0;
+  static int v5_variant = kDefaultAttnVariant;
   typedef void (*attn5_fn)(const CUtensorMap, __half*, int, int, float);
   struct Variant { attn5_fn fn; int threads, smem; };
   // v5 / v6 variants: {polynomial share, stagger}.  EVW_ATTN_V5=<index> or evw_set_attention_variant selects one.
@@ -1921,7 +2190,9 @@ int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, c
       {spatial_attn6_kernel<4, true>, kA6Threads, kA6Smem},  {spatial_attn6_kernel<0, false>, kA6Threads, kA6Smem},
       {spatial_attn6_kernel<8, false>, kA6Threads, kA6Smem}, {spatial_attn7_kernel<4, true>, kA2Threads, kA7Smem},
       {spatial_attn7_kernel<4, false>, kA2Threads, kA7Smem}, {spatial_attn7_kernel<0, true>, kA2Threads, kA7Smem},
-      {spatial_attn7_kernel<8, true>, kA2Threads, kA7Smem},  {spatial_attn7_kernel<0, false>, kA2Threads, kA7Smem}};
+      {spatial_attn7_kernel<8, true>, kA2Threads, kA7Smem},  {spatial_attn7_kernel<0, false>, kA2Threads, kA7Smem},
+      {spatial_attn8_kernel<0, false>, kA6Threads, kA8Smem}, {spatial_attn8_kernel<8, false>, kA6Threads, kA8Smem},
+      {spatial_attn8_kernel<0, true>, kA6Threads, kA8Smem}};
   if (!attr_set) {
     EVW_CUDA(cudaFuncSetAttribute(spatial_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     EVW_CUDA(cudaFuncSetAttribute(spatial_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2Smem));
@@ -1940,7 +2211,7 @@ int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, c
     if (g_attn_variant_override >= 0) v5_variant = g_attn_variant_override;
     use_v1 = use_v2 = use_v4 = false;
   }
-  if (v5_variant < 0 || v5_variant >= (int)(sizeof(v5_table) / sizeof(v5_table[0]))) v5_variant = 0;
+  if (v5_variant < 0 || v5_variant >= (int)(sizeof(v5_table) / sizeof(v5_table[0]))) v5_variant = kDefaultAttnVariant;
   alignas(64) CUtensorMap tmap;
   uint64_t dims[3] = {(uint64_t)3 * C, (uint64_t)S, (uint64_t)F};
   uint64_t str[2] = {(uint64_t)3 * C * 2, (uint64_t)3 * C * 2 * S};

@@ -113,3 +113,30 @@ def test_no_cpu_fallback():
         P.ray_c2w_to_plucker(ray, torch.zeros(2, 3, 4))
     with pytest.raises(RuntimeError):
         R.CubemapRenderer().cube_to_equirectangular_cuda({}, 64, 32, device="cpu")
+
+
+def test_splat_flags_and_workspace(built_lib):
+    """Flag word of evw_splat_cube_equirect (include/evoworld_b200.h) and the workspace it implies."""
+    assert R.splat_flags(False, False, False, False) == 0
+    assert R.splat_flags(True, True, True, True) == R.SPLAT_PRETEST | R.SPLAT_OVERLAP | R.SPLAT_V1_KERNELS | R.SPLAT_OVERLAP_BY_ROLE
+    one = 4 * 6 * 512 * 512 * 8
+    assert R.splat_workspace_bytes(4, 512, 0) == one
+    assert R.splat_workspace_bytes(4, 512, R.SPLAT_OVERLAP) == 2 * one  # two passes in flight
+    assert R.splat_workspace_bytes(4, 512, R.SPLAT_PRETEST | R.SPLAT_V1_KERNELS) == one
+
+
+def test_missing_confidence_defaults_to_ones():
+    """reproject_vggt_open3d_utils.py:224-247: a prediction dict without a confidence map filters with conf == 1."""
+    pp = R.PointCloudProcessor.__new__(R.PointCloudProcessor)
+    import logging
+
+    pp.logger = logging.getLogger("t")
+    pts = np.zeros((2, 3, 4, 3), dtype=np.float64)
+    got_pts, conf = pp._extract_point_data({"world_points_from_depth": pts}, "Depthmap and Camera Branch")
+    assert got_pts is pts and conf.shape == (2, 3, 4) and conf.dtype == np.float32 and (conf == 1).all()
+    tp = torch.zeros(2, 3, 4, 3, dtype=torch.float64)
+    _, conf_t = pp._extract_point_data({"world_points": tp}, "Predicted Pointmap")
+    assert isinstance(conf_t, torch.Tensor) and tuple(conf_t.shape) == (2, 3, 4) and bool((conf_t == 1).all())
+    c = np.full((2, 3, 4), 2.0, dtype=np.float32)
+    _, conf2 = pp._extract_point_data({"world_points_from_depth": pts, "depth_conf": c}, "x")
+    assert conf2 is c
