@@ -63,13 +63,16 @@ __global__ void plucker_kernel(const float* __restrict__ ray, const float* __res
 // ------------------------------------------------------------------------------------------
 // Equirect -> perspective, uint8 bilinear (horizontal and vertical wrap as pyequilib's sampler)
 // ------------------------------------------------------------------------------------------
-__global__ void equi2pers_kernel(const uint8_t* __restrict__ equi, const float* __restrict__ pix2dir,
-                                 uint8_t* __restrict__ out, int C, int He, int We, int Hp, int Wp) {
-  int b = blockIdx.z;
-  int x = blockIdx.x * blockDim.x + threadIdx.x;
-  int y = blockIdx.y * blockDim.y + threadIdx.y;
+__global__ void __launch_bounds__(256)
+equi2pers_kernel(const uint8_t* __restrict__ equi, const float* __restrict__ pix2dir, uint8_t* __restrict__ out, int C,
+                 int He, int We, int Hp, int Wp) {
+  const int b = blockIdx.z;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  __shared__ float A[9];  // one matrix per frame: read once per block instead of nine global loads per pixel
+  if (threadIdx.y == 0 && threadIdx.x < 9) A[threadIdx.x] = pix2dir[b * 9 + threadIdx.x];
+  __syncthreads();
   if (x >= Wp || y >= Hp) return;
-  const float* A = pix2dir + b * 9;
   float fx = (float)x, fy = (float)y;
   float mx = __fadd_rn(__fadd_rn(__fmul_rn(A[0], fx), __fmul_rn(A[1], fy)), A[2]);
   float my = __fadd_rn(__fadd_rn(__fmul_rn(A[3], fx), __fmul_rn(A[4], fy)), A[5]);
@@ -81,7 +84,7 @@ __global__ void equi2pers_kernel(const uint8_t* __restrict__ equi, const float* 
   float ui = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(theta, PI), (float)We), __fmul_rn(2.0f, PI)), 0.5f);
   float uj = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(phi, __fmul_rn(0.5f, PI)), (float)He), PI), 0.5f);
   // theta in [-pi, pi] and phi in [-pi/2, pi/2] put ui in [-We + 0.5, 0.5] and uj in [-He + 0.5, 0.5]: |u| < extent, where
-  // fmod is the identity.  libdevice's fmodf and the integer '%' were ~3/4 of this kernel's instructions; the general
+  // fmod is the identity.  libdevice's fmodf and the integer '%' were most of this kernel's instructions; the general
   // path stays behind a never-taken branch so the result is the same expression in every case.
   if (!(fabsf(ui) < (float)We)) ui = fmodf(ui, (float)We);
   if (ui < 0.f) ui = __fadd_rn(ui, (float)We);
@@ -96,15 +99,19 @@ __global__ void equi2pers_kernel(const uint8_t* __restrict__ equi, const float* 
   if (x1 >= We) x1 -= We;
   if (y1 >= He) y1 -= He;
   float wx0 = __fsub_rn(1.0f, dx), wy0 = __fsub_rn(1.0f, dy);
-  for (int c = 0; c < C; ++c) {
-    const uint8_t* img = equi + ((size_t)b * C + c) * He * We;
-    float q00 = img[(size_t)y0 * We + x0], q01 = img[(size_t)y0 * We + x1];
-    float q10 = img[(size_t)y1 * We + x0], q11 = img[(size_t)y1 * We + x1];
+  // 32-bit offsets inside one image plane; the plane base is the only 64-bit address
+  const unsigned o00 = (unsigned)y0 * We + x0, o01 = (unsigned)y0 * We + x1;
+  const unsigned o10 = (unsigned)y1 * We + x0, o11 = (unsigned)y1 * We + x1;
+  const size_t plane_in = (size_t)He * We, plane_out = (size_t)Hp * Wp;
+  const uint8_t* img = equi + (size_t)b * C * plane_in;
+  uint8_t* dst = out + (size_t)b * C * plane_out + (unsigned)y * Wp + x;
+  for (int c = 0; c < C; ++c, img += plane_in, dst += plane_out) {
+    float q00 = __ldg(img + o00), q01 = __ldg(img + o01), q10 = __ldg(img + o10), q11 = __ldg(img + o11);
     float top = __fadd_rn(__fmul_rn(q00, wx0), __fmul_rn(q01, dx));
     float bot = __fadd_rn(__fmul_rn(q10, wx0), __fmul_rn(q11, dx));
     float v = __fadd_rn(__fmul_rn(top, wy0), __fmul_rn(bot, dy));
     v = fminf(fmaxf(v, 0.f), 255.f);
-    out[(((size_t)b * C + c) * Hp + y) * Wp + x] = (uint8_t)v;  // truncation, as astype(uint8)
+    *dst = (uint8_t)v;  // truncation, as astype(uint8)
   }
 }
 

@@ -2169,8 +2169,9 @@ spatial_attn8_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
 
 }  // namespace
 
-// default kernel: v7, all exponentials on MUFU, no stagger (tools/attn_bench.py: 3.95 ms at 28 x 9216 x 5 heads vs 4.99 ms for v3)
-constexpr int kDefaultAttnVariant = 13;
+// default kernel: v8 (P in tensor memory, two threads per row), all exponentials on MUFU, no stagger
+// (tools/attn_bench.py at 28 frames x 9216 tokens x 5 heads: v3 4.99 ms, v5 4.66, v7 3.87, v8 3.69)
+constexpr int kDefaultAttnVariant = 14;
 static int g_attn_variant_override = -2;
 void set_attention_variant(int v) { g_attn_variant_override = v; }
 

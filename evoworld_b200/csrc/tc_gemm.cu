@@ -15,6 +15,7 @@
 #include "common.h"
 #include "tc_common.cuh"
 #include "tc_gemm.h"
+#include <cstdlib>
 
 namespace evw {
 
@@ -39,6 +40,7 @@ struct KernelParams {
   int8_t tap_dx[kMaxTaps], tap_dy[kMaxTaps], tap_dt[kMaxTaps], tap_src[kMaxTaps];
   int num_stages;
   int total_tiles;
+  int total_pairs;  // cluster mode: pairs of m-adjacent tiles sharing one weight tile (B multicast)
 };
 
 // exact-GELU 0.5 x (1 + erf(x / sqrt 2)) = max(x, 0) - |x| * 0.5 erfc(|x| / sqrt 2), branch free, with erfc from
@@ -158,9 +160,35 @@ __device__ __forceinline__ void store16(const GemmEpilogue& ep, const float (&v)
   }
 }
 
+// kCluster: CTAs are launched as clusters of two that work on m-adjacent tiles of the SAME n-tile.  Each CTA loads its own
+// activation tile and HALF of the weight tile, multicast into both CTAs' shared memory, so the weight bytes cross the
+// L2 -> SM path once per pair (ncu: that path would be 94 % busy at full tensor rate with 160-wide tiles).  The MMAs stay
+// cta_group::1; only the stage-release commit is multicast so that neither producer overwrites a stage its peer still reads.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_multicast(const CUtensorMap* m, uint32_t dst, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+
+template <bool kCluster>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
-               const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ KernelParams P) {
+               const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_bh,
+               const __grid_constant__ KernelParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -180,11 +208,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
     tma_prefetch_desc(&tmap_a0);
     tma_prefetch_desc(&tmap_a1);
     tma_prefetch_desc(&tmap_b);
+    if (kCluster) tma_prefetch_desc(&tmap_bh);
   }
+  const uint32_t crank = kCluster ? cluster_ctarank() : 0u;
+  // virtual tile index v -> tile: plain mode walks tiles, cluster mode walks pairs (rank picks the m-tile of the pair;
+  // an odd m-tile count leaves one phantom tile whose loads fall outside the tensor and whose rows are never stored)
+  const int v_first = kCluster ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int v_step = kCluster ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int v_limit = kCluster ? P.total_pairs : P.total_tiles;
+  auto to_tile = [&](int v) {
+    if (!kCluster) return v;
+    const int mp = v / P.n_tiles, nt = v - mp * P.n_tiles;
+    return (2 * mp + (int)crank) * P.n_tiles + nt;
+  };
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), kCluster ? 2 : 1);  // cluster: released by both CTAs' MMA commits
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -196,6 +236,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  if (kCluster) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -206,7 +247,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+    const uint32_t half_bytes = b_tile_bytes >> 1;
+    for (int v = v_first; v < v_limit; v += v_step) {
+      const int tile = to_tile(v);
       const int n_tile = tile % P.n_tiles;
       int m_tile = tile / P.n_tiles;
       const int tx = m_tile % P.tiles_x; m_tile /= P.tiles_x;
@@ -225,7 +268,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
             const uint32_t sa = smem_base + stage * stage_bytes;
             mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
             tma_load_5d(ma, sa, full_bar(stage), kc * kBlockK, cx, cy, ct, tb);
-            tma_load_2d(&tmap_b, sa + kATileBytes, full_bar(stage), kglob * kBlockK, n0);
+            if (kCluster)  // this CTA's half of the weight rows, delivered to the same offset in both CTAs
+              tma_load_2d_multicast(&tmap_bh, sa + kATileBytes + crank * half_bytes, full_bar(stage), kglob * kBlockK,
+                                    n0 + (int)crank * (P.block_n >> 1), (uint16_t)3);
+            else
+              tma_load_2d(&tmap_b, sa + kATileBytes, full_bar(stage), kglob * kBlockK, n0);
           }
           __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -238,7 +285,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+    for (int v = v_first; v < v_limit; v += v_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -254,7 +301,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k)
             umma_f16_ss(d_tmem, da + 2ull * k, db + 2ull * k, idesc, (kc | k) != 0);
-          tc_commit(empty_bar(stage));
+          if (kCluster) tc_commit_multicast(empty_bar(stage), (uint16_t)3);
+          else tc_commit(empty_bar(stage));
           if (kc == total_chunks - 1) tc_commit(tfull_bar(acc));
         }
         __syncwarp();
@@ -280,8 +328,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
     const int et = threadIdx.x - 128;    // 0 .. 32*kEpiWarps-1
     // residual operands stream from DRAM exactly once: pull the row segment of the NEXT tile into L2 one tile ahead
     // (prefetch.global.L2, no registers / shared memory), so the epilogue's loads find it there
-    auto prefetch_residuals = [&](int tile_p) {
-      if (tile_p >= P.total_tiles || (!ep.res1 && !ep.res2)) return;
+    auto prefetch_residuals = [&](int v_p) {
+      if (v_p >= v_limit || (!ep.res1 && !ep.res2)) return;
+      const int tile_p = to_tile(v_p);
+      if (tile_p >= P.total_tiles) return;
       const int n_tile_p = tile_p % P.n_tiles;
       int m_tile_p = tile_p / P.n_tiles;
       const int tx_p = m_tile_p % P.tiles_x; m_tile_p /= P.tiles_x;
@@ -302,10 +352,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
         for (int o = cgrp * 128; o < cols * 4; o += 128 * NG) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
       }
     };
-    prefetch_residuals(blockIdx.x);
+    prefetch_residuals(v_first);
     int it = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-      prefetch_residuals(tile + gridDim.x);
+    for (int v = v_first; v < v_limit; v += v_step, ++it) {
+      const int tile = to_tile(v);
+      prefetch_residuals(v + v_step);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int n_tile = tile % P.n_tiles;
@@ -316,7 +367,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
       const int tb = m_tile / P.T;
       const int mx = r % P.bx, my = r / P.bx;
       const int gx = tx * P.bx + mx, gy = ty * P.by + my;
-      const bool row_ok = gx < P.X && gy < P.Y;
+      const bool row_ok = gx < P.X && gy < P.Y && tile < P.total_tiles;
       const long long row = (((long long)tb * P.T + tt) * P.Y + gy) * P.X + gx;
       const long long rv_row = ep.rowvec ? (row / ep.rv_div) % ep.rv_mod : 0;
       const int n0 = n_tile * P.block_n;
@@ -412,6 +463,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (kCluster) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -470,6 +522,8 @@ static int pow2_floor(int v) {
   return p;
 }
 
+int gemm_cluster_mode();
+
 int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   EVW_CHECK_ARG(pr.C0 > 0 && pr.C0 % kBlockK == 0, "gemm: C0=%d must be a positive multiple of 64", pr.C0);
   EVW_CHECK_ARG(pr.C1 % kBlockK == 0, "gemm: C1=%d must be a multiple of 64", pr.C1);
@@ -516,9 +570,18 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   if (stages > 8) stages = 8;
   P.num_stages = stages;
   P.total_tiles = P.tiles_x * P.tiles_y * P.T * P.B * P.n_tiles;
+  const int m_tiles = P.tiles_x * P.tiles_y * P.T * P.B;
+  P.total_pairs = ((m_tiles + 1) / 2) * P.n_tiles;
   op->smem_bytes = stages * stage_bytes + 8 * (2 * stages + 4) + 16 + 2 * 256 * 4 + 1024;
   int sms = sm_count();
-  op->grid = P.total_tiles < sms ? P.total_tiles : sms;
+  // cluster (B-multicast) mode needs at least one full pair per cluster and a 1 KiB-aligned half tile (bn % 16 == 0 holds)
+  op->cluster = (gemm_cluster_mode() && m_tiles >= 2 && sms >= 2) ? 1 : 0;
+  if (op->cluster) {
+    const int want = 2 * P.total_pairs;
+    op->grid = want < (sms & ~1) ? want : (sms & ~1);
+  } else {
+    op->grid = P.total_tiles < sms ? P.total_tiles : sms;
+  }
   static_assert(sizeof(KernelParams) <= sizeof(op->params), "GemmOp::params too small");
   memcpy(op->params, &P, sizeof(P));
 
@@ -543,14 +606,28 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   uint32_t bbox[2] = {(uint32_t)kBlockK, (uint32_t)bn};
   rc = encode_tmap_f16(reinterpret_cast<CUtensorMap*>(op->tmap_b), pr.w, 2, bdims, bstr, bbox);
   if (rc) return rc;
+  uint32_t hbox[2] = {(uint32_t)kBlockK, (uint32_t)(bn / 2)};
+  rc = encode_tmap_f16(reinterpret_cast<CUtensorMap*>(op->tmap_bh), pr.w, 2, bdims, bstr, hbox);
+  if (rc) return rc;
   op->flops = 2.0 * pr.X * pr.Y * pr.T * pr.B * (double)pr.N * (double)pr.K_total;
   return EVW_OK;
 }
 
+static int g_gemm_cluster = -1;  // -1: EVW_GEMM_CLUSTER (default on)
+int gemm_cluster_mode() {
+  if (g_gemm_cluster < 0) {
+    const char* e = getenv("EVW_GEMM_CLUSTER");
+    g_gemm_cluster = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return g_gemm_cluster;
+}
+void set_gemm_cluster_mode(int on) { g_gemm_cluster = on < 0 ? -1 : (on ? 1 : 0); }
+
 int gemm_launch(const GemmOp& op, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(tc_gemm_kernel): %s", cudaGetErrorString(e));
       return EVW_ERR_CUDA;
@@ -559,10 +636,29 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream) {
   }
   KernelParams P;
   memcpy(&P, op.params, sizeof(P));
-  tc_gemm_kernel<<<op.grid, kThreads, op.smem_bytes, stream>>>(
-      *reinterpret_cast<const CUtensorMap*>(op.tmap_a0), *reinterpret_cast<const CUtensorMap*>(op.tmap_a1),
-      *reinterpret_cast<const CUtensorMap*>(op.tmap_b), P);
-  cudaError_t e = cudaGetLastError();
+  const CUtensorMap& ta0 = *reinterpret_cast<const CUtensorMap*>(op.tmap_a0);
+  const CUtensorMap& ta1 = *reinterpret_cast<const CUtensorMap*>(op.tmap_a1);
+  const CUtensorMap& tb = *reinterpret_cast<const CUtensorMap*>(op.tmap_b);
+  const CUtensorMap& tbh = *reinterpret_cast<const CUtensorMap*>(op.tmap_bh);
+  cudaError_t e;
+  if (op.cluster) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)op.grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)op.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<true>, ta0, ta1, tb, tbh, P);
+  } else {
+    tc_gemm_kernel<false><<<op.grid, kThreads, op.smem_bytes, stream>>>(ta0, ta1, tb, tbh, P);
+    e = cudaGetLastError();
+  }
   if (e != cudaSuccess) {
     set_error("tc_gemm_kernel launch: %s", cudaGetErrorString(e));
     return EVW_ERR_CUDA;
@@ -575,6 +671,8 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------
 // C ABI: one generic entry (used by the parity tests and by Python-side micro-benchmarks)
 // ------------------------------------------------------------------------------------------
+extern "C" void evw_set_gemm_cluster(int on) { evw::set_gemm_cluster_mode(on); }
+
 extern "C" int evw_gemm_f16(const void* a0, const void* a1, const void* w, int B, int T, int Y, int X, int C0, int C1,
                             int N, int num_taps, const int8_t* h_taps /*[num_taps,4] dx,dy,dt,src*/, void* out,
                             int out_fp16, const float* bias, const float* rowvec, int64_t rv_div, int64_t rv_mod,

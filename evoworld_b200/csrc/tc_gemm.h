@@ -49,13 +49,16 @@ struct alignas(64) GemmOp {
   alignas(64) unsigned char tmap_a0[128];
   alignas(64) unsigned char tmap_a1[128];
   alignas(64) unsigned char tmap_b[128];
+  alignas(64) unsigned char tmap_bh[128];  // half-height weight box (cluster mode: one half per CTA, multicast to the pair)
   unsigned char params[256];
   int grid = 0;
+  int cluster = 0;  // 1: launch as clusters of two CTAs sharing each weight tile (TMA multicast)
   int smem_bytes = 0;
   double flops = 0;
 };
 
 int gemm_plan(GemmOp* op, const GemmProblem& pr);
 int gemm_launch(const GemmOp& op, cudaStream_t stream);
+void set_gemm_cluster_mode(int on);  // -1 = EVW_GEMM_CLUSTER / default, 0 = off, 1 = on (takes effect at plan time)
 
 }  // namespace evw

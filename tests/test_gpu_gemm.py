@@ -14,11 +14,15 @@ def rel_l2(a, b):
     return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
 
 
-@pytest.fixture(autouse=True)
-def _seed(cuda_device, built_lib):
+@pytest.fixture(autouse=True, params=[1, 0], ids=["cluster", "plain"])
+def _seed(request, cuda_device, built_lib):
+    """Every case runs twice: with the 2-CTA cluster / weight-multicast launch (the default) and with the plain launch."""
     torch.manual_seed(0)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
+    built_lib.evw_set_gemm_cluster(request.param)
+    yield
+    built_lib.evw_set_gemm_cluster(-1)
 
 
 @pytest.mark.parametrize("M,K,N", [(128, 64, 64), (1000, 320, 320), (258, 640, 1280), (4096, 1280, 160), (2, 320, 1280),

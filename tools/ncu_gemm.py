@@ -16,6 +16,9 @@ elif case == "ff2":
     a = torch.randn(M, 1280, device=dev).half(); w = torch.randn(320, 1280, device=dev).half() * 0.03
     r = torch.randn(M, 320, device=dev)
     f = lambda: ops.gemm_f16(a, w, res1=r, out_dtype=torch.float32)
+elif case == "conv":
+    a = torch.randn(2, 14, 72, 128, 320, device=dev).half(); w = torch.randn(320, 9 * 320, device=dev).half() * 0.02
+    f = lambda: ops.gemm_f16(a, w, taps=ops.CONV3x3_TAPS)
 elif case == "attn":
     qkv = torch.randn(28 * 9216, 960, device=dev).half()
     f = lambda: ops.spatial_attention(qkv, 28, 9216, 5)
