@@ -1698,7 +1698,7 @@ spatial_attn7_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
       // ===================== TMA producer =====================
-      if (lane == 0) {
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
         tma_load_3d(&tmap, base + kA7OffQ, q_full, head * kD, q0, frame);
         tma_load_3d(&tmap, base + kA7OffQ + kTileBytes, q_full, head * kD, q0 + kBQ, frame);
@@ -1706,7 +1706,7 @@ spatial_attn7_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % kA7Stages;
         mbar_wait(kv_empty(st), ((j / kA7Stages) & 1) ^ 1u);
-        if (lane == 0) {
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(kv_full(st), 2 * kTileBytes);
           tma_load_3d(&tmap, base + kA7OffK + st * kTileBytes, kv_full(st), C + head * kD, j * kBKV, frame);
           tma_load_3d(&tmap, base + kA7OffV + st * kTileBytes, kv_full(st), 2 * C + head * kD, j * kBKV, frame);
@@ -1716,7 +1716,7 @@ spatial_attn7_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
     } else if (warp == 1 || warp == 2) {
       // ===================== MMA issuers: warp 1 drives group A, warp 2 drives group B (event driven) =====================
       const int g = warp - 1;
-      if (lane == 0 && (g == 0 || b_active)) {
+      if (elect_one_sync() && (g == 0 || b_active)) {
         const uint32_t idesc_s = make_idesc_f16(kBQ, kBKV, 0, 0, 0);
         const uint32_t idesc_o = make_idesc_f16(kBQ, kD, 0, 0, 1);
         const uint64_t dq = make_desc_k_sw128(base + kA7OffQ + g * kTileBytes);
@@ -1955,7 +1955,7 @@ spatial_attn8_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
         tma_load_3d(&tmap, base + kA7OffQ, q_full, head * kD, q0, frame);
         tma_load_3d(&tmap, base + kA7OffQ + kTileBytes, q_full, head * kD, q0 + kBQ, frame);
@@ -1963,7 +1963,7 @@ spatial_attn8_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % kA7Stages;
         mbar_wait(kv_empty(st), ((j / kA7Stages) & 1) ^ 1u);
-        if (lane == 0) {
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(kv_full(st), 2 * kTileBytes);
           tma_load_3d(&tmap, base + kA7OffK + st * kTileBytes, kv_full(st), C + head * kD, j * kBKV, frame);
           tma_load_3d(&tmap, base + kA7OffV + st * kTileBytes, kv_full(st), 2 * C + head * kD, j * kBKV, frame);
@@ -1972,7 +1972,7 @@ spatial_attn8_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
       }
     } else if (warp == 1 || warp == 2) {
       const int g = warp - 1;
-      if (lane == 0 && (g == 0 || b_active)) {
+      if (elect_one_sync() && (g == 0 || b_active)) {
         const uint32_t idesc_s = make_idesc_f16(kBQ, kBKV, 0, 0, 0);
         const uint32_t idesc_o = make_idesc_f16(kBQ, kD, 0, 0, 1);
         const uint64_t dq = make_desc_k_sw128(base + kA7OffQ + g * kTileBytes);

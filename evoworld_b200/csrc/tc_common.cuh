@@ -14,6 +14,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One thread of the (converged) warp: elect.sync lets ptxas prove that what follows runs on a single lane, so the uniform-
+// register operands of tcgen05.mma / commit need no per-value "waterfall" loop (ELECT + R2UR.BROADCAST + BRA.U.ANY per MMA,
+// ~125 SASS instructions per 64-wide k-block with `if (lane == 0)`: the issuing warp, not the tensor pipe, set the pace).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

@@ -264,7 +264,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
         const int cx = x0 + P.tap_dx[tap], cy = y0 + P.tap_dy[tap], ct = tt + P.tap_dt[tap];
         for (int kc = 0; kc < P.chunks[src]; ++kc, ++kglob) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          if (lane == 0) {
+          if (elect_one_sync()) {
             const uint32_t sa = smem_base + stage * stage_bytes;
             mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
             tma_load_5d(ma, sa, full_bar(stage), kc * kBlockK, cx, cy, ct, tb);
@@ -294,10 +294,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
       for (int kc = 0; kc < total_chunks; ++kc) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint64_t da = make_desc_k_sw128(sa);
-          const uint64_t db = make_desc_k_sw128(sa + kATileBytes);
+        const uint32_t sa = smem_base + stage * stage_bytes;
+        const uint64_t da = make_desc_k_sw128(sa);
+        const uint64_t db = make_desc_k_sw128(sa + kATileBytes);
+        if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k)
             umma_f16_ss(d_tmem, da + 2ull * k, db + 2ull * k, idesc, (kc | k) != 0);
