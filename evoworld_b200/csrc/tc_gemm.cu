@@ -613,11 +613,15 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   return EVW_OK;
 }
 
-static int g_gemm_cluster = -1;  // -1: EVW_GEMM_CLUSTER (default on)
+// -1: EVW_GEMM_CLUSTER, default OFF.  Measured on B200 (profiles/r01f_gemm_bench.log): the cluster / weight-multicast launch
+// is bit-identical and within +-3 % of the plain launch on every UNet shape — the 160-wide tiles are bound by the
+// shared-memory data pipe (tensor-core operand reads + TMA writes), which multicast does not relieve — so the simpler
+// launch stays the default and the mode is kept for the parity tests and further work (cta_group::2).
+static int g_gemm_cluster = -1;
 int gemm_cluster_mode() {
   if (g_gemm_cluster < 0) {
     const char* e = getenv("EVW_GEMM_CLUSTER");
-    g_gemm_cluster = (e && atoi(e) == 0) ? 0 : 1;
+    g_gemm_cluster = (e && atoi(e) != 0) ? 1 : 0;
   }
   return g_gemm_cluster;
 }

@@ -169,7 +169,7 @@ int evw_gemm_f16(const void* a0, const void* a1, const void* w, int B, int T, in
                  const float* res2, float s2, float s0, int geglu, int block_n, void* stream);
 
 /* Launch mode of the GEMM (takes effect when an op is planned): 1 = clusters of two CTAs on m-adjacent tiles sharing each
- * weight tile through TMA multicast (default), 0 = independent CTAs, -1 = restore the default / EVW_GEMM_CLUSTER. */
+ * weight tile through TMA multicast, 0 = independent CTAs (default), -1 = restore the default / EVW_GEMM_CLUSTER. */
 void evw_set_gemm_cluster(int on);
 
 /* Spatial self-attention (BasicTransformerBlock.attn1 -> F.scaled_dot_product_attention, head dim 64):
