@@ -292,7 +292,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default="auto", choices=["auto", "denoise", "reproj"])
-    ap.add_argument("--views-per-pass", type=int, default=4, choices=[1, 2, 4, 8])
+    ap.add_argument("--views-per-pass", type=int, default=2, choices=[1, 2, 4, 8])
     ap.add_argument("--frames", type=int, default=14)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

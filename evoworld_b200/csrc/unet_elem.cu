@@ -11,6 +11,7 @@
 #include "common.h"
 #include "unet_elem.h"
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace evw {
 namespace {
@@ -519,6 +520,169 @@ __global__ void add_f32_kernel(const float* __restrict__ a, const float* __restr
   if (i < n) out[i] = a[i] + b[i];
 }
 
+// ------------------------------------------------------------------------------------------
+// Temporal self-attention, tensor-core version: one warp per (b, s, head) problem.  The T x 64 q/k/v tiles are staged
+// in shared memory with coalesced 16-byte loads (144-byte row pitch: conflict-free fragment reads), S = Q K^T and
+// O = P V run on mma.sync.m16n8k16 (fp16 in, fp32 accumulate) with the score fragments re-used in registers as the
+// A operand of P V, the softmax reduces over the 4 lanes that share a row.  T = 14 frames cannot fill a 128-row tcgen05
+// tile (8 problems would have to be packed block-diagonally, 8x wasted MMA work), and at ~100 instructions per problem the
+// kernel is bound by its 4 x T x 128 bytes of HBM traffic instead of by 3500 scalar instructions per lane (v1: 0.44 ms at
+// 2 x 14 x 9216 x 5 heads = 1.5 TB/s).
+// ------------------------------------------------------------------------------------------
+constexpr int kTmWarps = 4;
+constexpr int kTmPitch = 72;  // halves per shared-memory row (64 + 8 pad)
+
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int MT>  // 16-frame tiles: 1 (T <= 16) or 2 (T <= 32)
+__global__ void __launch_bounds__(kTmWarps * 32)
+temporal_attn_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int Bn, int T, long long S, int heads,
+                         float scale_log2e) {
+  constexpr int R = 16 * MT;
+  extern __shared__ __align__(16) __half ta_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long nprob = (long long)Bn * S * heads;
+  const long long prob = (long long)blockIdx.x * kTmWarps + warp;
+  if (prob >= nprob) return;  // warps are independent: no block-level barrier below
+  __half* sq = ta_smem + (size_t)warp * 3 * R * kTmPitch;
+  __half* sk = sq + R * kTmPitch;
+  __half* sv = sk + R * kTmPitch;
+  const int h = (int)(prob % heads);
+  const long long bs = prob / heads;
+  const long long s = bs % S, b = bs / S;
+  const int C = heads * 64;
+  const long long ld = 3LL * C;
+  // stage q, k, v: 8 lanes x 16 bytes per row, 4 rows per trip; rows >= T are zero (P = 0 times garbage must stay 0)
+  for (int t = lane >> 3; t < R; t += 4) {
+    uint4 q4 = make_uint4(0, 0, 0, 0), k4 = q4, v4 = q4;
+    if (t < T) {
+      const __half* base = qkv + (((long long)b * T + t) * S + s) * ld + h * 64 + (lane & 7) * 8;
+      q4 = __ldg(reinterpret_cast<const uint4*>(base));
+      k4 = __ldg(reinterpret_cast<const uint4*>(base + C));
+      v4 = __ldg(reinterpret_cast<const uint4*>(base + 2 * C));
+    }
+    const int o = t * kTmPitch + (lane & 7) * 8;
+    *reinterpret_cast<uint4*>(sq + o) = q4;
+    *reinterpret_cast<uint4*>(sk + o) = k4;
+    *reinterpret_cast<uint4*>(sv + o) = v4;
+  }
+  __syncwarp();
+  const int g = lane >> 2, tig = lane & 3;
+  // ---- S = Q K^T
+  float sacc[MT][2 * MT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2 * MT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sacc[mt][nt][i] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int d0 = 16 * ks + 2 * tig;
+    uint32_t a[MT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const __half* r0 = sq + (16 * mt + g) * kTmPitch + d0;
+      const __half* r1 = r0 + 8 * kTmPitch;
+      a[mt][0] = *reinterpret_cast<const uint32_t*>(r0);
+      a[mt][1] = *reinterpret_cast<const uint32_t*>(r1);
+      a[mt][2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
+      a[mt][3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 2 * MT; ++nt) {
+      const __half* kr = sk + (8 * nt + g) * kTmPitch + d0;
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr), b1 = *reinterpret_cast<const uint32_t*>(kr + 8);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) mma_16816(sacc[mt][nt], a[mt], b0, b1);
+    }
+  }
+  // ---- softmax over the key frames of each row (rows 16 mt + g and + 8; a row lives in the 4 lanes of a quad)
+  float inv[MT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 2 * MT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = 8 * nt + 2 * tig + e;
+          float v = sacc[mt][nt][2 * hf + e];
+          v = j < T ? v : -INFINITY;
+          sacc[mt][nt][2 * hf + e] = v;
+          mx = fmaxf(mx, v);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 2 * MT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float pv = exp2f((sacc[mt][nt][2 * hf + e] - mx) * scale_log2e);  // exp2(-inf) = 0 for masked frames
+          sacc[mt][nt][2 * hf + e] = pv;
+          sum += pv;
+        }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      inv[mt][hf] = 1.0f / sum;
+    }
+  // ---- O = P V: the score fragments are the A fragments of the second product
+  float oacc[MT][8][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) oacc[mt][nt][i] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < MT; ++kt) {
+    uint32_t pa[MT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      __half2 h0 = __floats2half2_rn(sacc[mt][2 * kt][0], sacc[mt][2 * kt][1]);
+      __half2 h1 = __floats2half2_rn(sacc[mt][2 * kt][2], sacc[mt][2 * kt][3]);
+      __half2 h2 = __floats2half2_rn(sacc[mt][2 * kt + 1][0], sacc[mt][2 * kt + 1][1]);
+      __half2 h3 = __floats2half2_rn(sacc[mt][2 * kt + 1][2], sacc[mt][2 * kt + 1][3]);
+      pa[mt][0] = *reinterpret_cast<uint32_t*>(&h0);
+      pa[mt][1] = *reinterpret_cast<uint32_t*>(&h1);
+      pa[mt][2] = *reinterpret_cast<uint32_t*>(&h2);
+      pa[mt][3] = *reinterpret_cast<uint32_t*>(&h3);
+    }
+    const uint32_t vrow = (uint32_t)__cvta_generic_to_shared(sv + (16 * kt + (lane & 15)) * kTmPitch);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      uint32_t b0, b1;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(vrow + nt * 16));
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) mma_16816(oacc[mt][nt], pa[mt], b0, b1);
+    }
+  }
+  // ---- normalise, stage through the (now free) q tile, store 16 bytes per lane
+  __syncwarp();
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      __half2 lo = __floats2half2_rn(oacc[mt][nt][0] * inv[mt][0], oacc[mt][nt][1] * inv[mt][0]);
+      __half2 hi = __floats2half2_rn(oacc[mt][nt][2] * inv[mt][1], oacc[mt][nt][3] * inv[mt][1]);
+      *reinterpret_cast<__half2*>(sq + (16 * mt + g) * kTmPitch + 8 * nt + 2 * tig) = lo;
+      *reinterpret_cast<__half2*>(sq + (16 * mt + g + 8) * kTmPitch + 8 * nt + 2 * tig) = hi;
+    }
+  __syncwarp();
+  for (int t = lane >> 3; t < T; t += 4) {
+    const uint4 v = *reinterpret_cast<const uint4*>(sq + t * kTmPitch + (lane & 7) * 8);
+    *reinterpret_cast<uint4*>(out + (((long long)b * T + t) * S + s) * C + h * 64 + (lane & 7) * 8) = v;
+  }
+}
+
 inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 }  // namespace
@@ -597,6 +761,22 @@ int temporal_attention(const __half* qkv, __half* out, int B, int T, long long S
   EVW_CHECK_ARG(T >= 1 && T <= 32, "temporal_attention: T=%d must be in [1,32]", T);
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // head dim 64
   const long long nprob = (long long)B * S * heads;
+  static const bool use_v1 = getenv("EVW_TEMPORAL_ATTN_V1") != nullptr;  // scalar kernel, A/B timing only
+  if (!use_v1) {
+    static bool attr_set = false;
+    constexpr int smem1 = kTmWarps * 3 * 16 * kTmPitch * 2, smem2 = kTmWarps * 3 * 32 * kTmPitch * 2;
+    if (!attr_set) {
+      EVW_CUDA(cudaFuncSetAttribute(temporal_attn_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      attr_set = true;
+    }
+    const unsigned grid = (unsigned)((nprob + kTmWarps - 1) / kTmWarps);
+    if (T <= 16)
+      temporal_attn_mma_kernel<1><<<grid, kTmWarps * 32, smem1, st>>>(qkv, out, B, T, S, heads, scale_log2e);
+    else
+      temporal_attn_mma_kernel<2><<<grid, kTmWarps * 32, smem2, st>>>(qkv, out, B, T, S, heads, scale_log2e);
+    EVW_LAUNCH_CHECK();
+    return EVW_OK;
+  }
   if (T <= 16) {
     const long long per_block = kTaWarps * 2;
     temporal_attn_kernel<16><<<(unsigned)((nprob + per_block - 1) / per_block), kTaWarps * 32, 0, st>>>(

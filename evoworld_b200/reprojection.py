@@ -43,7 +43,7 @@ FACE_ORDER = tuple(CUBEMAP_TRANSFORMS.keys())  # z-buffer / lookup-table face nu
 FACE_RES = 512          # reproject_vggt_open3d_utils.py:617,636
 PANO_W, PANO_H = 2000, 1000  # :705
 Z_NEAR = 1e-6           # near plane of the point pass
-DEFAULT_VIEWS_PER_PASS = 4
+DEFAULT_VIEWS_PER_PASS = 2  # 0.54 ms per 24-view set vs 0.57 (G=4) and 0.65 (G=8) with the two-stream pipeline (profiles/r01g_reproj_bench.log)
 DEFAULT_PRETEST = os.environ.get("EVW_SPLAT_PRETEST", "0") != "0"  # read the cell before the 64-bit atomic min (slower on B200)
 DEFAULT_OVERLAP = os.environ.get("EVW_SPLAT_OVERLAP", "1") != "0"  # two-stream pass pipeline (include/evoworld_b200.h)
 DEFAULT_V1_KERNELS = os.environ.get("EVW_SPLAT_V1", "0") != "0"    # first-generation kernels, A/B timing only
