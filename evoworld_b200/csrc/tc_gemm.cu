@@ -27,8 +27,10 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // fp16 elements = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
-constexpr int kThreads = 384;        // 4 control warps + 8 epilogue warps
-constexpr int kEpiWarps = 8;
+constexpr int kCtrlThreads = 128;    // 4 control warps (TMA, MMA, TMEM allocator, spare)
+// epilogue warps: 8 by default; 16 for the GEGLU layers, whose epilogue (exact erf GELU, ~26 instructions per output) is
+// issue-bound with two warps per SM sub-partition (ncu: issue slots 59 % busy, tensor pipe 45 % at K = 320)
+constexpr int kEpiWarpsDefault = 8, kEpiWarpsGeglu = 16;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 
 struct KernelParams {
@@ -184,8 +186,8 @@ __device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t mask)
                : "memory");
 }
 
-template <bool kCluster>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool kCluster, int kEpiWarps>
+__global__ void __launch_bounds__(kCtrlThreads + 32 * kEpiWarps, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
                const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_bh,
                const __grid_constant__ KernelParams P) {
@@ -243,6 +245,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
   int total_chunks = 0;
   for (int t = 0; t < P.num_taps; ++t) total_chunks += P.chunks[P.tap_src[t]];
 
+  if (kEpiWarps > 8) {
+    // 640 threads launch with <= 96 registers each; the control warpgroup hands registers to the epilogue warpgroups
+    // (4 x 32 x 56 + 512 x 104 = 60 416 <= 640 x 96)
+    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+  }
   if (warp == 0) {
     // ===================== TMA producer =====================
     int stage = 0;
@@ -376,7 +384,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
 
       const uint32_t t_addr = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
-      if (ep.geglu) {
+      if (kEpiWarps > 8 || ep.geglu) {  // the 16-warp instantiation is GEGLU-only: the other branch folds away
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         // 32 accumulator columns = [16 value | 16 gate] -> 16 outputs
@@ -626,16 +634,25 @@ int gemm_cluster_mode() {
   return g_gemm_cluster;
 }
 void set_gemm_cluster_mode(int on) { g_gemm_cluster = on < 0 ? -1 : (on ? 1 : 0); }
+static int gemm_geglu_wide_epilogue() {  // EVW_GEMM_GEGLU_WARPS=8 restores the 8-warp epilogue (A/B timing)
+  static const int wide = [] { const char* e = getenv("EVW_GEMM_GEGLU_WARPS"); return (e && atoi(e) == 8) ? 0 : 1; }();
+  return wide;
+}
 
 int gemm_launch(const GemmOp& op, cudaStream_t stream) {
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const KernelParams);
+  static const KernelFn fns[2][2] = {{tc_gemm_kernel<false, kEpiWarpsDefault>, tc_gemm_kernel<false, kEpiWarpsGeglu>},
+                                     {tc_gemm_kernel<true, kEpiWarpsDefault>, tc_gemm_kernel<true, kEpiWarpsGeglu>}};
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(tc_gemm_kernel): %s", cudaGetErrorString(e));
-      return EVW_ERR_CUDA;
-    }
+    for (int c = 0; c < 2; ++c)
+      for (int w = 0; w < 2; ++w) {
+        cudaError_t e = cudaFuncSetAttribute(fns[c][w], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) {
+          set_error("cudaFuncSetAttribute(tc_gemm_kernel): %s", cudaGetErrorString(e));
+          return EVW_ERR_CUDA;
+        }
+      }
     attr_set = true;
   }
   KernelParams P;
@@ -644,11 +661,14 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream) {
   const CUtensorMap& ta1 = *reinterpret_cast<const CUtensorMap*>(op.tmap_a1);
   const CUtensorMap& tb = *reinterpret_cast<const CUtensorMap*>(op.tmap_b);
   const CUtensorMap& tbh = *reinterpret_cast<const CUtensorMap*>(op.tmap_bh);
+  const int wide = (P.ep.geglu && gemm_geglu_wide_epilogue()) ? 1 : 0;
+  const int threads = kCtrlThreads + 32 * (wide ? kEpiWarpsGeglu : kEpiWarpsDefault);
+  KernelFn fn = fns[op.cluster ? 1 : 0][wide];
   cudaError_t e;
   if (op.cluster) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)op.grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3((unsigned)threads);
     cfg.dynamicSmemBytes = (size_t)op.smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -658,9 +678,9 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<true>, ta0, ta1, tb, tbh, P);
+    e = cudaLaunchKernelEx(&cfg, fn, ta0, ta1, tb, tbh, P);
   } else {
-    tc_gemm_kernel<false><<<op.grid, kThreads, op.smem_bytes, stream>>>(ta0, ta1, tb, tbh, P);
+    fn<<<op.grid, threads, op.smem_bytes, stream>>>(ta0, ta1, tb, tbh, P);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) {
