@@ -28,8 +28,8 @@ constexpr int kBlockK = 64;  // fp16 elements = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
 constexpr int kCtrlThreads = 128;    // 4 control warps (TMA, MMA, TMEM allocator, spare)
-// epilogue warps: 8 by default; 16 for the GEGLU layers, whose epilogue (exact erf GELU, ~26 instructions per output) is
-// issue-bound with two warps per SM sub-partition (ncu: issue slots 59 % busy, tensor pipe 45 % at K = 320)
+// epilogue warps: 8; a 16-warp instantiation exists for the GEGLU layers (exact erf GELU, ~26 instructions per output:
+// issue slots 59 % busy, tensor pipe 45 % at K = 320) but measured slower and is off by default
 constexpr int kEpiWarpsDefault = 8, kEpiWarpsGeglu = 16;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 
@@ -634,8 +634,10 @@ int gemm_cluster_mode() {
   return g_gemm_cluster;
 }
 void set_gemm_cluster_mode(int on) { g_gemm_cluster = on < 0 ? -1 : (on ? 1 : 0); }
-static int gemm_geglu_wide_epilogue() {  // EVW_GEMM_GEGLU_WARPS=8 restores the 8-warp epilogue (A/B timing)
-  static const int wide = [] { const char* e = getenv("EVW_GEMM_GEGLU_WARPS"); return (e && atoi(e) == 8) ? 0 : 1; }();
+// EVW_GEMM_GEGLU_WARPS=16 selects the 16-warp GEGLU epilogue.  Measured slower than 8 warps (0.554 vs 0.514 ms at
+// 258048 x 2560 x 320, profiles/r01h_gemm_geglu_warps.log): the epilogue is bound by instruction count, not by latency.
+static int gemm_geglu_wide_epilogue() {
+  static const int wide = [] { const char* e = getenv("EVW_GEMM_GEGLU_WARPS"); return (e && atoi(e) == 16) ? 1 : 0; }();
   return wide;
 }
 
