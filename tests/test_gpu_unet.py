@@ -1,7 +1,10 @@
 """UNet forward / fused denoise step on the GPU against the fp32 PyTorch oracle (oracle/unet_torch.py)
-with identical weights and inputs.  Tolerance (north_star): relative L2 <= 1e-3 of the fp32 reference
-is the goal for the production shape; these tests assert the measured bound for fp16-operand /
-fp32-accumulate arithmetic and print the value."""
+with identical weights and inputs.  north_star asks for relative L2 <= 1e-3 of the fp32 reference (the reference
+runs its UNet in fp32: unified_loop_consistency.py:188).  With fp16 GEMM/attention operands, fp32 accumulation and
+an fp32 residual stream the measured error of one UNet forward is 1.04e-3 .. 1.15e-3 (profiles/r01f_unet_parity.log):
+the target is missed by 4-15 %, and the bound asserted here is TOL_UNET = 1.5e-3 — the measured figure plus margin,
+not the north-star figure.  One denoise step (CFG combine + Euler update of 700-sigma latents) is asserted at 1e-5
+(measured 4e-7 .. 1.3e-6)."""
 import math
 
 import pytest
@@ -11,6 +14,9 @@ from evoworld_b200.unet import UNetSpatioTemporalConditionModel
 from oracle import unet_torch as O
 
 pytestmark = pytest.mark.gpu
+
+TOL_UNET = 1.5e-3   # one UNet forward vs the fp32 oracle (see the module docstring)
+TOL_STEP = 1e-5     # latents after one fused denoise step vs the oracle's step
 
 SMALL = dict(in_channels=18, block_out_channels=(64, 128, 256, 256), num_attention_heads=(1, 2, 4, 4), cross_attention_dim=64)
 
@@ -55,7 +61,7 @@ def test_unet_forward_small_config(B, T, h, w, cuda_device, built_lib):
     err = rel_l2(got, want)
     print(f"unet small {B}x{T}x{h}x{w}: rel L2 = {err:.3e}")
     assert torch.isfinite(got).all()
-    assert err < 3e-3
+    assert err < TOL_UNET
     # return_dict path and determinism
     again = ours(x, torch.tensor(t), ehs, ids).sample
     assert torch.equal(again, got)
@@ -82,7 +88,7 @@ def test_denoise_step_small_config(cuda_device, built_lib):
         ours.denoise_step(x, cond, s, sn, ehs, ids, 1.0, 3.0)
         err = rel_l2(x, x_ref)
         print(f"denoise step {i}: sigma {s:.2f} -> {sn:.2f} rel L2 = {err:.3e}")
-        assert err < 3e-3
+        assert err < TOL_STEP
 
 
 def test_unet_forward_full_width(cuda_device, built_lib):
@@ -102,7 +108,7 @@ def test_unet_forward_full_width(cuda_device, built_lib):
     got = ours(x, 1.1, ehs, ids).sample
     err = rel_l2(got, want)
     print(f"unet full width: rel L2 = {err:.3e}")
-    assert err < 3e-3
+    assert err < TOL_UNET
     launches, flops = ours.plan_info()
     assert launches > 500 and flops > 0
 
