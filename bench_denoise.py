@@ -102,7 +102,7 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
         "metric": "denoise-steps/sec", "unit": "steps/s", "value": steps_per_s, "ms_per_step": ms / args.steps, "dtype": "fp16",
         "e2e": {"value": world * args.steps / e2e_s, "unit": "steps/s",
                 "h2d_bytes_per_step": lat_p.numel() * 4 + cond_p.numel() * 4, "d2h_bytes_per_step": out_p.numel() * 4},
-        "roofline": {"bound": "tensor", "kernel": "whole denoise step (tc_gemm_kernel + spatial_attn_kernel dominate)",
+        "roofline": {"bound": "tensor", "kernel": "whole denoise step (tc_gemm_kernel + spatial_attn8_kernel dominate; per-kernel figures under kernels)",
                      "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
                      "traffic": None, "algorithmic_tflop_per_step": fl, "executed_tflop_per_step": plan_flops / 1e12,
                      "kernels": kernels,
