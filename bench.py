@@ -294,6 +294,8 @@ def main():
     ap.add_argument("--path", default="auto", choices=["auto", "denoise", "reproj"])
     ap.add_argument("--views-per-pass", type=int, default=2, choices=[1, 2, 4, 8])
     ap.add_argument("--frames", type=int, default=14)
+    ap.add_argument("--pano-height", type=int, default=576, help="panorama height in pixels (latents = /8); 1024 for BASELINE config 5")
+    ap.add_argument("--pano-width", type=int, default=1024, help="panorama width in pixels; 2048 for BASELINE config 5")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -42,7 +42,8 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
     from evoworld_b200.scheduler import EulerDiscreteScheduler
     from evoworld_b200.unet import UNetSpatioTemporalConditionModel, algorithmic_flops, DEFAULT_CONFIG
 
-    T, h, w = args.frames, LAT_H, LAT_W
+    T = args.frames
+    h, w = getattr(args, "pano_height", 576) // 8, getattr(args, "pano_width", 1024) // 8
     unet = UNetSpatioTemporalConditionModel(**UNET_CFG).init_random(seed=0, device=dev)
     unet._ensure_handle()
     unet.free_master_parameters()
@@ -108,7 +109,7 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
                      "kernels": kernels,
                      "peak_source": peaks["source"] + " (sustained bf16/fp16 dense)"},
         "gpu_launches": launches * args.steps,
-        "config": {"workload": f"config 2: single 576x1024x{T}f clip, CFG batch 2, 72x128 latents, random-init 1.525B-param UNet, "
+        "config": {"workload": f"config 2: single {8 * h}x{8 * w}x{T}f clip, CFG batch 2, {h}x{w} latents, random-init 1.525B-param UNet, "
                                f"Karras sigmas (25-step schedule)", "frames": T, "finite_output": finite,
                    "collective": f"all-gather of latents {tuple(gathered.shape)} at the clip boundary",
                    "l2": "working set (activations + 3 GB of fp16 weights) >> 126 MB L2; K steps in one CUDA-event pair"},

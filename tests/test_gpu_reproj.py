@@ -226,6 +226,26 @@ def test_predictions_to_target_view_end_to_end(tmp_path, cuda_device, built_lib)
     assert scale > 0
 
 
+def test_pinned_host_buffers_give_the_same_panoramas(tmp_path, cuda_device, built_lib):
+    """The end-to-end bench path: page-locked torch predictions in, the renderer's page-locked buffer out
+    (CubemapRenderer(pinned_output=True)) — byte-identical to the numpy-in / fresh-array-out default."""
+    p = synthetic.reprojection_predictions(S=25, H=28, W=42, seed=5)
+    pts = O.unproject_depth_map_to_point_map(p["depth"], p["extrinsic"], p["intrinsic"])
+    preds = dict(world_points_from_depth=pts, depth_conf=p["depth_conf"], images=p["images"], extrinsic=p["extrinsic"])
+    want = R.predictions_to_target_view(preds, p["camera_pose"], conf_thres=50.0, prediction_mode="Depthmap and Camera Branch",
+                                        num_target_view=3, outdir=str(tmp_path / "a_0"))
+    pinned = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in preds.items() if k != "extrinsic"}
+    pinned["extrinsic"] = p["extrinsic"]
+    cr = R.CubemapRenderer(pinned_output=True)
+    got = R.predictions_to_target_view(pinned, p["camera_pose"], conf_thres=50.0, prediction_mode="Depthmap and Camera Branch",
+                                       num_target_view=3, outdir=str(tmp_path / "b_0"), cubemap_renderer=cr)
+    np.testing.assert_array_equal(got, want)
+    again = R.predictions_to_target_view(pinned, p["camera_pose"], conf_thres=50.0, prediction_mode="Depthmap and Camera Branch",
+                                         num_target_view=3, outdir=str(tmp_path / "c_0"), cubemap_renderer=cr)
+    assert again.ctypes.data == got.ctypes.data  # the page-locked buffer is reused (documented aliasing)
+    np.testing.assert_array_equal(again, want)
+
+
 def test_full_size_properties(cuda_device, built_lib):
     """BASELINE config-3 size (S=25 x 392x518 -> ~2.54 M points, 24 views, 512^2 faces, 2000x1000):
     size-independent properties — views-per-pass invariance, idempotence, subset consistency, and a
