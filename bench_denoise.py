@@ -109,7 +109,7 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
                      "kernels": kernels,
                      "peak_source": peaks["source"] + " (sustained bf16/fp16 dense)"},
         "gpu_launches": launches * args.steps,
-        "config": {"workload": f"config 2: single {8 * h}x{8 * w}x{T}f clip, CFG batch 2, {h}x{w} latents, random-init 1.525B-param UNet, "
+        "config": {"workload": f"{'config 2' if (h, w) == (LAT_H, LAT_W) else 'config 5 panorama size'}: single {8 * h}x{8 * w}x{T}f clip, CFG batch 2, {h}x{w} latents, random-init 1.525B-param UNet, "
                                f"Karras sigmas (25-step schedule)", "frames": T, "finite_output": finite,
                    "collective": f"all-gather of latents {tuple(gathered.shape)} at the clip boundary",
                    "l2": "working set (activations + 3 GB of fp16 weights) >> 126 MB L2; K steps in one CUDA-event pair"},
