@@ -37,6 +37,27 @@ def pix2dir_matrix(yaw: float, pitch: float, roll: float, height: int, width: in
     return (Rz @ Ry @ Rx) @ G @ np.linalg.inv(K)
 
 
+def pix2dir_matrices(rots, height: int, width: int, fov_x: float, skew: float = 0.0, z_down: bool = False) -> np.ndarray:
+    """Batched pix2dir_matrix: one [B,3,3] float64 array for a list of rotation dicts (same expression order per
+    element, so every matrix equals the scalar function's bit for bit); avoids B small numpy products per call."""
+    B = len(rots)
+    yaw = np.array([r.get("yaw", 0.0) for r in rots], dtype=np.float64)
+    pitch = np.array([r.get("pitch", 0.0) for r in rots], dtype=np.float64)
+    roll = np.array([r.get("roll", 0.0) for r in rots], dtype=np.float64)
+    if not z_down:
+        pitch, yaw = -pitch, -yaw
+    f = width / (2.0 * math.tan(math.radians(fov_x) / 2.0))
+    K = np.array([[f, skew, width / 2.0], [0.0, f, height / 2.0], [0.0, 0.0, 1.0]], dtype=np.float64)
+    G = np.array([[0.0, 0.0, 1.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0]], dtype=np.float64)
+    Kinv = np.linalg.inv(K)
+    one, zero = np.ones(B), np.zeros(B)
+    cr, sr, cp, sp, cy, sy = np.cos(roll), np.sin(roll), np.cos(pitch), np.sin(pitch), np.cos(yaw), np.sin(yaw)
+    Rx = np.stack([one, zero, zero, zero, cr, -sr, zero, sr, cr], axis=1).reshape(B, 3, 3)
+    Ry = np.stack([cp, zero, sp, zero, one, zero, -sp, zero, cp], axis=1).reshape(B, 3, 3)
+    Rz = np.stack([cy, -sy, zero, sy, cy, zero, zero, zero, one], axis=1).reshape(B, 3, 3)
+    return (((Rz @ Ry) @ Rx) @ G) @ Kinv  # same association as pix2dir_matrix
+
+
 class Equi2Pers:
     """Callable with pyequilib's constructor/`__call__` signature; uint8 bilinear only (the
     configuration EvoWorld uses).  Accepts numpy (host) or torch CUDA `equi`; returns the same kind."""
@@ -63,9 +84,7 @@ class Equi2Pers:
         dev = t.device if t.is_cuda else self.device
         t = t.to(dev, non_blocking=True).contiguous()
         B, C, He, We = t.shape
-        mats = np.stack([
-            pix2dir_matrix(r.get("yaw", 0.0), r.get("pitch", 0.0), r.get("roll", 0.0), self.height, self.width,
-                           self.fov_x, self.skew, self.z_down) for r in rots]).astype(np.float32)
+        mats = pix2dir_matrices(rots, self.height, self.width, self.fov_x, self.skew, self.z_down).astype(np.float32)
         m = torch.from_numpy(mats.reshape(B, 9)).to(dev)
         out = torch.empty((B, C, self.height, self.width), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):

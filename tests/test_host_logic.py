@@ -140,3 +140,19 @@ def test_missing_confidence_defaults_to_ones():
     c = np.full((2, 3, 4), 2.0, dtype=np.float32)
     _, conf2 = pp._extract_point_data({"world_points_from_depth": pts, "depth_conf": c}, "x")
     assert conf2 is c
+
+
+def test_pix2dir_matrices_batched_equals_scalar():
+    """The batched matrix builder used by Equi2Pers.__call__ is the scalar restatement, element for element."""
+    from evoworld_b200.equi2pers import pix2dir_matrices
+
+    rng = np.random.default_rng(0)
+    rots = [{"yaw": float(rng.uniform(-4, 4)), "pitch": float(rng.uniform(-1, 1)), "roll": float(rng.uniform(-1, 1))}
+            for _ in range(200)] + [{"yaw": 0.3}, {}]
+    got = pix2dir_matrices(rots, 384, 512, 90.0)
+    want = np.stack([pix2dir_matrix(r.get("yaw", 0.0), r.get("pitch", 0.0), r.get("roll", 0.0), 384, 512, 90.0) for r in rots])
+    np.testing.assert_array_equal(got, want)
+    got_zd = pix2dir_matrices(rots[:5], 96, 128, 70.0, skew=0.1, z_down=True)
+    want_zd = np.stack([pix2dir_matrix(r.get("yaw", 0.0), r.get("pitch", 0.0), r.get("roll", 0.0), 96, 128, 70.0, 0.1, True)
+                        for r in rots[:5]])
+    np.testing.assert_array_equal(got_zd, want_zd)
