@@ -3,14 +3,24 @@
 //   diffusers attention_processor.py AttnProcessor2_0 as used by BasicTransformerBlock.attn1:
 //   softmax(Q K^T / sqrt(64)) V per (frame, head) over S = h*w tokens.
 //
-// One CTA per (128-query tile, head, frame); 192 threads:
-//   warp 0      TMA producer   Q once, then a 3-stage ring of (K_j, V_j) 128x64 tiles (3-D tensor map over
-//                              the fused qkv buffer [F*S, 3C]; rows past S are zero-filled)
-//   warp 1      MMA issuer     S_j = Q K_j^T   (M128 N128 K64)  -> TMEM (double buffered)
-//                              O_j = P_j V_j   (M128 N64  K128) -> TMEM (double buffered), P_j from smem
-//   warps 2..5  softmax        one query row per thread: tcgen05.ld S_j -> running max / sum in the log2
-//                              domain -> P_j (fp16) written to smem in the 128B-swizzled K-major layout;
-//                              O_{j-1} is folded into register accumulators while PV_j runs
+// Kernel generations in this file (all behind evw_spatial_attention_f16; evw_set_attention_variant / EVW_ATTN_* pick one,
+// tests/test_gpu_unet_ops.py::test_spatial_attention_variants checks every one against the same fp32 reference):
+//   v1  spatial_attn_kernel    128 queries per CTA, 4 softmax warps, P through shared memory            (EVW_ATTN_V1)
+//   v2  spatial_attn2_kernel   two 128-query groups per CTA sharing each K/V tile, setmaxnreg            (EVW_ATTN_V2)
+//   v3  spatial_attn3_kernel   O and row sums accumulate in tensor memory, lazy rescale                  (variant -1)
+//   v4  spatial_attn4_kernel   P aliased onto S in tensor memory (serialised S/PV chain: slower)         (EVW_ATTN_V4)
+//   v5  spatial_attn5_kernel   v3 + the two groups take turns on the MUFU pipe (named-barrier token)     (variants 0-4)
+//   v6  spatial_attn6_kernel   v3 + two threads per query row (16 softmax warps)                         (variants 5-8)
+//   v7  spatial_attn7_kernel   P in its OWN tensor-memory columns, A operand of PV from TMEM, CUDA-core row sums (9-13)
+//   v8  spatial_attn8_kernel   v7 + two threads per query row — the DEFAULT (variant 14)
+// Measured at 28 frames x 9216 tokens x 5 heads (profiles/r01*_attn_bench*.log): v3 4.99 ms, v5 4.66, v6 4.62, v7 3.87,
+// v8 3.69 ms.  What moved the needle was taking P out of shared memory (v3-v6 saturate the shared-memory data pipe:
+// P written once and read twice per tile); v8 is bound by the MUFU pipe (77 % busy).
+//
+// Common structure: warp 0 = TMA producer (Q once, then a ring of (K_j, V_j) 128x64 tiles from the fused qkv buffer
+// [F*S, 3C] through a 3-D tensor map; rows past S are zero-filled), warps 1-2 = MMA issuers (S_j = Q K_j^T, M128 N128 K64;
+// O += P_j V_j, M128 N64 K128), remaining warps = softmax (one or two threads per query row: tcgen05.ld S_j -> running
+// max in the log2 domain -> P_j in fp16).
 #include "common.h"
 #include "tc_common.cuh"
 #include "unet_elem.h"
