@@ -7,11 +7,16 @@
 // accumulation in tensor memory.
 //
 //   warp 0      TMA producer: 5-D tiled loads of the activation tile (zero fill outside the image =
-//               the convolution padding) + 2-D loads of the weight tile, 128B swizzle, mbarrier ring
-//   warp 1      MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N (<=256), K=16 per instr.
+//               the convolution padding) + 2-D loads of the weight tile, 128B swizzle, mbarrier ring;
+//               issued under elect.sync
+//   warp 1      MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N (<=256), K=16 per instr.,
+//               issued under elect.sync (no uniform-operand waterfall: 65 SASS instructions per 64-wide k-block)
 //   warp 2      TMEM allocator (512 columns = two accumulator stages)
-//   warps 4..7  epilogue: tcgen05.ld -> bias / broadcast row vector / GEGLU / scaled residuals -> global
+//   warps 4..11 epilogue (8 warps; a 16-warp GEGLU-only instantiation exists, off by default):
+//               tcgen05.ld -> bias / broadcast row vector / GEGLU / scaled residuals -> global
 // The accumulator is double-buffered so the epilogue of tile i overlaps the main loop of tile i+1.
+// Optional launch mode (EVW_GEMM_CLUSTER=1): clusters of two CTAs on m-adjacent tiles share each weight tile
+// through TMA multicast; bit-identical, measured neutral, off by default.
 #include "common.h"
 #include "tc_common.cuh"
 #include "tc_gemm.h"
