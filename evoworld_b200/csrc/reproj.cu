@@ -576,8 +576,8 @@ __global__ void cube_gather_kernel(const uint8_t* __restrict__ faces, const uint
 // resolved x over y over z... exactly as coded below; keep z' > z_near; u = fmaf(f, x'/z', c) etc. as splat_one.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cube_splat_one(const float* __restrict__ m, float x, float y, float z, float focal, float c,
-                                               float z_near, int res, unsigned long long* __restrict__ zview, unsigned idx,
-                                               int pretest) {
+                                               float z_near, int res, unsigned long long* __restrict__ zview, unsigned low,
+                                               int pretest) {  // low = key bits 0..31: point index, or colour | index mod 256
   const float xc = fmaf(m[0], x, fmaf(m[1], y, fmaf(m[2], z, m[3])));
   const float yc = fmaf(m[4], x, fmaf(m[5], y, fmaf(m[6], z, m[7])));
   const float zc = fmaf(m[8], x, fmaf(m[9], y, fmaf(m[10], z, m[11])));
@@ -600,7 +600,7 @@ __device__ __forceinline__ void cube_splat_one(const float* __restrict__ m, floa
   const float fres = (float)res;
   if (!(u >= 0.f && u < fres && v >= 0.f && v < fres)) return;
   const int px = (int)floorf(u), py = (int)floorf(v);
-  const unsigned long long key = ((unsigned long long)__float_as_uint(fz) << 32) | idx;
+  const unsigned long long key = ((unsigned long long)__float_as_uint(fz) << 32) | low;
   unsigned long long* cell = zview + ((size_t)face * res + py) * res + px;
   if (!pretest || key < ld_relaxed_u64(cell)) atomicMin(cell, key);
 }
@@ -681,7 +681,7 @@ int splat_ctas_per_sm() {
 template <int G, int P>
 __global__ void __launch_bounds__(256)
 cube_splat2_kernel(const float4* __restrict__ pts, int64_t n_cap, const long long* __restrict__ n_dev,
-                   const float* __restrict__ w2c /*[G,12]*/, int res, float focal, float z_near, int pretest,
+                   const float* __restrict__ w2c /*[G,12]*/, int res, float focal, float z_near, int pretest, int color_key,
                    unsigned long long* __restrict__ zbuf /*[G,6,res,res]*/) {
   __shared__ __align__(16) float s_m[G * 12];
   for (int i = threadIdx.x; i < G * 12; i += blockDim.x) s_m[i] = w2c[i];
@@ -708,7 +708,10 @@ cube_splat2_kernel(const float4* __restrict__ pts, int64_t n_cap, const long lon
 #pragma unroll
       for (int k = 0; k < P; ++k) {
         const int64_t i = i0 + k * stride;
-        if (i < n) cube_splat_one(m, p[k].x, p[k].y, p[k].z, focal, c, z_near, res, zbuf + (size_t)g * view_sz, (unsigned)i, pretest);
+        // colour-key mode (EVW_SPLAT_COLOR_KEYS): the low key word is colour << 8 | index mod 256, so the resolve reads the
+        // colour out of the key instead of gathering it from the cloud
+        const unsigned low = color_key ? (((__float_as_uint(p[k].w) & 0xFFFFFFu) << 8) | ((unsigned)i & 0xFFu)) : (unsigned)i;
+        if (i < n) cube_splat_one(m, p[k].x, p[k].y, p[k].z, focal, c, z_near, res, zbuf + (size_t)g * view_sz, low, pretest);
       }
     }
   }
@@ -720,7 +723,7 @@ cube_splat2_kernel(const float4* __restrict__ pts, int64_t n_cap, const long lon
 template <int G>
 __global__ void __launch_bounds__(256)
 resolve_multi2_kernel(const unsigned long long* __restrict__ zbuf /*[G,6,res,res]*/, const float4* __restrict__ pts,
-                      const uint32_t* __restrict__ lut, int res, int64_t npix, int g_count,
+                      const uint32_t* __restrict__ lut, int res, int64_t npix, int g_count, int color_key,
                       uint8_t* __restrict__ out /*[G,npix,3]*/) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t p0 = q * 4;
@@ -740,15 +743,25 @@ resolve_multi2_kernel(const unsigned long long* __restrict__ zbuf /*[G,6,res,res
 #pragma unroll
     for (int j = 0; j < 4; ++j) key[g][j] = (g < g_count) ? zbuf[(size_t)g * view_sz + cell[j]] : kEmptyKey;
   uint32_t rgb[G][4];
+  if (color_key) {  // the colour travels in bits 8..31 of the key: no gather from the cloud
 #pragma unroll
-  for (int g = 0; g < G; ++g)
+    for (int g = 0; g < G; ++g)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const bool hit = key[g][j] != kEmptyKey && e[j] != 0xFFFFFFFFu;
-      const unsigned idx = hit ? (unsigned)(key[g][j] & 0xFFFFFFFFull) : 0u;
-      const uint32_t w = __float_as_uint(__ldg(&pts[idx].w));
-      rgb[g][j] = hit ? (w & 0xFFFFFFu) : 0u;
-    }
+      for (int j = 0; j < 4; ++j) {
+        const bool hit = key[g][j] != kEmptyKey && e[j] != 0xFFFFFFFFu;
+        rgb[g][j] = hit ? ((unsigned)(key[g][j] >> 8) & 0xFFFFFFu) : 0u;
+      }
+  } else {
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool hit = key[g][j] != kEmptyKey && e[j] != 0xFFFFFFFFu;
+        const unsigned idx = hit ? (unsigned)(key[g][j] & 0xFFFFFFFFull) : 0u;
+        const uint32_t w = __float_as_uint(__ldg(&pts[idx].w));
+        rgb[g][j] = hit ? (w & 0xFFFFFFu) : 0u;
+      }
+  }
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     if (g >= g_count) break;
@@ -764,6 +777,8 @@ int launch_cube_pass(const float4* pts, int64_t n_cap, const long long* n_dev, c
                      float z_near, int flags, unsigned long long* zbuf, const uint32_t* lut, int64_t npix, int g_count,
                      uint8_t* out, cudaStream_t st, int what = 3 /* bit 0: splat, bit 1: resolve */) {
   const int pretest = flags & EVW_SPLAT_PRETEST;
+  const int color_key = (flags & EVW_SPLAT_COLOR_KEYS) ? 1 : 0;
+  if (color_key) flags &= ~EVW_SPLAT_V1_KERNELS;  // the first-generation kernels only know index keys
   if (n_cap > 0 && (what & 1)) {
     if (flags & EVW_SPLAT_V1_KERNELS) {
       int64_t want = (n_cap + 255) / 256;
@@ -776,7 +791,7 @@ int launch_cube_pass(const float4* pts, int64_t n_cap, const long long* n_dev, c
       // resident CTAs per SM: < 8 leaves room for the neighbouring pass's resolve / clear to co-run (two-stream pipeline)
       int64_t cap = (int64_t)evw::sm_count() * ((flags & EVW_SPLAT_OVERLAP) ? splat_ctas_per_sm() : 8);
       cube_splat2_kernel<G, P><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(pts, n_cap, n_dev, w2c, res, focal,
-                                                                                      z_near, pretest, zbuf);
+                                                                                      z_near, pretest, color_key, zbuf);
     }
   }
   if (!(what & 2)) return 0;
@@ -784,7 +799,7 @@ int launch_cube_pass(const float4* pts, int64_t n_cap, const long long* n_dev, c
   if (flags & EVW_SPLAT_V1_KERNELS)
     resolve_multi_kernel<G><<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(zbuf, pts, lut, res, npix, g_count, out);
   else
-    resolve_multi2_kernel<G><<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(zbuf, pts, lut, res, npix, g_count, out);
+    resolve_multi2_kernel<G><<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(zbuf, pts, lut, res, npix, g_count, color_key, out);
   return 0;
 }
 

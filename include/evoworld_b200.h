@@ -117,10 +117,14 @@ int evw_splat_cubemap_equirect(const float* pts4, int64_t n_cap, const int64_t* 
  *                         gather-latency-bound resolve and its clear; the workspace must then hold
  *                         two passes: evw_splat_workspace_flags(views_per_pass, face_res, flags);
  *   EVW_SPLAT_V1_KERNELS  the first-generation kernels (one point per thread, dependent gathers) for A/B timing.
- * All flag combinations produce identical bytes. */
+ * All flag combinations except EVW_SPLAT_COLOR_KEYS produce identical bytes. */
 #define EVW_SPLAT_PRETEST 1
 #define EVW_SPLAT_OVERLAP 2
 #define EVW_SPLAT_V1_KERNELS 4
+#define EVW_SPLAT_COLOR_KEYS 16 /* OPTIONAL tie rule, off by default: the low key word carries colour << 8 | (index mod 256)
+                                  instead of the index, so the resolve needs no gather (faster).  Output identical to the
+                                  default unless two points of different colour have exactly the same float32 depth in one
+                                  cell: the default keeps the lowest index (draw order), this keeps the lowest packed colour */
 #define EVW_SPLAT_OVERLAP_BY_ROLE 8 /* with OVERLAP: one stream runs every splat, the other every clear + resolve (measured slower) */
 int64_t evw_splat_workspace_flags(int views_per_pass, int face_res, int flags);
 /* Tuning hook: resident splat CTAs per SM (1..8) while EVW_SPLAT_OVERLAP is set; fewer leaves SM slots for the

@@ -386,13 +386,16 @@ def front_w2c(target_c2w: np.ndarray) -> np.ndarray:
     return np.stack([np.linalg.inv(c)[:3, :4] for c in np.asarray(target_c2w, dtype=np.float64)]).astype(np.float32)
 
 
-def splat_keys_cube(pts4: np.ndarray, w2c_front: np.ndarray, res: int, focal: float, z_near: float) -> np.ndarray:
-    """Cube formulation (oracle_splat_keys_cube): one transform per (point, view), face = major axis."""
+def splat_keys_cube(pts4: np.ndarray, w2c_front: np.ndarray, res: int, focal: float, z_near: float,
+                    color_keys: bool = False) -> np.ndarray:
+    """Cube formulation (oracle_splat_keys_cube): one transform per (point, view), face = major axis.
+    color_keys: the low key word carries the packed colour instead of the point index (oracle_splat_keys_cube_colorkey)."""
     pts4 = np.ascontiguousarray(pts4, dtype=np.float32)
     w2c_front = np.ascontiguousarray(w2c_front, dtype=np.float32)
     V = w2c_front.shape[0]
     keys = np.empty((V, 6, res, res), dtype=np.uint64)
-    _clib().oracle_splat_keys_cube(
+    fn = _clib().oracle_splat_keys_cube_colorkey if color_keys else _clib().oracle_splat_keys_cube
+    fn(
         pts4.ctypes.data_as(C.c_void_p), C.c_int64(pts4.shape[0]), w2c_front.ctypes.data_as(C.c_void_p), C.c_int(V),
         C.c_int(res), C.c_float(focal), C.c_float(z_near), keys.ctypes.data_as(C.c_void_p))
     return keys
@@ -404,12 +407,16 @@ def keys_to_index(keys: np.ndarray) -> np.ndarray:
     return idx
 
 
-def resolve(keys: np.ndarray, pts4: np.ndarray, lut: np.ndarray) -> np.ndarray:
+def resolve(keys: np.ndarray, pts4: np.ndarray, lut: np.ndarray, color_keys: bool = False) -> np.ndarray:
     V, _, res, _ = keys.shape
     H, W = lut.shape
     out = np.empty((V, H, W, 3), dtype=np.uint8)
     lut = np.ascontiguousarray(lut, dtype=np.uint32)
     pts4 = np.ascontiguousarray(pts4, dtype=np.float32)
+    if color_keys:
+        _clib().oracle_resolve_colorkey(keys.ctypes.data_as(C.c_void_p), lut.ctypes.data_as(C.c_void_p), C.c_int(V), C.c_int(res),
+                                        C.c_int64(H * W), out.ctypes.data_as(C.c_void_p))
+        return out
     _clib().oracle_resolve(
         keys.ctypes.data_as(C.c_void_p), pts4.ctypes.data_as(C.c_void_p), lut.ctypes.data_as(C.c_void_p), C.c_int(V),
         C.c_int(res), C.c_int64(H * W), out.ctypes.data_as(C.c_void_p))
@@ -426,8 +433,9 @@ def render_panoramas(xyz: np.ndarray, rgb: np.ndarray, target_c2w: np.ndarray, r
 
 
 def render_panoramas_cube(xyz: np.ndarray, rgb: np.ndarray, target_c2w: np.ndarray, res: int = 512, width: int = 2000,
-                          height: int = 1000, z_near: float = 1e-6) -> np.ndarray:
-    """render_cubemaps_to_panoramas on the oracle, cube formulation (what the product's fast path computes)."""
+                          height: int = 1000, z_near: float = 1e-6, color_keys: bool = False) -> np.ndarray:
+    """render_cubemaps_to_panoramas on the oracle, cube formulation (what the product's fast path computes).
+    color_keys selects the colour-key tie rule of the optional EVW_SPLAT_COLOR_KEYS mode."""
     pts4 = pack_points(xyz, rgb)
-    keys = splat_keys_cube(pts4, front_w2c(target_c2w), res, res / 2.0, z_near)
-    return resolve(keys, pts4, cube_to_equirect_lut(width, height, res))
+    keys = splat_keys_cube(pts4, front_w2c(target_c2w), res, res / 2.0, z_near, color_keys)
+    return resolve(keys, pts4, cube_to_equirect_lut(width, height, res), color_keys)

@@ -52,8 +52,8 @@ void oracle_splat_keys(const float* pts4, int64_t n, const float* w2c, int V, in
  * the FRONT camera's w2c [V,12]; face = major axis, face-local coordinates = inv(T_face [Rz180]) applied exactly:
  *   front (x,y,z) | right (-z,y,x) | back (-x,y,-z) | left (z,y,-x) | top (-x,-z,-y) | bottom (-x,z,y)
  * (CUBEMAP_TRANSFORMS, reproject_vggt_open3d_utils.py:29-36; do_flip Rz(180) for top/bottom :619-622,652-655). */
-void oracle_splat_keys_cube(const float* pts4, int64_t n, const float* w2c_front, int V, int res, float focal,
-                            float z_near, uint64_t* keys) {
+static void splat_keys_cube_core(const float* pts4, int64_t n, const float* w2c_front, int V, int res, float focal,
+                                 float z_near, uint64_t* keys, int color_keys) {
   const float c = 0.5f * (float)res;
   const float fres = (float)res;
   const int64_t face_sz = (int64_t)res * res;
@@ -81,11 +81,27 @@ void oracle_splat_keys_cube(const float* pts4, int64_t n, const float* w2c_front
       float vv = fmaf(focal, fy / fz, c);
       if (!(u >= 0.f && u < fres && vv >= 0.f && vv < fres)) continue;
       int px = (int)floorf(u), py = (int)floorf(vv);
-      uint64_t key = ((uint64_t)f2u(fz) << 32) | (uint32_t)i;
+      /* low word: the point index (ties in depth -> lowest index), or — colour-key variant — the packed colour and
+       * the low 8 index bits (ties in depth -> lowest packed colour, then lowest index mod 256) */
+      const uint32_t low = color_keys ? (((f2u(pts4[i * 4 + 3]) & 0xFFFFFFu) << 8) | (uint32_t)(i & 0xFF)) : (uint32_t)i;
+      uint64_t key = ((uint64_t)f2u(fz) << 32) | low;
       uint64_t* cell = zv + ((int64_t)face * res + py) * res + px;
       if (key < *cell) *cell = key;
     }
   }
+}
+
+void oracle_splat_keys_cube(const float* pts4, int64_t n, const float* w2c_front, int V, int res, float focal,
+                            float z_near, uint64_t* keys) {
+  splat_keys_cube_core(pts4, n, w2c_front, V, res, focal, z_near, keys, 0);
+}
+
+/* Colour-key variant of the cube splat (EVW_SPLAT_COLOR_KEYS in include/evoworld_b200.h): same geometry, the key carries
+ * the colour so that the resolve needs no gather.  Identical panoramas unless two points of DIFFERENT colour have exactly
+ * the same float32 depth in the same cell. */
+void oracle_splat_keys_cube_colorkey(const float* pts4, int64_t n, const float* w2c_front, int V, int res, float focal,
+                                     float z_near, uint64_t* keys) {
+  splat_keys_cube_core(pts4, n, w2c_front, V, res, focal, z_near, keys, 1);
 }
 
 /* cube->equirect gather through the lookup table (reproject_vggt_open3d_utils.py:603-612):
@@ -104,6 +120,25 @@ void oracle_resolve(const uint64_t* keys, const float* pts4, const uint32_t* lut
       uint64_t key = keys[(int64_t)v * view_cells + ((int64_t)face * res + row) * res + col];
       if (key == UINT64_MAX) continue;
       uint32_t rgb = f2u(pts4[(key & 0xFFFFFFFFu) * 4 + 3]);
+      o[0] = rgb & 0xFF; o[1] = (rgb >> 8) & 0xFF; o[2] = (rgb >> 16) & 0xFF;
+    }
+  }
+}
+
+/* resolve for colour keys: the colour is bits 8..31 of the key */
+void oracle_resolve_colorkey(const uint64_t* keys, const uint32_t* lut, int V, int res, int64_t npix, uint8_t* out) {
+  const int64_t view_cells = (int64_t)6 * res * res;
+#pragma omp parallel for
+  for (int v = 0; v < V; ++v) {
+    for (int64_t p = 0; p < npix; ++p) {
+      uint8_t* o = out + ((int64_t)v * npix + p) * 3;
+      o[0] = o[1] = o[2] = 0;
+      uint32_t e = lut[p];
+      if (e == 0xFFFFFFFFu) continue;
+      uint32_t face = e >> 28, row = (e >> 14) & 0x3FFFu, col = e & 0x3FFFu;
+      uint64_t key = keys[(int64_t)v * view_cells + ((int64_t)face * res + row) * res + col];
+      if (key == UINT64_MAX) continue;
+      uint32_t rgb = (uint32_t)(key >> 8) & 0xFFFFFFu;
       o[0] = rgb & 0xFF; o[1] = (rgb >> 8) & 0xFF; o[2] = (rgb >> 16) & 0xFF;
     }
   }

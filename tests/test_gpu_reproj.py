@@ -317,6 +317,12 @@ def test_cube_fused_panoramas_bit_exact(G, cuda_device, built_lib):
         got = R.splat_to_panoramas_device(scene, w2c, 400, 200, res, G, pretest=pretest, overlap=overlap, v1_kernels=v1,
                                           by_role=by_role)
         np.testing.assert_array_equal(got.cpu().numpy(), want)
+    # optional colour-key tie rule (EVW_SPLAT_COLOR_KEYS): bit-exact against the oracle evaluated with the same rule
+    want_ck = O.render_panoramas_cube(xyz, rgb, cam, res=res, width=400, height=200, z_near=R.Z_NEAR, color_keys=True)
+    for overlap in (False, True):
+        got = R.splat_to_panoramas_device(scene, w2c, 400, 200, res, G, overlap=overlap, color_keys=True)
+        np.testing.assert_array_equal(got.cpu().numpy(), want_ck)
+    assert int((want_ck != want).any(-1).sum()) <= 8  # the two rules differ only where float32 depths tie exactly
     # a caller-provided workspace is reused across calls and passes: stale keys must never leak into a later view
     zb = torch.empty(R.splat_workspace_bytes(G, res, R.SPLAT_OVERLAP), dtype=torch.uint8, device=cuda_device)
     for _ in range(2):
