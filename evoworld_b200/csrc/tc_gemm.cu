@@ -50,20 +50,24 @@ struct KernelParams {
   int total_pairs;  // cluster mode: pairs of m-adjacent tiles sharing one weight tile (B multicast)
 };
 
-// exact-GELU 0.5 x (1 + erf(x / sqrt 2)) = max(x, 0) - |x| * 0.5 erfc(|x| / sqrt 2), branch free, with erfc from
-// Abramowitz-Stegun 7.1.26 (|abs err| < 4e-7, far below the fp16 rounding of the result): 2 MUFU + ~11 FMA-pipe
-// instructions per element — erff (and even IEEE 1/x) made the GEGLU epilogue slower than its main loop.
+// exact-GELU 0.5 x (1 + erf(x / sqrt 2)) = max(x, 0) - 0.5 |x| erfc(|x| / sqrt 2), branch free, with erfc from
+// Abramowitz-Stegun 7.1.26: erfc(z) = (a1 t + .. + a5 t^5) exp(-z^2), t = 1 / (1 + p z).  Since |x| = (1/t - 1) sqrt2 / p,
+// 0.5 |x| (a1 t + .. + a5 t^5) is itself a degree-5 polynomial B(t) = (sqrt2 / 2p) (1 - t) (a1 + a2 t + .. + a5 t^4), whose
+// coefficients are folded here: 2 MUFU + 10 FMA-pipe instructions per element (13 before the folding; erff, and even an IEEE
+// 1/x, made the GEGLU epilogue slower than its main loop).  |abs err| < 5e-7, relative L2 3e-8 against erf in float64
+// (tools/gelu_check.py) — far below the fp16 rounding of the result.
 __device__ __forceinline__ float gelu_erf(float x) {
   const float ax = fabsf(x);
   float t;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(ax, 0.3275911f * 0.70710678118654752f, 1.0f)));
-  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);  // 0.5 folded into the coefficients
-  p = fmaf(p, t, 0.5f * 1.421413741f);
-  p = fmaf(p, t, 0.5f * -0.284496736f);
-  p = fmaf(p, t, 0.5f * 0.254829592f);
+  float b = fmaf(-2.2910481280905266f, t, 5.427682952378112f);
+  b = fmaf(b, t, -6.204762423397693f);
+  b = fmaf(b, t, 3.6822150125075983f);
+  b = fmaf(b, t, -1.1641381704241662f);
+  b = fmaf(b, t, 0.5500507570266749f);
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170f));  // exp(-x^2 / 2)
-  return fmaf(-ax, p * t * e, fmaxf(x, 0.0f));
+  return fmaf(-b, e, fmaxf(x, 0.0f));
 }
 
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
@@ -385,7 +389,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
       const long long rv_row = ep.rowvec ? (row / ep.rv_div) % ep.rv_mod : 0;
       const int n0 = n_tile * P.block_n;
       float* bs = bias_s + acc * 256;
-      if (et < P.block_n) bs[et] = (ep.bias && n0 + et < P.N) ? __ldg(ep.bias + n0 + et) : 0.f;
+      if (et < P.block_n) {
+        float bv = (ep.bias && n0 + et < P.N) ? __ldg(ep.bias + n0 + et) : 0.f;
+        if ((kEpiWarps > 8 || ep.geglu) && (et & 16) == 0) bv *= ep.s0;  // GEGLU value columns: s0 folded into the bias
+        bs[et] = bv;
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
 
       const uint32_t t_addr = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
@@ -403,9 +411,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float hv = __uint_as_float(raw[i]) + bs[k * 32 + i];
+              const float hv = fmaf(__uint_as_float(raw[i]), ep.s0, bs[k * 32 + i]);  // s0 (value + bias)
               const float gv = __uint_as_float(raw[16 + i]) + bs[k * 32 + 16 + i];
-              v[i] = hv * gelu_erf(gv) * ep.s0;
+              v[i] = hv * gelu_erf(gv);
             }
             store16(ep, v, row * ldo + nh / 2, wide_ok);
           }
