@@ -171,7 +171,8 @@ struct Builder {
     const float* g = Wf(name + ".weight");
     const float* b = Wf(name + ".bias");
     double* st_ = stats;
-    push([=](cudaStream_t st) { return group_norm(src0, src0_fp16, C0, src1, C1, insts, rows, eps, g, b, silu, st_, out, raw, st); }, 4,
+    // 3 kernels (stats, finalize, apply); the statistics clear is a memset node and is not counted as a kernel launch
+    push([=](cudaStream_t st) { return group_norm(src0, src0_fp16, C0, src1, C1, insts, rows, eps, g, b, silu, st_, out, raw, st); }, 3,
          name, out, insts * rows * (C0 + C1), 1);
   }
   void lnorm(const float* x, const float* rowvec, long long rv_div, long long rv_mod, long long rows, int C,
