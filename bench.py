@@ -359,7 +359,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    if reproj is not None and not args.no_cpu_baseline:
+    if reproj is not None and not args.no_cpu_baseline and world == 1:  # the CPU baseline is an N = 1 figure (rank 0)
         reproj["cpu_baseline"] = run_reproj_cpu(REPROJ_CFG, views=4)
     primary = denoise if denoise is not None else reproj
     line = {

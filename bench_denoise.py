@@ -114,7 +114,7 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
                    "collective": f"all-gather of latents {tuple(gathered.shape)} at the clip boundary",
                    "l2": "working set (activations + 3 GB of fp16 weights) >> 126 MB L2; K steps in one CUDA-event pair"},
     }
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # the CPU baseline is an N = 1 figure
         res["cpu_baseline"] = run_cpu(T, steps=1)
     return res
 
