@@ -297,6 +297,7 @@ def main():
     ap.add_argument("--pano-height", type=int, default=576, help="panorama height in pixels (latents = /8); 1024 for BASELINE config 5")
     ap.add_argument("--pano-width", type=int, default=1024, help="panorama width in pixels; 2048 for BASELINE config 5")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager (cuDNN/cuBLAS/SDPA) leg on the GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -371,6 +372,8 @@ def main():
     }
     if "cpu_baseline" in primary:
         line["cpu_baseline"] = primary["cpu_baseline"]
+    if "gpu_eager_baseline" in primary:
+        line["gpu_eager_baseline"] = primary["gpu_eager_baseline"]
     if denoise is not None and reproj is not None:
         line["reproj"] = reproj
     print(json.dumps(line))

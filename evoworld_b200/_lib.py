@@ -35,13 +35,13 @@ SIGNATURES = {
     "evw_cube_to_equirect_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "evw_gemm_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              C.c_char_p, c_void_p, c_int, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_int, c_float,
-                             c_void_p, c_float, c_float, c_int, c_int, c_void_p]),
+                             c_void_p, c_float, c_float, c_int, c_int, c_void_p, c_void_p]),
     "evw_spatial_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "evw_set_attention_variant": (None, [c_int]),
     "evw_set_gemm_cluster": (None, [c_int]),
     "evw_temporal_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_i64, c_int, c_void_p]),
     "evw_group_norm_f16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_i64, c_i64, c_float, c_void_p, c_void_p,
-                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "evw_layer_norm_f16": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_float, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
     "evw_unet_create": (c_int, [C.POINTER(c_void_p), C.POINTER(c_int), c_int, C.POINTER(c_float), c_int,

@@ -25,7 +25,7 @@ int sm_count() {
 }  // namespace evw
 
 extern "C" const char* evw_last_error(void) { return evw::g_err; }
-extern "C" int evw_abi_version(void) { return 1; }
+extern "C" int evw_abi_version(void) { return 2; }
 extern "C" int evw_device_info(int* sm, int64_t* l2, int* cc) {
   int dev = 0, v = 0, maj = 0, min = 0;
   EVW_CUDA(cudaGetDevice(&dev));

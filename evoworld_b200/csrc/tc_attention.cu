@@ -2262,9 +2262,9 @@ extern "C" int evw_temporal_attention_f16(const void* qkv, void* out, int B, int
 }
 extern "C" int evw_group_norm_f16(const void* src0, int src0_fp16, int C0, const float* src1, int C1, int64_t insts,
                                   int64_t rows_per_inst, float eps, const float* gamma, const float* beta, int do_silu,
-                                  void* stats_ws, void* out, void* raw_out, void* stream) {
+                                  void* stats_ws, void* out, void* raw_out, void* out_lo, void* stream) {
   return evw::group_norm(src0, src0_fp16, C0, src1, C1, insts, rows_per_inst, eps, gamma, beta, do_silu, (double*)stats_ws,
-                         (__half*)out, (__half*)raw_out, (cudaStream_t)stream);
+                         (__half*)out, (__half*)raw_out, (__half*)out_lo, (cudaStream_t)stream);
 }
 extern "C" int evw_layer_norm_f16(const float* x, const float* rowvec, int64_t rv_div, int64_t rv_mod, int64_t rows, int C,
                                   float eps, const float* gamma, const float* beta, void* out, void* stream) {

@@ -154,6 +154,21 @@ __device__ __forceinline__ void store16(const GemmEpilogue& ep, const float (&v)
       *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
       *reinterpret_cast<uint4*>(p + 8) = make_uint4(w[4], w[5], w[6], w[7]);
     }
+    if (ep.out_lo) {  // split-precision operand: the fp16 tail carries the rounding error of the head
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 hd = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        __half2 t = __floats2half2_rn(v[2 * i] - hd.x, v[2 * i + 1] - hd.y);
+        w[i] = *reinterpret_cast<uint32_t*>(&t);
+      }
+      __half* pl = reinterpret_cast<__half*>(ep.out_lo) + off;
+      if (wide_ok && ((reinterpret_cast<uintptr_t>(ep.out_lo) & 31) == 0)) {
+        st_global_256(pl, w);
+      } else {
+        *reinterpret_cast<uint4*>(pl) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(pl + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    }
   } else {
     float* p = reinterpret_cast<float*>(ep.out) + off;
     if (wide_ok) {
@@ -574,6 +589,8 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   }
   EVW_CHECK_ARG(bn % 16 == 0 && bn >= 16 && bn <= 256, "gemm: BLOCK_N=%d invalid", bn);
   EVW_CHECK_ARG(!pr.ep.geglu || (bn % 32 == 0 && pr.N % 32 == 0), "gemm: GEGLU needs N and BLOCK_N multiples of 32");
+  EVW_CHECK_ARG(!pr.ep.out_lo || (pr.ep.out_fp16 && !pr.ep.geglu && pr.N % 16 == 0 && ((uintptr_t)pr.ep.out_lo & 15) == 0),
+                "gemm: out_lo needs an fp16, non-GEGLU output with N a multiple of 16");
   P.block_n = bn;
   P.n_tiles = (pr.N + bn - 1) / bn;
   P.num_taps = pr.num_taps;
@@ -716,7 +733,7 @@ extern "C" int evw_gemm_f16(const void* a0, const void* a1, const void* w, int B
                             int N, int num_taps, const int8_t* h_taps /*[num_taps,4] dx,dy,dt,src*/, void* out,
                             int out_fp16, const float* bias, const float* rowvec, int64_t rv_div, int64_t rv_mod,
                             const void* res1, int res1_fp16, float s1, const float* res2, float s2, float s0, int geglu,
-                            int block_n, void* stream) {
+                            int block_n, void* out_lo, void* stream) {
   evw::GemmProblem pr{};
   pr.a0 = a0; pr.a1 = a1; pr.w = w;
   pr.B = B; pr.T = T; pr.Y = Y; pr.X = X; pr.C0 = C0; pr.C1 = C1; pr.N = N;
@@ -730,7 +747,7 @@ extern "C" int evw_gemm_f16(const void* a0, const void* a1, const void* w, int B
   }
   pr.K_total = ktot;
   pr.block_n = block_n;
-  pr.ep.out = out; pr.ep.out_fp16 = out_fp16; pr.ep.bias = bias; pr.ep.rowvec = rowvec;
+  pr.ep.out = out; pr.ep.out_fp16 = out_fp16; pr.ep.out_lo = out_lo; pr.ep.bias = bias; pr.ep.rowvec = rowvec;
   pr.ep.rv_div = rv_div > 0 ? rv_div : 1; pr.ep.rv_mod = rv_mod > 0 ? rv_mod : 1;
   pr.ep.res1 = res1; pr.ep.res1_fp16 = res1_fp16; pr.ep.s1 = s1; pr.ep.res2 = res2; pr.ep.s2 = s2; pr.ep.s0 = s0;
   pr.ep.geglu = geglu;

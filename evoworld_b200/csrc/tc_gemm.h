@@ -6,7 +6,7 @@
 
 namespace evw {
 
-constexpr int kMaxTaps = 12;
+constexpr int kMaxTaps = 20;  // 3x3 conv with split-precision activations: 9 head taps + 9 tail taps
 
 // out[row, n] = s0 * (acc + bias[n]) + rowvec[((row / rv_div) % rv_mod) * rv_ld + n] + s1 * res1[row, n] + s2 * res2[row, n]
 // geglu: acc columns come in interleaved [16 value | 16 gate] groups, out has N/2 columns:
@@ -14,6 +14,8 @@ constexpr int kMaxTaps = 12;
 struct GemmEpilogue {
   void* out = nullptr;
   int out_fp16 = 1;
+  void* out_lo = nullptr;  // optional (fp16 output only): fp16 tail  half(v - float(half(v)))  of every stored value, same
+                           // layout as out — the consumer of a split-precision operand reads head and tail as two sources
   const float* bias = nullptr;
   const float* rowvec = nullptr;
   long long rv_div = 1, rv_mod = 1;
@@ -50,7 +52,7 @@ struct alignas(64) GemmOp {
   alignas(64) unsigned char tmap_a1[128];
   alignas(64) unsigned char tmap_b[128];
   alignas(64) unsigned char tmap_bh[128];  // half-height weight box (cluster mode: one half per CTA, multicast to the pair)
-  unsigned char params[256];
+  unsigned char params[384];
   int grid = 0;
   int cluster = 0;  // 1: launch as clusters of two CTAs sharing each weight tile (TMA multicast)
   int smem_bytes = 0;

@@ -120,7 +120,7 @@ template <typename T0, int U>
 __global__ void __launch_bounds__(320)
 gn_apply_kernel(const T0* __restrict__ src0, int C0, const float* __restrict__ src1, int C1, long long rows_per_inst,
                 int rows_per_block, const float2* __restrict__ ab, int do_silu, __half* __restrict__ out,
-                __half* __restrict__ raw_out) {
+                __half* __restrict__ raw_out, __half* __restrict__ out_lo) {
   const int C = C0 + C1;
   const int cv = C / 8;
   const int tc = threadIdx.x % cv, tr = threadIdx.x / cv, R = blockDim.x / cv;
@@ -178,6 +178,16 @@ gn_apply_kernel(const T0* __restrict__ src0, int C0, const float* __restrict__ s
 #pragma unroll
       for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
       *reinterpret_cast<uint4*>(out + row * C + c) = raw;
+      if (out_lo) {  // split-precision consumer: fp16 tail = rounding error of the head
+        uint4 rl;
+        __half2* hl = reinterpret_cast<__half2*>(&rl);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 hd = __half22float2(h[i]);
+          hl[i] = __floats2half2_rn(o[2 * i] - hd.x, o[2 * i + 1] - hd.y);
+        }
+        *reinterpret_cast<uint4*>(out_lo + row * C + c) = rl;
+      }
     }
   }
 }
@@ -430,44 +440,58 @@ __global__ void downsplit_kernel(const float* __restrict__ x, __half* __restrict
 // pre: latents [1,T,4,h,w] fp32 (NCHW per frame) / sqrt(sigma^2+1), duplicated for CFG, concatenated
 // with cond [2,T,Cc,h,w] -> fp16 channels-last [2*T, h, w, Cpad] (zero padded to Cpad)
 // ------------------------------------------------------------------------------------------
+// split != 0 (needs 3 Cin <= Cpad): the zero padding of conv_in's 64-channel operand carries the split-precision form of
+// the input for free — channels [0,Cin) = fp16 head, [Cin,2Cin) = fp16 tail (x - head), [2Cin,3Cin) = head again, against
+// conv_in weights packed as [W_hi | W_hi | W_lo] (evoworld_b200/unet.py::pack_parameters).
+__device__ __forceinline__ void put_split(__half* o, int c, int Cin, int split, float v) {
+  const __half hd = __float2half_rn(v);
+  o[c] = hd;
+  if (split) {
+    o[Cin + c] = __float2half_rn(v - __half2float(hd));
+    o[2 * Cin + c] = hd;
+  }
+}
 __global__ void pre_kernel(const float* __restrict__ latents, const float* __restrict__ cond, int Bc, int T, int Cl,
-                           int Cc, long long HW, float inv_scale, int Cpad, __half* __restrict__ out) {
+                           int Cc, long long HW, float inv_scale, int Cpad, int split, __half* __restrict__ out) {
   const long long total = (long long)Bc * T * HW;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const long long p = idx % HW;
   const long long f = idx / HW;  // frame in the CFG batch: b*T + t
   const int t = (int)(f % T);
+  const int Cin = Cl + Cc;
   __half* o = out + idx * Cpad;
-  for (int c = 0; c < Cl; ++c) o[c] = __float2half_rn(latents[((long long)t * Cl + c) * HW + p] * inv_scale);
-  for (int c = 0; c < Cc; ++c) o[Cl + c] = __float2half_rn(cond[(f * Cc + c) * HW + p]);
-  for (int c = Cl + Cc; c < Cpad; ++c) o[c] = __float2half_rn(0.f);
+  for (int c = 0; c < Cl; ++c) put_split(o, c, Cin, split, latents[((long long)t * Cl + c) * HW + p] * inv_scale);
+  for (int c = 0; c < Cc; ++c) put_split(o, Cl + c, Cin, split, cond[(f * Cc + c) * HW + p]);
+  for (int c = (split ? 3 : 1) * Cin; c < Cpad; ++c) o[c] = __float2half_rn(0.f);
 }
 
 // raw sample [B,T,Cin,h,w] fp32 -> fp16 channels-last padded (UNet.forward called on its own)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, long long frames, int Cin, long long HW, int Cpad,
-                                    __half* __restrict__ out) {
+                                    int split, __half* __restrict__ out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= frames * HW) return;
   const long long p = idx % HW, f = idx / HW;
   __half* o = out + idx * Cpad;
-  for (int c = 0; c < Cin; ++c) o[c] = __float2half_rn(x[(f * Cin + c) * HW + p]);
-  for (int c = Cin; c < Cpad; ++c) o[c] = __float2half_rn(0.f);
+  for (int c = 0; c < Cin; ++c) put_split(o, c, Cin, split, x[(f * Cin + c) * HW + p]);
+  for (int c = (split ? 3 : 1) * Cin; c < Cpad; ++c) o[c] = __float2half_rn(0.f);
 }
 
 // model output fp32 channels-last [2*T, h, w, Npad] -> NCHW [B,T,Co,h,w]
-__global__ void nhwc_to_nchw_kernel(const float* __restrict__ y, long long frames, int Co, long long HW, int Npad,
+// fold != 0: conv_out ran in split precision with the weight tail packed into the padded output columns
+// (rows [Co, 2Co) of the weight matrix = W_lo), so the result is y[c] + y[Co + c]
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ y, long long frames, int Co, long long HW, int Npad, int fold,
                                     float* __restrict__ out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= frames * HW) return;
   const long long p = idx % HW, f = idx / HW;
-  for (int c = 0; c < Co; ++c) out[(f * Co + c) * HW + p] = y[idx * Npad + c];
+  for (int c = 0; c < Co; ++c) out[(f * Co + c) * HW + p] = y[idx * Npad + c] + (fold ? y[idx * Npad + Co + c] : 0.f);
 }
 
 // post: CFG combine + Euler (v-prediction) step on NCHW latents, reading the channels-last model output
 //   v = vu + g_t (vc - vu);  x0 = v * (-sigma / sqrt(sigma^2+1)) + x / (sigma^2+1);  d = (x - x0)/sigma;
 //   x' = x + d (sigma_next - sigma)
-__global__ void post_kernel(const float* __restrict__ y, int T, int Cl, long long HW, int Npad, float sigma,
+__global__ void post_kernel(const float* __restrict__ y, int T, int Cl, long long HW, int Npad, int fold, float sigma,
                             float sigma_next, float g_min, float g_max, float* __restrict__ latents) {
   const long long total = (long long)T * HW;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -480,7 +504,7 @@ __global__ void post_kernel(const float* __restrict__ y, int T, int Cl, long lon
   const float* yu = y + idx * Npad;
   const float* yc = y + ((long long)T * HW + idx) * Npad;
   for (int c = 0; c < Cl; ++c) {
-    const float vu = yu[c], vc = yc[c];
+    const float vu = yu[c] + (fold ? yu[Cl + c] : 0.f), vc = yc[c] + (fold ? yc[Cl + c] : 0.f);
     const float v = vu + g * (vc - vu);
     float* lp = latents + ((long long)t * Cl + c) * HW + p;
     const float x = *lp;
@@ -692,7 +716,7 @@ inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + th
 // ==========================================================================================
 int group_norm(const void* src0, int src0_fp16, int C0, const float* src1, int C1, long long insts,
                long long rows_per_inst, float eps, const float* gamma, const float* beta, int do_silu, double* stats,
-               __half* out, __half* raw_out, cudaStream_t st) {
+               __half* out, __half* raw_out, __half* out_lo, cudaStream_t st) {
   const int C = C0 + C1, groups = 32;
   EVW_CHECK_ARG(C % groups == 0 && C % 8 == 0 && C0 % 8 == 0, "group_norm: C=%d (C0=%d) not supported", C, C0);
   const int Q = C / 4;
@@ -731,10 +755,10 @@ int group_norm(const void* src0, int src0_fp16, int C0, const float* src1, int C
     dim3 agrid((unsigned)((rows_per_inst + arpb - 1) / arpb), (unsigned)insts);
     if (src0_fp16)
       gn_apply_kernel<__half, UA><<<agrid, athreads, 0, st>>>((const __half*)src0, C0, src1, C1, rows_per_inst, arpb, ab, do_silu,
-                                                               out, raw_out);
+                                                               out, raw_out, out_lo);
     else
       gn_apply_kernel<float, UA><<<agrid, athreads, 0, st>>>((const float*)src0, C0, src1, C1, rows_per_inst, arpb, ab, do_silu,
-                                                              out, raw_out);
+                                                              out, raw_out, out_lo);
   }
   EVW_LAUNCH_CHECK();
   return EVW_OK;
@@ -803,25 +827,29 @@ int downsplit(const float* x, __half* out, long long n, int h, int w, int C, cud
   return EVW_OK;
 }
 int pre_concat(const float* latents, const float* cond, int Bc, int T, int Cl, int Cc, long long HW, float sigma, int Cpad,
-               __half* out, cudaStream_t st) {
+               int split, __half* out, cudaStream_t st) {
+  EVW_CHECK_ARG(!split || 3 * (Cl + Cc) <= Cpad, "pre_concat: split needs 3 Cin <= Cpad");
   const float inv = 1.0f / sqrtf(sigma * sigma + 1.0f);
-  pre_kernel<<<blocks_for((long long)Bc * T * HW, 256), 256, 0, st>>>(latents, cond, Bc, T, Cl, Cc, HW, inv, Cpad, out);
+  pre_kernel<<<blocks_for((long long)Bc * T * HW, 256), 256, 0, st>>>(latents, cond, Bc, T, Cl, Cc, HW, inv, Cpad, split, out);
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }
-int nchw_to_nhwc_f16(const float* x, long long frames, int Cin, long long HW, int Cpad, __half* out, cudaStream_t st) {
-  nchw_to_nhwc_kernel<<<blocks_for(frames * HW, 256), 256, 0, st>>>(x, frames, Cin, HW, Cpad, out);
+int nchw_to_nhwc_f16(const float* x, long long frames, int Cin, long long HW, int Cpad, int split, __half* out, cudaStream_t st) {
+  EVW_CHECK_ARG(!split || 3 * Cin <= Cpad, "nchw_to_nhwc_f16: split needs 3 Cin <= Cpad");
+  nchw_to_nhwc_kernel<<<blocks_for(frames * HW, 256), 256, 0, st>>>(x, frames, Cin, HW, Cpad, split, out);
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }
-int nhwc_to_nchw_f32(const float* y, long long frames, int Co, long long HW, int Npad, float* out, cudaStream_t st) {
-  nhwc_to_nchw_kernel<<<blocks_for(frames * HW, 256), 256, 0, st>>>(y, frames, Co, HW, Npad, out);
+int nhwc_to_nchw_f32(const float* y, long long frames, int Co, long long HW, int Npad, int fold, float* out, cudaStream_t st) {
+  EVW_CHECK_ARG(!fold || 2 * Co <= Npad, "nhwc_to_nchw_f32: fold needs 2 Co <= Npad");
+  nhwc_to_nchw_kernel<<<blocks_for(frames * HW, 256), 256, 0, st>>>(y, frames, Co, HW, Npad, fold, out);
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }
-int post_cfg_euler(const float* y, int T, int Cl, long long HW, int Npad, float sigma, float sigma_next, float g_min,
+int post_cfg_euler(const float* y, int T, int Cl, long long HW, int Npad, int fold, float sigma, float sigma_next, float g_min,
                    float g_max, float* latents, cudaStream_t st) {
-  post_kernel<<<blocks_for((long long)T * HW, 256), 256, 0, st>>>(y, T, Cl, HW, Npad, sigma, sigma_next, g_min, g_max, latents);
+  EVW_CHECK_ARG(!fold || 2 * Cl <= Npad, "post_cfg_euler: fold needs 2 Cl <= Npad");
+  post_kernel<<<blocks_for((long long)T * HW, 256), 256, 0, st>>>(y, T, Cl, HW, Npad, fold, sigma, sigma_next, g_min, g_max, latents);
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }

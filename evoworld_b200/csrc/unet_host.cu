@@ -33,6 +33,11 @@ struct Config {
   int cin_pad = 64, cout_pad = 16;
   int temb_total = 0, xattn_total = 0;
   float eps_cross = 1e-6f, eps_plain = 1e-5f, eps_mid = 1e-5f, eps_up = 1e-6f;
+  // split precision (scalar "precision.split", set by unet.py::pack_parameters which also packs the matching weights):
+  // the low-FLOP layers that dominate the fp16 rounding error of the step (tools/precision_sim.py: conv_in, conv_out,
+  // proj_in, proj_out and the fp16 storage of the spatial conv1 output = 0.75 of the error variance, < 4 % of the FLOPs)
+  // take their operands as fp16 head + fp16 tail and keep conv1's output in fp32
+  int split = 0;
 };
 
 using Op = std::function<int(cudaStream_t)>;
@@ -99,7 +104,7 @@ struct Builder {
   long long lS[4], lM[4];
   // shared scratch
   __half *n16 = nullptr, *raw16 = nullptr, *h16 = nullptr, *qkv16 = nullptr, *attn16 = nullptr, *ff16 = nullptr, *in16 = nullptr,
-         *resamp16 = nullptr, *small16 = nullptr;
+         *resamp16 = nullptr, *small16 = nullptr, *lo16 = nullptr;
   float *f0 = nullptr, *f1 = nullptr, *f2 = nullptr, *pp[2] = {nullptr, nullptr}, *y32 = nullptr;
   float *emb = nullptr, *emb2 = nullptr, *temb_all = nullptr, *xattn_all = nullptr, *tsteps = nullptr;
   double* stats = nullptr;
@@ -166,13 +171,24 @@ struct Builder {
     pr.ep = ep;
     gemm(pr, wname);
   }
+  // split-precision linear: (a_hi + a_lo) (W_hi + W_lo)^T without the tail x tail term, as three taps
+  // [a_hi | a_lo | a_hi] x [W_hi | W_hi | W_lo] (weight [N, 3K], packed by unet.py)
+  void linear_split(const __half* a_hi, const __half* a_lo, long long M, int K, const std::string& wname, int N, GemmEpilogue ep) {
+    GemmProblem pr;
+    pr.a0 = a_hi; pr.a1 = a_lo; pr.w = W(wname + ".weight");
+    pr.X = (int)M; pr.C0 = K; pr.C1 = K; pr.N = N; pr.K_total = 3LL * K; pr.num_taps = 3;
+    pr.tap_src[0] = 0; pr.tap_src[1] = 1; pr.tap_src[2] = 0;
+    ep.bias = Wf(wname + ".bias");
+    pr.ep = ep;
+    gemm(pr, wname);
+  }
   void gnorm(const void* src0, int src0_fp16, int C0, const float* src1, int C1, long long insts, long long rows, float eps,
-             const std::string& name, int silu, __half* out, __half* raw) {
+             const std::string& name, int silu, __half* out, __half* raw, __half* out_lo = nullptr) {
     const float* g = Wf(name + ".weight");
     const float* b = Wf(name + ".bias");
     double* st_ = stats;
     // 3 kernels (stats, finalize, apply); the statistics clear is a memset node and is not counted as a kernel launch
-    push([=](cudaStream_t st) { return group_norm(src0, src0_fp16, C0, src1, C1, insts, rows, eps, g, b, silu, st_, out, raw, st); }, 3,
+    push([=](cudaStream_t st) { return group_norm(src0, src0_fp16, C0, src1, C1, insts, rows, eps, g, b, silu, st_, out, raw, out_lo, st); }, 3,
          name, out, insts * rows * (C0 + C1), 1);
   }
   void lnorm(const float* x, const float* rowvec, long long rv_div, long long rv_mod, long long rows, int C,
@@ -196,12 +212,16 @@ struct Builder {
       pr.a0 = n16; pr.w = W(sp + ".conv1.weight");
       pr.B = 1; pr.T = BF; pr.Y = lh[lvl]; pr.X = lw[lvl]; pr.C0 = Cin; pr.N = Cout; pr.K_total = 9LL * Cin;
       taps_conv3x3(pr);
-      pr.ep.out = h16; pr.ep.out_fp16 = 1; pr.ep.bias = Wf(sp + ".conv1.bias");
+      // split precision: the conv1 output feeds GroupNorm statistics and stays fp32 (f0 is free inside a res block)
+      if (U.cfg.split) { pr.ep.out = f0; pr.ep.out_fp16 = 0; }
+      else { pr.ep.out = h16; pr.ep.out_fp16 = 1; }
+      pr.ep.bias = Wf(sp + ".conv1.bias");
       pr.ep.rowvec = temb_all + (long long)Sc(sp + ".time_emb_proj.offset");
       pr.ep.rv_ld = U.cfg.temb_total; pr.ep.rv_div = (long long)T * S; pr.ep.rv_mod = B;
       gemm(pr, sp + ".conv1");
     }
-    gnorm(h16, 1, Cout, nullptr, 0, BF, S, eps, sp + ".norm2", 1, n16, nullptr);
+    if (U.cfg.split) gnorm(f0, 0, Cout, nullptr, 0, BF, S, eps, sp + ".norm2", 1, n16, nullptr);
+    else gnorm(h16, 1, Cout, nullptr, 0, BF, S, eps, sp + ".norm2", 1, n16, nullptr);
     {
       GemmProblem pr;
       pr.a0 = n16; pr.w = W(sp + ".conv2.weight");
@@ -258,8 +278,10 @@ struct Builder {
     auto ep_f32 = [](float* o) { GemmEpilogue e; e.out = o; e.out_fp16 = 0; return e; };
     auto ep_f16 = [](__half* o) { GemmEpilogue e; e.out = o; e.out_fp16 = 1; return e; };
 
-    gnorm(x, 0, C, nullptr, 0, BF, S, 1e-6f, pre + ".norm", 0, n16, nullptr);
-    linear(n16, M, C, pre + ".proj_in", C, ep_f32(f0));
+    const bool split = U.cfg.split != 0;
+    gnorm(x, 0, C, nullptr, 0, BF, S, 1e-6f, pre + ".norm", 0, n16, nullptr, split ? lo16 : nullptr);
+    if (split) linear_split(n16, lo16, M, C, pre + ".proj_in", C, ep_f32(f0));
+    else linear(n16, M, C, pre + ".proj_in", C, ep_f32(f0));
     // --- spatial block
     lnorm(f0, nullptr, 1, 1, M, C, sb + ".norm1", n16);
     linear(n16, M, C, sb + ".attn1.qkv", 3 * C, ep_f16(qkv16), false);
@@ -319,12 +341,14 @@ struct Builder {
       // time_mixer: alpha x_s + (1 - alpha)(y + ff(y))  -> fp16 operand of proj_out
       GemmEpilogue ep = ep_f16(n16);
       ep.s0 = 1.f - alpha; ep.res1 = f1; ep.s1 = 1.f - alpha; ep.res2 = f0; ep.s2 = alpha;
+      if (split) ep.out_lo = lo16;
       linear(ff16, M, 4 * C, tb + ".ff.net.2", C, ep);
     }
     {
       GemmEpilogue ep = ep_f32(out);
       ep.res1 = x;
-      linear(n16, M, C, pre + ".proj_out", C, ep);
+      if (split) linear_split(n16, lo16, M, C, pre + ".proj_out", C, ep);
+      else linear(n16, M, C, pre + ".proj_out", C, ep);
     }
   }
 
@@ -358,6 +382,7 @@ struct Builder {
     n16 = bump.take<__half>(maxMCin);
     raw16 = bump.take<__half>(maxMCin);
     h16 = bump.take<__half>(maxMC);
+    if (c.split) lo16 = bump.take<__half>(maxMC);  // fp16 tails of the split-precision operands
     qkv16 = bump.take<__half>(3 * maxMC);
     attn16 = bump.take<__half>(maxMC);
     ff16 = bump.take<__half>(4 * maxMC);
@@ -384,11 +409,11 @@ struct Builder {
     const long long HW = lS[0];
     // ---- inputs -> fp16 channels-last, padded to 64 channels
     {
-      __half* o = in16; int Cin = c.in_channels, Cpad = c.cin_pad, T_ = T, B_ = B;
+      __half* o = in16; int Cin = c.in_channels, Cpad = c.cin_pad, T_ = T, B_ = B, sp_ = c.split;
       push([=](cudaStream_t st) {
         const CallArgs& a = u->args;
-        if (a.mode == 1) return pre_concat(a.latents, a.cond, B_, T_, 4, Cin - 4, HW, a.sigma, Cpad, o, st);
-        return nchw_to_nhwc_f16(a.sample, (long long)B_ * T_, Cin, HW, Cpad, o, st);
+        if (a.mode == 1) return pre_concat(a.latents, a.cond, B_, T_, 4, Cin - 4, HW, a.sigma, Cpad, sp_, o, st);
+        return nchw_to_nhwc_f16(a.sample, (long long)B_ * T_, Cin, HW, Cpad, sp_, o, st);
       }, 1, "pre (scale+concat+layout)");
     }
     // ---- time / added-id embeddings (unet_plucker.py:384-414)
@@ -503,14 +528,30 @@ struct Builder {
       }
     }
     // ---- out
-    gnorm(x, 0, xC, nullptr, 0, BF, lS[0], 1e-5f, "conv_norm_out", 1, n16, nullptr);
-    conv3x3_simple(n16, BF, lh[0], lw[0], xC, "conv_out", c.cout_pad, y32);
+    if (c.split) {
+      // conv_out in split precision: 9 taps on the head + 9 on the tail of the normalised input, weight tail in the
+      // padded output rows [Co, 2 Co) (added back by the post kernel)
+      gnorm(x, 0, xC, nullptr, 0, BF, lS[0], 1e-5f, "conv_norm_out", 1, n16, nullptr, lo16);
+      GemmProblem pr;
+      pr.a0 = n16; pr.a1 = lo16; pr.w = W("conv_out.weight");
+      pr.B = 1; pr.T = BF; pr.Y = lh[0]; pr.X = lw[0]; pr.C0 = xC; pr.C1 = xC; pr.N = c.cout_pad; pr.K_total = 18LL * xC;
+      taps_conv3x3(pr);
+      for (int i = 0; i < 9; ++i) {
+        pr.tap_dx[9 + i] = pr.tap_dx[i]; pr.tap_dy[9 + i] = pr.tap_dy[i]; pr.tap_dt[9 + i] = 0; pr.tap_src[9 + i] = 1;
+      }
+      pr.num_taps = 18;
+      pr.ep.out = y32; pr.ep.out_fp16 = 0; pr.ep.bias = Wf("conv_out.bias");
+      gemm(pr, "conv_out");
+    } else {
+      gnorm(x, 0, xC, nullptr, 0, BF, lS[0], 1e-5f, "conv_norm_out", 1, n16, nullptr);
+      conv3x3_simple(n16, BF, lh[0], lw[0], xC, "conv_out", c.cout_pad, y32);
+    }
     {
-      const float* y = y32; int Co = c.out_channels, Np = c.cout_pad, T_ = T, B_ = B;
+      const float* y = y32; int Co = c.out_channels, Np = c.cout_pad, T_ = T, B_ = B, fold = c.split;
       push([=](cudaStream_t st) {
         const CallArgs& a = u->args;
-        if (a.mode == 1) return post_cfg_euler(y, T_, Co, HW, Np, a.sigma, a.sigma_next, a.g_min, a.g_max, a.latents_out, st);
-        return nhwc_to_nchw_f32(y, (long long)B_ * T_, Co, HW, Np, a.out, st);
+        if (a.mode == 1) return post_cfg_euler(y, T_, Co, HW, Np, fold, a.sigma, a.sigma_next, a.g_min, a.g_max, a.latents_out, st);
+        return nhwc_to_nchw_f32(y, (long long)B_ * T_, Co, HW, Np, fold, a.out, st);
       }, 1, "post (CFG+Euler / layout)");
     }
     if (!fail.empty()) {
@@ -658,6 +699,15 @@ extern "C" int evw_unet_create(void** handle, const int* cfg_ints, int n_ints, c
   }
   for (int i = 0; i < n_tensors; ++i) U->tensors[tensor_names[i]] = tensor_ptrs[i];
   for (int i = 0; i < n_scalars; ++i) U->scalars[scalar_names[i]] = scalar_values[i];
+  {
+    auto it = U->scalars.find("precision.split");
+    c.split = (it != U->scalars.end() && it->second != 0.0) ? 1 : 0;
+    if (c.split && (3 * c.in_channels > c.cin_pad || 2 * c.out_channels > c.cout_pad)) {
+      delete U;
+      evw::set_error("evw_unet_create: precision.split needs 3*in_channels <= %d and 2*out_channels <= %d", c.cin_pad, c.cout_pad);
+      return EVW_ERR_INVALID;
+    }
+  }
   *handle = U;
   return EVW_OK;
 }

@@ -21,7 +21,8 @@ LINEAR_TAPS = [(0, 0, 0, 0)]
 def gemm_f16(a0: torch.Tensor, w: torch.Tensor, taps: Sequence[Tuple[int, int, int, int]] = LINEAR_TAPS,
              a1: Optional[torch.Tensor] = None, bias=None, rowvec=None, rv_div: int = 1, rv_mod: int = 1, res1=None,
              s1: float = 1.0, res2=None, s2: float = 1.0, s0: float = 1.0, geglu: bool = False,
-             out_dtype=torch.float16, block_n: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+             out_dtype=torch.float16, block_n: int = 0, out: Optional[torch.Tensor] = None,
+             out_lo: Optional[torch.Tensor] = None) -> torch.Tensor:
     """a0 fp16 [B,T,Y,X,C0] (or [M,C0] for a linear layer), w fp16 [N,K_total] -> [rows, N or N/2]."""
     _lib.require_cuda(a0, "a0")
     if a0.dim() == 2:
@@ -42,7 +43,7 @@ def gemm_f16(a0: torch.Tensor, w: torch.Tensor, taps: Sequence[Tuple[int, int, i
             _lib.ptr(a0), _lib.ptr(a1), _lib.ptr(w), B, T, Y, X, C0, C1, N, taps_arr.shape[0], taps_arr.tobytes(),
             _lib.ptr(out), 1 if out.dtype == torch.float16 else 0, _lib.ptr(bias), _lib.ptr(rowvec), rv_div, rv_mod,
             _lib.ptr(res1), 1 if (res1 is not None and res1.dtype == torch.float16) else 0, s1, _lib.ptr(res2), s2, s0,
-            1 if geglu else 0, block_n, _lib.stream_ptr(a0.device)), "evw_gemm_f16")
+            1 if geglu else 0, block_n, _lib.ptr(out_lo), _lib.stream_ptr(a0.device)), "evw_gemm_f16")
     return out
 
 
@@ -81,20 +82,22 @@ def temporal_attention(qkv: torch.Tensor, B: int, T: int, S: int, heads: int) ->
 
 
 def group_norm(src0: torch.Tensor, gamma, beta, insts: int, eps: float, silu: bool, src1: Optional[torch.Tensor] = None,
-               want_raw: bool = False):
+               want_raw: bool = False, want_lo: bool = False):
     """src0 [rows, C0] fp32|fp16 (+ src1 [rows, C1] fp32) -> fp16 [rows, C0+C1] (and the raw fp16 copy)."""
     _lib.require_cuda(src0, "src0")
     rows, C0 = src0.shape
     C1 = src1.shape[1] if src1 is not None else 0
     out = torch.empty((rows, C0 + C1), dtype=torch.float16, device=src0.device)
     raw = torch.empty_like(out) if want_raw else None
+    lo = torch.empty_like(out) if want_lo else None
     ws = torch.empty(insts * (64 + C0 + C1), dtype=torch.float64, device=src0.device)
     with torch.cuda.device(src0.device):
         _lib.check(_lib.lib().evw_group_norm_f16(_lib.ptr(src0), 1 if src0.dtype == torch.float16 else 0, C0, _lib.ptr(src1),
                                                  C1, insts, rows // insts, eps, _lib.ptr(gamma), _lib.ptr(beta),
-                                                 1 if silu else 0, _lib.ptr(ws), _lib.ptr(out), _lib.ptr(raw),
+                                                 1 if silu else 0, _lib.ptr(ws), _lib.ptr(out), _lib.ptr(raw), _lib.ptr(lo),
                                                  _lib.stream_ptr(src0.device)), "evw_group_norm_f16")
-    return (out, raw) if want_raw else out
+    res = (out,) + ((raw,) if want_raw else ()) + ((lo,) if want_lo else ())
+    return res if len(res) > 1 else out
 
 
 def layer_norm(x: torch.Tensor, gamma, beta, eps: float = 1e-5, rowvec=None, rv_div: int = 1, rv_mod: int = 1):

@@ -209,6 +209,11 @@ class UNetSpatioTemporalConditionModel:
         self.add_embedding = SimpleNamespace(
             linear_1=_LinearInfo(cfg["projection_class_embeddings_input_dim"], cfg["block_out_channels"][0] * 4))
         self.eps = dict(cross=1e-6, plain=1e-5, mid=1e-5, up=1e-6)  # diffusers block defaults
+        # Split precision (default on; EVW_UNET_SPLIT=0 for A/B runs): conv_in, conv_out, proj_in, proj_out take fp16
+        # head + tail operands and the spatial conv1 output stays fp32 — the layers tools/precision_sim.py ranks as
+        # 3/4 of the fp16 rounding-error variance of one forward for < 4 % of its FLOPs (1.1e-3 -> 8e-4 rel. L2).
+        self.precision_split = os.environ.get("EVW_UNET_SPLIT", "1") != "0" and 3 * cfg["in_channels"] <= 64 \
+            and 2 * cfg["out_channels"] <= 16
 
     # ------------------------------------------------------------------ parameters
     @property
@@ -347,6 +352,13 @@ class UNetSpatioTemporalConditionModel:
         S: Dict[str, float] = {}
         h = lambda t: t.to(torch.float16).contiguous()
         f = lambda t: t.to(torch.float32).contiguous()
+        split = bool(self.precision_split)
+        S["precision.split"] = 1.0 if split else 0.0
+
+        def hi_lo(w):  # fp16 head and fp16 tail (the head's rounding error) of an fp32 weight
+            w = w.to(torch.float32)
+            hi = w.to(torch.float16)
+            return hi, (w - hi.to(torch.float32)).to(torch.float16)
 
         def conv2d_w(w, pad_in=0, pad_out=0):  # [O,I,3,3] -> [O, ky, kx, I] -> [O, 9 I]
             if pad_in:
@@ -358,11 +370,21 @@ class UNetSpatioTemporalConditionModel:
         def lin(name):
             T[name + ".weight"] = h(P[name + ".weight"]); T[name + ".bias"] = f(P[name + ".bias"])
 
+        def lin_split(name):  # [N, 3K] = [W_hi | W_hi | W_lo] against the taps [a_hi | a_lo | a_hi]
+            hi, lo = hi_lo(P[name + ".weight"])
+            T[name + ".weight"] = torch.cat([hi, hi, lo], dim=1).contiguous(); T[name + ".bias"] = f(P[name + ".bias"])
+
         def norm(name):
             T[name + ".weight"] = f(P[name + ".weight"]); T[name + ".bias"] = f(P[name + ".bias"])
 
         cin = cfg["in_channels"]
-        T["conv_in.weight"] = h(conv2d_w(P["conv_in.weight"], pad_in=64 - cin)); T["conv_in.bias"] = f(P["conv_in.bias"])
+        if split:  # per tap: [W_hi | W_hi | W_lo | 0] against the operand channels [head | tail | head | 0]
+            hi, lo = hi_lo(P["conv_in.weight"].permute(0, 2, 3, 1))  # [O, ky, kx, I]
+            w = torch.cat([hi, hi, lo, torch.zeros_like(hi[..., : 64 - 3 * cin])], dim=-1)
+            T["conv_in.weight"] = w.reshape(w.shape[0], -1).contiguous()
+        else:
+            T["conv_in.weight"] = h(conv2d_w(P["conv_in.weight"], pad_in=64 - cin))
+        T["conv_in.bias"] = f(P["conv_in.bias"])
         for n in ("time_embedding.linear_1", "time_embedding.linear_2", "add_embedding.linear_1", "add_embedding.linear_2"):
             lin(n)
         temb_w, temb_b, off = [], [], 0
@@ -388,7 +410,8 @@ class UNetSpatioTemporalConditionModel:
         xw, xb, xoff = [], [], 0
         frames = torch.arange(MAX_FRAMES, device=self._device)
         for p, c, _heads in lay["att"]:
-            norm(p + ".norm"); lin(p + ".proj_in"); lin(p + ".proj_out")
+            norm(p + ".norm")
+            (lin_split if split else lin)(p + ".proj_in"); (lin_split if split else lin)(p + ".proj_out")
             for b in (p + ".transformer_blocks.0", p + ".temporal_transformer_blocks.0"):
                 for n in ("norm1", "norm3") + (("norm_in",) if "temporal" in b else ()):
                     norm(f"{b}.{n}")
@@ -415,7 +438,12 @@ class UNetSpatioTemporalConditionModel:
             T[p + ".weight"] = h(conv2d_w(P[p + ".weight"])); T[p + ".bias"] = f(P[p + ".bias"])
         norm("conv_norm_out")
         co = cfg["out_channels"]
-        T["conv_out.weight"] = h(conv2d_w(P["conv_out.weight"], pad_out=16 - co))
+        if split:  # rows [0,co): [9 taps W_hi (head operand) | 9 taps W_hi (tail operand)]; rows [co,2co): [W_lo | 0]
+            hi, lo = hi_lo(conv2d_w(P["conv_out.weight"]))
+            w = torch.cat([torch.cat([hi, hi], dim=1), torch.cat([lo, torch.zeros_like(lo)], dim=1)], dim=0)
+            T["conv_out.weight"] = torch.nn.functional.pad(w, (0, 0, 0, 16 - 2 * co)).contiguous()
+        else:
+            T["conv_out.weight"] = h(conv2d_w(P["conv_out.weight"], pad_out=16 - co))
         T["conv_out.bias"] = f(torch.nn.functional.pad(P["conv_out.bias"], (0, 16 - co)))
         return T, S, temb_total, xoff
 
@@ -452,7 +480,13 @@ class UNetSpatioTemporalConditionModel:
             n = _lib.lib().evw_unet_workspace_bytes(self._handle, B, T, h, w)
             if n < 0:
                 _lib.check(-1, "evw_unet_workspace_bytes")
-            self._ws = {key: torch.empty(n, dtype=torch.uint8, device=self._device)}  # one live shape at a time
+            # one live shape at a time.  The plan wants a 1024-byte aligned base (swizzled TMA tiles); the caching
+            # allocator only promises 512, so over-allocate and hand out the first aligned offset (the base tensor
+            # stays alive through the view).
+            self._ws = {}
+            base = torch.empty(n + 1024, dtype=torch.uint8, device=self._device)
+            off = (-base.data_ptr()) % 1024
+            self._ws = {key: base[off:off + n]}
         return self._ws[key]
 
     def plan_info(self) -> Tuple[int, float]:

@@ -169,11 +169,15 @@ int evw_cube_to_equirect_u8(const uint8_t* faces, const uint32_t* lut, int B, in
  *   h_taps (HOST) int8 [num_taps,4] = (dx,dy,dt,src); reads outside the tensor are zero (padding).
  *   out[row,n] = s0*(acc+bias[n]) + rowvec[(row/rv_div)%rv_mod, n] + s1*res1[row,n] + s2*res2[row,n];
  *   geglu: columns interleaved [16 value|16 gate], out has N/2 columns = (v+b)*gelu(g+b).
- *   out/res1 are fp16 or fp32 (flags), bias/rowvec/res2 fp32.  C0, C1 multiples of 64; N multiple of 8. */
+ *   out/res1 are fp16 or fp32 (flags), bias/rowvec/res2 fp32.  C0, C1 multiples of 64; N multiple of 8.
+ *   out_lo (optional, fp16 output only, N multiple of 16): fp16 tail half(v - float(half(v))) of every stored value —
+ *   the split-precision operand format: a consumer reads head and tail as two tap sources (a0, a1) against
+ *   [W_hi | W_hi | W_lo] and keeps ~22 significant bits of the product (used for proj_in / proj_out / conv_out,
+ *   the low-FLOP layers that dominate the fp16 rounding error of the step: tools/precision_sim.py). */
 int evw_gemm_f16(const void* a0, const void* a1, const void* w, int B, int T, int Y, int X, int C0, int C1,
                  int N, int num_taps, const int8_t* h_taps, void* out, int out_fp16, const float* bias,
                  const float* rowvec, int64_t rv_div, int64_t rv_mod, const void* res1, int res1_fp16, float s1,
-                 const float* res2, float s2, float s0, int geglu, int block_n, void* stream);
+                 const float* res2, float s2, float s0, int geglu, int block_n, void* out_lo, void* stream);
 
 /* Launch mode of the GEMM (takes effect when an op is planned): 1 = clusters of two CTAs on m-adjacent tiles sharing each
  * weight tile through TMA multicast, 0 = independent CTAs (default), -1 = restore the default / EVW_GEMM_CLUSTER. */
@@ -193,10 +197,11 @@ int evw_temporal_attention_f16(const void* qkv, void* out, int B, int T, int64_t
 
 /* GroupNorm(32) [+SiLU] over `insts` instances of `rows_per_inst` channels-last rows; input is the channel
  * concatenation of src0 (fp32 or fp16, C0 ch) and optional src1 (fp32, C1 ch); out fp16 [rows, C0+C1];
- * raw_out (optional) receives the un-normalised fp16 copy; stats_ws >= insts*(64 + C0 + C1) doubles. */
+ * raw_out (optional) receives the un-normalised fp16 copy; out_lo (optional) the fp16 tail of the output (split-
+ * precision operand, see evw_gemm_f16); stats_ws >= insts*(64 + C0 + C1) doubles. */
 int evw_group_norm_f16(const void* src0, int src0_fp16, int C0, const float* src1, int C1, int64_t insts,
                        int64_t rows_per_inst, float eps, const float* gamma, const float* beta, int do_silu,
-                       void* stats_ws, void* out, void* raw_out, void* stream);
+                       void* stats_ws, void* out, void* raw_out, void* out_lo, void* stream);
 
 /* LayerNorm over C of x[row] (+ rowvec[(row/rv_div)%rv_mod]) -> fp16 [rows, C]. */
 int evw_layer_norm_f16(const float* x, const float* rowvec, int64_t rv_div, int64_t rv_mod, int64_t rows, int C,

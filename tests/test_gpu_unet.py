@@ -1,10 +1,12 @@
 """UNet forward / fused denoise step on the GPU against the fp32 PyTorch oracle (oracle/unet_torch.py)
 with identical weights and inputs.  north_star asks for relative L2 <= 1e-3 of the fp32 reference (the reference
-runs its UNet in fp32: unified_loop_consistency.py:188).  With fp16 GEMM/attention operands, fp32 accumulation and
-an fp32 residual stream the measured error of one UNet forward is 1.04e-3 .. 1.15e-3 (profiles/r01f_unet_parity.log):
-the target is missed by 4-15 %, and the bound asserted here is TOL_UNET = 1.5e-3 — the measured figure plus margin,
-not the north-star figure.  One denoise step (CFG combine + Euler update of 700-sigma latents) is asserted at 1e-5
-(measured 4e-7 .. 1.3e-6)."""
+runs its UNet in fp32: unified_loop_consistency.py:188), and that is the bound asserted here: TOL_UNET = 1e-3, at the
+small test configuration, at the full-width 1.525 B-parameter network and at the BASELINE shapes ([2,14,18,72,128] and
+[2,25,18,72,128]: the fp32 oracle runs on the GPU with TF32 off and its spatial attention chunked over frames).
+fp16 GEMM/attention operands with fp32 accumulation gave 1.04e-3 .. 1.15e-3 (profiles/r01f_unet_parity.log); the
+split-precision treatment of conv_in / conv_out / proj_in / proj_out and the fp32 conv1 output (tools/precision_sim.py
+ranks them as 3/4 of the error variance) brings one forward to ~8e-4 (profiles/r02*_unet_parity.log).
+One denoise step (CFG combine + Euler update of 700-sigma latents) is asserted at 1e-5 (measured 4e-7 .. 1.3e-6)."""
 import math
 
 import pytest
@@ -15,7 +17,7 @@ from oracle import unet_torch as O
 
 pytestmark = pytest.mark.gpu
 
-TOL_UNET = 1.5e-3   # one UNet forward vs the fp32 oracle (see the module docstring)
+TOL_UNET = 1e-3     # one UNet forward vs the fp32 oracle: the north-star bound
 TOL_STEP = 1e-5     # latents after one fused denoise step vs the oracle's step
 
 SMALL = dict(in_channels=18, block_out_channels=(64, 128, 256, 256), num_attention_heads=(1, 2, 4, 4), cross_attention_dim=64)
@@ -111,6 +113,46 @@ def test_unet_forward_full_width(cuda_device, built_lib):
     assert err < TOL_UNET
     launches, flops = ours.plan_info()
     assert launches > 500 and flops > 0
+
+
+def _chunk_oracle_attention(oracle, frames_per_chunk=4):
+    """The oracle materialises softmax(QK^T) ([28, 5, 9216, 9216] fp32 = 48 GB at the BASELINE shape): evaluate its
+    spatial self-attention a few frames at a time instead (same arithmetic, same order within a frame)."""
+    for name, mod in oracle.named_modules():
+        if isinstance(mod, O.Attention) and name.endswith("transformer_blocks.0.attn1") and "temporal" not in name:
+            plain = mod.forward
+
+            def chunked(x, context=None, plain=plain):
+                return torch.cat([plain(x[i:i + frames_per_chunk]) for i in range(0, x.shape[0], frames_per_chunk)])
+
+            mod.forward = chunked
+
+
+@pytest.mark.parametrize("T", [14, 25])
+def test_unet_forward_baseline_config(T, cuda_device, built_lib):
+    """BASELINE config 2 (576x1024 -> 72x128 latents, CFG batch 2, full-width UNet, T = 14 benchmark / 25 reference
+    default) against the fp32 oracle on the same inputs bench.py uses, at the north-star tolerance."""
+    import bench_denoise as bd
+
+    dev = cuda_device
+    cfg = dict(in_channels=18, block_out_channels=(320, 640, 1280, 1280), num_attention_heads=(5, 10, 20, 20),
+               cross_attention_dim=1024)
+    oracle, ours = make_pair(cfg, dev, seed=11)
+    _chunk_oracle_attention(oracle)
+    h, w = 72, 128
+    lat, cond, ehs, ids = [t.to(dev) for t in bd.make_inputs(T, h, w, dev, seed=0)]
+    sigma = 700.0  # first step of the schedule: the scaled latents are ~N(0,1)
+    x_in = torch.cat([torch.cat([lat] * 2) / (sigma ** 2 + 1) ** 0.5, cond], dim=2)
+    t = 0.25 * math.log(sigma)
+    got = ours(x_in, t, ehs, ids).sample
+    ours.free_master_parameters()
+    with torch.no_grad():
+        want = oracle(x_in, t, ehs, ids)
+    err = rel_l2(got, want)
+    per_frame = [(rel_l2(got[b, f], want[b, f])) for b in range(2) for f in range(T)]
+    print(f"unet BASELINE [2,{T},18,{h},{w}]: rel L2 = {err:.3e} (worst frame {max(per_frame):.3e})")
+    assert torch.isfinite(got).all()
+    assert err < TOL_UNET
 
 
 def test_full_size_properties(cuda_device, built_lib):
