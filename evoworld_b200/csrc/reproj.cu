@@ -11,6 +11,7 @@
 // gather index) is specified so that it is bit-reproducible: the projection uses explicit fmaf /
 // IEEE division in a fixed order and is mirrored instruction-for-instruction by oracle/reproj_oracle.c.
 #include "common.h"
+#include <mutex>
 #include <math_constants.h>
 #include <cstdlib>
 
@@ -794,12 +795,16 @@ int launch_cube_pass(const float4* pts, int64_t n_cap, const long long* n_dev, c
                                                                                       z_near, pretest, color_key, zbuf);
     }
   }
-  if (!(what & 2)) return 0;
+  if (!(what & 2)) {
+    EVW_LAUNCH_CHECK();
+    return 0;
+  }
   const int64_t quads = (npix + 3) / 4;
   if (flags & EVW_SPLAT_V1_KERNELS)
     resolve_multi_kernel<G><<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(zbuf, pts, lut, res, npix, g_count, out);
   else
     resolve_multi2_kernel<G><<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(zbuf, pts, lut, res, npix, g_count, color_key, out);
+  EVW_LAUNCH_CHECK();  // a failed launch in an early pass is reported by that pass, not by the last one
   return 0;
 }
 
@@ -1046,6 +1051,7 @@ namespace {
 // Two internal streams for the pass pipeline (fork/join around the caller's stream with events; capturable).
 constexpr int kMaxPassEvents = 64;
 struct SplatStreams {
+  std::mutex mu;  // the two streams + events are per device: one pass pipeline at a time per device (host threads serialise)
   cudaStream_t s[2] = {nullptr, nullptr};
   cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
   cudaEvent_t cleared[kMaxPassEvents] = {}, splatted[kMaxPassEvents] = {};
@@ -1053,6 +1059,8 @@ struct SplatStreams {
 };
 int splat_streams(SplatStreams** out) {
   static SplatStreams per_dev[16];
+  static std::mutex init_mu;
+  std::lock_guard<std::mutex> init_guard(init_mu);
   int dev = 0;
   EVW_CUDA(cudaGetDevice(&dev));
   EVW_CHECK_ARG(dev >= 0 && dev < 16, "evw_splat_cube_equirect: device index %d out of range", dev);
@@ -1078,9 +1086,11 @@ int cube_pass_dispatch(int G, const float4* p4, int64_t n_cap, const long long* 
                        uint8_t* o, cudaStream_t st, int what = 3) {
   const size_t view_cells = (size_t)6 * res * res;
   if (g < G) {  // short tail: single-view passes
-    for (int j = 0; j < g; ++j)
-      launch_cube_pass<1>(p4, n_cap, n_dev, m + (size_t)j * 12, res, focal, z_near, flags, zbuf + (size_t)j * view_cells, lut,
-                          npix, 1, o + (size_t)j * npix * 3, st, what);
+    for (int j = 0; j < g; ++j) {
+      const int rc = launch_cube_pass<1>(p4, n_cap, n_dev, m + (size_t)j * 12, res, focal, z_near, flags,
+                                         zbuf + (size_t)j * view_cells, lut, npix, 1, o + (size_t)j * npix * 3, st, what);
+      if (rc) return rc;
+    }
     return 0;
   }
   switch (G) {
@@ -1115,9 +1125,11 @@ extern "C" int evw_splat_cube_equirect(const float* pts4, int64_t n_cap, const i
   const bool overlap = (flags & EVW_SPLAT_OVERLAP) && passes > 1;
   const bool by_role = overlap && (flags & EVW_SPLAT_OVERLAP_BY_ROLE) && passes <= kMaxPassEvents;
   SplatStreams* ss = nullptr;
+  std::unique_lock<std::mutex> guard;
   if (overlap) {
     int rc = splat_streams(&ss);
     if (rc) return rc;
+    guard = std::unique_lock<std::mutex>(ss->mu);  // held until every launch of this call is enqueued
     EVW_CUDA(cudaEventRecord(ss->fork, st));
     EVW_CUDA(cudaStreamWaitEvent(ss->s[0], ss->fork, 0));
     EVW_CUDA(cudaStreamWaitEvent(ss->s[1], ss->fork, 0));
@@ -1141,10 +1153,12 @@ extern "C" int evw_splat_cube_equirect(const float* pts4, int64_t n_cap, const i
       const float* m = w2c_front + (size_t)v0 * 12;
       uint8_t* o = out + (size_t)v0 * npix * 3;
       EVW_CUDA(cudaStreamWaitEvent(sa, ss->cleared[pass], 0));
-      cube_pass_dispatch(G, p4, n_cap, (const long long*)n_dev, m, face_res, focal, z_near, flags, zb_of(pass), lut, npix, g, o, sa, 1);
+      if ((rc = cube_pass_dispatch(G, p4, n_cap, (const long long*)n_dev, m, face_res, focal, z_near, flags, zb_of(pass), lut, npix, g, o, sa, 1)))
+        return rc;
       EVW_CUDA(cudaEventRecord(ss->splatted[pass], sa));
       EVW_CUDA(cudaStreamWaitEvent(sb, ss->splatted[pass], 0));
-      cube_pass_dispatch(G, p4, n_cap, (const long long*)n_dev, m, face_res, focal, z_near, flags, zb_of(pass), lut, npix, g, o, sb, 2);
+      if ((rc = cube_pass_dispatch(G, p4, n_cap, (const long long*)n_dev, m, face_res, focal, z_near, flags, zb_of(pass), lut, npix, g, o, sb, 2)))
+        return rc;
       if (pass + 2 < passes && (rc = clear(pass + 2))) return rc;
     }
   } else {
@@ -1154,8 +1168,9 @@ extern "C" int evw_splat_cube_equirect(const float* pts4, int64_t n_cap, const i
       cudaStream_t ps = overlap ? ss->s[pass & 1] : st;
       unsigned long long* zb = zbuf + (overlap ? (size_t)(pass & 1) * G * view_cells : 0);
       EVW_CUDA(cudaMemsetAsync(zb, 0xFF, (size_t)G * view_cells * 8, ps));
-      cube_pass_dispatch(G, p4, n_cap, (const long long*)n_dev, w2c_front + (size_t)v0 * 12, face_res, focal, z_near, flags, zb,
-                         lut, npix, g, out + (size_t)v0 * npix * 3, ps);
+      const int rc = cube_pass_dispatch(G, p4, n_cap, (const long long*)n_dev, w2c_front + (size_t)v0 * 12, face_res, focal,
+                                        z_near, flags, zb, lut, npix, g, out + (size_t)v0 * npix * 3, ps);
+      if (rc) return rc;
     }
   }
   if (overlap) {

@@ -1,0 +1,78 @@
+"""Image pre-processing of the CLIP conditioning branch (once per clip, torch ops on the image's device).
+
+Mirrors evoworld/pipeline/pipeline_evoworld.py:255-291 (`_encode_image`: x*2-1 -> anti-aliased resize to 224x224 ->
+(x+1)/2 -> CLIP mean/std normalisation) and :746-850 (`_resize_with_antialiasing` = separable Gaussian blur with reflect
+padding, sigma = max((factor-1)/2, 0.001), window = odd(int(max(4 sigma, 3))), then bicubic `interpolate` with
+align_corners=True).  Pinned against the identical function in evoworld/trainer/trainer_utils.py:68-179, which imports in
+the build container (tests/golden/make_pipeline_golden.py -> tests/golden/pipeline_golden.npz).
+"""
+from __future__ import annotations
+
+from typing import Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+# transformers' OPENAI_CLIP_MEAN / OPENAI_CLIP_STD: what CLIPImageProcessor(do_normalize=True) applies
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+CLIP_SIZE = (224, 224)
+
+
+def blur_window(size: int, factor: float) -> Tuple[int, float]:
+    """(odd window length, sigma) of the anti-aliasing Gaussian for a down-scaling factor in/out."""
+    sigma = max((factor - 1.0) / 2.0, 0.001)
+    k = int(max(2.0 * 2 * sigma, 3))
+    return (k + 1 if k % 2 == 0 else k), sigma
+
+
+def gaussian_taps(k: int, sigma: torch.Tensor) -> torch.Tensor:
+    """Normalised Gaussian taps centred on k // 2, evaluated in sigma's dtype (a 0-d tensor)."""
+    x = torch.arange(k, device=sigma.device, dtype=sigma.dtype) - k // 2
+    if k % 2 == 0:
+        x = x + 0.5
+    g = torch.exp(-x.pow(2.0) / (2 * sigma.pow(2.0)))
+    return g / g.sum(-1, keepdim=True)
+
+
+def _blur_axis(x: torch.Tensor, taps: torch.Tensor, axis: int) -> torch.Tensor:
+    """Depth-wise 1-D correlation along H (axis -2) or W (axis -1) with reflect padding."""
+    b, c, h, w = x.shape
+    k = taps.numel()
+    front, rear = (k - 1) // 2, (k - 1) - (k - 1) // 2
+    if axis == -1:
+        x = F.pad(x, (front, rear, 0, 0), mode="reflect")
+        kern = taps.to(x.dtype).reshape(1, 1, 1, k).expand(c, 1, 1, k)
+    else:
+        x = F.pad(x, (0, 0, front, rear), mode="reflect")
+        kern = taps.to(x.dtype).reshape(1, 1, k, 1).expand(c, 1, k, 1)
+    return F.conv2d(x, kern.contiguous(), groups=c)
+
+
+def resize_with_antialiasing(image: torch.Tensor, size: Sequence[int], interpolation: str = "bicubic",
+                             align_corners: bool = True) -> torch.Tensor:
+    """image [B,C,H,W] float -> [B,C,size[0],size[1]]: Gaussian pre-filter (W first, then H) + bicubic resample."""
+    if image.dim() != 4:
+        raise ValueError(f"resize_with_antialiasing expects [B,C,H,W], got {tuple(image.shape)}")
+    h, w = image.shape[-2:]
+    (ky, sy), (kx, sx) = blur_window(h, h / size[0]), blur_window(w, w / size[1])
+    sig = torch.tensor([sy, sx], dtype=image.dtype, device=image.device)
+    out = _blur_axis(image, gaussian_taps(kx, sig[1]), -1)
+    out = _blur_axis(out, gaussian_taps(ky, sig[0]), -2)
+    return F.interpolate(out, size=tuple(size), mode=interpolation, align_corners=align_corners)
+
+
+def clip_preprocess(image01: torch.Tensor, feature_extractor=None) -> torch.Tensor:
+    """image in [0,1] [B,3,H,W] -> CLIP pixel_values [B,3,224,224] (pipeline_evoworld.py:270-286).  With a
+    transformers CLIPImageProcessor the normalisation is delegated to it exactly as the reference does; without one the
+    CLIP mean/std above are applied."""
+    x = image01 * 2.0 - 1.0
+    x = resize_with_antialiasing(x, CLIP_SIZE)
+    x = (x + 1.0) / 2.0
+    if feature_extractor is not None:
+        pv = feature_extractor(images=x, do_normalize=True, do_center_crop=False, do_resize=False, do_rescale=False,
+                               return_tensors="pt").pixel_values
+        return pv.to(x.device)
+    mean = torch.tensor(CLIP_MEAN, dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
+    std = torch.tensor(CLIP_STD, dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
+    return (x - mean) / std

@@ -2,9 +2,11 @@
 
 Mirrors evoworld/pipeline/pipeline_evoworld.py:211-741 StableVideoDiffusionPipeline for the part on
 the hot path: conditioning assembly (:570-643), guidance schedule (:677) and the denoise loop
-(:689-725), which runs as one fused evw_denoise_step per iteration.  VAE and CLIP are SURVEY §8f
-"next" rows (not built): pass precomputed `image_latents` / `image_embeddings`, or inject any objects
-with diffusers' `vae.encode/decode` and `image_encoder` interfaces.
+(:689-725), which runs as one fused evw_denoise_step per iteration.  The CLIP pre-processing (:255-291: x*2-1 ->
+anti-aliased resize to 224x224 -> (x+1)/2 -> CLIP mean/std) is evoworld_b200/image_ops.py.  The VAE and the CLIP
+network themselves are SURVEY §8f "next" rows: `from_pretrained` loads them through transformers / diffusers when those
+libraries are importable, objects with the same interfaces can be injected, or pass precomputed `image_latents` /
+`image_embeddings`.
 """
 from __future__ import annotations
 
@@ -12,9 +14,13 @@ from dataclasses import dataclass
 from types import SimpleNamespace
 from typing import Callable, Dict, List, Optional, Union
 
+import os
+
 import numpy as np
 import torch
+import torch.nn.functional as F
 
+from .image_ops import clip_preprocess
 from .scheduler import EulerDiscreteScheduler
 from .unet import UNetSpatioTemporalConditionModel
 
@@ -44,10 +50,48 @@ class StableVideoDiffusionPipeline:
 
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, unet=None, vae=None, image_encoder=None, feature_extractor=None,
-                        **kwargs):
+                        scheduler=None, strict_components: bool = True, **kwargs):
+        """Reference call pattern: `from_pretrained(ckpt, unet=unet, local_files_only=True, low_cpu_mem_usage=True)`
+        (forward_evoworld.py:103, navigator_evoworld.py:112, unified_loop_consistency.py:195).  Components that are not
+        passed are loaded from the checkpoint's sub-folders: `unet/` and `scheduler/` natively, `image_encoder/` +
+        `feature_extractor/` through transformers, `vae/` through diffusers.  If a sub-folder exists but its library is
+        not importable the call fails here with a clear message instead of at the first pipeline call
+        (`strict_components=False` leaves the component None: then pass `image_latents=` / `image_embeddings=`)."""
+        root = str(pretrained_model_name_or_path)
         if unet is None:
-            unet = UNetSpatioTemporalConditionModel.from_pretrained(pretrained_model_name_or_path, subfolder="unet")
-        sched = EulerDiscreteScheduler.from_pretrained(pretrained_model_name_or_path, subfolder="scheduler")
+            unet = UNetSpatioTemporalConditionModel.from_pretrained(root, subfolder="unet")
+        sched = scheduler or EulerDiscreteScheduler.from_pretrained(root, subfolder="scheduler")
+
+        def load(sub, what, loader):
+            if not os.path.isdir(os.path.join(root, sub)):
+                return None
+            try:
+                return loader(os.path.join(root, sub))
+            except ImportError as exc:
+                if strict_components:
+                    raise ImportError(f"StableVideoDiffusionPipeline.from_pretrained: `{sub}/` needs {what}, which is not "
+                                      f"importable here ({exc}); install it, pass `{sub}=` explicitly, or use "
+                                      f"strict_components=False and feed precomputed latents / embeddings") from exc
+                return None
+
+        if image_encoder is None:
+            def _clip(path):
+                from transformers import CLIPVisionModelWithProjection
+
+                return CLIPVisionModelWithProjection.from_pretrained(path, local_files_only=True).eval()
+            image_encoder = load("image_encoder", "transformers", _clip)
+        if feature_extractor is None:
+            def _fe(path):
+                from transformers import CLIPImageProcessor
+
+                return CLIPImageProcessor.from_pretrained(path, local_files_only=True)
+            feature_extractor = load("feature_extractor", "transformers", _fe)
+        if vae is None:
+            def _vae(path):
+                from diffusers import AutoencoderKLTemporalDecoder
+
+                return AutoencoderKLTemporalDecoder.from_pretrained(path, local_files_only=True).eval()
+            vae = load("vae", "diffusers (AutoencoderKLTemporalDecoder)", _vae)
         return cls(vae=vae, image_encoder=image_encoder, unet=unet, scheduler=sched, feature_extractor=feature_extractor)
 
     def to(self, device=None, dtype=None):
@@ -102,25 +146,95 @@ class StableVideoDiffusionPipeline:
     def prepare_latents(self, batch_size, num_frames, num_channels_latents, height, width, dtype, device, generator, latents=None):
         shape = (batch_size, num_frames, 4, height // self.vae_scale_factor, width // self.vae_scale_factor)
         if latents is None:
-            gdev = generator.device if generator is not None else device
-            latents = torch.randn(shape, generator=generator, device=gdev, dtype=dtype).to(device)
+            latents = self._randn(shape, generator, device, dtype)
         else:
             latents = latents.to(device)
         return latents * self.scheduler.init_noise_sigma
 
-    def _encode_vae_image(self, image, device, do_cfg):
+    def _encode_vae_image(self, image, device, num_videos_per_prompt=1, do_classifier_free_guidance=True):
+        """:307-328 — `latent_dist.mode()`, NOT multiplied by the scaling factor; zeros for the unconditional half."""
         if self.vae is None:
             raise RuntimeError("StableVideoDiffusionPipeline: no VAE attached (SURVEY §8f: VAE is not built); pass "
                                "`image_latents=[B, 1+T_mem, 4, h, w]` or inject a `vae`.")
         lat = self.vae.encode(image.to(device)).latent_dist.mode()
-        return torch.cat([torch.zeros_like(lat), lat]) if do_cfg else lat
+        lat = lat.repeat(num_videos_per_prompt, 1, 1, 1)
+        return torch.cat([torch.zeros_like(lat), lat]) if do_classifier_free_guidance else lat
 
-    def _encode_image(self, image, device, do_cfg):
+    def _encode_image(self, image, device, num_videos_per_prompt=1, do_classifier_free_guidance=True):
+        """:255-305 — `image` is a tensor in [0,1]: x*2-1 -> `_resize_with_antialiasing`(224,224) -> (x+1)/2 -> CLIP
+        normalisation (`feature_extractor` when attached, else the CLIP mean/std) -> image_encoder(...).image_embeds."""
         if self.image_encoder is None:
             raise RuntimeError("StableVideoDiffusionPipeline: no CLIP image encoder attached (SURVEY §8f: not built); pass "
                                "`image_embeddings=[B, 1, 1024]` or inject an `image_encoder`.")
-        emb = self.image_encoder(image.to(device)).image_embeds.unsqueeze(1)
-        return torch.cat([torch.zeros_like(emb), emb]) if do_cfg else emb
+        if not isinstance(image, torch.Tensor):
+            arr = np.stack([np.asarray(im, dtype=np.float32) / 255.0 for im in (image if isinstance(image, list) else [image])])
+            image = torch.from_numpy(arr).permute(0, 3, 1, 2)
+        pv = clip_preprocess(image.to(device, torch.float32), self.feature_extractor)
+        try:
+            dtype = next(self.image_encoder.parameters()).dtype
+        except (StopIteration, AttributeError, TypeError):
+            dtype = pv.dtype
+        emb = self.image_encoder(pv.to(device=device, dtype=dtype)).image_embeds.unsqueeze(1)
+        bs, seq, _ = emb.shape
+        emb = emb.repeat(1, num_videos_per_prompt, 1).view(bs * num_videos_per_prompt, seq, -1)
+        return torch.cat([torch.zeros_like(emb), emb]) if do_classifier_free_guidance else emb
+
+    @staticmethod
+    def _video_preprocess(image01, height, width):
+        """diffusers VideoProcessor.preprocess for a tensor in [0,1] (:597): resize when the size differs, then 2x-1."""
+        if tuple(image01.shape[-2:]) != (height, width):
+            image01 = F.interpolate(image01, size=(height, width))
+        return 2.0 * image01 - 1.0
+
+    @staticmethod
+    def _randn(shape, generator, device, dtype):
+        """diffusers randn_tensor: a CPU generator (navigator_evoworld.py:198) draws on the CPU, then moves."""
+        if generator is not None and generator.device.type != torch.device(device).type:
+            return torch.randn(shape, generator=generator, device=generator.device, dtype=dtype).to(device)
+        return torch.randn(shape, generator=generator, device=device, dtype=dtype)
+
+    def prepare_conditioning(self, image, memorized_pixel_values, plucker_embedding, height, width, num_frames, fps,
+                             motion_bucket_id, noise_aug_strength, generator, mask_mem, image_embeddings=None,
+                             image_latents=None):
+        """Steps 2-5 of `__call__` (:570-656): returns (image_embeddings [2,1,D], conditional_latents
+        [2,T,4+4+6,h,w], added_time_ids [2,3])."""
+        device = self._device
+        batch_size = image.shape[0]
+        pix01 = None
+        if image_embeddings is None or image_latents is None:
+            if memorized_pixel_values is None:
+                raise ValueError("memorized_pixel_values [B, T_mem, 3, H, W] is required")
+            pix01 = torch.cat([image.unsqueeze(1), memorized_pixel_values.to(image.device)], dim=1) / 2.0 + 0.5  # :570,:579
+        if image_embeddings is None:
+            image_embeddings = self._encode_image(pix01[:, 0], device, 1, True)                                   # :588
+        else:
+            emb = image_embeddings.to(device, torch.float32)
+            image_embeddings = torch.cat([torch.zeros_like(emb), emb]) if emb.shape[0] == batch_size else emb
+        if image_latents is None:
+            n_cond = pix01.shape[1]
+            flat = pix01.reshape(-1, *pix01.shape[2:])                                                            # :596
+            flat = self._video_preprocess(flat, height, width).to(device)                                         # :597
+            noise = self._randn(flat.shape, generator, device, flat.dtype)                                        # :598
+            flat = flat + noise_aug_strength * noise                                                              # :599
+            lat = self._encode_vae_image(flat, device, 1, True).to(image_embeddings.dtype)                        # :610-616
+            lat = lat.reshape(2 * batch_size, n_cond, *lat.shape[1:])                                             # :617
+        else:
+            lat = image_latents.to(device, torch.float32)
+            if lat.shape[0] == batch_size:
+                lat = torch.cat([torch.zeros_like(lat), lat])
+            lat = lat.clone()
+        if mask_mem:
+            lat[:, 1:] = 0                                                                                        # :629-631
+        if plucker_embedding is None:
+            raise ValueError("plucker_embedding [B, T, 6, h, w] is required")
+        plucker = plucker_embedding.to(device, torch.float32)
+        plucker = torch.cat([plucker, plucker], dim=0)  # NOT zeroed for the unconditional branch (:635)
+        if lat.shape[1] - 1 != num_frames or plucker.shape[1] != num_frames:
+            raise ValueError(f"expected {num_frames} memory frames and Plücker frames, got {lat.shape[1] - 1} and {plucker.shape[1]}")
+        cond_first = lat[:, 0:1].repeat(1, num_frames, 1, 1, 1)                                                   # :642
+        conditional_latents = torch.cat([cond_first, lat[:, 1:], plucker], dim=2).contiguous()                    # :643
+        added_time_ids = self._get_add_time_ids(fps, motion_bucket_id, noise_aug_strength, torch.float32, batch_size, True).to(device)
+        return image_embeddings, conditional_latents, added_time_ids
 
     @torch.no_grad()
     def __call__(self, image: torch.Tensor, height: int = 576, width: int = 1024, num_frames: Optional[int] = None,
@@ -145,41 +259,12 @@ class StableVideoDiffusionPipeline:
         do_cfg = self.do_classifier_free_guidance
         if not do_cfg:
             raise NotImplementedError("max_guidance_scale <= 1 (no classifier-free guidance) is not built")
-        # 3./4. conditioning: CLIP embedding of the first frame, VAE latents of first frame + memory frames
-        if image_embeddings is None:
-            pix = torch.cat([image.unsqueeze(1), memorized_pixel_values], dim=1) / 2.0 + 0.5
-            image_embeddings = self._encode_image(pix[:, 0], device, do_cfg)
-        else:
-            emb = image_embeddings.to(device, torch.float32)
-            image_embeddings = torch.cat([torch.zeros_like(emb), emb]) if emb.shape[0] == batch_size else emb
+        # 3.-5. conditioning: CLIP embedding of the first frame, VAE latents of first frame + memory frames, added ids
         fps = fps - 1
-        if image_latents is None:
-            pix = torch.cat([image.unsqueeze(1), memorized_pixel_values], dim=1)
-            n_cond = pix.shape[1]
-            flat = pix.reshape(-1, *pix.shape[2:]).to(device)
-            noise = torch.randn(flat.shape, generator=generator, device=generator.device if generator is not None else device,
-                                dtype=flat.dtype).to(device)
-            flat = flat + noise_aug_strength * noise
-            lat = self._encode_vae_image(flat, device, do_cfg)
-            lat = lat.reshape(2 * batch_size, n_cond, *lat.shape[1:])
-        else:
-            lat = image_latents.to(device, torch.float32)
-            if lat.shape[0] == batch_size:
-                lat = torch.cat([torch.zeros_like(lat), lat])
-        lat = lat.clone()
-        if mask_mem:
-            lat[:, 1:] = 0
-        _, _, _, h_lat, w_lat = lat.shape
-        if plucker_embedding is None:
-            raise ValueError("plucker_embedding [B, T, 6, h, w] is required")
-        plucker = plucker_embedding.to(device, torch.float32)
-        plucker = torch.cat([plucker, plucker], dim=0)  # NOT zeroed for the unconditional branch (:635)
-        if lat.shape[1] - 1 != num_frames or plucker.shape[1] != num_frames:
-            raise ValueError(f"expected {num_frames} memory frames and Plücker frames, got {lat.shape[1] - 1} and {plucker.shape[1]}")
-        cond_first = lat[:, 0:1].repeat(1, num_frames, 1, 1, 1)
-        conditional_latents = torch.cat([cond_first, lat[:, 1:], plucker], dim=2).contiguous()
-        # 5. added time ids, 6. timesteps, 7. latents, 8. guidance
-        added_time_ids = self._get_add_time_ids(fps, motion_bucket_id, noise_aug_strength, torch.float32, batch_size, do_cfg).to(device)
+        image_embeddings, conditional_latents, added_time_ids = self.prepare_conditioning(
+            image, memorized_pixel_values, plucker_embedding, height, width, num_frames, fps, motion_bucket_id,
+            noise_aug_strength, generator, mask_mem, image_embeddings, image_latents)
+        # 6. timesteps, 7. latents, 8. guidance
         self.scheduler.set_timesteps(num_inference_steps, device=device, sigmas=sigmas)
         timesteps = self.scheduler.timesteps
         latents = self.prepare_latents(batch_size, num_frames, self.unet.config.in_channels, height, width, torch.float32,

@@ -349,7 +349,12 @@ class PointCloudProcessor:
         if filter_by_frames not in ("all", "All"):
             sel = self._parse_frame_filter(filter_by_frames)
             if sel is not None:
-                points, conf, images = points[sel:sel + 1], conf[sel:sel + 1], images[sel:sel + 1]
+                # the reference slices the predictions dict IN PLACE here (:199-203): later stages — align_extrinsics in
+                # predictions_to_target_view — then see only the selected frame's extrinsic
+                points, conf = points[sel:sel + 1], conf[sel:sel + 1]
+                predictions["images"] = images = images[sel:sel + 1]
+                if "extrinsic" in predictions:
+                    predictions["extrinsic"] = predictions["extrinsic"][sel:sel + 1]
 
         def dev(x, dtype=None):
             t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))

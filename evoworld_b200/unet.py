@@ -260,7 +260,9 @@ class UNetSpatioTemporalConditionModel:
             if k in sd:
                 if tuple(sd[k].shape) != tuple(shape):
                     raise RuntimeError(f"size mismatch for {k}: {tuple(sd[k].shape)} vs {shape}")
-                self._params[k] = sd[k].detach().to(self._device, torch.float32)
+                # always a private, freshly allocated (hence 512-byte aligned) copy: the kernels read parameters with
+                # 16-byte vector loads, and a caller's tensors may be views at arbitrary offsets of one flat buffer
+                self._params[k] = sd[k].detach().to(self._device, torch.float32, copy=True).contiguous()
         self._invalidate()
         return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
 

@@ -118,9 +118,9 @@ int evw_splat_cubemap_equirect(const float* pts4, int64_t n_cap, const int64_t* 
  *                         two passes: evw_splat_workspace_flags(views_per_pass, face_res, flags);
  *   EVW_SPLAT_V1_KERNELS  the first-generation kernels (one point per thread, dependent gathers) for A/B timing.
  * All flag combinations except EVW_SPLAT_COLOR_KEYS produce identical bytes.  With EVW_SPLAT_OVERLAP the call uses two
- * library-owned streams per device (created on first use, forked from / joined to `stream` with events, capturable): like
- * the reference's process model (one Python thread per process and GPU) it must not be entered concurrently from several
- * host threads for the same device. */
+ * library-owned streams per device (created on first use, forked from / joined to `stream` with events, capturable);
+ * a per-device mutex serialises host threads that enter the call concurrently for the same device (the enqueue is
+ * short; the reference's process model is one Python thread per process and GPU anyway). */
 #define EVW_SPLAT_PRETEST 1
 #define EVW_SPLAT_OVERLAP 2
 #define EVW_SPLAT_V1_KERNELS 4
