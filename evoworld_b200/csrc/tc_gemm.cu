@@ -9,14 +9,19 @@
 //   warp 0      TMA producer: 5-D tiled loads of the activation tile (zero fill outside the image =
 //               the convolution padding) + 2-D loads of the weight tile, 128B swizzle, mbarrier ring;
 //               issued under elect.sync
-//   warp 1      MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N (<=256), K=16 per instr.,
-//               issued under elect.sync (no uniform-operand waterfall: 65 SASS instructions per 64-wide k-block)
+//   warp 1      MMA issuer: tcgen05.mma kind::f16, N=BLOCK_N (<=256), K=16 per instr.; cta_group::2 M=256 issued by the
+//               leader CTA of each pair (cta_group::1 M=128 in the single-CTA mode), under elect.sync (no uniform-operand
+//               waterfall: 65 SASS instructions per 64-wide k-block)
 //   warp 2      TMEM allocator (512 columns = two accumulator stages)
 //   warps 4..11 epilogue (8 warps; a 16-warp GEGLU-only instantiation exists, off by default):
 //               tcgen05.ld -> bias / broadcast row vector / GEGLU / scaled residuals -> global
 // The accumulator is double-buffered so the epilogue of tile i overlaps the main loop of tile i+1.
-// Optional launch mode (EVW_GEMM_CLUSTER=1): clusters of two CTAs on m-adjacent tiles share each weight tile
-// through TMA multicast; bit-identical, measured neutral, off by default.
+// Default launch mode (k2Cta): CTA PAIRS (clusters of two, one TPC) run tcgen05.mma.cta_group::2 with M = 256 — the two
+// CTAs work on m-adjacent 128-row tiles of the SAME n-tile, each loads its own activation tile and HALF of the weight
+// tile, and the leader CTA's single MMA stream drives both tensor cores.  Per CTA and k-block that is 16 KB + BLOCK_N*64 B
+// of operand traffic instead of 16 KB + BLOCK_N*128 B: the shared-memory data pipe (TMA writes + tensor-core operand
+// reads), which capped the 160-wide tiles of every N = 320 / 640 layer at ~1.05 PFLOP/s, drops from ~1.8x to ~1.25x of
+// its per-MMA budget.  EVW_GEMM_CLUSTER=0 / evw_set_gemm_cluster(0) selects the independent-CTA (cta_group::1) launch.
 #include "common.h"
 #include "tc_common.cuh"
 #include "tc_gemm.h"
@@ -186,10 +191,13 @@ __device__ __forceinline__ void store16(const GemmEpilogue& ep, const float (&v)
   }
 }
 
-// kCluster: CTAs are launched as clusters of two that work on m-adjacent tiles of the SAME n-tile.  Each CTA loads its own
-// activation tile and HALF of the weight tile, multicast into both CTAs' shared memory, so the weight bytes cross the
-// L2 -> SM path once per pair (ncu: that path would be 94 % busy at full tensor rate with 160-wide tiles).  The MMAs stay
-// cta_group::1; only the stage-release commit is multicast so that neither producer overwrites a stage its peer still reads.
+// k2Cta: CTAs are launched as clusters of two (a CTA pair on one TPC) that work on m-adjacent tiles of the SAME n-tile.
+// Protocol (CTA rank 0 = leader):
+//   full[s]    lives in the leader: its producer arrives once with expect_tx = both CTAs' bytes, BOTH producers' TMA loads
+//              (cp.async.bulk.tensor ... cta_group::2) complete_tx on it; only the leader's MMA warp waits on it
+//   empty[s]   one per CTA, released by the leader's tcgen05.commit.cta_group::2 multicast to both CTAs
+//   tfull[a]   one per CTA (multicast commit): each CTA's epilogue drains its own 128 TMEM lanes
+//   tempty[a]  lives in the leader, count = 2 x epilogue warps: the peer's epilogue warps arrive remotely
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -199,18 +207,53 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_2d_multicast(const CUtensorMap* m, uint32_t dst, uint32_t bar, int c0, int c1, uint16_t mask) {
+// shared::cluster address of `local` (a shared::cta address) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// TMA loads of a CTA pair: destination in the executing CTA, completion on `cluster_bar` (the leader's barrier)
+__device__ __forceinline__ void tma_load_5d_2cta(const CUtensorMap* m, uint32_t dst, uint32_t cluster_bar, int c0, int c1, int c2,
+                                                 int c3, int c4) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
-__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+__device__ __forceinline__ void tma_load_2d_2cta(const CUtensorMap* m, uint32_t dst, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2cta(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
 }
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
 
-template <bool kCluster, int kEpiWarps>
+template <bool k2Cta, int kEpiWarps>
 __global__ void __launch_bounds__(kCtrlThreads + 32 * kEpiWarps, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
                const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_bh,
@@ -219,7 +262,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stages = P.num_stages;
-  const uint32_t b_tile_bytes = (uint32_t)P.block_n * kBlockK * 2;
+  // weight bytes per stage in THIS CTA: the whole BLOCK_N x 64 tile, or half of it in a CTA pair
+  const uint32_t b_tile_bytes = (uint32_t)P.block_n * kBlockK * (k2Cta ? 1 : 2);
   const uint32_t stage_bytes = kATileBytes + b_tile_bytes;
   const uint32_t bar_base = smem_base + stages * stage_bytes;  // 8-byte barriers
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -234,35 +278,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
     tma_prefetch_desc(&tmap_a0);
     tma_prefetch_desc(&tmap_a1);
     tma_prefetch_desc(&tmap_b);
-    if (kCluster) tma_prefetch_desc(&tmap_bh);
+    if (k2Cta) tma_prefetch_desc(&tmap_bh);
   }
-  const uint32_t crank = kCluster ? cluster_ctarank() : 0u;
+  const uint32_t crank = k2Cta ? cluster_ctarank() : 0u;
   // virtual tile index v -> tile: plain mode walks tiles, cluster mode walks pairs (rank picks the m-tile of the pair;
   // an odd m-tile count leaves one phantom tile whose loads fall outside the tensor and whose rows are never stored)
-  const int v_first = kCluster ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int v_step = kCluster ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int v_limit = kCluster ? P.total_pairs : P.total_tiles;
+  const int v_first = k2Cta ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int v_step = k2Cta ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int v_limit = k2Cta ? P.total_pairs : P.total_tiles;
   auto to_tile = [&](int v) {
-    if (!kCluster) return v;
+    if (!k2Cta) return v;
     const int mp = v / P.n_tiles, nt = v - mp * P.n_tiles;
     return (2 * mp + (int)crank) * P.n_tiles + nt;
   };
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), kCluster ? 2 : 1);  // cluster: released by both CTAs' MMA commits
+      mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiWarps);
+      mbar_init(tempty_bar(a), k2Cta ? 2 * kEpiWarps : kEpiWarps);  // pair: both CTAs' epilogues release the leader's MMA
     }
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 2) {
+    if (k2Cta) tmem_alloc_2cta(tmem_slot, 512);  // issued by the same warp of both CTAs of the pair
+    else tmem_alloc(tmem_slot, 512);
+  }
   tc_fence_before();
   __syncthreads();
-  if (kCluster) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast into them
+  if (k2Cta) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -279,7 +326,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t half_bytes = b_tile_bytes >> 1;
     for (int v = v_first; v < v_limit; v += v_step) {
       const int tile = to_tile(v);
       const int n_tile = tile % P.n_tiles;
@@ -298,22 +344,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
           mbar_wait(empty_bar(stage), phase ^ 1u);
           if (elect_one_sync()) {
             const uint32_t sa = smem_base + stage * stage_bytes;
-            mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
-            tma_load_5d(ma, sa, full_bar(stage), kc * kBlockK, cx, cy, ct, tb);
-            if (kCluster)  // this CTA's half of the weight rows, delivered to the same offset in both CTAs
-              tma_load_2d_multicast(&tmap_bh, sa + kATileBytes + crank * half_bytes, full_bar(stage), kglob * kBlockK,
-                                    n0 + (int)crank * (P.block_n >> 1), (uint16_t)3);
-            else
+            if (k2Cta) {
+              // own activation tile + own half of the weight rows; both CTAs' bytes complete on the leader's barrier
+              const uint32_t lead_full = mapa_cluster(full_bar(stage), 0);
+              if (crank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * stage_bytes);
+              tma_load_5d_2cta(ma, sa, lead_full, kc * kBlockK, cx, cy, ct, tb);
+              tma_load_2d_2cta(&tmap_bh, sa + kATileBytes, lead_full, kglob * kBlockK, n0 + (int)crank * (P.block_n >> 1));
+            } else {
+              mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+              tma_load_5d(ma, sa, full_bar(stage), kc * kBlockK, cx, cy, ct, tb);
               tma_load_2d(&tmap_b, sa + kATileBytes, full_bar(stage), kglob * kBlockK, n0);
+            }
           }
           __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc_f16(kBlockM, P.block_n);
+  } else if (warp == 1 && (!k2Cta || crank == 0)) {
+    // ===================== MMA issuer (the leader CTA of a pair) =====================
+    const uint32_t idesc = make_idesc_f16(k2Cta ? 2 * kBlockM : kBlockM, P.block_n);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -330,12 +380,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
         const uint64_t da = make_desc_k_sw128(sa);
         const uint64_t db = make_desc_k_sw128(sa + kATileBytes);
         if (elect_one_sync()) {
+          if (k2Cta) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k)
-            umma_f16_ss(d_tmem, da + 2ull * k, db + 2ull * k, idesc, (kc | k) != 0);
-          if (kCluster) tc_commit_multicast(empty_bar(stage), (uint16_t)3);
-          else tc_commit(empty_bar(stage));
-          if (kc == total_chunks - 1) tc_commit(tfull_bar(acc));
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_f16_ss_2cta(d_tmem, da + 2ull * k, db + 2ull * k, idesc, (kc | k) != 0);
+            tc_commit_2cta(empty_bar(stage), (uint16_t)3);
+            if (kc == total_chunks - 1) tc_commit_2cta(tfull_bar(acc), (uint16_t)3);
+          } else {
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_f16_ss(d_tmem, da + 2ull * k, db + 2ull * k, idesc, (kc | k) != 0);
+            tc_commit(empty_bar(stage));
+            if (kc == total_chunks - 1) tc_commit(tfull_bar(acc));
+          }
         }
         __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -493,16 +550,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (k2Cta) mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));
+        else mbar_arrive(tempty_bar(acc));
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (kCluster) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or arrive on its barriers
+  if (k2Cta) cluster_sync_all();  // no CTA leaves while its peer may still arrive on its barriers or read its operands
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (k2Cta) tmem_dealloc_2cta(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -603,17 +664,17 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
     ktot += pr.tap_src[t] ? pr.C1 : pr.C0;
   }
   EVW_CHECK_ARG(ktot == pr.K_total, "gemm: K_total=%lld but taps cover %lld", (long long)pr.K_total, ktot);
-  const uint32_t stage_bytes = kATileBytes + bn * kBlockK * 2;
-  int stages = (int)((227 * 1024 - 4096) / stage_bytes);
-  if (stages > 8) stages = 8;
-  P.num_stages = stages;
   P.total_tiles = P.tiles_x * P.tiles_y * P.T * P.B * P.n_tiles;
   const int m_tiles = P.tiles_x * P.tiles_y * P.T * P.B;
   P.total_pairs = ((m_tiles + 1) / 2) * P.n_tiles;
-  op->smem_bytes = stages * stage_bytes + 8 * (2 * stages + 4) + 16 + 2 * 256 * 4 + 1024;
   int sms = sm_count();
-  // cluster (B-multicast) mode needs at least one full pair per cluster and a 1 KiB-aligned half tile (bn % 16 == 0 holds)
+  // CTA-pair (cta_group::2) mode needs at least one full pair and a 1 KiB-aligned half weight tile (bn % 16 == 0 holds)
   op->cluster = (gemm_cluster_mode() && m_tiles >= 2 && sms >= 2) ? 1 : 0;
+  const uint32_t stage_bytes = kATileBytes + bn * kBlockK * (op->cluster ? 1 : 2);  // a pair member holds half the weight tile
+  int stages = (int)((227 * 1024 - 4096) / stage_bytes);
+  if (stages > 8) stages = 8;
+  P.num_stages = stages;
+  op->smem_bytes = stages * stage_bytes + 8 * (2 * stages + 4) + 16 + 2 * 256 * 4 + 1024;
   if (op->cluster) {
     const int want = 2 * P.total_pairs;
     op->grid = want < (sms & ~1) ? want : (sms & ~1);
@@ -651,15 +712,15 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   return EVW_OK;
 }
 
-// -1: EVW_GEMM_CLUSTER, default OFF.  Measured on B200 (profiles/r01f_gemm_bench.log): the cluster / weight-multicast launch
-// is bit-identical and within +-3 % of the plain launch on every UNet shape — the 160-wide tiles are bound by the
-// shared-memory data pipe (tensor-core operand reads + TMA writes), which multicast does not relieve — so the simpler
-// launch stays the default and the mode is kept for the parity tests and further work (cta_group::2).
+// -1: EVW_GEMM_CLUSTER, default ON = CTA pairs with tcgen05.mma.cta_group::2 (M = 256).  Round 1's cluster mode only
+// multicast the weight tile between two cta_group::1 CTAs and measured neutral (profiles/r01f_gemm_bench.log): the
+// 160-wide tiles are bound by the shared-memory data pipe (tensor-core operand reads + TMA writes), which multicast does
+// not relieve; halving the weight operand per CTA does (profiles/r02*_gemm_bench.log).  0 = independent CTAs.
 static int g_gemm_cluster = -1;
 int gemm_cluster_mode() {
   if (g_gemm_cluster < 0) {
     const char* e = getenv("EVW_GEMM_CLUSTER");
-    g_gemm_cluster = (e && atoi(e) != 0) ? 1 : 0;
+    g_gemm_cluster = (e && atoi(e) == 0) ? 0 : 1;
   }
   return g_gemm_cluster;
 }

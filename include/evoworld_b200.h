@@ -179,8 +179,9 @@ int evw_gemm_f16(const void* a0, const void* a1, const void* w, int B, int T, in
                  const float* rowvec, int64_t rv_div, int64_t rv_mod, const void* res1, int res1_fp16, float s1,
                  const float* res2, float s2, float s0, int geglu, int block_n, void* out_lo, void* stream);
 
-/* Launch mode of the GEMM (takes effect when an op is planned): 1 = clusters of two CTAs on m-adjacent tiles sharing each
- * weight tile through TMA multicast, 0 = independent CTAs (default), -1 = restore the default / EVW_GEMM_CLUSTER. */
+/* Launch mode of the GEMM (takes effect when an op is planned): 1 = CTA pairs (clusters of two) on m-adjacent tiles running
+ * tcgen05.mma.cta_group::2 with M = 256, each CTA holding half of the weight tile (default), 0 = independent CTAs
+ * (cta_group::1, M = 128), -1 = restore the default / EVW_GEMM_CLUSTER. */
 void evw_set_gemm_cluster(int on);
 
 /* Spatial self-attention (BasicTransformerBlock.attn1 -> F.scaled_dot_product_attention, head dim 64):

@@ -134,3 +134,57 @@ def test_large_persistent(cuda_device):
     got = ops.gemm_f16(a, w, out_dtype=torch.float16)
     want = (a @ w.T).float()
     assert rel_l2(got, want) < 3e-3
+
+
+def _hi_lo(x):
+    hi = x.half()
+    return hi, (x - hi.float()).half()
+
+
+@pytest.mark.parametrize("M,K,N", [(1000, 320, 320), (4096, 640, 640), (258, 1280, 1280)])
+def test_split_precision_linear(M, K, N, cuda_device):
+    """proj_in / proj_out in split precision: [a_hi | a_lo | a_hi] x [W_hi | W_hi | W_lo] keeps ~22 bits of the
+    product (error 100x below the plain fp16-operand GEMM) — tools/precision_sim.py's "split" mode on the device."""
+    a = torch.randn(M, K, device=cuda_device)
+    w = torch.randn(N, K, device=cuda_device) / K ** 0.5
+    b = torch.randn(N, device=cuda_device)
+    want = a.double() @ w.double().T + b.double()
+    a_hi, a_lo = _hi_lo(a)
+    w_hi, w_lo = _hi_lo(w)
+    wk = torch.cat([w_hi, w_hi, w_lo], dim=1).contiguous()
+    got = ops.gemm_f16(a_hi, wk, taps=[(0, 0, 0, 0), (0, 0, 0, 1), (0, 0, 0, 0)], a1=a_lo, bias=b, out_dtype=torch.float32)
+    plain = ops.gemm_f16(a_hi, w_hi, bias=b, out_dtype=torch.float32)
+    e_split, e_plain = rel_l2(got, want), rel_l2(plain, want)
+    print(f"split-precision linear {M}x{N}x{K}: rel L2 {e_split:.2e} (plain fp16 operands {e_plain:.2e})")
+    assert e_split < 5e-6 and e_plain > 20 * e_split
+
+
+def test_epilogue_tail_output(cuda_device):
+    """out_lo: the fp16 tail written next to an fp16 output restores the fp32 value (head + tail)."""
+    M, K, N = 700, 320, 320
+    a = torch.randn(M, K, device=cuda_device).half()
+    w = (torch.randn(N, K, device=cuda_device) / K ** 0.5).half()
+    r1 = torch.randn(M, N, device=cuda_device)
+    want = ops.gemm_f16(a, w, res1=r1, s1=0.5, out_dtype=torch.float32)
+    lo = torch.full((M, N), 7.0, dtype=torch.float16, device=cuda_device)
+    hi = ops.gemm_f16(a, w, res1=r1, s1=0.5, out_dtype=torch.float16, out_lo=lo)
+    assert torch.equal(hi, want.half())
+    assert torch.equal(lo, (want - want.half().float()).half())
+    assert rel_l2(hi.float() + lo.float(), want) < 2e-7
+
+
+def test_conv3x3_split_taps(cuda_device):
+    """conv_out in split precision: 9 taps on the head + 9 on the tail of the input, weight tail in extra output rows."""
+    B, T, Y, X, C, Co = 1, 2, 16, 32, 64, 4
+    x = torch.randn(B * T, C, Y, X, device=cuda_device)
+    w = torch.randn(Co, C, 3, 3, device=cuda_device) / (9 * C) ** 0.5
+    want = F.conv2d(x.double(), w.double(), padding=1).permute(0, 2, 3, 1).reshape(-1, Co)
+    xl = x.permute(0, 2, 3, 1).reshape(B, T, Y, X, C).contiguous()
+    x_hi, x_lo = _hi_lo(xl)
+    w_hi, w_lo = _hi_lo(w.permute(0, 2, 3, 1).reshape(Co, 9 * C))
+    wk = torch.cat([torch.cat([w_hi, w_hi], 1), torch.cat([w_lo, torch.zeros_like(w_lo)], 1)], 0)
+    wk = F.pad(wk, (0, 0, 0, 16 - 2 * Co)).contiguous()
+    taps = ops.CONV3x3_TAPS + [(dx, dy, dt, 1) for dx, dy, dt, _ in ops.CONV3x3_TAPS]
+    y = ops.gemm_f16(x_hi, wk, taps=taps, a1=x_lo, out_dtype=torch.float32)
+    got = y[:, :Co] + y[:, Co:2 * Co]
+    assert rel_l2(got, want) < 5e-6

@@ -104,3 +104,35 @@ def test_layer_norm(rows, C, cuda_device):
     idx = (torch.arange(rows, device=cuda_device) // S) % T
     got = ops.layer_norm(x, g, b, rowvec=rv, rv_div=S, rv_mod=T)
     assert rel_l2(got, F.layer_norm(x + rv[idx], (C,), g, b, 1e-5)) < 1.5e-3
+
+
+def test_group_norm_tail_output(cuda_device):
+    """out_lo: fp16 tail of the normalised output (split-precision operand of proj_in / conv_out)."""
+    insts, rows, C = 3, 200, 320
+    x = torch.randn(insts * rows, C, device=cuda_device) * 2 + 0.5
+    g, b = torch.randn(C, device=cuda_device), torch.randn(C, device=cuda_device)
+    hi, lo = ops.group_norm(x, g, b, insts, 1e-6, True, want_lo=True)
+    assert torch.equal(hi, ops.group_norm(x, g, b, insts, 1e-6, True))
+    want = F.silu(F.group_norm(x.view(insts, rows, C).permute(0, 2, 1), 32, g, b, eps=1e-6)).permute(0, 2, 1).reshape(-1, C)
+    e_hi, e_sum = rel_l2(hi, want), rel_l2(hi.float() + lo.float(), want)
+    assert e_sum < 2e-5 and e_sum < 0.1 * e_hi  # limited by silu_fast / fp32 statistics, not by fp16 storage
+
+
+def test_state_dict_views_are_copied(cuda_device, built_lib):
+    """Parameters handed over as views at odd offsets of one flat buffer (16-byte misaligned) must not reach the kernels'
+    vector loads: load_state_dict takes private, freshly allocated copies (round-2 smoke failure)."""
+    from evoworld_b200.unet import UNetSpatioTemporalConditionModel
+
+    cfg = dict(in_channels=18, block_out_channels=(64, 64, 64, 64), num_attention_heads=(1, 1, 1, 1), cross_attention_dim=64)
+    a = UNetSpatioTemporalConditionModel(**cfg).init_random(seed=3, device=cuda_device)
+    sd = a.state_dict()
+    flat = torch.empty(sum(v.numel() + 1 for v in sd.values()) + 1, device=cuda_device)
+    views, off = {}, 1
+    for k, v in sd.items():
+        views[k] = flat[off:off + v.numel()].view(v.shape).copy_(v)
+        off += v.numel() + 1
+    b = UNetSpatioTemporalConditionModel(**cfg).to(cuda_device)
+    b.load_state_dict(views)
+    x = torch.randn(2, 2, 18, 8, 16, device=cuda_device)
+    ehs, ids = torch.randn(2, 1, 64, device=cuda_device), torch.tensor([[6.0, 127.0, 0.02]] * 2, device=cuda_device)
+    assert torch.equal(a(x, 0.5, ehs, ids).sample, b(x, 0.5, ehs, ids).sample)
