@@ -69,9 +69,11 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     from evoworld_b200.distributed import gather_latents
 
+    replays0 = unet.graph_replays()
     e0.record()
     for i in range(args.steps):
         step(i, x)
+    graph_replays_timed = unet.graph_replays() - replays0
     gathered = gather_latents(x)  # clip boundary: the only collective of the path (no-op at world == 1)
     e1.record()
     torch.cuda.synchronize(dev)
@@ -112,7 +114,9 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
         "config": {"workload": f"{'config 2' if (h, w) == (LAT_H, LAT_W) else 'config 5 panorama size'}: single {8 * h}x{8 * w}x{T}f clip, CFG batch 2, {h}x{w} latents, random-init 1.525B-param UNet, "
                                f"Karras sigmas (25-step schedule)", "frames": T, "finite_output": finite,
                    "collective": f"all-gather of latents {tuple(gathered.shape)} at the clip boundary",
-                   "l2": "working set (activations + 3 GB of fp16 weights) >> 126 MB L2; K steps in one CUDA-event pair"},
+                   "l2": "working set (activations + 3 GB of fp16 weights) >> 126 MB L2; K steps in one CUDA-event pair",
+                   "graph_replays": graph_replays_timed,
+                   "launch": "each step = 1 set-args kernel + 1 cudaGraphLaunch of the captured plan (gpu_launches counts the kernels inside)"},
     }
     if rank == 0 and world == 1 and not getattr(args, "no_eager_baseline", False):
         try:

@@ -54,6 +54,7 @@ SIGNATURES = {
     "evw_denoise_step": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_float, c_float,
                                  c_int, c_int, c_int, c_void_p, c_i64, c_void_p]),
     "evw_unet_plan_info": (c_int, [c_void_p, C.POINTER(c_i64), C.POINTER(C.c_double)]),
+    "evw_unet_graph_replays": (c_i64, [c_void_p]),
     "evw_splat_cube_equirect": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p,
                                         c_int, c_int, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p]),
     "evw_splat_cube_faces_debug": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_float, c_float, c_void_p,

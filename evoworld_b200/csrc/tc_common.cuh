@@ -71,11 +71,27 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // n
       : "memory");
   return ok != 0;
 }
+// try_wait with an explicit suspend-time hint (ns): the waiting warp sleeps in hardware until the phase completes (or the
+// hint expires) instead of re-issuing the poll — idle producer / MMA warps otherwise spend 5-6 % of the SM's issue slots
+// on the spin loop, slots the two epilogue warps of the same scheduler are short of (profiles/r02c_ncu_gemm_epilogue.txt).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
     if (clock64() - t0 > 8000000000ll) __trap();
   }
 }

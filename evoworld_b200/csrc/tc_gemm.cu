@@ -43,8 +43,31 @@ constexpr int kCtrlThreads = 128;    // 4 control warps (TMA, MMA, TMEM allocato
 constexpr int kEpiWarpsDefault = 8, kEpiWarpsGeglu = 16;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 
+// Division by a run-time constant d (1 <= d, dividend < 2^31) as umulhi + add + shift (Granlund-Montgomery round-up):
+// the tile-index decomposition runs per thread per tile and cost ~100 instructions per warp and tile with IDIV sequences
+// (13 % of all instructions issued by the K = 320 GEMMs, profiles/r02c_ncu_gemm_epilogue.txt).
+struct FastDiv {
+  uint32_t d = 1, mul = 1, shr = 0;
+};
+__host__ inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d ? d : 1;
+  uint32_t shr = 0;
+  while ((1ull << shr) < f.d) ++shr;
+  f.shr = shr;
+  f.mul = (uint32_t)((((1ull << 32) * ((1ull << shr) - f.d)) / f.d) + 1);
+  return f;
+}
+__device__ __forceinline__ uint32_t fd_div(uint32_t n, const FastDiv& f) { return (__umulhi(n, f.mul) + n) >> f.shr; }
+__device__ __forceinline__ void fd_divmod(uint32_t n, const FastDiv& f, uint32_t& q, uint32_t& rem) {
+  q = fd_div(n, f);
+  rem = n - q * f.d;
+}
+
 struct KernelParams {
   GemmEpilogue ep;
+  FastDiv fd_n_tiles, fd_tiles_x, fd_tiles_y, fd_T, fd_rv_div, fd_rv_mod;
+  int bx_shift;
   int tiles_x, tiles_y, T, B, X, Y, bx, by;
   int n_tiles, block_n, N;
   int num_taps;
@@ -253,6 +276,78 @@ __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+// Non-GEGLU epilogue of one 128 x BLOCK_N tile for this thread's row: columns [16 k, 16 k + 16) for k = cgrp, cgrp + NG, ...
+//   out = s0 * acc + bias' [+ rowvec] [+ s1 * res1] [+ s2 * res2]        (bias' = s0 * bias, staged in shared memory)
+// RV / R1 / R2 select the operands at compile time.  res1 (the HBM-resident residual stream) is software-pipelined over
+// two register sets: the loads of step k + NG are issued before the TMEM wait of step k.  The broadcast row vector (one
+// row per frame or batch element: L1-resident) and res2 (one layer) are loaded at the point of use.
+// out_off / rv_off are element offsets of column n0 of this row (of the broadcast row); ncols = N - n0.
+template <bool RV, bool R1, bool R2>
+__device__ __noinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_addr, const float* bs, int cgrp, int NG, int nsteps,
+                                          bool row_ok, int ncols, long long out_off, long long rv_off, bool wide_ok,
+                                          uint32_t bar_full, uint32_t phase) {
+  auto load_r1 = [&](float (&x)[16], int k) {
+    if constexpr (!R1) return;
+    const int c = k * 16;
+    if (!(row_ok && k < nsteps && c < ncols)) return;
+    load16(ep.res1, ep.res1_fp16, out_off + c, c + 16 <= ncols, x);
+  };
+  auto step = [&](int k, const float (&cur)[16], float (&nxt)[16], int k_next) {
+    uint32_t raw[16];
+    __syncwarp();
+    tmem_ld_32x32b_x16(t_addr + k * 16, raw);
+    load_r1(nxt, k_next);
+    tmem_ld_wait();
+    const int c = k * 16;
+    if (row_ok && c < ncols) {
+      const bool full = c + 16 <= ncols;
+      float v[16];
+      const float4* b4 = reinterpret_cast<const float4*>(bs + k * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 t4 = b4[i];
+        v[4 * i] = fmaf(__uint_as_float(raw[4 * i]), ep.s0, t4.x);
+        v[4 * i + 1] = fmaf(__uint_as_float(raw[4 * i + 1]), ep.s0, t4.y);
+        v[4 * i + 2] = fmaf(__uint_as_float(raw[4 * i + 2]), ep.s0, t4.z);
+        v[4 * i + 3] = fmaf(__uint_as_float(raw[4 * i + 3]), ep.s0, t4.w);
+      }
+      if constexpr (R1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(ep.s1, cur[i], v[i]);
+      }
+      if constexpr (RV) {
+        float rv[16];
+        load16(ep.rowvec, 0, rv_off + c, full, rv);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += rv[i];
+      }
+      if constexpr (R2) {
+        float r2[16];
+        load16(ep.res2, 0, out_off + c, full, r2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(ep.s2, r2[i], v[i]);
+      }
+      if (full) {
+        store16(ep, v, out_off + c, wide_ok);
+      } else {  // N tail: only the first 8 columns exist (N is a multiple of 8)
+        float v8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v8[i] = v[i];
+        if (ep.out_fp16) store8(reinterpret_cast<__half*>(ep.out) + out_off + c, v8);
+        else store8(reinterpret_cast<float*>(ep.out) + out_off + c, v8);
+      }
+    }
+  };
+  float A[16], B[16];
+  load_r1(A, cgrp);
+  mbar_wait(bar_full, phase);
+  tc_fence_after();
+  for (int k = cgrp; k < nsteps; k += 2 * NG) {
+    step(k, A, B, k + NG);
+    if (k + NG < nsteps) step(k + NG, B, A, k + 2 * NG);
+  }
+}
+
 template <bool k2Cta, int kEpiWarps>
 __global__ void __launch_bounds__(kCtrlThreads + 32 * kEpiWarps, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
@@ -315,6 +410,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
 
   int total_chunks = 0;
   for (int t = 0; t < P.num_taps; ++t) total_chunks += P.chunks[P.tap_src[t]];
+  // tile index -> (n-tile, x-tile, y-tile, frame, batch)
+  auto decode = [&](int tile, int& n_tile, int& tx, int& ty, int& tt, int& tb) {
+    uint32_t m, a, b, c, d;
+    fd_divmod((uint32_t)tile, P.fd_n_tiles, m, a);
+    n_tile = (int)a;
+    fd_divmod(m, P.fd_tiles_x, m, b);
+    tx = (int)b;
+    fd_divmod(m, P.fd_tiles_y, m, c);
+    ty = (int)c;
+    fd_divmod(m, P.fd_T, m, d);
+    tt = (int)d;
+    tb = (int)m;
+  };
 
   if (kEpiWarps > 8) {
     // 640 threads launch with <= 96 registers each; the control warpgroup hands registers to the epilogue warpgroups
@@ -328,12 +436,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
     uint32_t phase = 0;
     for (int v = v_first; v < v_limit; v += v_step) {
       const int tile = to_tile(v);
-      const int n_tile = tile % P.n_tiles;
-      int m_tile = tile / P.n_tiles;
-      const int tx = m_tile % P.tiles_x; m_tile /= P.tiles_x;
-      const int ty = m_tile % P.tiles_y; m_tile /= P.tiles_y;
-      const int tt = m_tile % P.T;
-      const int tb = m_tile / P.T;
+      int n_tile, tx, ty, tt, tb;
+      decode(tile, n_tile, tx, ty, tt, tb);
       const int x0 = tx * P.bx, y0 = ty * P.by, n0 = n_tile * P.block_n;
       int kglob = 0;
       for (int tap = 0; tap < P.num_taps; ++tap) {
@@ -400,10 +504,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    // Two warps share each TMEM lane quarter and alternate column steps.  Per step: issue the TMEM load, issue the
-    // global loads of the NEXT step's residual / row-vector operands (software pipeline: their latency overlaps this
-    // step's work), wait for TMEM, apply the epilogue, store one full 32-byte sector per row where alignment allows.
-    // The bias slice of the tile is staged in shared memory once per tile.
+    // Two warps share each TMEM lane quarter and alternate 16-column steps.  Per step: issue the TMEM load, issue the
+    // global loads of the NEXT step's residual / row-vector operands (software pipeline over two register sets: their
+    // latency overlaps this step's work), wait for TMEM, one FFMA per output against the pre-scaled bias staged in shared
+    // memory (128-bit reads), store one full 32-byte sector per row where alignment allows.  The hot loop is compiled
+    // per operand combination (epi_plain<RV, R1, R2>): with two epilogue warps per scheduler the loop is bound by issue
+    // slots, and the generic version spent 4/5 of them on moves, predicates and index arithmetic.
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;         // row of the 128-row tile
     const int cgrp = (warp - 4) >> 2;    // column group of this warp
@@ -415,18 +521,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
     const bool wide_ok = (((long long)ldo * esz) % 32 == 0) && ((reinterpret_cast<uintptr_t>(ep.out) & 31) == 0);
     float* bias_s = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 8 * (2 * stages + 4) + 16);
     const int et = threadIdx.x - 128;    // 0 .. 32*kEpiWarps-1
+    const int mx = r & (P.bx - 1), my = r >> P.bx_shift;  // bx is a power of two
+    const bool is_geglu = kEpiWarps > 8 || ep.geglu;      // the 16-warp instantiation is GEGLU-only
     // residual operands stream from DRAM exactly once: pull the row segment of the NEXT tile into L2 one tile ahead
     // (prefetch.global.L2, no registers / shared memory), so the epilogue's loads find it there
     auto prefetch_residuals = [&](int v_p) {
       if (v_p >= v_limit || (!ep.res1 && !ep.res2)) return;
       const int tile_p = to_tile(v_p);
       if (tile_p >= P.total_tiles) return;
-      const int n_tile_p = tile_p % P.n_tiles;
-      int m_tile_p = tile_p / P.n_tiles;
-      const int tx_p = m_tile_p % P.tiles_x; m_tile_p /= P.tiles_x;
-      const int ty_p = m_tile_p % P.tiles_y; m_tile_p /= P.tiles_y;
-      const int tt_p = m_tile_p % P.T, tb_p = m_tile_p / P.T;
-      const int gx_p = tx_p * P.bx + r % P.bx, gy_p = ty_p * P.by + r / P.bx;
+      int n_tile_p, tx_p, ty_p, tt_p, tb_p;
+      decode(tile_p, n_tile_p, tx_p, ty_p, tt_p, tb_p);
+      const int gx_p = tx_p * P.bx + mx, gy_p = ty_p * P.by + my;
       if (gx_p >= P.X || gy_p >= P.Y) return;
       const long long row_p = (((long long)tb_p * P.T + tt_p) * P.Y + gy_p) * P.X + gx_p;
       const long long off = row_p * ldo + (long long)n_tile_p * P.block_n;
@@ -448,28 +553,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
       prefetch_residuals(v + v_step);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int n_tile = tile % P.n_tiles;
-      int m_tile = tile / P.n_tiles;
-      const int tx = m_tile % P.tiles_x; m_tile /= P.tiles_x;
-      const int ty = m_tile % P.tiles_y; m_tile /= P.tiles_y;
-      const int tt = m_tile % P.T;
-      const int tb = m_tile / P.T;
-      const int mx = r % P.bx, my = r / P.bx;
+      int n_tile, tx, ty, tt, tb;
+      decode(tile, n_tile, tx, ty, tt, tb);
       const int gx = tx * P.bx + mx, gy = ty * P.by + my;
       const bool row_ok = gx < P.X && gy < P.Y && tile < P.total_tiles;
       const long long row = (((long long)tb * P.T + tt) * P.Y + gy) * P.X + gx;
-      const long long rv_row = ep.rowvec ? (row / ep.rv_div) % ep.rv_mod : 0;
       const int n0 = n_tile * P.block_n;
       float* bs = bias_s + acc * 256;
       if (et < P.block_n) {
         float bv = (ep.bias && n0 + et < P.N) ? __ldg(ep.bias + n0 + et) : 0.f;
-        if ((kEpiWarps > 8 || ep.geglu) && (et & 16) == 0) bv *= ep.s0;  // GEGLU value columns: s0 folded into the bias
+        // s0 is folded into the staged bias: out = s0 * acc + s0 * bias (GEGLU: value columns only)
+        if (!is_geglu || (et & 16) == 0) bv *= ep.s0;
         bs[et] = bv;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
 
       const uint32_t t_addr = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
-      if (kEpiWarps > 8 || ep.geglu) {  // the 16-warp instantiation is GEGLU-only: the other branch folds away
+      if (is_geglu) {
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         // 32 accumulator columns = [16 value | 16 gate] -> 16 outputs
@@ -480,73 +580,41 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
           tmem_ld_wait();
           const int nh = n0 + k * 32;
           if (row_ok && nh < P.N) {
-            float v[16];
+            float vv[16];
+            const float4* b4 = reinterpret_cast<const float4*>(bs + k * 32);  // [16 value | 16 gate] biases, 128-bit reads
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float hv = fmaf(__uint_as_float(raw[i]), ep.s0, bs[k * 32 + i]);  // s0 (value + bias)
-              const float gv = __uint_as_float(raw[16 + i]) + bs[k * 32 + 16 + i];
-              v[i] = hv * gelu_erf(gv);
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 bh = b4[i4], bg = b4[4 + i4];
+              const float bhv[4] = {bh.x, bh.y, bh.z, bh.w}, bgv[4] = {bg.x, bg.y, bg.z, bg.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int i = 4 * i4 + j;
+                const float hv = fmaf(__uint_as_float(raw[i]), ep.s0, bhv[j]);  // s0 (value + bias)
+                const float gv = __uint_as_float(raw[16 + i]) + bgv[j];
+                vv[i] = hv * gelu_erf(gv);
+              }
             }
-            store16(ep, v, row * ldo + nh / 2, wide_ok);
+            store16(ep, vv, row * ldo + nh / 2, wide_ok);
           }
         }
       } else {
-        const int nsteps = P.block_n / 16;
-        float r1n[16], rvn[16];
-        auto prefetch = [&](int k) {
-          const int n = n0 + k * 16;
-          const bool ok = row_ok && k < nsteps && n < P.N;
-          const bool full = n + 16 <= P.N;
-          if (ep.res1) {
-            if (ok) load16(ep.res1, ep.res1_fp16, row * ldo + n, full, r1n);
-          }
-          if (ep.rowvec) {
-            if (ok) load16(ep.rowvec, 0, rv_row * rv_ld + n, full, rvn);
-          }
-        };
-        prefetch(cgrp);
-        mbar_wait(tfull_bar(acc), acc_phase);
-        tc_fence_after();
-        for (int k = cgrp; k < nsteps; k += NG) {
-          uint32_t raw[16];
-          float r1[16], rv[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { r1[i] = r1n[i]; rv[i] = rvn[i]; }
-          __syncwarp();
-          tmem_ld_32x32b_x16(t_addr + k * 16, raw);
-          prefetch(k + NG);
-          tmem_ld_wait();
-          const int n = n0 + k * 16;
-          if (row_ok && n < P.N) {
-            const bool full = n + 16 <= P.N;
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = (__uint_as_float(raw[i]) + bs[k * 16 + i]) * ep.s0;
-            if (ep.rowvec) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += rv[i];
-            }
-            if (ep.res1) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = fmaf(ep.s1, r1[i], v[i]);
-            }
-            if (ep.res2) {
-              float r2[16];
-              load16(ep.res2, 0, row * ldo + n, full, r2);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = fmaf(ep.s2, r2[i], v[i]);
-            }
-            if (full) {
-              store16(ep, v, row * ldo + n, wide_ok);
-            } else {  // N tail: only the first 8 columns exist (N is a multiple of 8)
-              float v8[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v8[i] = v[i];
-              if (ep.out_fp16) store8(reinterpret_cast<__half*>(ep.out) + row * ldo + n, v8);
-              else store8(reinterpret_cast<float*>(ep.out) + row * ldo + n, v8);
-            }
-          }
+        const long long out_off = row * ldo + n0;
+        long long rv_off = 0;
+        if (ep.rowvec) {
+          const uint32_t rq = fd_div((uint32_t)row, P.fd_rv_div);
+          uint32_t qq, rem;
+          fd_divmod(rq, P.fd_rv_mod, qq, rem);
+          rv_off = (long long)rem * rv_ld + n0;
         }
+        const int nsteps = P.block_n / 16;
+        const int ncols = P.N - n0;  // valid columns of this tile (may exceed block_n)
+        const uint32_t bar_full = tfull_bar(acc);
+#define EVW_EPI(RV, R1, R2) \
+  epi_plain<RV, R1, R2>(ep, t_addr, bs, cgrp, NG, nsteps, row_ok, ncols, out_off, rv_off, wide_ok, bar_full, acc_phase)
+        if (ep.res2) { if (ep.rowvec) EVW_EPI(true, true, true); else EVW_EPI(false, true, true); }
+        else if (ep.res1) { if (ep.rowvec) EVW_EPI(true, true, false); else EVW_EPI(false, true, false); }
+        else { if (ep.rowvec) EVW_EPI(true, false, false); else EVW_EPI(false, false, false); }
+#undef EVW_EPI
       }
       tc_fence_before();
       __syncwarp();
@@ -620,6 +688,7 @@ static int pow2_floor(int v) {
 }
 
 int gemm_cluster_mode();
+int gemm_pair_min_k();
 
 int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   EVW_CHECK_ARG(pr.C0 > 0 && pr.C0 % kBlockK == 0, "gemm: C0=%d must be a positive multiple of 64", pr.C0);
@@ -654,6 +723,20 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
                 "gemm: out_lo needs an fp16, non-GEGLU output with N a multiple of 16");
   P.block_n = bn;
   P.n_tiles = (pr.N + bn - 1) / bn;
+  {
+    const long long rows_total = (long long)pr.B * pr.T * pr.Y * pr.X;
+    EVW_CHECK_ARG(rows_total < (1ll << 31) && pr.ep.rv_div < (1ll << 31) && pr.ep.rv_mod < (1ll << 31) && pr.ep.rv_div > 0 &&
+                      pr.ep.rv_mod > 0,
+                  "gemm: more than 2^31 rows (or a broadcast period out of range)");
+    P.fd_n_tiles = make_fastdiv((uint32_t)P.n_tiles);
+    P.fd_tiles_x = make_fastdiv((uint32_t)P.tiles_x);
+    P.fd_tiles_y = make_fastdiv((uint32_t)P.tiles_y);
+    P.fd_T = make_fastdiv((uint32_t)pr.T);
+    P.fd_rv_div = make_fastdiv((uint32_t)pr.ep.rv_div);
+    P.fd_rv_mod = make_fastdiv((uint32_t)pr.ep.rv_mod);
+    P.bx_shift = 0;
+    while ((1 << P.bx_shift) < P.bx) ++P.bx_shift;
+  }
   P.num_taps = pr.num_taps;
   P.chunks[0] = pr.C0 / kBlockK;
   P.chunks[1] = pr.C1 / kBlockK;
@@ -669,7 +752,11 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   P.total_pairs = ((m_tiles + 1) / 2) * P.n_tiles;
   int sms = sm_count();
   // CTA-pair (cta_group::2) mode needs at least one full pair and a 1 KiB-aligned half weight tile (bn % 16 == 0 holds)
-  op->cluster = (gemm_cluster_mode() && m_tiles >= 2 && sms >= 2) ? 1 : 0;
+  // Auto mode pairs CTAs only where the main loop dominates: with K_total < gemm_pair_min_k() (K = 320 / 640 linears, whose
+  // tiles are epilogue-bound) the pair's lock-step accumulator hand-over costs more than the halved weight traffic saves
+  // (profiles/r02b_gemm_bench.log: 320->320 linear 596 -> 457 TFLOP/s, 3x3 convolutions 935 -> 1172 / 956 -> 1269).
+  const int mode = gemm_cluster_mode();
+  op->cluster = ((mode == 1 || (mode == 2 && pr.K_total >= gemm_pair_min_k())) && m_tiles >= 2 && sms >= 2) ? 1 : 0;
   const uint32_t stage_bytes = kATileBytes + bn * kBlockK * (op->cluster ? 1 : 2);  // a pair member holds half the weight tile
   int stages = (int)((227 * 1024 - 4096) / stage_bytes);
   if (stages > 8) stages = 8;
@@ -716,13 +803,18 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
 // multicast the weight tile between two cta_group::1 CTAs and measured neutral (profiles/r01f_gemm_bench.log): the
 // 160-wide tiles are bound by the shared-memory data pipe (tensor-core operand reads + TMA writes), which multicast does
 // not relieve; halving the weight operand per CTA does (profiles/r02*_gemm_bench.log).  0 = independent CTAs.
+// returns 0 = never pair, 1 = always pair (forced: tests, A/B runs), 2 = auto (pair when K_total >= gemm_pair_min_k())
 static int g_gemm_cluster = -1;
 int gemm_cluster_mode() {
   if (g_gemm_cluster < 0) {
     const char* e = getenv("EVW_GEMM_CLUSTER");
-    g_gemm_cluster = (e && atoi(e) == 0) ? 0 : 1;
+    g_gemm_cluster = !e ? 2 : (atoi(e) == 0 ? 0 : (atoi(e) == 1 ? 1 : 2));
   }
   return g_gemm_cluster;
+}
+int gemm_pair_min_k() {
+  static const int k = [] { const char* e = getenv("EVW_GEMM_PAIR_MIN_K"); return e ? atoi(e) : 1024; }();
+  return k;
 }
 void set_gemm_cluster_mode(int on) { g_gemm_cluster = on < 0 ? -1 : (on ? 1 : 0); }
 // EVW_GEMM_GEGLU_WARPS=16 selects the 16-warp GEGLU epilogue.  Measured slower than 8 warps (0.554 vs 0.514 ms at

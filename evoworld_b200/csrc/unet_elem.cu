@@ -451,8 +451,22 @@ __device__ __forceinline__ void put_split(__half* o, int c, int Cin, int split, 
     o[2 * Cin + c] = hd;
   }
 }
+// The per-step scalars (sigma, guidance, ...) live in a small DEVICE array written by set_step_args_kernel right before
+// the plan runs, so that the captured CUDA graph of the plan does not bake them in:
+//   dargs[0] = 1/sqrt(sigma^2+1), [1] = sigma, [2] = sigma_next, [3] = g_min, [4] = g_max
+__global__ void set_step_args_kernel(float* __restrict__ tsteps, int B, float* __restrict__ dargs, float timestep, float sigma,
+                                     float sigma_next, float g_min, float g_max) {
+  const int i = threadIdx.x;
+  if (i < B) tsteps[i] = timestep;
+  if (i == 0) {
+    dargs[0] = 1.0f / sqrtf(sigma * sigma + 1.0f);
+    dargs[1] = sigma; dargs[2] = sigma_next; dargs[3] = g_min; dargs[4] = g_max;
+  }
+}
+
 __global__ void pre_kernel(const float* __restrict__ latents, const float* __restrict__ cond, int Bc, int T, int Cl,
-                           int Cc, long long HW, float inv_scale, int Cpad, int split, __half* __restrict__ out) {
+                           int Cc, long long HW, const float* __restrict__ dargs, int Cpad, int split, __half* __restrict__ out) {
+  const float inv_scale = dargs[0];
   const long long total = (long long)Bc * T * HW;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -491,8 +505,9 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ y, long long frame
 // post: CFG combine + Euler (v-prediction) step on NCHW latents, reading the channels-last model output
 //   v = vu + g_t (vc - vu);  x0 = v * (-sigma / sqrt(sigma^2+1)) + x / (sigma^2+1);  d = (x - x0)/sigma;
 //   x' = x + d (sigma_next - sigma)
-__global__ void post_kernel(const float* __restrict__ y, int T, int Cl, long long HW, int Npad, int fold, float sigma,
-                            float sigma_next, float g_min, float g_max, float* __restrict__ latents) {
+__global__ void post_kernel(const float* __restrict__ y, int T, int Cl, long long HW, int Npad, int fold,
+                            const float* __restrict__ dargs, float* __restrict__ latents) {
+  const float sigma = dargs[1], sigma_next = dargs[2], g_min = dargs[3], g_max = dargs[4];
   const long long total = (long long)T * HW;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -826,11 +841,17 @@ int downsplit(const float* x, __half* out, long long n, int h, int w, int C, cud
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }
-int pre_concat(const float* latents, const float* cond, int Bc, int T, int Cl, int Cc, long long HW, float sigma, int Cpad,
+int set_step_args(float* tsteps, int B, float* dargs, float timestep, float sigma, float sigma_next, float g_min, float g_max,
+                  cudaStream_t st) {
+  EVW_CHECK_ARG(B >= 1 && B <= 32, "set_step_args: B=%d", B);
+  set_step_args_kernel<<<1, 32, 0, st>>>(tsteps, B, dargs, timestep, sigma, sigma_next, g_min, g_max);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+int pre_concat(const float* latents, const float* cond, int Bc, int T, int Cl, int Cc, long long HW, const float* dargs, int Cpad,
                int split, __half* out, cudaStream_t st) {
   EVW_CHECK_ARG(!split || 3 * (Cl + Cc) <= Cpad, "pre_concat: split needs 3 Cin <= Cpad");
-  const float inv = 1.0f / sqrtf(sigma * sigma + 1.0f);
-  pre_kernel<<<blocks_for((long long)Bc * T * HW, 256), 256, 0, st>>>(latents, cond, Bc, T, Cl, Cc, HW, inv, Cpad, split, out);
+  pre_kernel<<<blocks_for((long long)Bc * T * HW, 256), 256, 0, st>>>(latents, cond, Bc, T, Cl, Cc, HW, dargs, Cpad, split, out);
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }
@@ -846,10 +867,10 @@ int nhwc_to_nchw_f32(const float* y, long long frames, int Co, long long HW, int
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }
-int post_cfg_euler(const float* y, int T, int Cl, long long HW, int Npad, int fold, float sigma, float sigma_next, float g_min,
-                   float g_max, float* latents, cudaStream_t st) {
+int post_cfg_euler(const float* y, int T, int Cl, long long HW, int Npad, int fold, const float* dargs, float* latents,
+                   cudaStream_t st) {
   EVW_CHECK_ARG(!fold || 2 * Cl <= Npad, "post_cfg_euler: fold needs 2 Cl <= Npad");
-  post_kernel<<<blocks_for((long long)T * HW, 256), 256, 0, st>>>(y, T, Cl, HW, Npad, fold, sigma, sigma_next, g_min, g_max, latents);
+  post_kernel<<<blocks_for((long long)T * HW, 256), 256, 0, st>>>(y, T, Cl, HW, Npad, fold, dargs, latents);
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }

@@ -23,12 +23,16 @@ int upsample2x(const float* x, __half* out, long long n, int h, int w, int C, cu
 int downsplit(const float* x, __half* out, long long n, int h, int w, int C, cudaStream_t st);
 // split: conv_in operand in split precision inside the channel padding ([head | tail | head], 3 Cin <= Cpad);
 // fold: conv_out's weight tail lives in output columns [Co, 2Co) and is added back here
-int pre_concat(const float* latents, const float* cond, int Bc, int T, int Cl, int Cc, long long HW, float sigma, int Cpad,
+// per-step scalars on the device (so a captured graph of the plan stays valid from step to step):
+// tsteps[0..B) = timestep; dargs = {1/sqrt(sigma^2+1), sigma, sigma_next, g_min, g_max}
+int set_step_args(float* tsteps, int B, float* dargs, float timestep, float sigma, float sigma_next, float g_min, float g_max,
+                  cudaStream_t st);
+int pre_concat(const float* latents, const float* cond, int Bc, int T, int Cl, int Cc, long long HW, const float* dargs, int Cpad,
                int split, __half* out, cudaStream_t st);
 int nchw_to_nhwc_f16(const float* x, long long frames, int Cin, long long HW, int Cpad, int split, __half* out, cudaStream_t st);
 int nhwc_to_nchw_f32(const float* y, long long frames, int Co, long long HW, int Npad, int fold, float* out, cudaStream_t st);
-int post_cfg_euler(const float* y, int T, int Cl, long long HW, int Npad, int fold, float sigma, float sigma_next, float g_min,
-                   float g_max, float* latents, cudaStream_t st);
+int post_cfg_euler(const float* y, int T, int Cl, long long HW, int Npad, int fold, const float* dargs, float* latents,
+                   cudaStream_t st);
 int timestep_embed(const float* t, int n, int dim, __half* out, cudaStream_t st);
 int silu_f16(const float* x, __half* out, long long n, cudaStream_t st);
 int cast_f16(const float* x, __half* out, long long n, cudaStream_t st);

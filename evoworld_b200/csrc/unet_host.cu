@@ -62,6 +62,17 @@ struct OpMeta {
   int fp16 = 0;
 };
 
+// Pointers baked into a captured graph of the plan (kernel parameters); the per-step scalars are not (set_step_args).
+struct GraphKey {
+  int mode = -1;
+  const void *sample = nullptr, *latents = nullptr, *cond = nullptr, *latents_out = nullptr, *out = nullptr, *ehs = nullptr,
+             *added = nullptr;
+  bool operator==(const GraphKey& o) const {
+    return mode == o.mode && sample == o.sample && latents == o.latents && cond == o.cond && latents_out == o.latents_out &&
+           out == o.out && ehs == o.ehs && added == o.added;
+  }
+};
+
 struct Plan {
   std::vector<OpMeta> meta;
   int B = 0, T = 0, h = 0, w = 0;
@@ -70,6 +81,19 @@ struct Plan {
   std::vector<Op> ops;
   long long launches = 0;
   double flops = 0;
+  float *tsteps = nullptr, *dargs = nullptr;  // device-side per-step scalars (in the workspace)
+  // plan-owned copies of the small / per-call tensors, so that the captured graph sees constant addresses:
+  // encoder_hidden_states [B, cross], added_time_ids [B, 3], and for forward() the sample and the output
+  float *ehs_stage = nullptr, *added_stage = nullptr, *sample_stage = nullptr, *out_stage = nullptr;
+  // whole-plan CUDA graphs, one per distinct set of caller pointers (the denoise loop re-uses its buffers: one capture)
+  bool warm = false, graphs_ok = true;
+  cudaStream_t capture_stream = nullptr;
+  std::vector<std::pair<GraphKey, cudaGraphExec_t>> graphs;
+  long long graph_replays = 0;
+  ~Plan() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+    if (capture_stream) cudaStreamDestroy(capture_stream);
+  }
 };
 
 struct UNet {
@@ -106,7 +130,7 @@ struct Builder {
   __half *n16 = nullptr, *raw16 = nullptr, *h16 = nullptr, *qkv16 = nullptr, *attn16 = nullptr, *ff16 = nullptr, *in16 = nullptr,
          *resamp16 = nullptr, *small16 = nullptr, *lo16 = nullptr;
   float *f0 = nullptr, *f1 = nullptr, *f2 = nullptr, *pp[2] = {nullptr, nullptr}, *y32 = nullptr;
-  float *emb = nullptr, *emb2 = nullptr, *temb_all = nullptr, *xattn_all = nullptr, *tsteps = nullptr;
+  float *emb = nullptr, *emb2 = nullptr, *temb_all = nullptr, *xattn_all = nullptr, *tsteps = nullptr, *dargs = nullptr;
   double* stats = nullptr;
   std::string fail;
 
@@ -404,29 +428,33 @@ struct Builder {
     temb_all = bump.take<float>((long long)B * c.temb_total);
     xattn_all = bump.take<float>((long long)B * c.xattn_total);
     tsteps = bump.take<float>(64);
+    dargs = bump.take<float>(64);
+    P.tsteps = tsteps; P.dargs = dargs;
+    P.ehs_stage = bump.take<float>((long long)B * c.cross_dim);
+    P.added_stage = bump.take<float>(64);
+    P.sample_stage = bump.take<float>((long long)BF * c.in_channels * lS[0]);
+    P.out_stage = bump.take<float>((long long)BF * c.out_channels * lS[0]);
 
     UNet* u = &U;
     const long long HW = lS[0];
     // ---- inputs -> fp16 channels-last, padded to 64 channels
     {
-      __half* o = in16; int Cin = c.in_channels, Cpad = c.cin_pad, T_ = T, B_ = B, sp_ = c.split;
+      __half* o = in16; int Cin = c.in_channels, Cpad = c.cin_pad, T_ = T, B_ = B, sp_ = c.split; const float* da = dargs;
       push([=](cudaStream_t st) {
         const CallArgs& a = u->args;
-        if (a.mode == 1) return pre_concat(a.latents, a.cond, B_, T_, 4, Cin - 4, HW, a.sigma, Cpad, sp_, o, st);
+        if (a.mode == 1) return pre_concat(a.latents, a.cond, B_, T_, 4, Cin - 4, HW, da, Cpad, sp_, o, st);
         return nchw_to_nhwc_f16(a.sample, (long long)B_ * T_, Cin, HW, Cpad, sp_, o, st);
       }, 1, "pre (scale+concat+layout)");
     }
     // ---- time / added-id embeddings (unet_plucker.py:384-414)
     {
       float* ts = tsteps; __half* s16 = small16; int B_ = B, add_dim = c.add_dim, c0 = c.boc[0];
-      push([=](cudaStream_t st) {
+      push([=](cudaStream_t st) {  // ts[0..B) = timestep is written by set_step_args before the plan runs
         const CallArgs& a = u->args;
-        int rc0 = fill_f32(ts, a.timestep, B_, st);
-        if (rc0) return rc0;
         int rc = timestep_embed(ts, B_, c0, s16, st);
         if (rc) return rc;
         return timestep_embed(a.added, B_ * 3, add_dim, s16 + kSmall, st);  // [B*3, 256] == [B, 768]
-      }, 3, "timestep embeddings");
+      }, 2, "timestep embeddings");
       GemmEpilogue e1; e1.out = emb; e1.out_fp16 = 0;
       linear(small16, B, c.boc[0], "time_embedding.linear_1", c.temb_dim, e1);
       { float* x = emb; __half* o = small16 + 2 * kSmall; long long n = (long long)B * c.temb_dim;
@@ -547,10 +575,10 @@ struct Builder {
       conv3x3_simple(n16, BF, lh[0], lw[0], xC, "conv_out", c.cout_pad, y32);
     }
     {
-      const float* y = y32; int Co = c.out_channels, Np = c.cout_pad, T_ = T, B_ = B, fold = c.split;
+      const float* y = y32; int Co = c.out_channels, Np = c.cout_pad, T_ = T, B_ = B, fold = c.split; const float* da = dargs;
       push([=](cudaStream_t st) {
         const CallArgs& a = u->args;
-        if (a.mode == 1) return post_cfg_euler(y, T_, Co, HW, Np, fold, a.sigma, a.sigma_next, a.g_min, a.g_max, a.latents_out, st);
+        if (a.mode == 1) return post_cfg_euler(y, T_, Co, HW, Np, fold, da, a.latents_out, st);
         return nhwc_to_nchw_f32(y, (long long)B_ * T_, Co, HW, Np, fold, a.out, st);
       }, 1, "post (CFG+Euler / layout)");
     }
@@ -628,9 +656,72 @@ int run_plan_profiled(UNet* U, cudaStream_t st, const char* path) {
   return EVW_OK;
 }
 
+// Replay the plan as ONE CUDA graph launch.  The first call of a plan runs eagerly (it also performs the one-time
+// cudaFuncSetAttribute calls of the kernels); the second call captures the ~830 launches on an internal stream (the
+// caller's stream may be the legacy default stream, which cannot be captured) and from then on every call with the same
+// caller pointers is: set_step_args kernel + cudaGraphLaunch on the caller's stream.  EVW_UNET_GRAPH=0 disables.
+int run_plan_graph(UNet* U, cudaStream_t st, bool* done) {
+  Plan& P = *U->plan;
+  *done = false;
+  static const bool enabled = [] { const char* e = getenv("EVW_UNET_GRAPH"); return !(e && atoi(e) == 0); }();
+  if (!enabled || !P.graphs_ok) return EVW_OK;
+  if (!P.warm) {
+    P.warm = true;
+    return EVW_OK;
+  }
+  const CallArgs& a = U->args;
+  GraphKey key;
+  key.mode = a.mode; key.sample = a.sample; key.latents = a.latents; key.cond = a.cond; key.latents_out = a.latents_out;
+  key.out = a.out; key.ehs = a.ehs; key.added = a.added;
+  cudaGraphExec_t exec = nullptr;
+  for (auto& g : P.graphs)
+    if (g.first == key) exec = g.second;
+  if (!exec) {
+    if (P.graphs.size() >= 8) {  // callers that hand over fresh buffers every call: stay eager
+      P.graphs_ok = false;
+      return EVW_OK;
+    }
+    if (!P.capture_stream) EVW_CUDA(cudaStreamCreateWithFlags(&P.capture_stream, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    EVW_CUDA(cudaStreamBeginCapture(P.capture_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = EVW_OK;
+    for (auto& op : P.ops)
+      if ((rc = op(P.capture_stream))) break;
+    cudaError_t e = cudaStreamEndCapture(P.capture_stream, &graph);
+    if (rc || e != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      P.graphs_ok = false;  // fall back to eager launches for this plan
+      return rc;
+    }
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      P.graphs_ok = false;
+      return EVW_OK;
+    }
+    P.graphs.emplace_back(key, exec);
+  }
+  EVW_CUDA(cudaGraphLaunch(exec, st));
+  ++P.graph_replays;
+  *done = true;
+  return EVW_OK;
+}
+
 int run_plan(UNet* U, cudaStream_t st) {
   static const bool debug = getenv("EVW_UNET_DEBUG") != nullptr;
+  {
+    const CallArgs& a = U->args;
+    int rc = set_step_args(U->plan->tsteps, U->plan->B, U->plan->dargs, a.timestep, a.sigma, a.sigma_next, a.g_min, a.g_max, st);
+    if (rc) return rc;
+  }
   if (const char* prof = getenv("EVW_UNET_PROFILE")) return run_plan_profiled(U, st, prof);
+  if (!debug) {
+    bool done = false;
+    int rc = run_plan_graph(U, st, &done);
+    if (rc || done) return rc;
+  }
   size_t i = 0;
   for (auto& op : U->plan->ops) {
     int rc = op(st);
@@ -736,8 +827,17 @@ extern "C" int evw_unet_forward(void* handle, const float* sample, float timeste
   if (rc) return rc;
   evw::CallArgs& a = U->args;
   a = evw::CallArgs();
-  a.mode = 0; a.sample = sample; a.timestep = timestep; a.ehs = ehs; a.added = added_time_ids; a.out = out;
-  return evw::run_plan(U, (cudaStream_t)stream);
+  evw::Plan& P = *U->plan;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t hw = (size_t)h * w, bf = (size_t)B * T;
+  EVW_CUDA(cudaMemcpyAsync(P.sample_stage, sample, bf * U->cfg.in_channels * hw * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  EVW_CUDA(cudaMemcpyAsync(P.ehs_stage, ehs, (size_t)B * U->cfg.cross_dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  EVW_CUDA(cudaMemcpyAsync(P.added_stage, added_time_ids, (size_t)B * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  a.mode = 0; a.sample = P.sample_stage; a.timestep = timestep; a.ehs = P.ehs_stage; a.added = P.added_stage; a.out = P.out_stage;
+  rc = evw::run_plan(U, st);
+  if (rc) return rc;
+  EVW_CUDA(cudaMemcpyAsync(out, P.out_stage, bf * U->cfg.out_channels * hw * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return EVW_OK;
 }
 
 extern "C" int evw_denoise_step(void* handle, float* latents, const float* cond_latents, float sigma, float sigma_next,
@@ -750,10 +850,19 @@ extern "C" int evw_denoise_step(void* handle, float* latents, const float* cond_
   if (rc) return rc;
   evw::CallArgs& a = U->args;
   a = evw::CallArgs();
+  evw::Plan& P = *U->plan;
+  cudaStream_t st = (cudaStream_t)stream;
+  EVW_CUDA(cudaMemcpyAsync(P.ehs_stage, ehs, (size_t)2 * U->cfg.cross_dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  EVW_CUDA(cudaMemcpyAsync(P.added_stage, added_time_ids, (size_t)2 * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   a.mode = 1; a.latents = latents; a.latents_out = latents; a.cond = cond_latents; a.sigma = sigma; a.sigma_next = sigma_next;
   a.timestep = 0.25f * logf(sigma);
-  a.ehs = ehs; a.added = added_time_ids; a.g_min = g_min; a.g_max = g_max;
-  return evw::run_plan(U, (cudaStream_t)stream);
+  a.ehs = P.ehs_stage; a.added = P.added_stage; a.g_min = g_min; a.g_max = g_max;
+  return evw::run_plan(U, st);
+}
+
+extern "C" int64_t evw_unet_graph_replays(void* handle) {
+  UNet* U = (UNet*)handle;
+  return (U && U->plan) ? U->plan->graph_replays : -1;
 }
 
 extern "C" int evw_unet_plan_info(void* handle, int64_t* launches, double* flops) {
@@ -763,7 +872,7 @@ extern "C" int evw_unet_plan_info(void* handle, int64_t* launches, double* flops
     evw::set_error("evw_unet_plan_info: no plan yet (call forward first)");
     return EVW_ERR_STATE;
   }
-  if (launches) *launches = U->plan->launches;
+  if (launches) *launches = U->plan->launches + 1;  // + set_step_args
   if (flops) *flops = U->plan->flops;
   return EVW_OK;
 }

@@ -496,6 +496,10 @@ class UNetSpatioTemporalConditionModel:
         _lib.check(_lib.lib().evw_unet_plan_info(self._handle, C.byref(launches), C.byref(flops)), "evw_unet_plan_info")
         return launches.value, flops.value
 
+    def graph_replays(self) -> int:
+        """Calls served by replaying the captured CUDA graph of the current plan (-1 before the first call)."""
+        return int(_lib.lib().evw_unet_graph_replays(self._handle)) if self._handle is not None else -1
+
     # ------------------------------------------------------------------ compute
     @torch.no_grad()
     def forward(self, sample: torch.Tensor, timestep: Union[torch.Tensor, float, int], encoder_hidden_states: torch.Tensor,

@@ -179,9 +179,11 @@ int evw_gemm_f16(const void* a0, const void* a1, const void* w, int B, int T, in
                  const float* rowvec, int64_t rv_div, int64_t rv_mod, const void* res1, int res1_fp16, float s1,
                  const float* res2, float s2, float s0, int geglu, int block_n, void* out_lo, void* stream);
 
-/* Launch mode of the GEMM (takes effect when an op is planned): 1 = CTA pairs (clusters of two) on m-adjacent tiles running
- * tcgen05.mma.cta_group::2 with M = 256, each CTA holding half of the weight tile (default), 0 = independent CTAs
- * (cta_group::1, M = 128), -1 = restore the default / EVW_GEMM_CLUSTER. */
+/* Launch mode of the GEMM (takes effect when an op is planned): 1 = always CTA pairs (clusters of two) on m-adjacent tiles
+ * running tcgen05.mma.cta_group::2 with M = 256, each CTA holding half of the weight tile; 0 = always independent CTAs
+ * (cta_group::1, M = 128); -1 = default (EVW_GEMM_CLUSTER, else automatic: pairs where K_total >= EVW_GEMM_PAIR_MIN_K,
+ * 1024 by default — the main-loop-bound convolutions and wide linears — and single CTAs for the epilogue-bound K = 320 /
+ * 640 linears).  All modes are bit-identical. */
 void evw_set_gemm_cluster(int on);
 
 /* Spatial self-attention (BasicTransformerBlock.attn1 -> F.scaled_dot_product_attention, head dim 64):
@@ -230,6 +232,10 @@ int evw_unet_forward(void* handle, const float* sample, float timestep, const fl
 int evw_denoise_step(void* handle, float* latents, const float* cond_latents, float sigma, float sigma_next,
                      const float* ehs, const float* added_time_ids, float g_min, float g_max, int T, int h, int w,
                      void* workspace, int64_t workspace_bytes, void* stream);
+/* How many calls on the current plan were served by replaying its captured CUDA graph (one cudaGraphLaunch instead of
+ * ~830 kernel launches; the first call of a plan runs eagerly, the second captures).  -1 without a plan.  EVW_UNET_GRAPH=0
+ * disables graph replay. */
+int64_t evw_unet_graph_replays(void* handle);
 /* Kernel launches and algorithmic FLOPs of the current plan (after the first forward / step). */
 int evw_unet_plan_info(void* handle, int64_t* launches, double* flops);
 

@@ -12,6 +12,13 @@ if case == "geglu":
 elif case == "linear":
     a = torch.randn(M, 320, device=dev).half(); w = torch.randn(320, 320, device=dev).half() * 0.05
     f = lambda: ops.gemm_f16(a, w)
+elif case == "qkv":
+    a = torch.randn(M, 320, device=dev).half(); w = torch.randn(960, 320, device=dev).half() * 0.05
+    f = lambda: ops.gemm_f16(a, w)
+elif case == "to_out":
+    a = torch.randn(M, 320, device=dev).half(); w = torch.randn(320, 320, device=dev).half() * 0.05
+    r = torch.randn(M, 320, device=dev); b = torch.randn(320, device=dev)
+    f = lambda: ops.gemm_f16(a, w, bias=b, res1=r, out_dtype=torch.float32)
 elif case == "ff2":
     a = torch.randn(M, 1280, device=dev).half(); w = torch.randn(320, 1280, device=dev).half() * 0.03
     r = torch.randn(M, 320, device=dev)
