@@ -8,7 +8,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libevoworld_b200.so"
+import os as _os
+
+# EVW_LIB: load another build of the same library (A/B experiments with differently compiled kernels); default = the in-tree build
+_LIB_PATH = Path(_os.environ["EVW_LIB"]) if _os.environ.get("EVW_LIB") else Path(__file__).resolve().parent / "_lib" / "libevoworld_b200.so"
 _lib = None
 
 c_void_p, c_int, c_i64, c_float = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -21,6 +24,7 @@ SIGNATURES = {
     "evw_plucker": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "evw_equi2pers_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "evw_lift_depth": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "evw_lift_pack_points": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "evw_pack_points": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_i64, c_void_p]),
     "evw_conf_select_workspace": (c_i64, [c_i64]),
     "evw_conf_select": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_float, c_int, c_void_p, c_void_p,

@@ -119,6 +119,51 @@ equi2pers_kernel(const uint8_t* __restrict__ equi, const float* __restrict__ pix
 // ------------------------------------------------------------------------------------------
 // Depth lift (float64 world transform as the numpy reference)
 // ------------------------------------------------------------------------------------------
+// World position of pixel p of frame s: camera coordinates rounded to float32 (geometry.py:104-109), float64 world
+// transform with c2w = [R^T | -R^T t] where -R^T t is evaluated in float32 (numpy matmul of f32 arrays).
+__device__ __forceinline__ void lift_point(const float* __restrict__ depth, const float* __restrict__ extr,
+                                           const float* __restrict__ intr, int s, int p, int H, int W, double& wx, double& wy,
+                                           double& wz) {
+  const float* E = extr + s * 12;
+  const float* K = intr + s * 9;
+  float r[9], t[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r[i * 3 + j] = E[j * 4 + i];
+    float acc = __fmul_rn(E[0 * 4 + i], E[3]);
+    acc = __fadd_rn(acc, __fmul_rn(E[1 * 4 + i], E[7]));
+    acc = __fadd_rn(acc, __fmul_rn(E[2 * 4 + i], E[11]));
+    t[i] = -acc;
+  }
+  const int v = p / W, u = p - v * W;
+  const double d = (double)depth[(size_t)s * H * W + p];
+  const float xc = (float)(((double)u - (double)K[2]) * d / (double)K[0]);
+  const float yc = (float)(((double)v - (double)K[5]) * d / (double)K[4]);
+  const float zc = (float)d;
+  wx = ((double)xc * r[0] + (double)yc * r[1]) + (double)zc * r[2] + (double)t[0];
+  wy = ((double)xc * r[3] + (double)yc * r[4]) + (double)zc * r[5] + (double)t[1];
+  wz = ((double)xc * r[6] + (double)yc * r[7]) + (double)zc * r[8] + (double)t[2];
+}
+
+// Fused lift + pack for the device-resident point memory: depth + NCHW float colours -> float4 {x,y,z,rgb} per pixel, the
+// same bits as lift_kernel (f64) followed by pack_points_kernel (f64 -> f32 round, colour = trunc(x*255)), without the
+// 24 B/point float64 intermediate: 16 B in (depth + 3 colour floats), 16 B out.
+__global__ void lift_pack_kernel(const float* __restrict__ depth, const float* __restrict__ extr, const float* __restrict__ intr,
+                                 const float* __restrict__ images, float4* __restrict__ out, int H, int W) {
+  const int s = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int HW = H * W;
+  if (p >= HW) return;
+  double wx, wy, wz;
+  lift_point(depth, extr, intr, s, p, H, W, wx, wy, wz);
+  const float* im = images + (size_t)s * 3 * HW + p;
+  const unsigned r = (unsigned)(uint8_t)(int)__fmul_rn(im[0], 255.0f);
+  const unsigned g = (unsigned)(uint8_t)(int)__fmul_rn(im[(size_t)HW], 255.0f);
+  const unsigned b = (unsigned)(uint8_t)(int)__fmul_rn(im[2 * (size_t)HW], 255.0f);
+  out[(size_t)s * HW + p] = make_float4((float)wx, (float)wy, (float)wz, __uint_as_float(r | (g << 8) | (b << 16)));
+}
+
 __global__ void lift_kernel(const float* __restrict__ depth, const float* __restrict__ extr,
                             const float* __restrict__ intr, double* __restrict__ out64,
                             float* __restrict__ out32, int H, int W) {
@@ -852,6 +897,17 @@ extern "C" int evw_lift_depth(const float* depth, const float* extr, const float
   EVW_CHECK_ARG(S > 0 && H > 0 && W > 0 && S <= 65535, "evw_lift_depth: bad shape");
   dim3 grd((H * W + 255) / 256, S);
   lift_kernel<<<grd, 256, 0, (cudaStream_t)stream>>>(depth, extr, intr, out_f64, out_f32, H, W);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+
+extern "C" int evw_lift_pack_points(const float* depth, const float* extr, const float* intr, const float* images_f32,
+                                    float* out_pts4, int S, int H, int W, void* stream) {
+  EVW_CHECK_ARG(depth && extr && intr && images_f32 && out_pts4, "evw_lift_pack_points: null pointer");
+  EVW_CHECK_ARG(S > 0 && H > 0 && W > 0 && S <= 65535, "evw_lift_pack_points: bad shape");
+  EVW_CHECK_ARG(((uintptr_t)out_pts4 & 15) == 0, "evw_lift_pack_points: out_pts4 must be 16-byte aligned");
+  dim3 grd((H * W + 255) / 256, S);
+  lift_pack_kernel<<<grd, 256, 0, (cudaStream_t)stream>>>(depth, extr, intr, images_f32, reinterpret_cast<float4*>(out_pts4), H, W);
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }

@@ -91,7 +91,11 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+#ifdef EVW_NO_WAIT_HINT
+  while (!mbar_try_wait(bar, parity)) {
+#else
   while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+#endif
     if (clock64() - t0 > 8000000000ll) __trap();
   }
 }

@@ -282,8 +282,9 @@ __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols
 // two register sets: the loads of step k + NG are issued before the TMEM wait of step k.  The broadcast row vector (one
 // row per frame or batch element: L1-resident) and res2 (one layer) are loaded at the point of use.
 // out_off / rv_off are element offsets of column n0 of this row (of the broadcast row); ncols = N - n0.
+// (must be inlined: as a real call the tcgen05.ld results were consumed before they arrived — 40 of 80 GEMM tests failed)
 template <bool RV, bool R1, bool R2>
-__device__ __noinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_addr, const float* bs, int cgrp, int NG, int nsteps,
+__device__ __forceinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_addr, const float* bs, int cgrp, int NG, int nsteps,
                                           bool row_ok, int ncols, long long out_off, long long rv_off, bool wide_ok,
                                           uint32_t bar_full, uint32_t phase) {
   auto load_r1 = [&](float (&x)[16], int k) {
@@ -315,17 +316,28 @@ __device__ __noinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_addr, 
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = fmaf(ep.s1, cur[i], v[i]);
       }
+      // row vector / second residual: loaded at the point of use, eight columns at a time (register pressure)
       if constexpr (RV) {
-        float rv[16];
-        load16(ep.rowvec, 0, rv_off + c, full, rv);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += rv[i];
+        for (int hf = 0; hf < 2; ++hf) {
+          if (hf == 0 || full) {
+            float rv[8];
+            load8_plain(ep.rowvec + rv_off + c + 8 * hf, rv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * hf + i] += rv[i];
+          }
+        }
       }
       if constexpr (R2) {
-        float r2[16];
-        load16(ep.res2, 0, out_off + c, full, r2);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaf(ep.s2, r2[i], v[i]);
+        for (int hf = 0; hf < 2; ++hf) {
+          if (hf == 0 || full) {
+            float r2[8];
+            load8_plain(ep.res2 + out_off + c + 8 * hf, r2);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * hf + i] = fmaf(ep.s2, r2[i], v[8 * hf + i]);
+          }
+        }
       }
       if (full) {
         store16(ep, v, out_off + c, wide_ok);
@@ -348,7 +360,12 @@ __device__ __noinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_addr, 
   }
 }
 
-template <bool k2Cta, int kEpiWarps>
+// kEpi selects the epilogue at compile time — 8 = GEGLU, else a bit set (1 = row vector, 2 = res1, 4 = res2) of the plain
+// epilogue's operands: one kernel body per combination.  Compiled into one body they pushed each other into spills (every
+// variant needs 66-144 registers on its own, all six together hit the 168-register ceiling with 150 B of spill traffic,
+// and GEGLU beside them went from 0.52 to 0.69 ms).
+constexpr int kEpiGeglu = 8;
+template <bool k2Cta, int kEpiWarps, int kEpi>
 __global__ void __launch_bounds__(kCtrlThreads + 32 * kEpiWarps, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
                const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_bh,
@@ -522,7 +539,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
     float* bias_s = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 8 * (2 * stages + 4) + 16);
     const int et = threadIdx.x - 128;    // 0 .. 32*kEpiWarps-1
     const int mx = r & (P.bx - 1), my = r >> P.bx_shift;  // bx is a power of two
-    const bool is_geglu = kEpiWarps > 8 || ep.geglu;      // the 16-warp instantiation is GEGLU-only
+    constexpr bool is_geglu = kEpi == kEpiGeglu;
     // residual operands stream from DRAM exactly once: pull the row segment of the NEXT tile into L2 one tile ahead
     // (prefetch.global.L2, no registers / shared memory), so the epilogue's loads find it there
     auto prefetch_residuals = [&](int v_p) {
@@ -569,7 +586,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
 
       const uint32_t t_addr = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
-      if (is_geglu) {
+      if constexpr (is_geglu) {
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         // 32 accumulator columns = [16 value | 16 gate] -> 16 outputs
@@ -581,18 +598,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
           const int nh = n0 + k * 32;
           if (row_ok && nh < P.N) {
             float vv[16];
-            const float4* b4 = reinterpret_cast<const float4*>(bs + k * 32);  // [16 value | 16 gate] biases, 128-bit reads
 #pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-              const float4 bh = b4[i4], bg = b4[4 + i4];
-              const float bhv[4] = {bh.x, bh.y, bh.z, bh.w}, bgv[4] = {bg.x, bg.y, bg.z, bg.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int i = 4 * i4 + j;
-                const float hv = fmaf(__uint_as_float(raw[i]), ep.s0, bhv[j]);  // s0 (value + bias)
-                const float gv = __uint_as_float(raw[16 + i]) + bgv[j];
-                vv[i] = hv * gelu_erf(gv);
-              }
+            for (int i = 0; i < 16; ++i) {
+              const float hv = fmaf(__uint_as_float(raw[i]), ep.s0, bs[k * 32 + i]);  // s0 (value + bias)
+              const float gv = __uint_as_float(raw[16 + i]) + bs[k * 32 + 16 + i];
+              vv[i] = hv * gelu_erf(gv);
             }
             store16(ep, vv, row * ldo + nh / 2, wide_ok);
           }
@@ -609,12 +619,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
         const int nsteps = P.block_n / 16;
         const int ncols = P.N - n0;  // valid columns of this tile (may exceed block_n)
         const uint32_t bar_full = tfull_bar(acc);
-#define EVW_EPI(RV, R1, R2) \
-  epi_plain<RV, R1, R2>(ep, t_addr, bs, cgrp, NG, nsteps, row_ok, ncols, out_off, rv_off, wide_ok, bar_full, acc_phase)
-        if (ep.res2) { if (ep.rowvec) EVW_EPI(true, true, true); else EVW_EPI(false, true, true); }
-        else if (ep.res1) { if (ep.rowvec) EVW_EPI(true, true, false); else EVW_EPI(false, true, false); }
-        else { if (ep.rowvec) EVW_EPI(true, false, false); else EVW_EPI(false, false, false); }
-#undef EVW_EPI
+        epi_plain<(kEpi & 1) != 0, (kEpi & 2) != 0, (kEpi & 4) != 0>(ep, t_addr, bs, cgrp, NG, nsteps, row_ok, ncols, out_off, rv_off,
+                                                                      wide_ok, bar_full, acc_phase);
       }
       tc_fence_before();
       __syncwarp();
@@ -719,6 +725,7 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   }
   EVW_CHECK_ARG(bn % 16 == 0 && bn >= 16 && bn <= 256, "gemm: BLOCK_N=%d invalid", bn);
   EVW_CHECK_ARG(!pr.ep.geglu || (bn % 32 == 0 && pr.N % 32 == 0), "gemm: GEGLU needs N and BLOCK_N multiples of 32");
+  EVW_CHECK_ARG(!pr.ep.res2 || pr.ep.res1, "gemm: res2 needs res1 (the two-residual epilogue loads both)");
   EVW_CHECK_ARG(!pr.ep.out_lo || (pr.ep.out_fp16 && !pr.ep.geglu && pr.N % 16 == 0 && ((uintptr_t)pr.ep.out_lo & 15) == 0),
                 "gemm: out_lo needs an fp16, non-GEGLU output with N a multiple of 16");
   P.block_n = bn;
@@ -826,12 +833,18 @@ static int gemm_geglu_wide_epilogue() {
 
 int gemm_launch(const GemmOp& op, cudaStream_t stream) {
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const KernelParams);
-  static const KernelFn fns[2][2] = {{tc_gemm_kernel<false, kEpiWarpsDefault>, tc_gemm_kernel<false, kEpiWarpsGeglu>},
-                                     {tc_gemm_kernel<true, kEpiWarpsDefault>, tc_gemm_kernel<true, kEpiWarpsGeglu>}};
+  // [pair mode][epilogue]: 0..5 = plain epilogue by operand set {none, rv, r1, rv+r1, r1+r2, rv+r1+r2}, 6 = GEGLU with
+  // 8 epilogue warps, 7 = GEGLU with 16
+#define EVW_GEMM_ROW(C)                                                                                                          \
+  {tc_gemm_kernel<C, kEpiWarpsDefault, 0>, tc_gemm_kernel<C, kEpiWarpsDefault, 1>, tc_gemm_kernel<C, kEpiWarpsDefault, 2>,       \
+   tc_gemm_kernel<C, kEpiWarpsDefault, 3>, tc_gemm_kernel<C, kEpiWarpsDefault, 6>, tc_gemm_kernel<C, kEpiWarpsDefault, 7>,       \
+   tc_gemm_kernel<C, kEpiWarpsDefault, kEpiGeglu>, tc_gemm_kernel<C, kEpiWarpsGeglu, kEpiGeglu>}
+  static const KernelFn fns[2][8] = {EVW_GEMM_ROW(false), EVW_GEMM_ROW(true)};
+#undef EVW_GEMM_ROW
   static bool attr_set = false;
   if (!attr_set) {
     for (int c = 0; c < 2; ++c)
-      for (int w = 0; w < 2; ++w) {
+      for (int w = 0; w < 8; ++w) {
         cudaError_t e = cudaFuncSetAttribute(fns[c][w], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
           set_error("cudaFuncSetAttribute(tc_gemm_kernel): %s", cudaGetErrorString(e));
@@ -848,7 +861,11 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream) {
   const CUtensorMap& tbh = *reinterpret_cast<const CUtensorMap*>(op.tmap_bh);
   const int wide = (P.ep.geglu && gemm_geglu_wide_epilogue()) ? 1 : 0;
   const int threads = kCtrlThreads + 32 * (wide ? kEpiWarpsGeglu : kEpiWarpsDefault);
-  KernelFn fn = fns[op.cluster ? 1 : 0][wide];
+  int epi;
+  if (P.ep.geglu) epi = 6 + wide;
+  else if (P.ep.res2) epi = P.ep.rowvec ? 5 : 4;  // res2 is only ever used together with res1
+  else epi = (P.ep.rowvec ? 1 : 0) + (P.ep.res1 ? 2 : 0);
+  KernelFn fn = fns[op.cluster ? 1 : 0][epi];
   cudaError_t e;
   if (op.cluster) {
     cudaLaunchConfig_t cfg{};

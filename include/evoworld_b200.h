@@ -61,6 +61,13 @@ int evw_equi2pers_u8(const uint8_t* equi, const float* pix2dir, uint8_t* out, in
 int evw_lift_depth(const float* depth, const float* extr, const float* intr, double* out_f64,
                    float* out_f32, int S, int H, int W, void* stream);
 
+/* Fused lift + pack (device-resident point memory, the caller row next to the path: unified_loop_consistency.py:352-367
+ * followed by reproject_vggt_open3d_utils.py:224-292): depth [S,H,W] f32, extr [S,3,4], intr [S,3,3], images NCHW
+ * [S,3,H,W] f32 in [0,1] -> out_pts4 [S*H*W] float4 {x,y,z,rgb-bits}; bit-identical to evw_lift_depth (f64) followed by
+ * evw_pack_points, without the float64 intermediate. */
+int evw_lift_pack_points(const float* depth, const float* extr, const float* intr, const float* images_f32,
+                         float* out_pts4, int S, int H, int W, void* stream);
+
 /* Pack a point cloud for splatting: xyz (f64 or f32, exactly one non-NULL) [N,3] and colours.
  * Colour source is either rgb_u8 [N,3] or images_f32 NCHW [S,3,H,W] in [0,1] (then N=S*H*W and
  * the byte is trunc(x*255) as reproject_vggt_open3d_utils.py:286-292 _extract_colors).
