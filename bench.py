@@ -291,7 +291,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--path", default="auto", choices=["auto", "denoise", "reproj"])
+    ap.add_argument("--path", default="auto", choices=["auto", "denoise", "reproj", "iterative"],
+                    help="auto = denoise step (primary) + reprojection + the 3-clip iterative episode")
+    ap.add_argument("--iter-frames", type=int, default=25, help="frames per clip of the iterative episode (the reference's 25)")
+    ap.add_argument("--iter-steps", type=int, default=25, help="denoise steps per clip of the iterative episode (config 5: 50)")
+    ap.add_argument("--iter-mode", default="incremental", choices=["incremental", "reference"])
+    ap.add_argument("--iter-episodes", type=int, default=1)
+    ap.add_argument("--no-iterative", action="store_true", help="skip the iterative episode in --path auto")
     ap.add_argument("--views-per-pass", type=int, default=2, choices=[1, 2, 4, 8])
     ap.add_argument("--frames", type=int, default=14)
     ap.add_argument("--pano-height", type=int, default=576, help="panorama height in pixels (latents = /8); 1024 for BASELINE config 5")
@@ -351,6 +357,11 @@ def main():
     reproj = None
     if args.path in ("auto", "reproj"):
         reproj = run_reproj_ours(args, dev, rank, world)
+    iterative = None
+    if args.path == "iterative" or (args.path == "auto" and have_denoise and not args.no_iterative):
+        import bench_iterative
+
+        iterative = bench_iterative.run_ours(args, dev, rank, world, barrier, allreduce_max, measured_peaks())
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -362,7 +373,12 @@ def main():
 
     if reproj is not None and not args.no_cpu_baseline and world == 1:  # the CPU baseline is an N = 1 figure (rank 0)
         reproj["cpu_baseline"] = run_reproj_cpu(REPROJ_CFG, views=4)
-    primary = denoise if denoise is not None else reproj
+    primary = denoise if denoise is not None else (reproj if reproj is not None else iterative)
+    if primary is iterative:
+        primary.setdefault("ms_per_step", primary["ms_per_episode"] / 3)
+        primary.setdefault("e2e", None)
+        primary.setdefault("roofline", None)
+        primary.setdefault("gpu_launches", None)
     line = {
         "metric": primary["metric"], "value": primary["value"], "unit": primary["unit"], "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": primary["ms_per_step"], "higher_is_better": True,
@@ -376,6 +392,8 @@ def main():
         line["gpu_eager_baseline"] = primary["gpu_eager_baseline"]
     if denoise is not None and reproj is not None:
         line["reproj"] = reproj
+    if iterative is not None and primary is not iterative:
+        line["iterative"] = iterative
     print(json.dumps(line))
     if _DIST["on"]:
         import torch.distributed as dist

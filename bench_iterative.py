@@ -1,0 +1,156 @@
+"""Iterative arm of bench.py (BASELINE configs 3 / 5): the 3-clip loop of unified_loop_consistency.process_episode
+(unified_loop_consistency.py:398-492) with everything device-resident.
+
+Per scene (one per rank), for segment 0, 1, 2:
+  1. generate      `steps` fused denoise steps (evw_denoise_step) of a T-frame clip, CFG batch 2            [built: hot path 1]
+  2. decode        VAE temporal decode -> T panoramas                                                        [NOT built: stand-in =
+                   a fixed uint8 [T,3,H,W] device buffer; stated in the JSON]
+  and, when another segment follows (:442-485):
+  3. pano -> pers  Equi2Pers(384, 512, fov 90) with the look-at yaw of every frame                           [built: evw_equi2pers_u8]
+                   reference: ALL frames so far (25, then 49); incremental: only the segment's new frames
+  4. VGGT-1B       depth / confidence / pose of the perspective frames                                       [NOT built: stand-in =
+                   seeded synthetic predictions already resident on the device]
+  5. lift + pack   new frames appended to the device-resident PointMemory (evw_lift_pack_points)             [built]
+  6. filter        joint 50th-percentile confidence filter + compaction (evw_conf_select)                    [built]
+  7. align         similarity alignment of the GT trajectory (host numpy float64, 24 poses)                  [built: host]
+  8. splat         24 target views: cube splat + cube->equirect resolve (evw_splat_cube_equirect)            [built: hot path 2]
+  9. memory frames 24 panoramas 1000x2000 -> 576x1024 (antialiased bilinear, as PIL Resize), [-1,1]          [torch op on device]
+ 10. VAE encode    memory latents of the next clip                                                           [NOT built: stand-in =
+                   8x average pool to 4 channels]
+`mode="reference"` re-warps and re-lifts every frame generated so far each segment, as the reference does;
+`mode="incremental"` (default) only touches the new frames — the scene the splat sees is bit-identical
+(tests/test_gpu_reproj.py::test_point_memory_incremental_equals_one_shot).
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import numpy as np
+
+
+def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
+    import torch
+    import torch.nn.functional as F
+
+    import bench_denoise as bd
+    from evoworld_b200 import reprojection as R
+    from evoworld_b200 import segments, synthetic
+    from evoworld_b200.equi2pers import Equi2Pers
+    from evoworld_b200.memory import PointMemory
+    from evoworld_b200.scheduler import EulerDiscreteScheduler
+    from evoworld_b200.unet import UNetSpatioTemporalConditionModel
+
+    T = args.iter_frames
+    steps = args.iter_steps
+    H, W = args.pano_height, args.pano_width
+    h, w = H // 8, W // 8
+    n_seg = 3
+    mode = args.iter_mode
+    unet = UNetSpatioTemporalConditionModel(**bd.UNET_CFG).init_random(seed=0, device=dev)
+    unet._ensure_handle()
+    unet.free_master_parameters()
+    lat0, cond0, ehs, ids = [t.to(dev) for t in bd.make_inputs(T, h, w, dev, seed=rank)]
+    sched = EulerDiscreteScheduler()
+    sched.set_timesteps(steps)
+    sig = [float(s) for s in sched.sigmas]
+    # stand-ins for the two un-built networks, resident on the device before the clock starts
+    g = torch.Generator(device="cpu").manual_seed(100 + rank)
+    frames_u8 = torch.randint(0, 256, (T, 3, H, W), generator=g, dtype=torch.uint8).to(dev)      # "decoded" panoramas
+    S_all = (n_seg - 1) * (T - 1) + 1                                                              # 49 frames after two segments
+    p = synthetic.reprojection_predictions(S=S_all, H=392, W=518, seed=rank)
+    vggt = {k: torch.from_numpy(p[k]).to(dev) for k in ("depth", "depth_conf", "images", "extrinsic", "intrinsic")}
+    poses = synthetic.curve_trajectory().astype(np.float64)                                         # [126, 6] RDF, degrees
+    e2p = Equi2Pers(height=384, width=512, fov_x=90, mode="bilinear", device=dev)
+    mem = PointMemory(392, 518, capacity_frames=S_all, device=dev)
+    sb = R.SceneBuilder(dev)
+    G = args.views_per_pass
+    zbuf = torch.empty(R.splat_workspace_bytes(G, 512), dtype=torch.uint8, device=dev)
+    panos = torch.empty((24, 1000, 2000, 3), dtype=torch.uint8, device=dev)
+    all_frames = torch.empty((S_all, 3, H, W), dtype=torch.uint8, device=dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def episode(timers=None):
+        mem.reset()
+        cond = cond0.clone()
+        n_frames = 0
+        stage = {}
+
+        def mark(name, e0, e1):
+            if timers is not None:
+                timers.setdefault(name, []).append((e0, e1))
+
+        for seg in range(n_seg):
+            e0 = ev(); e0.record()
+            x = lat0.clone()
+            for i in range(steps):
+                unet.denoise_step(x, cond, sig[i], sig[i + 1], ehs, ids, 1.0, 3.0)
+            e1 = ev(); e1.record(); mark("denoise", e0, e1)
+            # decode stand-in: the segment's frames (the first frame of a later segment repeats the previous last one)
+            new = frames_u8 if seg == 0 else frames_u8[1:]
+            all_frames[n_frames:n_frames + new.shape[0]].copy_(new)
+            first_new, n_frames = n_frames, n_frames + new.shape[0]
+            if seg == n_seg - 1:
+                break
+            e2 = ev(); e2.record()
+            _, _, look_at = segments.calculate_segment_indices(seg)
+            lo = 0 if mode == "reference" else first_new
+            rots = [{"pitch": 0.0, "roll": 0.0, "yaw": segments.calculate_target_yaw(poses, i + 1, look_at)} for i in range(lo, n_frames)]
+            pers = e2p(all_frames[lo:n_frames], rots)                                                # -> VGGT (not built)
+            e3 = ev(); e3.record(); mark("equi2pers", e2, e3)
+            if mode == "reference":
+                mem.reset()
+                sl = slice(0, n_frames)
+            else:
+                sl = slice(first_new, n_frames)
+            mem.append(vggt["depth"][sl], vggt["depth_conf"][sl], vggt["images"][sl], vggt["extrinsic"][sl], vggt["intrinsic"][sl])
+            scene = mem.scene(50.0)
+            e4 = ev(); e4.record(); mark("lift+filter", e3, e4)
+            tgt = sb.align_extrinsics(p["camera_pose"], p["extrinsic"][:n_frames], 24, f"bench_{seg}", False)
+            w2c = torch.from_numpy(R.front_w2c_matrices(tgt)).to(dev, non_blocking=True)
+            R.splat_to_panoramas_device(scene, w2c, 2000, 1000, 512, G, out=panos, zbuf=zbuf)
+            e5 = ev(); e5.record(); mark("splat", e4, e5)
+            # memory frames of the next clip: slot 0 = the episode's first frame, slots 1..24 = the reprojections
+            m = F.interpolate(panos.permute(0, 3, 1, 2).float(), size=(H, W), mode="bilinear", antialias=True, align_corners=False)
+            m = m / 127.5 - 1.0
+            first = frames_u8[0:1].float() / 127.5 - 1.0
+            mem_frames = torch.cat([first, m], dim=0)[:T]                                           # [T,3,H,W]
+            mem_lat = F.avg_pool2d(mem_frames, 8)                                                    # VAE-encode stand-in
+            mem_lat = torch.cat([mem_lat, mem_lat.mean(1, keepdim=True)], dim=1)                     # 4 "latent" channels
+            cond = cond0.clone()
+            cond[1, :, 4:8] = mem_lat
+            e6 = ev(); e6.record(); mark("memory frames", e5, e6)
+            stage["points"] = stage.get("points", []) + [scene]
+        return x, stage
+
+    # warm-up: one full episode (plans, graphs, allocator)
+    for _ in range(max(1, min(args.warmup, 1))):
+        episode()
+    torch.cuda.synchronize(dev)
+    barrier(world)
+    n_ep = max(1, args.iter_episodes)
+    timers = {}
+    e_start, e_end = ev(), ev()
+    t0 = time.perf_counter()
+    e_start.record()
+    for _ in range(n_ep):
+        x, stage = episode(timers)
+    e_end.record()
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0
+    barrier(world)
+    ms = e_start.elapsed_time(e_end)
+    ms = allreduce_max(ms, dev, world)
+    clips = n_ep * n_seg
+    per_stage = {k: sum(a.elapsed_time(b) for a, b in v) / n_ep for k, v in timers.items()}
+    pts = [int(s.num_points()) for s in stage["points"]]
+    return {
+        "metric": "iterative clips/sec (3-clip episode, evolving point memory)", "unit": "clips/s",
+        "value": world * clips / (ms * 1e-3), "ms_per_episode": ms / n_ep, "episodes": n_ep, "wall_s": wall,
+        "ms_per_stage_per_episode": per_stage, "memory_points_per_segment": pts, "finite_output": bool(torch.isfinite(x).all()),
+        "config": {"workload": f"config 3: 3-clip iterative episode, {H}x{W}x{T}f clips, {steps} denoise steps per clip, CFG batch 2, "
+                               f"evolving point memory {pts} points (S = {T}, {S_all} frames), 24 target views per segment",
+                   "mode": mode, "scenes_per_rank": 1,
+                   "stand_ins": "VAE decode/encode and VGGT-1B are not built: fixed uint8 frames, seeded synthetic VGGT predictions "
+                                "resident on the device, 8x average-pool 'latents' (see bench_iterative.py)"},
+    }

@@ -352,7 +352,7 @@ __device__ __forceinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_add
   };
   float A[16], B[16];
   load_r1(A, cgrp);
-  mbar_wait(bar_full, phase);
+  mbar_wait_relaxed(bar_full, phase);
   tc_fence_after();
   for (int k = cgrp; k < nsteps; k += 2 * NG) {
     step(k, A, B, k + NG);
@@ -462,7 +462,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
         const CUtensorMap* ma = src ? &tmap_a1 : &tmap_a0;
         const int cx = x0 + P.tap_dx[tap], cy = y0 + P.tap_dy[tap], ct = tt + P.tap_dt[tap];
         for (int kc = 0; kc < P.chunks[src]; ++kc, ++kglob) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_wait_relaxed(empty_bar(stage), phase ^ 1u);
           if (elect_one_sync()) {
             const uint32_t sa = smem_base + stage * stage_bytes;
             if (k2Cta) {
@@ -587,7 +587,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
 
       const uint32_t t_addr = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
       if constexpr (is_geglu) {
-        mbar_wait(tfull_bar(acc), acc_phase);
+        mbar_wait_relaxed(tfull_bar(acc), acc_phase);
         tc_fence_after();
         // 32 accumulator columns = [16 value | 16 gate] -> 16 outputs
         for (int k = cgrp; k * 32 < P.block_n; k += NG) {

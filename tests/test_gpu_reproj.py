@@ -332,3 +332,52 @@ def test_cube_fused_panoramas_bit_exact(G, cuda_device, built_lib):
     got2 = R.splat_to_panoramas_device(scene2, w2c, 400, 200, res, G)
     want2 = O.render_panoramas_cube(xyz[: n // 3], rgb[: n // 3], cam, res=res, width=400, height=200, z_near=R.Z_NEAR)
     np.testing.assert_array_equal(got2.cpu().numpy(), want2)
+
+
+def test_lift_pack_fused_matches_lift_then_pack(cuda_device, built_lib):
+    """evw_lift_pack_points == evw_lift_depth (f64) -> evw_pack_points, bit for bit (same camera / colour arithmetic)."""
+    from evoworld_b200.lift import lift_depth_device
+    from evoworld_b200.memory import PointMemory
+
+    p = synthetic.reprojection_predictions(S=5, H=28, W=36, seed=3)
+    dev = cuda_device
+    depth, conf, images = (torch.from_numpy(p[k]).to(dev) for k in ("depth", "depth_conf", "images"))
+    extr, intr = torch.from_numpy(p["extrinsic"]).to(dev), torch.from_numpy(p["intrinsic"]).to(dev)
+    want = R.pack_points_device(lift_depth_device(depth, extr, intr, torch.float64).reshape(-1, 3), images_nchw=images)
+    mem = PointMemory(28, 36, capacity_frames=8, device=dev).append(depth, conf, images, extr, intr)
+    assert len(mem) == 5 * 28 * 36
+    assert torch.equal(mem.pts4[:len(mem)].view(torch.int32), want.view(torch.int32))
+    assert torch.equal(mem.conf[:len(mem)], conf.reshape(-1))
+
+
+def test_point_memory_incremental_equals_one_shot(cuda_device, built_lib):
+    """Appending a segment's new frames to the device-resident memory and filtering jointly gives the same PointScene
+    (count, order, bits) as the reference-shaped one-shot path over all frames (filter_predictions on host arrays)."""
+    from evoworld_b200.memory import PointMemory
+    from oracle import reproj_np as O
+
+    S, H, W = 7, 28, 36
+    p = synthetic.reprojection_predictions(S=S, H=H, W=W, seed=5)
+    dev = cuda_device
+    preds = dict(p)
+    preds["world_points_from_depth"] = O.unproject_depth_map_to_point_map(p["depth"], p["extrinsic"], p["intrinsic"])
+    one_shot, _ = R.PointCloudProcessor(dev).filter_predictions_device(preds, 50.0, prediction_mode="depth_unproject")
+    mem = PointMemory(H, W, capacity_frames=S, device=dev)
+    for a, b in ((0, 3), (3, 4), (4, 7)):  # three "segments"
+        mem.append(*(torch.from_numpy(p[k][a:b]) for k in ("depth", "depth_conf", "images", "extrinsic", "intrinsic")))
+    scene = mem.scene(50.0)
+    n = one_shot.num_points()
+    assert scene.num_points() == n and 0 < n < S * H * W
+    assert torch.equal(scene.pts4[:n].view(torch.int32), one_shot.pts4[:n].view(torch.int32))
+    # a later window only (frames 3..7) == one shot over those frames
+    sub = {k: (v[3:] if k != "camera_pose" else v) for k, v in preds.items()}
+    want, _ = R.PointCloudProcessor(dev).filter_predictions_device(sub, 30.0, prediction_mode="depth_unproject")
+    got = mem.scene(30.0, first_frame=3)
+    m = want.num_points()
+    assert got.num_points() == m and torch.equal(got.pts4[:m].view(torch.int32), want.pts4[:m].view(torch.int32))
+    with pytest.raises(ValueError, match="capacity"):
+        mem.append(*(torch.from_numpy(p[k][:1]) for k in ("depth", "depth_conf", "images", "extrinsic", "intrinsic")))
+    mem.reset()
+    assert len(mem) == 0
+    with pytest.raises(ValueError, match="no frames"):
+        mem.scene()
