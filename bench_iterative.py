@@ -67,12 +67,16 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
     G = args.views_per_pass
     zbuf = torch.empty(R.splat_workspace_bytes(G, 512), dtype=torch.uint8, device=dev)
     panos = torch.empty((24, 1000, 2000, 3), dtype=torch.uint8, device=dev)
-    all_frames = torch.empty((S_all, 3, H, W), dtype=torch.uint8, device=dev)
+    all_frames = torch.empty((n_seg * (T - 1) + 1, 3, H, W), dtype=torch.uint8, device=dev)     # every frame of the episode
     ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    # persistent device buffers: the captured graph of the denoise plan is keyed on the latents / conditioning addresses
+    x = lat0.clone()
+    cond = cond0.clone()
 
     def episode(timers=None):
         mem.reset()
-        cond = cond0.clone()
+        cond.copy_(cond0)
         n_frames = 0
         stage = {}
 
@@ -82,7 +86,7 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
 
         for seg in range(n_seg):
             e0 = ev(); e0.record()
-            x = lat0.clone()
+            x.copy_(lat0)
             for i in range(steps):
                 unet.denoise_step(x, cond, sig[i], sig[i + 1], ehs, ids, 1.0, 3.0)
             e1 = ev(); e1.record(); mark("denoise", e0, e1)
@@ -117,7 +121,6 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
             mem_frames = torch.cat([first, m], dim=0)[:T]                                           # [T,3,H,W]
             mem_lat = F.avg_pool2d(mem_frames, 8)                                                    # VAE-encode stand-in
             mem_lat = torch.cat([mem_lat, mem_lat.mean(1, keepdim=True)], dim=1)                     # 4 "latent" channels
-            cond = cond0.clone()
             cond[1, :, 4:8] = mem_lat
             e6 = ev(); e6.record(); mark("memory frames", e5, e6)
             stage["points"] = stage.get("points", []) + [scene]

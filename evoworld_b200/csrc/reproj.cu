@@ -116,6 +116,69 @@ equi2pers_kernel(const uint8_t* __restrict__ equi, const float* __restrict__ pix
   }
 }
 
+// Pure-yaw fast path (the only rotation EvoWorld uses: unified_loop_consistency.py:329 passes pitch = roll = 0).  A rotation
+// about the vertical axis only shifts the longitude, so the per-pixel (theta, phi) -> (ui, uj) of the yaw = 0 camera is
+// tabulated once per (Hp, Wp, fov, He, We) with exactly the expressions of equi2pers_kernel, and a frame is a pure gather:
+// ui = ui0 + yaw_shift (in source pixels), wrapped — no asinf / atan2f / sqrtf per pixel and frame (the general kernel
+// spent its time there: 8.5 % of the HBM roofline, profiles/r01g_secondary_bench.log).
+__global__ void equi2pers_table_kernel(const float* __restrict__ pix2dir0, float2* __restrict__ table, int He, int We, int Hp,
+                                       int Wp) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= Wp || y >= Hp) return;
+  const float* A = pix2dir0;
+  float fx = (float)x, fy = (float)y;
+  float mx = __fadd_rn(__fadd_rn(__fmul_rn(A[0], fx), __fmul_rn(A[1], fy)), A[2]);
+  float my = __fadd_rn(__fadd_rn(__fmul_rn(A[3], fx), __fmul_rn(A[4], fy)), A[5]);
+  float mz = __fadd_rn(__fadd_rn(__fmul_rn(A[6], fx), __fmul_rn(A[7], fy)), A[8]);
+  float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(mx, mx), __fmul_rn(my, my)), __fmul_rn(mz, mz)));
+  float phi = asinf(__fdiv_rn(mz, nrm));
+  float theta = atan2f(my, mx);
+  const float PI = 3.14159265358979323846f;
+  float ui = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(theta, PI), (float)We), __fmul_rn(2.0f, PI)), 0.5f);
+  float uj = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(phi, __fmul_rn(0.5f, PI)), (float)He), PI), 0.5f);
+  if (!(fabsf(uj) < (float)He)) uj = fmodf(uj, (float)He);
+  if (uj < 0.f) uj = __fadd_rn(uj, (float)He);
+  table[(size_t)y * Wp + x] = make_float2(ui, uj);  // ui unwrapped (in [-We + 0.5, 0.5]); uj wrapped to [0, He)
+}
+
+__global__ void __launch_bounds__(256)
+equi2pers_yaw_kernel(const uint8_t* __restrict__ equi, const float2* __restrict__ table, const float* __restrict__ shift_px,
+                     uint8_t* __restrict__ out, int C, int He, int We, int Hp, int Wp) {
+  const int b = blockIdx.z;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= Wp || y >= Hp) return;
+  const float2 t = __ldg(table + (size_t)y * Wp + x);
+  float ui = __fadd_rn(t.x, __ldg(shift_px + b));  // |shift| <= We / 2 (the host reduces the yaw to [-pi, pi])
+  const float uj = t.y;
+  const float fWe = (float)We;
+  if (!(fabsf(ui) < fWe)) ui = fmodf(ui, fWe);
+  if (ui < 0.f) ui = __fadd_rn(ui, fWe);
+  float x0f = floorf(ui), y0f = floorf(uj);
+  float dx = __fsub_rn(ui, x0f), dy = __fsub_rn(uj, y0f);
+  int x0 = (int)x0f, y0 = (int)y0f;
+  if (x0 >= We) x0 -= We;
+  if (y0 >= He) y0 -= He;
+  int x1 = x0 + 1, y1 = y0 + 1;
+  if (x1 >= We) x1 -= We;
+  if (y1 >= He) y1 -= He;
+  float wx0 = __fsub_rn(1.0f, dx), wy0 = __fsub_rn(1.0f, dy);
+  const unsigned o00 = (unsigned)y0 * We + x0, o01 = (unsigned)y0 * We + x1;
+  const unsigned o10 = (unsigned)y1 * We + x0, o11 = (unsigned)y1 * We + x1;
+  const size_t plane_in = (size_t)He * We, plane_out = (size_t)Hp * Wp;
+  const uint8_t* img = equi + (size_t)b * C * plane_in;
+  uint8_t* dst = out + (size_t)b * C * plane_out + (unsigned)y * Wp + x;
+  for (int c = 0; c < C; ++c, img += plane_in, dst += plane_out) {
+    float q00 = __ldg(img + o00), q01 = __ldg(img + o01), q10 = __ldg(img + o10), q11 = __ldg(img + o11);
+    float top = __fadd_rn(__fmul_rn(q00, wx0), __fmul_rn(q01, dx));
+    float bot = __fadd_rn(__fmul_rn(q10, wx0), __fmul_rn(q11, dx));
+    float v = __fadd_rn(__fmul_rn(top, wy0), __fmul_rn(bot, dy));
+    v = fminf(fmaxf(v, 0.f), 255.f);
+    *dst = (uint8_t)v;  // truncation, as astype(uint8)
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Depth lift (float64 world transform as the numpy reference)
 // ------------------------------------------------------------------------------------------
@@ -651,67 +714,6 @@ __device__ __forceinline__ void cube_splat_one(const float* __restrict__ m, floa
   if (!pretest || key < ld_relaxed_u64(cell)) atomicMin(cell, key);
 }
 
-template <int G>
-__global__ void __launch_bounds__(256)
-cube_splat_kernel(const float4* __restrict__ pts, int64_t n_cap, const long long* __restrict__ n_dev,
-                  const float* __restrict__ w2c /*[G,12]*/, int res, float focal, float z_near, int pretest,
-                  unsigned long long* __restrict__ zbuf /*[G,6,res,res]*/) {
-  __shared__ float s_m[G * 12];
-  for (int i = threadIdx.x; i < G * 12; i += blockDim.x) s_m[i] = w2c[i];
-  __syncthreads();
-  int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
-  const float c = 0.5f * (float)res;
-  const size_t view_sz = (size_t)6 * res * res;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 p = ld_stream_f4(pts + i);
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-      cube_splat_one(s_m + g * 12, p.x, p.y, p.z, focal, c, z_near, res, zbuf + (size_t)g * view_sz, (unsigned)i, pretest);
-  }
-}
-
-// resolve G views at once: the lookup-table entry of a pixel quad is read once for all views of the pass
-template <int G>
-__global__ void resolve_multi_kernel(const unsigned long long* __restrict__ zbuf /*[G,6,res,res]*/,
-                                     const float4* __restrict__ pts, const uint32_t* __restrict__ lut, int res,
-                                     int64_t npix, int g_count, uint8_t* __restrict__ out /*[G,npix,3]*/) {
-  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t p0 = q * 4;
-  if (p0 >= npix) return;
-  uint32_t e[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) e[j] = (p0 + j < npix) ? lut[p0 + j] : 0xFFFFFFFFu;
-  const size_t view_sz = (size_t)6 * res * res;
-#pragma unroll
-  for (int g = 0; g < G; ++g) {
-    if (g >= g_count) break;
-    unsigned rgb[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      rgb[j] = 0;
-      if (e[j] != 0xFFFFFFFFu) {
-        const unsigned face = e[j] >> 28, row = (e[j] >> 14) & 0x3FFFu, col = e[j] & 0x3FFFu;
-        const unsigned long long key = zbuf[(size_t)g * view_sz + ((size_t)face * res + row) * res + col];
-        if (key != kEmptyKey) rgb[j] = __float_as_uint(__ldg(&pts[(unsigned)(key & 0xFFFFFFFFull)].w)) & 0xFFFFFFu;
-      }
-    }
-    uint8_t* o8 = out + ((size_t)g * npix + p0) * 3;
-    if (p0 + 3 < npix) {
-      uint32_t* o = reinterpret_cast<uint32_t*>(o8);  // (g*npix + p0)*3 is a multiple of 4 when npix % 4 == 0
-      o[0] = rgb[0] | (rgb[1] << 24);
-      o[1] = (rgb[1] >> 8) | (rgb[2] << 16);
-      o[2] = (rgb[2] >> 16) | (rgb[3] << 8);
-    } else {
-      for (int j = 0; j < 4 && p0 + j < npix; ++j) {
-        o8[j * 3 + 0] = rgb[j] & 0xFF;
-        o8[j * 3 + 1] = (rgb[j] >> 8) & 0xFF;
-        o8[j * 3 + 2] = (rgb[j] >> 16) & 0xFF;
-      }
-    }
-  }
-}
-
-
 int g_splat_ctas_per_sm = 0;  // 0 = EVW_SPLAT_CTAS_PER_SM or the default
 int splat_ctas_per_sm() {
   if (g_splat_ctas_per_sm == 0) {
@@ -824,31 +826,20 @@ int launch_cube_pass(const float4* pts, int64_t n_cap, const long long* n_dev, c
                      uint8_t* out, cudaStream_t st, int what = 3 /* bit 0: splat, bit 1: resolve */) {
   const int pretest = flags & EVW_SPLAT_PRETEST;
   const int color_key = (flags & EVW_SPLAT_COLOR_KEYS) ? 1 : 0;
-  if (color_key) flags &= ~EVW_SPLAT_V1_KERNELS;  // the first-generation kernels only know index keys
   if (n_cap > 0 && (what & 1)) {
-    if (flags & EVW_SPLAT_V1_KERNELS) {
-      int64_t want = (n_cap + 255) / 256;
-      int64_t cap = (int64_t)evw::sm_count() * 8;
-      cube_splat_kernel<G><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(pts, n_cap, n_dev, w2c, res, focal, z_near,
-                                                                                  pretest, zbuf);
-    } else {
-      constexpr int P = 2;
-      int64_t want = (n_cap + 256 * P - 1) / (256 * P);
-      // resident CTAs per SM: < 8 leaves room for the neighbouring pass's resolve / clear to co-run (two-stream pipeline)
-      int64_t cap = (int64_t)evw::sm_count() * ((flags & EVW_SPLAT_OVERLAP) ? splat_ctas_per_sm() : 8);
-      cube_splat2_kernel<G, P><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(pts, n_cap, n_dev, w2c, res, focal,
-                                                                                      z_near, pretest, color_key, zbuf);
-    }
+    constexpr int P = 2;
+    int64_t want = (n_cap + 256 * P - 1) / (256 * P);
+    // resident CTAs per SM: < 8 leaves room for the neighbouring pass's resolve / clear to co-run (two-stream pipeline)
+    int64_t cap = (int64_t)evw::sm_count() * ((flags & EVW_SPLAT_OVERLAP) ? splat_ctas_per_sm() : 8);
+    cube_splat2_kernel<G, P><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(pts, n_cap, n_dev, w2c, res, focal, z_near,
+                                                                                    pretest, color_key, zbuf);
   }
   if (!(what & 2)) {
     EVW_LAUNCH_CHECK();
     return 0;
   }
   const int64_t quads = (npix + 3) / 4;
-  if (flags & EVW_SPLAT_V1_KERNELS)
-    resolve_multi_kernel<G><<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(zbuf, pts, lut, res, npix, g_count, out);
-  else
-    resolve_multi2_kernel<G><<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(zbuf, pts, lut, res, npix, g_count, color_key, out);
+  resolve_multi2_kernel<G><<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(zbuf, pts, lut, res, npix, g_count, color_key, out);
   EVW_LAUNCH_CHECK();  // a failed launch in an early pass is reported by that pass, not by the last one
   return 0;
 }
@@ -886,6 +877,26 @@ extern "C" int evw_equi2pers_u8(const uint8_t* equi, const float* pix2dir, uint8
                 "evw_equi2pers_u8: bad shape");
   dim3 blk(32, 8), grd((Wp + 31) / 32, (Hp + 7) / 8, B);
   equi2pers_kernel<<<grd, blk, 0, (cudaStream_t)stream>>>(equi, pix2dir, out, C, He, We, Hp, Wp);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+
+extern "C" int evw_equi2pers_table(const float* pix2dir0, float* table, int He, int We, int Hp, int Wp, void* stream) {
+  EVW_CHECK_ARG(pix2dir0 && table, "evw_equi2pers_table: null pointer");
+  EVW_CHECK_ARG(He > 0 && We > 0 && Hp > 0 && Wp > 0 && ((uintptr_t)table & 7) == 0, "evw_equi2pers_table: bad shape / alignment");
+  dim3 blk(32, 8), grd((Wp + 31) / 32, (Hp + 7) / 8);
+  equi2pers_table_kernel<<<grd, blk, 0, (cudaStream_t)stream>>>(pix2dir0, reinterpret_cast<float2*>(table), He, We, Hp, Wp);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+
+extern "C" int evw_equi2pers_yaw_u8(const uint8_t* equi, const float* table, const float* shift_px, uint8_t* out, int B, int C,
+                                    int He, int We, int Hp, int Wp, void* stream) {
+  EVW_CHECK_ARG(equi && table && shift_px && out, "evw_equi2pers_yaw_u8: null pointer");
+  EVW_CHECK_ARG(B > 0 && C > 0 && He > 0 && We > 0 && Hp > 0 && Wp > 0 && B <= 65535, "evw_equi2pers_yaw_u8: bad shape");
+  dim3 blk(32, 8), grd((Wp + 31) / 32, (Hp + 7) / 8, B);
+  equi2pers_yaw_kernel<<<grd, blk, 0, (cudaStream_t)stream>>>(equi, reinterpret_cast<const float2*>(table), shift_px, out, C, He,
+                                                              We, Hp, Wp);
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }
@@ -1254,9 +1265,9 @@ extern "C" int evw_splat_cube_faces_debug(const float* pts4, int64_t n, const fl
   for (int v = 0; v < V; ++v) {
     EVW_CUDA(cudaMemsetAsync(zbuf, 0xFF, (size_t)view_cells * 8, st));
     if (n > 0) {
-      int64_t want = (n + 255) / 256, cap = (int64_t)evw::sm_count() * 8;
-      cube_splat_kernel<1><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(
-          reinterpret_cast<const float4*>(pts4), n, nullptr, w2c_front + (size_t)v * 12, face_res, focal, z_near, 1, zbuf);
+      int64_t want = (n + 511) / 512, cap = (int64_t)evw::sm_count() * 8;
+      cube_splat2_kernel<1, 2><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(
+          reinterpret_cast<const float4*>(pts4), n, nullptr, w2c_front + (size_t)v * 12, face_res, focal, z_near, 1, 0, zbuf);
     }
     zbuf_to_index_kernel<<<(unsigned)((view_cells + 255) / 256), 256, 0, st>>>(zbuf, view_cells,
                                                                                (long long*)win_idx + (size_t)v * view_cells);

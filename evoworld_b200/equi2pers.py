@@ -63,12 +63,34 @@ class Equi2Pers:
     configuration EvoWorld uses).  Accepts numpy (host) or torch CUDA `equi`; returns the same kind."""
 
     def __init__(self, height: int, width: int, fov_x: float, skew: float = 0.0, z_down: bool = False,
-                 mode: str = "bilinear", clip_output: bool = True, device: Union[str, torch.device] = "cuda"):
+                 mode: str = "bilinear", clip_output: bool = True, device: Union[str, torch.device] = "cuda",
+                 fast_yaw: bool = True):
         if mode != "bilinear":
             raise NotImplementedError(f"Equi2Pers mode {mode!r}: only 'bilinear' is built (EvoWorld's setting)")
         self.height, self.width, self.fov_x, self.skew, self.z_down = height, width, fov_x, skew, z_down
         self.mode = mode
         self.device = torch.device(device)
+        self.fast_yaw = fast_yaw  # pitch = roll = 0 -> tabulated yaw = 0 camera + longitude shift (False: always the general kernel)
+        self._tables = {}  # (device, He, We) -> float2 table of the yaw = 0 camera (pure-yaw fast path)
+
+    def _table(self, dev, He: int, We: int) -> torch.Tensor:
+        key = (str(dev), He, We)
+        if key not in self._tables:
+            m0 = pix2dir_matrix(0.0, 0.0, 0.0, self.height, self.width, self.fov_x, self.skew, self.z_down).astype(np.float32)
+            m0 = torch.from_numpy(m0.reshape(9)).to(dev)
+            table = torch.empty((self.height * self.width, 2), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().evw_equi2pers_table(_lib.ptr(m0), _lib.ptr(table), He, We, self.height, self.width,
+                                                          _lib.stream_ptr(dev)), "evw_equi2pers_table")
+            self._tables[key] = table
+        return self._tables[key]
+
+    def yaw_shift_px(self, yaw: float, We: int) -> float:
+        """Longitude shift of a yaw rotation in source pixels: R = Rz(-yaw) for z_down = False (pyequilib's default),
+        reduced to [-We/2, We/2] so that ui0 + shift stays within one wrap."""
+        a = yaw if self.z_down else -yaw
+        a = math.remainder(a, 2.0 * math.pi)
+        return a * We / (2.0 * math.pi)
 
     def __call__(self, equi, rots: Union[Dict[str, float], List[Dict[str, float]]], **_):
         is_numpy = isinstance(equi, np.ndarray)
@@ -84,12 +106,20 @@ class Equi2Pers:
         dev = t.device if t.is_cuda else self.device
         t = t.to(dev, non_blocking=True).contiguous()
         B, C, He, We = t.shape
-        mats = pix2dir_matrices(rots, self.height, self.width, self.fov_x, self.skew, self.z_down).astype(np.float32)
-        m = torch.from_numpy(mats.reshape(B, 9)).to(dev)
         out = torch.empty((B, C, self.height, self.width), dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
-            _lib.check(_lib.lib().evw_equi2pers_u8(_lib.ptr(t), _lib.ptr(m), _lib.ptr(out), B, C, He, We, self.height,
-                                                   self.width, _lib.stream_ptr(dev)), "evw_equi2pers_u8")
+        pure_yaw = self.fast_yaw and all(r.get("pitch", 0.0) == 0.0 and r.get("roll", 0.0) == 0.0 for r in rots)
+        if pure_yaw:  # EvoWorld's only usage: a table look-up + longitude shift per frame
+            shift = torch.tensor([self.yaw_shift_px(float(r.get("yaw", 0.0)), We) for r in rots], dtype=torch.float32).to(dev)
+            table = self._table(dev, He, We)
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().evw_equi2pers_yaw_u8(_lib.ptr(t), _lib.ptr(table), _lib.ptr(shift), _lib.ptr(out), B, C, He,
+                                                           We, self.height, self.width, _lib.stream_ptr(dev)), "evw_equi2pers_yaw_u8")
+        else:
+            mats = pix2dir_matrices(rots, self.height, self.width, self.fov_x, self.skew, self.z_down).astype(np.float32)
+            m = torch.from_numpy(mats.reshape(B, 9)).to(dev)
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().evw_equi2pers_u8(_lib.ptr(t), _lib.ptr(m), _lib.ptr(out), B, C, He, We, self.height,
+                                                       self.width, _lib.stream_ptr(dev)), "evw_equi2pers_u8")
         if single:
             out = out[0]
         return out.cpu().numpy() if is_numpy else out

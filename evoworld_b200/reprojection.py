@@ -46,17 +46,15 @@ Z_NEAR = 1e-6           # near plane of the point pass
 DEFAULT_VIEWS_PER_PASS = 2  # 0.54 ms per 24-view set vs 0.57 (G=4) and 0.65 (G=8) with the two-stream pipeline (profiles/r01g_reproj_bench.log)
 DEFAULT_PRETEST = os.environ.get("EVW_SPLAT_PRETEST", "0") != "0"  # read the cell before the 64-bit atomic min (slower on B200)
 DEFAULT_OVERLAP = os.environ.get("EVW_SPLAT_OVERLAP", "1") != "0"  # two-stream pass pipeline (include/evoworld_b200.h)
-DEFAULT_V1_KERNELS = os.environ.get("EVW_SPLAT_V1", "0") != "0"    # first-generation kernels, A/B timing only
 DEFAULT_BY_ROLE = os.environ.get("EVW_SPLAT_BY_ROLE", "0") != "0"  # alternative overlap scheme (splat stream / resolve stream)
 DEFAULT_COLOR_KEYS = os.environ.get("EVW_SPLAT_COLOR_KEYS", "0") != "0"  # optional tie rule (include/evoworld_b200.h); off
-SPLAT_PRETEST, SPLAT_OVERLAP, SPLAT_V1_KERNELS, SPLAT_OVERLAP_BY_ROLE, SPLAT_COLOR_KEYS = 1, 2, 4, 8, 16
+SPLAT_PRETEST, SPLAT_OVERLAP, SPLAT_OVERLAP_BY_ROLE, SPLAT_COLOR_KEYS = 1, 2, 8, 16  # bit 4 was the round-1 v1-kernel switch
 
 
-def splat_flags(pretest: Optional[bool] = None, overlap: Optional[bool] = None, v1: Optional[bool] = None,
-                by_role: Optional[bool] = None, color_keys: Optional[bool] = None) -> int:
+def splat_flags(pretest: Optional[bool] = None, overlap: Optional[bool] = None, by_role: Optional[bool] = None,
+                color_keys: Optional[bool] = None) -> int:
     f = SPLAT_PRETEST if (DEFAULT_PRETEST if pretest is None else pretest) else 0
     f |= SPLAT_OVERLAP if (DEFAULT_OVERLAP if overlap is None else overlap) else 0
-    f |= SPLAT_V1_KERNELS if (DEFAULT_V1_KERNELS if v1 is None else v1) else 0
     f |= SPLAT_OVERLAP_BY_ROLE if (DEFAULT_BY_ROLE if by_role is None else by_role) else 0
     f |= SPLAT_COLOR_KEYS if (DEFAULT_COLOR_KEYS if color_keys is None else color_keys) else 0
     return f
@@ -272,14 +270,14 @@ def splat_to_panoramas_device(scene: PointScene, w2c: torch.Tensor, width: int =
                               face_res: int = FACE_RES, views_per_pass: int = DEFAULT_VIEWS_PER_PASS,
                               z_near: float = Z_NEAR, out: Optional[torch.Tensor] = None,
                               zbuf: Optional[torch.Tensor] = None, pretest: Optional[bool] = None,
-                              overlap: Optional[bool] = None, v1_kernels: Optional[bool] = None,
+                              overlap: Optional[bool] = None,
                               by_role: Optional[bool] = None, color_keys: Optional[bool] = None) -> torch.Tensor:
     """Fused splat + resolve -> uint8 [V,height,width,3] (CUDA).
     w2c [V,3,4]: cube formulation (front-face camera, one transform per point-view; the fast path);
     w2c [V,6,3,4]: six independent per-face cameras (the literal restatement of render_cubemap)."""
     dev = scene.device
     V = w2c.shape[0]
-    flags = splat_flags(pretest, overlap, v1_kernels, by_role, color_keys)
+    flags = splat_flags(pretest, overlap, by_role, color_keys)
     w2c = w2c.to(dev, torch.float32).contiguous()
     lut = cube_lut_device(width, height, face_res, dev)
     L = _lib.lib()

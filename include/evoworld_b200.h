@@ -55,6 +55,15 @@ int evw_plucker(const float* ray, const float* c2w, float* out, int T, int H, in
 int evw_equi2pers_u8(const uint8_t* equi, const float* pix2dir, uint8_t* out, int B, int C, int He,
                      int We, int Hp, int Wp, void* stream);
 
+/* Pure-yaw fast path of the same warp (pitch = roll = 0 — the only call EvoWorld makes, unified_loop_consistency.py:329).
+ * evw_equi2pers_table tabulates, once per (Hp, Wp, fov, He, We), the source coordinates (ui, uj) of every output pixel for
+ * the yaw = 0 camera (pix2dir0 [9] f32 = G K^-1; table [Hp*Wp] float2, ui left unwrapped) with the expressions above;
+ * evw_equi2pers_yaw_u8 then warps B frames as a pure gather: ui = ui0 + shift_px[b] (the yaw as a longitude shift in
+ * source pixels: -yaw We / 2pi for z_down = False, reduced to [-We/2, We/2]), wrapped; same bilinear sampling. */
+int evw_equi2pers_table(const float* pix2dir0, float* table, int He, int We, int Hp, int Wp, void* stream);
+int evw_equi2pers_yaw_u8(const uint8_t* equi, const float* table, const float* shift_px, uint8_t* out, int B, int C,
+                         int He, int We, int Hp, int Wp, void* stream);
+
 /* Depth lift.  Replaces third_party/vggt/vggt/utils/geometry.py:12-111
  * unproject_depth_map_to_point_map.  depth [S,H,W] f32, extr [S,3,4] f32 (cam-from-world),
  * intr [S,3,3] f32.  Exactly one of out_f64 [S,H,W,3] / out_f32 [S,H,W,3] may be NULL. */
@@ -123,14 +132,12 @@ int evw_splat_cubemap_equirect(const float* pts4, int64_t n_cap, const int64_t* 
  *                         splat and resolve on stream p % 2, so one pass's L2-atomic-bound splat overlaps its neighbour's
  *                         gather-latency-bound resolve and its clear; the workspace must then hold
  *                         two passes: evw_splat_workspace_flags(views_per_pass, face_res, flags);
- *   EVW_SPLAT_V1_KERNELS  the first-generation kernels (one point per thread, dependent gathers) for A/B timing.
  * All flag combinations except EVW_SPLAT_COLOR_KEYS produce identical bytes.  With EVW_SPLAT_OVERLAP the call uses two
  * library-owned streams per device (created on first use, forked from / joined to `stream` with events, capturable);
  * a per-device mutex serialises host threads that enter the call concurrently for the same device (the enqueue is
  * short; the reference's process model is one Python thread per process and GPU anyway). */
 #define EVW_SPLAT_PRETEST 1
 #define EVW_SPLAT_OVERLAP 2
-#define EVW_SPLAT_V1_KERNELS 4
 #define EVW_SPLAT_COLOR_KEYS 16 /* OPTIONAL tie rule, off by default: the low key word carries colour << 8 | (index mod 256)
                                   instead of the index, so the resolve needs no gather (faster).  Output identical to the
                                   default unless two points of different colour have exactly the same float32 depth in one
@@ -197,8 +204,9 @@ void evw_set_gemm_cluster(int on);
  * qkv fp16 [F*S, 3*heads*64] (columns [q|k|v], each [heads,64]) -> out fp16 [F*S, heads*64]; softmax over
  * the S tokens of each frame.  tcgen05 flash-attention forward (csrc/tc_attention.cu). */
 int evw_spatial_attention_f16(const void* qkv, void* out, int F, int S, int heads, void* stream);
-/* Micro-benchmark hook: pick the spatial-attention kernel generation at run time.  -2 = default (environment),
- * -1 = v3 (groups in lockstep), k >= 0 = v5 variant k (csrc/tc_attention.cu: polynomial share / stagger table). */
+/* Micro-benchmark hook: pick the spatial-attention kernel variant at run time.  -2 = default (EVW_ATTN_VARIANT, else 0);
+ * 0 = v8 (the default kernel), 1 = v8 with every 8th exponential on the FMA pipe, 2 = v8 with staggered groups,
+ * 3 = v7 (one thread per query row), 4 = v7 with every 4th exponential on the FMA pipe (csrc/tc_attention.cu). */
 void evw_set_attention_variant(int variant);
 
 /* Temporal self-attention (TemporalBasicTransformerBlock.attn1): same qkv layout with rows ordered

@@ -154,6 +154,40 @@ def equi2pers(equi: np.ndarray, yaw: float, pitch: float = 0.0, roll: float = 0.
     return np.clip(v, 0, 255).astype(np.uint8)
 
 
+def equi2pers_yaw(equi: np.ndarray, yaw: float, Hp: int = 384, Wp: int = 512, fov_x: float = 90.0) -> np.ndarray:
+    """Pure-yaw form of `equi2pers` (pitch = roll = 0, EvoWorld's only call): the (ui, uj) of the yaw = 0 camera, then the
+    yaw as a longitude shift -yaw We / 2pi in source pixels (reduced to [-We/2, We/2]); float32 in the kernel's order."""
+    f32 = np.float32
+    C_, He, We = equi.shape
+    A = equi2pers_matrix(0.0, 0.0, 0.0, Hp, Wp, fov_x).astype(f32)
+    xs = np.arange(Wp, dtype=f32)[None, :]
+    ys = np.arange(Hp, dtype=f32)[:, None]
+    mx = (A[0, 0] * xs + A[0, 1] * ys) + A[0, 2]
+    my = (A[1, 0] * xs + A[1, 1] * ys) + A[1, 2]
+    mz = (A[2, 0] * xs + A[2, 1] * ys) + A[2, 2]
+    nrm = np.sqrt((mx * mx + my * my) + mz * mz)
+    phi = np.arcsin(mz / nrm)
+    theta = np.arctan2(my, mx)
+    PI = f32(np.pi)
+    ui0 = ((theta - PI) * f32(We)) / (f32(2.0) * PI) + f32(0.5)
+    uj = ((phi - f32(0.5) * PI) * f32(He)) / PI + f32(0.5)
+    uj = np.fmod(uj, f32(He)); uj = np.where(uj < 0, uj + f32(He), uj).astype(f32)
+    shift = f32(math.remainder(-yaw, 2.0 * math.pi) * We / (2.0 * math.pi))
+    ui = (ui0 + shift).astype(f32)
+    ui = np.fmod(ui, f32(We)); ui = np.where(ui < 0, ui + f32(We), ui).astype(f32)
+    x0f, y0f = np.floor(ui), np.floor(uj)
+    dx, dy = (ui - x0f).astype(f32), (uj - y0f).astype(f32)
+    x0 = x0f.astype(np.int64) % We
+    y0 = y0f.astype(np.int64) % He
+    x1, y1 = (x0 + 1) % We, (y0 + 1) % He
+    img = equi.astype(f32)
+    wx0, wy0 = f32(1.0) - dx, f32(1.0) - dy
+    top = img[:, y0, x0] * wx0 + img[:, y0, x1] * dx
+    bot = img[:, y1, x0] * wx0 + img[:, y1, x1] * dx
+    v = top * wy0 + bot * dy
+    return np.clip(v, 0, 255).astype(np.uint8)
+
+
 # ---------------------------------------------------------------------------------------------
 # lift / filter
 # ---------------------------------------------------------------------------------------------

@@ -41,14 +41,24 @@ def test_equi2pers_vs_oracle(yaw, cuda_device, built_lib):
     He, We = 144, 256
     yy, xx = np.meshgrid(np.arange(He), np.arange(We), indexing="ij")
     equi = np.stack([(xx * 255 // (We - 1)), (yy * 255 // (He - 1)), rng.integers(0, 256, (He, We))]).astype(np.uint8)
-    want = O.equi2pers(equi, yaw, Hp=96, Wp=128)
-    got = Equi2Pers(height=96, width=128, fov_x=90, mode="bilinear")(equi=equi, rots={"pitch": 0, "roll": 0, "yaw": yaw})
-    assert got.shape == want.shape and got.dtype == np.uint8
-    diff = np.abs(got.astype(int) - want.astype(int))
-    # smooth channels: asinf/atan2f differ by ulps between libm and CUDA -> at most 1 LSB, rarely
-    assert diff[:2].max() <= 1 and (diff[:2] > 0).mean() < 0.02
-    # noise channel: a coordinate ulp moves the bilinear weights by ~1e-5 -> still <= 1 LSB
-    assert diff[2].max() <= 1 and (diff[2] > 0).mean() < 0.02
+    rots = {"pitch": 0, "roll": 0, "yaw": yaw}
+    # general kernel (any rotation) vs its restatement, and the pure-yaw fast path (the default) vs ITS restatement
+    for fast, want in ((False, O.equi2pers(equi, yaw, Hp=96, Wp=128)), (True, O.equi2pers_yaw(equi, yaw, Hp=96, Wp=128))):
+        got = Equi2Pers(height=96, width=128, fov_x=90, mode="bilinear", fast_yaw=fast)(equi=equi, rots=rots)
+        assert got.shape == want.shape and got.dtype == np.uint8
+        diff = np.abs(got.astype(int) - want.astype(int))
+        # smooth channels: asinf/atan2f differ by ulps between libm and CUDA -> at most 1 LSB, rarely
+        assert diff[:2].max() <= 1 and (diff[:2] > 0).mean() < 0.02, fast
+        # noise channel: a coordinate ulp moves the bilinear weights by ~1e-5 -> still <= 1 LSB
+        assert diff[2].max() <= 1 and (diff[2] > 0).mean() < 0.02, fast
+    # the two forms describe the same warp: they differ by float32 rounding of the longitude (~1e-4 px)
+    a = Equi2Pers(height=96, width=128, fov_x=90, fast_yaw=True)(equi=equi, rots=rots).astype(int)
+    b = Equi2Pers(height=96, width=128, fov_x=90, fast_yaw=False)(equi=equi, rots=rots).astype(int)
+    assert np.abs(a - b).max() <= 1 and (np.abs(a - b)[:2] > 0).mean() < 0.02 and (np.abs(a - b)[2] > 0).mean() < 0.08
+    # any pitch / roll falls back to the general kernel
+    c = Equi2Pers(height=96, width=128, fov_x=90)(equi=equi, rots={"pitch": 0.1, "roll": 0, "yaw": yaw})
+    wc = O.equi2pers(equi, yaw, pitch=0.1, Hp=96, Wp=128)
+    assert np.abs(c.astype(int) - wc.astype(int)).max() <= 1
 
 
 def test_equi2pers_full_size_properties(cuda_device, built_lib):
@@ -310,12 +320,10 @@ def test_cube_fused_panoramas_bit_exact(G, cuda_device, built_lib):
     want = O.render_panoramas_cube(xyz, rgb, cam, res=res, width=400, height=200, z_near=R.Z_NEAR)
     scene = R.SceneBuilder().build_open3d_scene(xyz, rgb)
     w2c = torch.from_numpy(R.front_w2c_matrices(cam)).to(cuda_device)
-    # every flag combination (pre-test, two-stream pass pipeline, first-generation kernels) must give the same bytes
-    for pretest, overlap, v1, by_role in [(True, False, True, False), (False, False, True, False), (False, True, False, False),
-                                          (True, True, False, False), (False, False, False, False), (False, True, True, False),
-                                          (False, True, False, True), (True, True, True, True)]:
-        got = R.splat_to_panoramas_device(scene, w2c, 400, 200, res, G, pretest=pretest, overlap=overlap, v1_kernels=v1,
-                                          by_role=by_role)
+    # every flag combination (pre-test, two-stream pass pipeline, role-split streams) must give the same bytes
+    for pretest, overlap, by_role in [(True, False, False), (False, False, False), (False, True, False), (True, True, False),
+                                      (False, True, True), (True, True, True)]:
+        got = R.splat_to_panoramas_device(scene, w2c, 400, 200, res, G, pretest=pretest, overlap=overlap, by_role=by_role)
         np.testing.assert_array_equal(got.cpu().numpy(), want)
     # optional colour-key tie rule (EVW_SPLAT_COLOR_KEYS): bit-exact against the oracle evaluated with the same rule
     want_ck = O.render_panoramas_cube(xyz, rgb, cam, res=res, width=400, height=200, z_near=R.Z_NEAR, color_keys=True)
@@ -360,7 +368,9 @@ def test_point_memory_incremental_equals_one_shot(cuda_device, built_lib):
     p = synthetic.reprojection_predictions(S=S, H=H, W=W, seed=5)
     dev = cuda_device
     preds = dict(p)
-    preds["world_points_from_depth"] = O.unproject_depth_map_to_point_map(p["depth"], p["extrinsic"], p["intrinsic"])
+    # the caller's lift (unified_loop_consistency.py:366) through the drop-in: float64 host array, as the reference passes it
+    preds["world_points_from_depth"] = unproject_depth_map_to_point_map(p["depth"], p["extrinsic"], p["intrinsic"])
+    assert preds["world_points_from_depth"].dtype == np.float64
     one_shot, _ = R.PointCloudProcessor(dev).filter_predictions_device(preds, 50.0, prediction_mode="depth_unproject")
     mem = PointMemory(H, W, capacity_frames=S, device=dev)
     for a, b in ((0, 3), (3, 4), (4, 7)):  # three "segments"

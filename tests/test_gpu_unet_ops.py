@@ -39,11 +39,11 @@ def test_spatial_attention(frames, S, heads, scale, cuda_device):
     assert rel_l2(got, want) < 3e-3
 
 
-@pytest.mark.parametrize("variant", [-1, 0, 2, 4, 5, 6, 7, 9, 10, 11, 12, 13, 14, 15, 16])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("frames,S,heads", [(2, 576, 3), (1, 129, 2), (1, 2304, 2), (3, 144, 5), (1, 300, 1), (1, 1, 1)])
 def test_spatial_attention_variants(variant, frames, S, heads, cuda_device):
-    """Every kernel generation / variant behind evw_set_attention_variant (v3 lockstep, v5 staggered groups,
-    v6 two threads per row, v7 P in tensor memory) against the same fp32 reference."""
+    """Every variant behind evw_set_attention_variant (v8 default / partial FMA-pipe exponentials / staggered groups,
+    v7 one thread per row) against the same fp32 reference."""
     from evoworld_b200 import _lib
 
     C = heads * 64

@@ -117,13 +117,13 @@ def test_no_cpu_fallback():
 
 def test_splat_flags_and_workspace(built_lib):
     """Flag word of evw_splat_cube_equirect (include/evoworld_b200.h) and the workspace it implies."""
-    assert R.splat_flags(False, False, False, False, False) == 0
-    assert R.splat_flags(False, False, False, False, True) == R.SPLAT_COLOR_KEYS == 16
-    assert R.splat_flags(True, True, True, True, False) == R.SPLAT_PRETEST | R.SPLAT_OVERLAP | R.SPLAT_V1_KERNELS | R.SPLAT_OVERLAP_BY_ROLE
+    assert R.splat_flags(False, False, False, False) == 0
+    assert R.splat_flags(False, False, False, True) == R.SPLAT_COLOR_KEYS == 16
+    assert R.splat_flags(True, True, True, False) == R.SPLAT_PRETEST | R.SPLAT_OVERLAP | R.SPLAT_OVERLAP_BY_ROLE
     one = 4 * 6 * 512 * 512 * 8
     assert R.splat_workspace_bytes(4, 512, 0) == one
     assert R.splat_workspace_bytes(4, 512, R.SPLAT_OVERLAP) == 2 * one  # two passes in flight
-    assert R.splat_workspace_bytes(4, 512, R.SPLAT_PRETEST | R.SPLAT_V1_KERNELS) == one
+    assert R.splat_workspace_bytes(4, 512, R.SPLAT_PRETEST) == one
 
 
 def test_missing_confidence_defaults_to_ones():

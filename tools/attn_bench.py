@@ -25,13 +25,9 @@ def timeit(fn, n=5):
     return e0.elapsed_time(e1) / n
 
 
-VARIANTS = {-1: "v3 lockstep", 0: "v5 poly1/4 stagger", 1: "v5 poly1/8 stagger", 2: "v5 poly0 stagger", 3: "v5 poly1/2 stagger",
-            4: "v5 poly1/4 no-stagger", 5: "v6 2thr/row poly1/4", 6: "v6 2thr/row poly1/4 stagger", 7: "v6 2thr/row poly0",
-            8: "v6 2thr/row poly1/8", 9: "v7 P-in-TMEM poly1/4 stagger", 10: "v7 P-in-TMEM poly1/4", 11: "v7 P-in-TMEM poly0 stagger",
-            12: "v7 P-in-TMEM poly1/8 stagger", 13: "v7 P-in-TMEM poly0", 14: "v8 v7+2thr/row poly0", 15: "v8 v7+2thr/row poly1/8",
-            16: "v8 v7+2thr/row poly0 stagger"}
+VARIANTS = {0: "v8 (default)", 1: "v8 poly1/8", 2: "v8 stagger", 3: "v7 1thr/row", 4: "v7 poly1/4"}
 if "--new-only" in sys.argv:
-    VARIANTS = {k: v for k, v in VARIANTS.items() if k in (-1, 13, 14, 15, 16)}
+    VARIANTS = {0: VARIANTS[0]}
 shapes = {"L0 spatial": (28, 9216, 5), "L1 spatial": (28, 2304, 10), "L2 spatial": (28, 576, 20), "mid": (28, 144, 20)}
 qkvs = {k: torch.randn(f * s, 3 * h * 64, device=dev).half() for k, (f, s, h) in shapes.items()}
 f_, s_, h_ = shapes["L1 spatial"]

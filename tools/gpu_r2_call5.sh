@@ -2,13 +2,13 @@
 # round 2, call 5: relaxed-wait placement, PointMemory tests, iterative episode bench (both modes), full default bench
 cd "$GRAFT_REPO_ROOT" || exit 1
 O=gpurun_out; mkdir -p $O
-timeout 600 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_reproj.py -x -q > $O/r02e_tests.log 2>&1; echo "tests rc=$?" | tee $O/r02e_rc.txt
+timeout 900 python -m pytest tests -m gpu -x -q > $O/r02e_tests.log 2>&1; echo "tests rc=$?" | tee $O/r02e_rc.txt
 tail -3 $O/r02e_tests.log
-timeout 300 python tools/attn_bench.py > $O/r02e_attn_bench.log 2>&1; echo "attn bench rc=$?" | tee -a $O/r02e_rc.txt
+timeout 300 python tools/secondary_bench.py > $O/r02e_secondary_bench.log 2>&1; echo "secondary bench rc=$?" | tee -a $O/r02e_rc.txt
 timeout 600 python bench.py --path iterative --iter-mode incremental > $O/r02e_bench_iterative.json 2> $O/r02e_bench_iterative.err; echo "iter rc=$?" | tee -a $O/r02e_rc.txt
 timeout 600 python bench.py --path iterative --iter-mode reference > $O/r02e_bench_iterative_reference_mode.json 2> $O/r02e_bench_iterative_ref.err; echo "iter ref-mode rc=$?" | tee -a $O/r02e_rc.txt
 timeout 900 python bench.py > $O/r02e_bench_n1.json 2> $O/r02e_bench_n1.err; echo "bench rc=$?" | tee -a $O/r02e_rc.txt
-tail -5 $O/r02e_attn_bench.log
+grep -i "equi\|conf\|lift" $O/r02e_secondary_bench.log
 tail -3 $O/r02e_bench_iterative.err
 python - <<'PY'
 import json

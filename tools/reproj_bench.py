@@ -27,14 +27,14 @@ ref = None
 print(f"points {n}, algorithmic bytes {algo / 1e9:.3f} GB")
 L = R._lib.lib()
 ref_ck = None
-for G, overlap, v1, ctas, by_role, ck in [(4, False, True, 0, False, False), (4, False, False, 0, False, False), (4, True, False, 8, False, False),
-                                          (2, True, False, 8, False, False), (4, True, False, 8, True, False), (8, True, False, 8, False, False),
-                                          (4, False, False, 0, False, True), (4, True, False, 8, False, True), (2, True, False, 8, False, True)]:
+for G, overlap, ctas, by_role, ck in [(4, False, 0, False, False), (4, True, 8, False, False), (2, True, 8, False, False),
+                                      (4, True, 8, True, False), (8, True, 8, False, False), (4, False, 0, False, True),
+                                      (4, True, 8, False, True), (2, True, 8, False, True)]:
     pretest = False
     L.evw_set_splat_ctas_per_sm(ctas)
-    zb = torch.empty(R.splat_workspace_bytes(G, c["face_res"], R.splat_flags(pretest, overlap, v1, by_role, ck)), dtype=torch.uint8, device=dev)
+    zb = torch.empty(R.splat_workspace_bytes(G, c["face_res"], R.splat_flags(pretest, overlap, by_role, ck)), dtype=torch.uint8, device=dev)
     run = lambda: R.splat_to_panoramas_device(scene, w2c, c["pano"][1], c["pano"][0], c["face_res"], G, out=out, zbuf=zb,
-                                              pretest=pretest, overlap=overlap, v1_kernels=v1, by_role=by_role, color_keys=ck)
+                                              pretest=pretest, overlap=overlap, by_role=by_role, color_keys=ck)
     for _ in range(3):
         run()
     torch.cuda.synchronize()
@@ -54,6 +54,6 @@ for G, overlap, v1, ctas, by_role, ck in [(4, False, True, 0, False, False), (4,
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
     m = sorted(ms)[len(ms) // 2]
-    print(f"G={G} overlap={int(overlap)} by_role={int(by_role)} v1={int(v1)} colour_keys={int(ck)} ctas/SM={ctas}: median {m:.4f} ms (min {min(ms):.4f})  {algo / m / 1e6:8.1f} GB/s algorithmic "
+    print(f"G={G} overlap={int(overlap)} by_role={int(by_role)} colour_keys={int(ck)} ctas/SM={ctas}: median {m:.4f} ms (min {min(ms):.4f})  {algo / m / 1e6:8.1f} GB/s algorithmic "
           f"{n * c['V'] / m / 1e6:8.1f} G pv/s  identical={same}", flush=True)
 L.evw_set_splat_ctas_per_sm(0)

@@ -44,7 +44,16 @@ B = 49
 equi = torch.randint(0, 256, (B, 3, 576, 1024), dtype=torch.uint8, device=dev)
 e2p = Equi2Pers(384, 512, 90.0, mode="bilinear", device=dev)
 rots = [{"yaw": 0.1 * i, "pitch": 0.0, "roll": 0.0} for i in range(B)]
-report(f"equi2pers B={B} via Equi2Pers() (host matrices + H2D)", B * 3 * (576 * 1024 + 384 * 512), timed(lambda: e2p(equi, rots)))
+report(f"equi2pers B={B} via Equi2Pers() pure-yaw fast path (table + H2D of {B} shifts)", B * 3 * (576 * 1024 + 384 * 512), timed(lambda: e2p(equi, rots)))
+e2p_gen = Equi2Pers(384, 512, 90.0, mode="bilinear", device=dev, fast_yaw=False)
+report(f"equi2pers B={B} via Equi2Pers(fast_yaw=False) (host matrices + H2D)", B * 3 * (576 * 1024 + 384 * 512), timed(lambda: e2p_gen(equi, rots)))
+shift = torch.tensor([e2p.yaw_shift_px(r["yaw"], 1024) for r in rots], dtype=torch.float32, device=dev)
+table = e2p._table(dev, 576, 1024)
+yaw_out = torch.empty((B, 3, 384, 512), dtype=torch.uint8, device=dev)
+from evoworld_b200 import _lib as _l2
+report(f"equi2pers B={B} kernel only (evw_equi2pers_yaw_u8)", B * 3 * (576 * 1024 + 384 * 512),
+       timed(lambda: _l2.check(_l2.lib().evw_equi2pers_yaw_u8(equi.data_ptr(), table.data_ptr(), shift.data_ptr(), yaw_out.data_ptr(), B, 3,
+                                                             576, 1024, 384, 512, _l2.stream_ptr(dev)))))
 from evoworld_b200.equi2pers import pix2dir_matrix
 from evoworld_b200 import _lib
 mats = torch.from_numpy(np.stack([pix2dir_matrix(r["yaw"], 0.0, 0.0, 384, 512, 90.0) for r in rots]).astype(np.float32).reshape(B, 9)).to(dev)
@@ -64,6 +73,11 @@ for S in (25, 49):
     report(f"lift S={S} (f64 out)", npix * (4 + 24), timed(lambda: lift_depth_device(depth, extr, intr, torch.float64)))
     report(f"lift S={S} (f32 out)", npix * (4 + 12), timed(lambda: lift_depth_device(depth, extr, intr, torch.float32)))
     pts64 = lift_depth_device(depth, extr, intr, torch.float64)
+    from evoworld_b200.memory import PointMemory
+    mem = PointMemory(392, 518, capacity_frames=S, device=dev)
+    def fused():
+        mem.reset(); mem.append(depth, conf, images, extr, intr)
+    report(f"lift+pack fused S={S} (PointMemory.append)", npix * (4 + 12 + 16 + 8), timed(fused))
     report(f"pack S={S} (f64 xyz + f32 rgb)", npix * (24 + 12 + 16), timed(lambda: R.pack_points_device(pts64.reshape(-1, 3), images_nchw=images)))
     pts4 = R.pack_points_device(pts64.reshape(-1, 3), images_nchw=images)
     # select: 4 B/point x (3 histogram + 1 rank + 2 compaction passes) + 16 B in + 16 B out per kept point (~half)
