@@ -74,6 +74,8 @@ struct KernelParams {
   int chunks[2];
   int8_t tap_dx[kMaxTaps], tap_dy[kMaxTaps], tap_dt[kMaxTaps], tap_src[kMaxTaps];
   int num_stages;
+  int res_slots;  // > 0 (a power of two): res1 comes through a ring of res_slots 16 KiB boxes (128 rows x 32 fp32 columns)
+  int res_shift;  // log2(res_slots)
   int total_tiles;
   int total_pairs;  // cluster mode: pairs of m-adjacent tiles sharing one weight tile (B multicast)
 };
@@ -283,12 +285,22 @@ __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols
 // row per frame or batch element: L1-resident) and res2 (one layer) are loaded at the point of use.
 // out_off / rv_off are element offsets of column n0 of this row (of the broadcast row); ncols = N - n0.
 // (must be inlined: as a real call the tcgen05.ld results were consumed before they arrived — 40 of 80 GEMM tests failed)
-template <bool RV, bool R1, bool R2>
+// RT: res1 does not come from global memory through registers but from a shared-memory ring of 128-row x 32-column fp32
+// boxes that warp 3 fills with TMA (128B swizzle) several boxes ahead: the residual stream is then fetched in full lines
+// by the copy engine with 64 KB in flight per SM, instead of 32 uncoalesced 16-byte requests per warp instruction whose
+// latency two epilogue warps per scheduler cannot hide (to_out at K = 320 ran at 2.2x its HBM bound).  Box j of a tile
+// serves steps 2j (column group 0) and 2j + 1 (column group 1); res_box0 = index of the tile's first box in the ring.
+struct ResRing {
+  uint32_t base, full_bar, empty_bar;  // shared-memory addresses: boxes, full[slots], empty[slots]
+  uint32_t slots_mask, shift, box0;
+  int row, lane;
+};
+template <bool RV, bool R1, bool R2, bool RT>
 __device__ __forceinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_addr, const float* bs, int cgrp, int NG, int nsteps,
                                           bool row_ok, int ncols, long long out_off, long long rv_off, bool wide_ok,
-                                          uint32_t bar_full, uint32_t phase) {
+                                          uint32_t bar_full, uint32_t phase, const ResRing& rr) {
   auto load_r1 = [&](float (&x)[16], int k) {
-    if constexpr (!R1) return;
+    if constexpr (!R1 || RT) return;
     const int c = k * 16;
     if (!(row_ok && k < nsteps && c < ncols)) return;
     load16(ep.res1, ep.res1_fp16, out_off + c, c + 16 <= ncols, x);
@@ -298,6 +310,24 @@ __device__ __forceinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_add
     __syncwarp();
     tmem_ld_32x32b_x16(t_addr + k * 16, raw);
     load_r1(nxt, k_next);
+    float rs[16];
+    if constexpr (RT) {  // this step's 16 residual columns of this thread's row from the staged box
+      const uint32_t cnt = rr.box0 + (uint32_t)(k >> 1);
+      const uint32_t slot = cnt & rr.slots_mask;
+      mbar_wait(rr.full_bar + 8u * slot, (cnt >> rr.shift) & 1u);
+      const uint32_t rowp = rr.base + slot * 16384u + (uint32_t)rr.row * 128u;
+      const uint32_t sw = (uint32_t)(rr.row & 7);
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) {
+        const uint32_t chunk = ((uint32_t)((k & 1) * 4 + qd)) ^ sw;  // 128B swizzle: 16-byte chunk index XOR (row % 8)
+        float4 t4;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t4.x), "=f"(t4.y), "=f"(t4.z), "=f"(t4.w) : "r"(rowp + chunk * 16u));
+        rs[4 * qd] = t4.x; rs[4 * qd + 1] = t4.y; rs[4 * qd + 2] = t4.z; rs[4 * qd + 3] = t4.w;
+      }
+      // the box is released at the END of the step, after the loaded values have been consumed: arriving right after
+      // issuing the loads let the next TMA write overtake them (a 16-byte chunk of a row, a few thousand times per 80 M
+      // outputs — tools/rt_probe.py); either this data dependency or a fence.proxy.async before the arrive removes it
+    }
     tmem_ld_wait();
     const int c = k * 16;
     if (row_ok && c < ncols) {
@@ -314,7 +344,7 @@ __device__ __forceinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_add
       }
       if constexpr (R1) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaf(ep.s1, cur[i], v[i]);
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(ep.s1, RT ? rs[i] : cur[i], v[i]);
       }
       // row vector / second residual: loaded at the point of use, eight columns at a time (register pressure)
       if constexpr (RV) {
@@ -349,14 +379,24 @@ __device__ __forceinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_add
         else store8(reinterpret_cast<float*>(ep.out) + out_off + c, v8);
       }
     }
+    if constexpr (RT) {  // 8 arrivals (one per epilogue warp) free the box for the residual producer
+      const uint32_t cnt2 = rr.box0 + (uint32_t)(k >> 1);
+      __syncwarp();
+      if (rr.lane == 0) mbar_arrive(rr.empty_bar + 8u * (cnt2 & rr.slots_mask));
+    }
   };
-  float A[16], B[16];
+  // res1 runs TWO steps ahead over three register sets: with one step of look-ahead the epilogue of a K = 320 GEMM sat
+  // in long-scoreboard stalls (30 % of its samples, profiles/r02c_ncu_gemm_epilogue.txt) — 8 warps x 2 KB in flight per SM
+  // cannot cover the latency of the residual stream
+  float A[16], B[16], C[16];
   load_r1(A, cgrp);
+  load_r1(B, cgrp + NG);
   mbar_wait_relaxed(bar_full, phase);
   tc_fence_after();
-  for (int k = cgrp; k < nsteps; k += 2 * NG) {
-    step(k, A, B, k + NG);
-    if (k + NG < nsteps) step(k + NG, B, A, k + 2 * NG);
+  for (int k = cgrp; k < nsteps; k += 3 * NG) {
+    step(k, A, C, k + 2 * NG);
+    if (k + NG < nsteps) step(k + NG, B, A, k + 3 * NG);
+    if (k + 2 * NG < nsteps) step(k + 2 * NG, C, B, k + 4 * NG);
   }
 }
 
@@ -369,7 +409,7 @@ template <bool k2Cta, int kEpiWarps, int kEpi>
 __global__ void __launch_bounds__(kCtrlThreads + 32 * kEpiWarps, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
                const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_bh,
-               const __grid_constant__ KernelParams P) {
+               const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ KernelParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -377,12 +417,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
   // weight bytes per stage in THIS CTA: the whole BLOCK_N x 64 tile, or half of it in a CTA pair
   const uint32_t b_tile_bytes = (uint32_t)P.block_n * kBlockK * (k2Cta ? 1 : 2);
   const uint32_t stage_bytes = kATileBytes + b_tile_bytes;
-  const uint32_t bar_base = smem_base + stages * stage_bytes;  // 8-byte barriers
+  constexpr bool kResTma = (kEpi & 16) != 0;  // res1 staged through shared memory by TMA (warp 3)
+  const uint32_t res_base = smem_base + stages * stage_bytes;  // kResTma: P.res_slots boxes of 16 KiB
+  const uint32_t bar_base = res_base + (kResTma ? (uint32_t)P.res_slots * 16384u : 0u);  // 8-byte barriers
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * stages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * stages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
+  auto res_full_bar = [&](int s) { return bar_base + 8u * (2 * stages + 4) + 16u + 8u * s; };
+  auto res_empty_bar = [&](int s) { return bar_base + 8u * (2 * stages + 4) + 16u + 64u + 8u * s; };
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -411,6 +455,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), k2Cta ? 2 * kEpiWarps : kEpiWarps);  // pair: both CTAs' epilogues release the leader's MMA
+    }
+    if (kResTma) {
+      for (int r = 0; r < P.res_slots; ++r) {
+        mbar_init(res_full_bar(r), 1);
+        mbar_init(res_empty_bar(r), kEpiWarps);  // every epilogue warp reads each box once
+      }
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -519,6 +569,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
     }
+  } else if (warp == 3 && kResTma) {
+    // ===================== residual producer: res1 boxes (128 rows x 32 fp32 columns) of every tile, in order =====================
+    if (lane == 0) tma_prefetch_desc(&tmap_r);
+    const int boxes = P.block_n >> 5;
+    uint32_t cnt = 0;
+    for (int v = v_first; v < v_limit; v += v_step) {
+      const int tile = to_tile(v);
+      int n_tile, tx, ty, tt, tb;
+      decode(tile, n_tile, tx, ty, tt, tb);
+      const int x0 = tx * P.bx, y0 = ty * P.by, n0 = n_tile * P.block_n;
+      for (int j = 0; j < boxes; ++j, ++cnt) {
+        const uint32_t slot = cnt & (uint32_t)(P.res_slots - 1);
+        mbar_wait_relaxed(res_empty_bar(slot), ((cnt >> P.res_shift) & 1u) ^ 1u);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(res_full_bar(slot), 16384u);
+          tma_load_5d(&tmap_r, res_base + slot * 16384u, res_full_bar(slot), n0 + 32 * j, x0, y0, tt, tb);
+        }
+        __syncwarp();
+      }
+    }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     // Two warps share each TMEM lane quarter and alternate 16-column steps.  Per step: issue the TMEM load, issue the
@@ -536,14 +606,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
     const int rv_ld = ep.rv_ld ? ep.rv_ld : ldo;
     const int esz = ep.out_fp16 ? 2 : 4;
     const bool wide_ok = (((long long)ldo * esz) % 32 == 0) && ((reinterpret_cast<uintptr_t>(ep.out) & 31) == 0);
-    float* bias_s = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 8 * (2 * stages + 4) + 16);
+    float* bias_s = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 8 * (2 * stages + 4) + 16 + 128);
     const int et = threadIdx.x - 128;    // 0 .. 32*kEpiWarps-1
     const int mx = r & (P.bx - 1), my = r >> P.bx_shift;  // bx is a power of two
     constexpr bool is_geglu = kEpi == kEpiGeglu;
     // residual operands stream from DRAM exactly once: pull the row segment of the NEXT tile into L2 one tile ahead
     // (prefetch.global.L2, no registers / shared memory), so the epilogue's loads find it there
     auto prefetch_residuals = [&](int v_p) {
-      if (v_p >= v_limit || (!ep.res1 && !ep.res2)) return;
+      if (v_p >= v_limit || ((kResTma || !ep.res1) && !ep.res2)) return;
       const int tile_p = to_tile(v_p);
       if (tile_p >= P.total_tiles) return;
       int n_tile_p, tx_p, ty_p, tt_p, tb_p;
@@ -553,7 +623,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
       const long long row_p = (((long long)tb_p * P.T + tt_p) * P.Y + gy_p) * P.X + gx_p;
       const long long off = row_p * ldo + (long long)n_tile_p * P.block_n;
       const int cols = min(P.block_n, P.N - n_tile_p * P.block_n);
-      if (ep.res1) {
+      if (ep.res1 && !kResTma) {
         const int e1 = ep.res1_fp16 ? 2 : 4;
         const char* b = reinterpret_cast<const char*>(ep.res1) + off * e1;
         for (int o = cgrp * 128; o < cols * e1; o += 128 * NG) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
@@ -619,8 +689,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
         const int nsteps = P.block_n / 16;
         const int ncols = P.N - n0;  // valid columns of this tile (may exceed block_n)
         const uint32_t bar_full = tfull_bar(acc);
-        epi_plain<(kEpi & 1) != 0, (kEpi & 2) != 0, (kEpi & 4) != 0>(ep, t_addr, bs, cgrp, NG, nsteps, row_ok, ncols, out_off, rv_off,
-                                                                      wide_ok, bar_full, acc_phase);
+        ResRing rr;
+        rr.base = res_base; rr.full_bar = res_full_bar(0); rr.empty_bar = res_empty_bar(0);
+        rr.slots_mask = (uint32_t)(P.res_slots - 1); rr.shift = (uint32_t)P.res_shift;
+        rr.box0 = (uint32_t)it * (uint32_t)(P.block_n >> 5); rr.row = r; rr.lane = lane;
+        epi_plain<(kEpi & 1) != 0, (kEpi & 2) != 0, (kEpi & 4) != 0, kResTma>(ep, t_addr, bs, cgrp, NG, nsteps, row_ok, ncols, out_off,
+                                                                               rv_off, wide_ok, bar_full, acc_phase, rr);
       }
       tc_fence_before();
       __syncwarp();
@@ -660,8 +734,18 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
+static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box);
 int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box) {
+  return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, base, rank, dims, strides_bytes, box);
+}
+int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+  return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box);
+}
+static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -675,7 +759,7 @@ int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t
     estr[i] = 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+  CUresult r = fn(out, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -765,10 +849,17 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   const int mode = gemm_cluster_mode();
   op->cluster = ((mode == 1 || (mode == 2 && pr.K_total >= gemm_pair_min_k())) && m_tiles >= 2 && sms >= 2) ? 1 : 0;
   const uint32_t stage_bytes = kATileBytes + bn * kBlockK * (op->cluster ? 1 : 2);  // a pair member holds half the weight tile
-  int stages = (int)((227 * 1024 - 4096) / stage_bytes);
+  // TMA-staged residual: fp32 res1, whole 32-column boxes, a row pitch the tensor map accepts; EVW_GEMM_RES_TMA=0 disables
+  static const bool res_tma_enabled = [] { const char* e = getenv("EVW_GEMM_RES_TMA"); return !(e && atoi(e) == 0); }();
+  op->res_tma = (res_tma_enabled && pr.ep.res1 && !pr.ep.res1_fp16 && !pr.ep.geglu && bn % 32 == 0 && pr.N % 4 == 0 &&
+                 ((uintptr_t)pr.ep.res1 & 15) == 0) ? 1 : 0;
+  P.res_slots = op->res_tma ? 4 : 0;  // 64 KiB of residual in flight per SM
+  P.res_shift = 2;
+  int stages = (int)((227 * 1024 - 4096 - P.res_slots * 16384) / stage_bytes);
   if (stages > 8) stages = 8;
+  EVW_CHECK_ARG(stages >= 2, "gemm: not enough shared memory for BLOCK_N=%d", bn);
   P.num_stages = stages;
-  op->smem_bytes = stages * stage_bytes + 8 * (2 * stages + 4) + 16 + 2 * 256 * 4 + 1024;
+  op->smem_bytes = stages * stage_bytes + P.res_slots * 16384 + 8 * (2 * stages + 4) + 16 + 128 + 2 * 256 * 4 + 1024;
   if (op->cluster) {
     const int want = 2 * P.total_pairs;
     op->grid = want < (sms & ~1) ? want : (sms & ~1);
@@ -802,6 +893,16 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   uint32_t hbox[2] = {(uint32_t)kBlockK, (uint32_t)(bn / 2)};
   rc = encode_tmap_f16(reinterpret_cast<CUtensorMap*>(op->tmap_bh), pr.w, 2, bdims, bstr, hbox);
   if (rc) return rc;
+  if (op->res_tma) {
+    uint64_t rdims[5] = {(uint64_t)pr.N, (uint64_t)pr.X, (uint64_t)pr.Y, (uint64_t)pr.T, (uint64_t)pr.B};
+    uint64_t rstr[4] = {(uint64_t)pr.N * 4, (uint64_t)pr.N * 4 * pr.X, (uint64_t)pr.N * 4 * pr.X * pr.Y,
+                        (uint64_t)pr.N * 4 * pr.X * pr.Y * pr.T};
+    uint32_t rbox[5] = {32u, (uint32_t)P.bx, (uint32_t)P.by, 1, 1};
+    rc = encode_tmap_f32(reinterpret_cast<CUtensorMap*>(op->tmap_r), pr.ep.res1, 5, rdims, rstr, rbox);
+    if (rc) return rc;
+  } else {
+    memcpy(op->tmap_r, op->tmap_a0, sizeof(op->tmap_a0));
+  }
   op->flops = 2.0 * pr.X * pr.Y * pr.T * pr.B * (double)pr.N * (double)pr.K_total;
   return EVW_OK;
 }
@@ -832,19 +933,22 @@ static int gemm_geglu_wide_epilogue() {
 }
 
 int gemm_launch(const GemmOp& op, cudaStream_t stream) {
-  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const KernelParams);
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                           const KernelParams);
   // [pair mode][epilogue]: 0..5 = plain epilogue by operand set {none, rv, r1, rv+r1, r1+r2, rv+r1+r2}, 6 = GEGLU with
-  // 8 epilogue warps, 7 = GEGLU with 16
+  // 8 epilogue warps, 7 = GEGLU with 16, 8..11 = the four residual sets {r1, rv+r1, r1+r2, rv+r1+r2} with res1 staged by TMA
 #define EVW_GEMM_ROW(C)                                                                                                          \
   {tc_gemm_kernel<C, kEpiWarpsDefault, 0>, tc_gemm_kernel<C, kEpiWarpsDefault, 1>, tc_gemm_kernel<C, kEpiWarpsDefault, 2>,       \
    tc_gemm_kernel<C, kEpiWarpsDefault, 3>, tc_gemm_kernel<C, kEpiWarpsDefault, 6>, tc_gemm_kernel<C, kEpiWarpsDefault, 7>,       \
-   tc_gemm_kernel<C, kEpiWarpsDefault, kEpiGeglu>, tc_gemm_kernel<C, kEpiWarpsGeglu, kEpiGeglu>}
-  static const KernelFn fns[2][8] = {EVW_GEMM_ROW(false), EVW_GEMM_ROW(true)};
+   tc_gemm_kernel<C, kEpiWarpsDefault, kEpiGeglu>, tc_gemm_kernel<C, kEpiWarpsGeglu, kEpiGeglu>,                                 \
+   tc_gemm_kernel<C, kEpiWarpsDefault, 16 + 2>, tc_gemm_kernel<C, kEpiWarpsDefault, 16 + 3>,                                     \
+   tc_gemm_kernel<C, kEpiWarpsDefault, 16 + 6>, tc_gemm_kernel<C, kEpiWarpsDefault, 16 + 7>}
+  static const KernelFn fns[2][12] = {EVW_GEMM_ROW(false), EVW_GEMM_ROW(true)};
 #undef EVW_GEMM_ROW
   static bool attr_set = false;
   if (!attr_set) {
     for (int c = 0; c < 2; ++c)
-      for (int w = 0; w < 8; ++w) {
+      for (int w = 0; w < 12; ++w) {
         cudaError_t e = cudaFuncSetAttribute(fns[c][w], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
           set_error("cudaFuncSetAttribute(tc_gemm_kernel): %s", cudaGetErrorString(e));
@@ -865,7 +969,9 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream) {
   if (P.ep.geglu) epi = 6 + wide;
   else if (P.ep.res2) epi = P.ep.rowvec ? 5 : 4;  // res2 is only ever used together with res1
   else epi = (P.ep.rowvec ? 1 : 0) + (P.ep.res1 ? 2 : 0);
+  if (op.res_tma) epi = 8 + (epi - 2);  // epi in {2,3,4,5} -> {8,9,10,11}
   KernelFn fn = fns[op.cluster ? 1 : 0][epi];
+  const CUtensorMap& tr = *reinterpret_cast<const CUtensorMap*>(op.tmap_r);
   cudaError_t e;
   if (op.cluster) {
     cudaLaunchConfig_t cfg{};
@@ -880,9 +986,9 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, fn, ta0, ta1, tb, tbh, P);
+    e = cudaLaunchKernelEx(&cfg, fn, ta0, ta1, tb, tbh, tr, P);
   } else {
-    fn<<<op.grid, threads, op.smem_bytes, stream>>>(ta0, ta1, tb, tbh, P);
+    fn<<<op.grid, threads, op.smem_bytes, stream>>>(ta0, ta1, tb, tbh, tr, P);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) {

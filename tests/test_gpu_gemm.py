@@ -188,3 +188,21 @@ def test_conv3x3_split_taps(cuda_device):
     y = ops.gemm_f16(x_hi, wk, taps=taps, a1=x_lo, out_dtype=torch.float32)
     got = y[:, :Co] + y[:, Co:2 * Co]
     assert rel_l2(got, want) < 5e-6
+
+
+@pytest.mark.parametrize("M,K,N", [(258048, 320, 320), (64512, 640, 640), (40000, 1280, 1280)])
+def test_residual_ring_at_scale(M, K, N, cuda_device):
+    """fp32 residual staged through the TMA-filled shared-memory ring, many tiles per CTA, separate and in place: the first
+    version released a box before its loads had landed and corrupted a few thousand 16-byte chunks per 80 M outputs — only
+    at sizes where the ring wraps many times (tools/rt_probe.py)."""
+    a = torch.randn(M, K, device=cuda_device).half()
+    w = (torch.randn(N, K, device=cuda_device) / K ** 0.5).half()
+    b = torch.randn(N, device=cuda_device)
+    r = torch.randn(M, N, device=cuda_device)
+    want = a.float() @ w.float().T + b + r
+    for _ in range(2):
+        got = ops.gemm_f16(a, w, bias=b, res1=r, out_dtype=torch.float32)
+        assert int(((got - want).abs() > 1e-2).sum()) == 0 and rel_l2(got, want) < 2e-5
+        buf = r.clone()
+        ops.gemm_f16(a, w, bias=b, res1=buf, out=buf)
+        assert int(((buf - want).abs() > 1e-2).sum()) == 0 and rel_l2(buf, want) < 2e-5

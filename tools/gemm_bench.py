@@ -15,6 +15,9 @@ shapes = [
     ("L0 qkv 320->960", dict(M=BF * 9216, K=320, N=960)),
     ("L0 geglu 320->2560", dict(M=BF * 9216, K=320, N=2560, geglu=True)),
     ("L0 ff2 1280->320", dict(M=BF * 9216, K=1280, N=320)),
+    ("L0 to_out 320->320 +res f32", dict(M=BF * 9216, K=320, N=320, res=True)),
+    ("L0 ff2 1280->320 +res f32", dict(M=BF * 9216, K=1280, N=320, res=True)),
+    ("L1 to_out 640->640 +res f32", dict(M=BF * 2304, K=640, N=640, res=True)),
     ("L1 geglu 640->5120", dict(M=BF * 2304, K=640, N=5120, geglu=True)),
     ("L1 ff2 2560->640", dict(M=BF * 2304, K=2560, N=640)),
     ("L2 geglu 1280->10240", dict(M=BF * 576, K=1280, N=10240, geglu=True)),
@@ -24,6 +27,8 @@ for name, s in shapes:
     a = torch.randn(s["M"], s["K"], device=dev).half()
     w = (torch.randn(s["N"], s["K"], device=dev) / s["K"] ** 0.5).half()
     kw = dict(geglu=True) if s.get("geglu") else {}
+    if s.get("res"):
+        kw = dict(res1=torch.randn(s["M"], s["N"], device=dev), out_dtype=torch.float32, bias=torch.randn(s["N"], device=dev))
     for bn in ([0] if "--sweep" not in sys.argv else [128, 160, 256]):
         if s.get("geglu") and bn % 32:
             continue

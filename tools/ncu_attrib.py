@@ -42,7 +42,7 @@ for r in data:
 tot, ts = sum(byline.values()), max(1, sum(samples.values()))
 print(f"warp instructions executed: {tot}")
 print("opcode mix:", ", ".join(f"{k} {100 * v / tot:.1f}%" for k, v in mix.most_common(14)))
-root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "evoworld_b200", "csrc")
+root = os.environ.get("EVW_SRC_DIR") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "evoworld_b200", "csrc")
 src = {f: open(os.path.join(root, f)).read().split("\n") for f in os.listdir(root) if f.endswith((".cu", ".cuh", ".h"))}
 for k, v in byline.most_common(top):
     if k is None:
