@@ -202,8 +202,13 @@ def run_reproj_ours(args, dev, rank, world):
                      "achieved": algo / (ms_splat * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": algo / (ms_splat * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": ncu_traffic("reproj_24view_set"),
                      "limiter": "L2 atomics: 10.3 M 64-bit RED sectors per 4-view pass at 46 % of the L2 RED peak, tag lookups 61 %, "
-                                "SM->L2 request path 56 % (profiles/r01c_ncu_full_reproj.txt); DRAM itself is 13 % busy",
-                     "algorithmic_bytes": algo, "ms": ms_splat, "peak_source": peaks["source"]},
+                                "SM->L2 request path 56 % (profiles/r01c_ncu_full_reproj.txt); DRAM itself is 13 % busy; point order "
+                                "is not the limiter (3D-Morton / target-cell sorted clouds: 0.55 -> 0.49-0.50 ms, "
+                                "profiles/r02a_splat_sort_experiment.log)",
+                     "algorithmic_bytes": algo, "ms": ms_splat, "peak_source": peaks["source"],
+                     # SURVEY §8(d) time base: a11 (percentile select + compaction) + a14 + a15 = the whole timed step
+                     "frac_with_a11": algo / (ms_total / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "ms_with_a11": ms_total / args.steps},
         "gpu_launches": launches * args.steps,
         "config": {"workload": "config 3 segment 1: S=25x392x518 -> 50th-percentile filter -> ~2.54M points, V=24, "
                                "6x512^2 faces -> 2000x1000", "views_per_pass": G,

@@ -42,9 +42,13 @@ SIGNATURES = {
     "evw_gemm_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              C.c_char_p, c_void_p, c_int, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_int, c_float,
                              c_void_p, c_float, c_float, c_int, c_int, c_void_p, c_void_p]),
+    "evw_gemm_f16_gn": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                C.c_char_p, c_void_p, c_int, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_int, c_float,
+                                c_void_p, c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_i64, c_void_p]),
     "evw_spatial_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "evw_set_attention_variant": (None, [c_int]),
     "evw_set_gemm_cluster": (None, [c_int]),
+    "evw_set_gemm_gn_stats": (None, [c_int]),
     "evw_temporal_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_i64, c_int, c_void_p]),
     "evw_group_norm_f16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_i64, c_i64, c_float, c_void_p, c_void_p,
                                    c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -61,6 +65,7 @@ SIGNATURES = {
                                  c_int, c_int, c_int, c_void_p, c_i64, c_void_p]),
     "evw_unet_plan_info": (c_int, [c_void_p, C.POINTER(c_i64), C.POINTER(C.c_double)]),
     "evw_unet_graph_replays": (c_i64, [c_void_p]),
+    "evw_unet_gn_fused": (c_i64, [c_void_p]),
     "evw_splat_cube_equirect": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p,
                                         c_int, c_int, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p]),
     "evw_splat_cube_faces_debug": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_float, c_float, c_void_p,

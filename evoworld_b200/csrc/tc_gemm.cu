@@ -66,7 +66,8 @@ __device__ __forceinline__ void fd_divmod(uint32_t n, const FastDiv& f, uint32_t
 
 struct KernelParams {
   GemmEpilogue ep;
-  FastDiv fd_n_tiles, fd_tiles_x, fd_tiles_y, fd_T, fd_rv_div, fd_rv_mod;
+  FastDiv fd_n_tiles, fd_tiles_x, fd_tiles_y, fd_T, fd_rv_div, fd_rv_mod, fd_gn_cg, fd_gn_rpi;
+  long long gn_rows_per_inst;
   int bx_shift;
   int tiles_x, tiles_y, T, B, X, Y, bx, by;
   int n_tiles, block_n, N;
@@ -295,10 +296,35 @@ struct ResRing {
   uint32_t slots_mask, shift, box0;
   int row, lane;
 };
-template <bool RV, bool R1, bool R2, bool RT>
+// ST: GroupNorm statistics of the output.  Each step's 16 columns x 32 rows of the warp are summed over the rows by
+// recursive halving (lanes exchange half of their column sums at each of four stages: 15 shuffles per quantity instead of
+// 80), lanes 2c / 2c + 1 then hold column c's sum / sum of squares; a segmented reduction over the columns (4 shuffles per
+// quantity) leaves each group's part of the step in the lane of its first column, which stores it to a slot of its own
+// (warp quarter, step, group within the step) in shared memory.  No atomics, fixed summation order: the per-tile sums are
+// reproducible.  The caller adds a tile's slots up (double) and sends them to global memory once per tile and group.
+constexpr int kStatsSub = 3;  // groups a 16-column step can touch with >= 8 channels per group
+struct StatsCtx {
+  float2* slots;  // shared memory: [16 steps][kStatsSub] of this warp quarter and accumulator stage
+  FastDiv cg;     // channels per group
+  int n0;         // first column of the tile
+  int lane;
+};
+__device__ __forceinline__ void stats_halve(float (&s)[16], int w, int lane_bit, int lane) {
+  // keep the half of the 2w live values selected by this lane's bit, add the partner's copy of the same half
+  const bool hi = (lane & lane_bit) != 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < w) {
+      const float keep = hi ? s[w + i] : s[i];
+      const float send = hi ? s[i] : s[w + i];
+      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, lane_bit);
+    }
+  }
+}
+template <bool RV, bool R1, bool R2, bool RT, bool ST>
 __device__ __forceinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_addr, const float* bs, int cgrp, int NG, int nsteps,
                                           bool row_ok, int ncols, long long out_off, long long rv_off, bool wide_ok,
-                                          uint32_t bar_full, uint32_t phase, const ResRing& rr) {
+                                          uint32_t bar_full, uint32_t phase, const ResRing& rr, const StatsCtx& sx) {
   auto load_r1 = [&](float (&x)[16], int k) {
     if constexpr (!R1 || RT) return;
     const int c = k * 16;
@@ -330,6 +356,11 @@ __device__ __forceinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_add
     }
     tmem_ld_wait();
     const int c = k * 16;
+    float sv[16];
+    if constexpr (ST) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sv[i] = 0.f;
+    }
     if (row_ok && c < ncols) {
       const bool full = c + 16 <= ncols;
       float v[16];
@@ -369,6 +400,10 @@ __device__ __forceinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_add
           }
         }
       }
+      if constexpr (ST) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sv[i] = (full || i < 8) ? v[i] : 0.f;
+      }
       if (full) {
         store16(ep, v, out_off + c, wide_ok);
       } else {  // N tail: only the first 8 columns exist (N is a multiple of 8)
@@ -377,6 +412,34 @@ __device__ __forceinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_add
         for (int i = 0; i < 8; ++i) v8[i] = v[i];
         if (ep.out_fp16) store8(reinterpret_cast<__half*>(ep.out) + out_off + c, v8);
         else store8(reinterpret_cast<float*>(ep.out) + out_off + c, v8);
+      }
+    }
+    if constexpr (ST) {  // executed by every lane (rows outside the tensor contribute zeros)
+      if (c < ncols) {   // warp-uniform
+        float sq[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sq[i] = sv[i] * sv[i];
+        stats_halve(sv, 8, 16, sx.lane); stats_halve(sq, 8, 16, sx.lane);
+        stats_halve(sv, 4, 8, sx.lane);  stats_halve(sq, 4, 8, sx.lane);
+        stats_halve(sv, 2, 4, sx.lane);  stats_halve(sq, 2, 4, sx.lane);
+        stats_halve(sv, 1, 2, sx.lane);  stats_halve(sq, 1, 2, sx.lane);
+        float ts = sv[0] + __shfl_xor_sync(0xffffffffu, sv[0], 1);
+        float tq = sq[0] + __shfl_xor_sync(0xffffffffu, sq[0], 1);
+        const int ci = sx.lane >> 1;  // lanes 2 ci and 2 ci + 1 hold column ci of this step
+        uint32_t g, rem;              // group of the column and its position inside the group
+        fd_divmod((uint32_t)(sx.n0 + c + ci), sx.cg, g, rem);
+#pragma unroll
+        for (int d = 1; d < 16; d *= 2) {  // add column ci + d while it belongs to the same group (and to this step)
+          const float os = __shfl_down_sync(0xffffffffu, ts, 2 * d);
+          const float oq = __shfl_down_sync(0xffffffffu, tq, 2 * d);
+          const bool same = ci + d < 16 && rem + (uint32_t)d < sx.cg.d;
+          ts += same ? os : 0.f;
+          tq += same ? oq : 0.f;
+        }
+        if ((sx.lane & 1) == 0 && (ci == 0 || rem == 0)) {
+          const uint32_t g0 = fd_div((uint32_t)(sx.n0 + c), sx.cg);
+          sx.slots[k * kStatsSub + (int)(g - g0)] = make_float2(ts, tq);
+        }
       }
     }
     if constexpr (RT) {  // 8 arrivals (one per epilogue warp) free the box for the residual producer
@@ -405,6 +468,7 @@ __device__ __forceinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_add
 // variant needs 66-144 registers on its own, all six together hit the 168-register ceiling with 150 B of spill traffic,
 // and GEGLU beside them went from 0.52 to 0.69 ms).
 constexpr int kEpiGeglu = 8;
+constexpr int kStatsBytes = 2 * 4 * 16 * kStatsSub * 8;  // shared memory of the GroupNorm partial sums (kStats)
 template <bool k2Cta, int kEpiWarps, int kEpi>
 __global__ void __launch_bounds__(kCtrlThreads + 32 * kEpiWarps, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
@@ -418,6 +482,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
   const uint32_t b_tile_bytes = (uint32_t)P.block_n * kBlockK * (k2Cta ? 1 : 2);
   const uint32_t stage_bytes = kATileBytes + b_tile_bytes;
   constexpr bool kResTma = (kEpi & 16) != 0;  // res1 staged through shared memory by TMA (warp 3)
+  constexpr bool kStats = (kEpi & 32) != 0;   // GroupNorm statistics of the output accumulated by the epilogue
   const uint32_t res_base = smem_base + stages * stage_bytes;  // kResTma: P.res_slots boxes of 16 KiB
   const uint32_t bar_base = res_base + (kResTma ? (uint32_t)P.res_slots * 16384u : 0u);  // 8-byte barriers
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -607,7 +672,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
     const int esz = ep.out_fp16 ? 2 : 4;
     const bool wide_ok = (((long long)ldo * esz) % 32 == 0) && ((reinterpret_cast<uintptr_t>(ep.out) & 31) == 0);
     float* bias_s = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 8 * (2 * stages + 4) + 16 + 128);
+    // kStats: [2 accumulator stages][4 warp quarters][16 steps][kStatsSub] partial group sums of a tile
+    float2* stats_s = reinterpret_cast<float2*>(bias_s + 2 * 256);
     const int et = threadIdx.x - 128;    // 0 .. 32*kEpiWarps-1
+    int prev_inst = -1, prev_gfirst = 0, prev_ng = 0, prev_n0 = 0, prev_cols = 0;  // kStats: the tile still in shared memory
+    auto flush_stats = [&](int acc_prev) {  // after a barrier that follows the tile's last step; one thread per group
+      if (prev_inst >= 0 && et < prev_ng) {
+        const int g = prev_gfirst + et, cg = (int)P.fd_gn_cg.d;
+        const int lo = max(g * cg, prev_n0) - prev_n0, hi = min((g + 1) * cg, prev_n0 + prev_cols) - 1 - prev_n0;
+        double s = 0.0, sq = 0.0;
+        for (int k = lo >> 4; k <= hi >> 4; ++k) {
+          const int sub = g - (int)fd_div((uint32_t)(prev_n0 + 16 * k), P.fd_gn_cg);
+          for (int qq = 0; qq < 4; ++qq) {
+            const float2 v = stats_s[((acc_prev * 4 + qq) * 16 + k) * kStatsSub + sub];
+            s += (double)v.x;
+            sq += (double)v.y;
+          }
+        }
+        double* dst = ep.gn_stats + ((long long)prev_inst * 32 + g) * 2;
+        atomicAdd(dst, s);
+        atomicAdd(dst + 1, sq);
+      }
+    };
     const int mx = r & (P.bx - 1), my = r >> P.bx_shift;  // bx is a power of two
     constexpr bool is_geglu = kEpi == kEpiGeglu;
     // residual operands stream from DRAM exactly once: pull the row segment of the NEXT tile into L2 one tile ahead
@@ -654,6 +740,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
         bs[et] = bv;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      StatsCtx sx;
+      if (kStats) {
+        flush_stats(acc ^ 1);  // every warp has finished the previous tile (barrier above)
+        const int ncols_t = min(P.block_n, P.N - n0);
+        sx.cg = P.fd_gn_cg; sx.n0 = n0; sx.lane = lane;
+        sx.slots = stats_s + (acc * 4 + q) * 16 * kStatsSub;
+        // all rows of a tile belong to one GroupNorm instance (checked by gemm_enable_gn_stats)
+        const uint32_t row0 = (uint32_t)((((long long)tb * P.T + tt) * P.Y + ty * P.by) * P.X + tx * P.bx);
+        prev_inst = (tile < P.total_tiles) ? (int)fd_div(row0, P.fd_gn_rpi) : -1;
+        prev_gfirst = (int)fd_div((uint32_t)n0, P.fd_gn_cg);
+        prev_ng = (int)fd_div((uint32_t)(n0 + ncols_t - 1), P.fd_gn_cg) - prev_gfirst + 1;
+        prev_n0 = n0;
+        prev_cols = ncols_t;
+      }
 
       const uint32_t t_addr = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
       if constexpr (is_geglu) {
@@ -693,8 +793,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
         rr.base = res_base; rr.full_bar = res_full_bar(0); rr.empty_bar = res_empty_bar(0);
         rr.slots_mask = (uint32_t)(P.res_slots - 1); rr.shift = (uint32_t)P.res_shift;
         rr.box0 = (uint32_t)it * (uint32_t)(P.block_n >> 5); rr.row = r; rr.lane = lane;
-        epi_plain<(kEpi & 1) != 0, (kEpi & 2) != 0, (kEpi & 4) != 0, kResTma>(ep, t_addr, bs, cgrp, NG, nsteps, row_ok, ncols, out_off,
-                                                                               rv_off, wide_ok, bar_full, acc_phase, rr);
+        epi_plain<(kEpi & 1) != 0, (kEpi & 2) != 0, (kEpi & 4) != 0, kResTma, kStats>(ep, t_addr, bs, cgrp, NG, nsteps, row_ok, ncols,
+                                                                                       out_off, rv_off, wide_ok, bar_full, acc_phase,
+                                                                                       rr, sx);
       }
       tc_fence_before();
       __syncwarp();
@@ -702,6 +803,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
         if (k2Cta) mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));
         else mbar_arrive(tempty_bar(acc));
       }
+    }
+    if (kStats) {  // the last tile's sums
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      flush_stats((it - 1) & 1);
     }
   }
 
@@ -855,11 +960,16 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
                  ((uintptr_t)pr.ep.res1 & 15) == 0) ? 1 : 0;
   P.res_slots = op->res_tma ? 4 : 0;  // 64 KiB of residual in flight per SM
   P.res_shift = 2;
-  int stages = (int)((227 * 1024 - 4096 - P.res_slots * 16384) / stage_bytes);
-  if (stages > 8) stages = 8;
+  // operand stages + residual ring + barriers, TMEM slot, residual barriers + staged bias + GroupNorm partial sums + 1 KiB
+  // of alignment slack: as many stages (<= 8) as fit into the 227 KiB a CTA may use
+  auto smem_for = [&](int s) {
+    return (long long)s * stage_bytes + P.res_slots * 16384 + 8 * (2 * s + 4) + 16 + 128 + 2 * 256 * 4 + kStatsBytes + 1024;
+  };
+  int stages = 8;
+  while (stages > 1 && smem_for(stages) > 227 * 1024) --stages;
   EVW_CHECK_ARG(stages >= 2, "gemm: not enough shared memory for BLOCK_N=%d", bn);
   P.num_stages = stages;
-  op->smem_bytes = stages * stage_bytes + P.res_slots * 16384 + 8 * (2 * stages + 4) + 16 + 128 + 2 * 256 * 4 + 1024;
+  op->smem_bytes = (int)smem_for(stages);
   if (op->cluster) {
     const int want = 2 * P.total_pairs;
     op->grid = want < (sms & ~1) ? want : (sms & ~1);
@@ -907,6 +1017,40 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   return EVW_OK;
 }
 
+// -1: EVW_GEMM_GN_STATS (default on), 0 / 1: forced (tests, A/B runs); read when a GroupNorm asks its producer for statistics
+static int g_gemm_gn_stats = -1;
+static bool gemm_gn_stats_enabled() {
+  if (g_gemm_gn_stats < 0) {
+    const char* e = getenv("EVW_GEMM_GN_STATS");
+    g_gemm_gn_stats = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return g_gemm_gn_stats != 0;
+}
+void set_gemm_gn_stats(int on) { g_gemm_gn_stats = on < 0 ? -1 : (on ? 1 : 0); }
+
+// Ask a planned GEMM to accumulate the GroupNorm(32) statistics of its output (see GemmEpilogue::gn_stats).
+// Returns 0 when enabled, 1 when this GEMM cannot provide them (the caller keeps its own statistics pass).
+int gemm_enable_gn_stats(GemmOp* op, double* stats, long long rows_per_inst) {
+  if (!gemm_gn_stats_enabled()) return 1;
+  KernelParams P;
+  memcpy(&P, op->params, sizeof(P));
+  const long long rows = (long long)P.B * P.T * P.Y * P.X;
+  if (P.ep.geglu || P.ep.res2 || (P.ep.res1 && !op->res_tma) || P.N % 32 != 0 || !stats || rows_per_inst <= 0) return 1;
+  const int cg = P.N / 32;
+  if (cg < 8) return 1;  // a 16-column step may touch at most kStatsSub groups
+  if (rows % rows_per_inst != 0) return 1;
+  const bool flat = P.Y == 1 && P.T == 1 && P.B == 1;  // token rows: a tile is 128 consecutive rows
+  if (flat ? (rows_per_inst % kBlockM != 0) : (rows_per_inst % ((long long)P.X * P.Y) != 0)) return 1;
+  static const int plain_wide = [] { const char* e = getenv("EVW_GEMM_PLAIN_WARPS"); return (e && atoi(e) == 16) ? 1 : 0; }();
+  if (plain_wide) return 1;
+  P.ep.gn_stats = stats; P.ep.gn_cg = cg;
+  P.gn_rows_per_inst = rows_per_inst;
+  P.fd_gn_cg = make_fastdiv((uint32_t)cg);
+  P.fd_gn_rpi = make_fastdiv((uint32_t)rows_per_inst);
+  memcpy(op->params, &P, sizeof(P));
+  return 0;
+}
+
 // -1: EVW_GEMM_CLUSTER, default ON = CTA pairs with tcgen05.mma.cta_group::2 (M = 256).  Round 1's cluster mode only
 // multicast the weight tile between two cta_group::1 CTAs and measured neutral (profiles/r01f_gemm_bench.log): the
 // 160-wide tiles are bound by the shared-memory data pipe (tensor-core operand reads + TMA writes), which multicast does
@@ -942,13 +1086,16 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream) {
    tc_gemm_kernel<C, kEpiWarpsDefault, 3>, tc_gemm_kernel<C, kEpiWarpsDefault, 6>, tc_gemm_kernel<C, kEpiWarpsDefault, 7>,       \
    tc_gemm_kernel<C, kEpiWarpsDefault, kEpiGeglu>, tc_gemm_kernel<C, kEpiWarpsGeglu, kEpiGeglu>,                                 \
    tc_gemm_kernel<C, kEpiWarpsDefault, 16 + 2>, tc_gemm_kernel<C, kEpiWarpsDefault, 16 + 3>,                                     \
-   tc_gemm_kernel<C, kEpiWarpsDefault, 16 + 6>, tc_gemm_kernel<C, kEpiWarpsDefault, 16 + 7>}
-  static const KernelFn fns[2][12] = {EVW_GEMM_ROW(false), EVW_GEMM_ROW(true)};
+   tc_gemm_kernel<C, kEpiWarpsDefault, 16 + 6>, tc_gemm_kernel<C, kEpiWarpsDefault, 16 + 7>,                                     \
+   tc_gemm_kernel<C, kEpiWarpsGeglu, 0>, tc_gemm_kernel<C, kEpiWarpsGeglu, 1>, /* 12, 13: no-residual epilogues, 16 warps */ \
+   tc_gemm_kernel<C, kEpiWarpsDefault, 32 + 0>, tc_gemm_kernel<C, kEpiWarpsDefault, 32 + 1>,                                     \
+   tc_gemm_kernel<C, kEpiWarpsDefault, 32 + 16 + 2>} /* 14..16: GroupNorm statistics of the output {none, rv, r1 by TMA} */
+  static const KernelFn fns[2][17] = {EVW_GEMM_ROW(false), EVW_GEMM_ROW(true)};
 #undef EVW_GEMM_ROW
   static bool attr_set = false;
   if (!attr_set) {
     for (int c = 0; c < 2; ++c)
-      for (int w = 0; w < 12; ++w) {
+      for (int w = 0; w < 17; ++w) {
         cudaError_t e = cudaFuncSetAttribute(fns[c][w], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
           set_error("cudaFuncSetAttribute(tc_gemm_kernel): %s", cudaGetErrorString(e));
@@ -963,13 +1110,31 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream) {
   const CUtensorMap& ta1 = *reinterpret_cast<const CUtensorMap*>(op.tmap_a1);
   const CUtensorMap& tb = *reinterpret_cast<const CUtensorMap*>(op.tmap_b);
   const CUtensorMap& tbh = *reinterpret_cast<const CUtensorMap*>(op.tmap_bh);
-  const int wide = (P.ep.geglu && gemm_geglu_wide_epilogue()) ? 1 : 0;
+  // EVW_GEMM_GEGLU_WARPS=16 / EVW_GEMM_PLAIN_WARPS=16: sixteen epilogue warps for the GEGLU / the residual-free epilogues
+  static const int plain_wide = [] { const char* e = getenv("EVW_GEMM_PLAIN_WARPS"); return (e && atoi(e) == 16) ? 1 : 0; }();
+  int wide = (P.ep.geglu && gemm_geglu_wide_epilogue()) ? 1 : 0;
+  if (!P.ep.geglu && !P.ep.res1 && !P.ep.res2 && plain_wide) wide = 1;
   const int threads = kCtrlThreads + 32 * (wide ? kEpiWarpsGeglu : kEpiWarpsDefault);
   int epi;
   if (P.ep.geglu) epi = 6 + wide;
   else if (P.ep.res2) epi = P.ep.rowvec ? 5 : 4;  // res2 is only ever used together with res1
   else epi = (P.ep.rowvec ? 1 : 0) + (P.ep.res1 ? 2 : 0);
   if (op.res_tma) epi = 8 + (epi - 2);  // epi in {2,3,4,5} -> {8,9,10,11}
+  if (!P.ep.geglu && wide) epi = 12 + epi;  // epi in {0,1} -> {12,13}
+  if (P.ep.gn_stats) {
+    epi = epi == 0 ? 14 : (epi == 1 ? 15 : (epi == 8 ? 16 : -1));
+    if (epi < 0) {
+      set_error("gemm: GroupNorm statistics are not built for this epilogue");
+      return EVW_ERR_INVALID;
+    }
+    // [instances, 32, 2] doubles, instances = rows / rows per instance
+    const long long rows = (long long)P.B * P.T * P.Y * P.X;
+    cudaError_t em = cudaMemsetAsync(P.ep.gn_stats, 0, sizeof(double) * 64 * (rows / P.gn_rows_per_inst), stream);
+    if (em != cudaSuccess) {
+      set_error("gemm: clearing the GroupNorm statistics: %s", cudaGetErrorString(em));
+      return EVW_ERR_CUDA;
+    }
+  }
   KernelFn fn = fns[op.cluster ? 1 : 0][epi];
   const CUtensorMap& tr = *reinterpret_cast<const CUtensorMap*>(op.tmap_r);
   cudaError_t e;
@@ -1004,12 +1169,13 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream) {
 // C ABI: one generic entry (used by the parity tests and by Python-side micro-benchmarks)
 // ------------------------------------------------------------------------------------------
 extern "C" void evw_set_gemm_cluster(int on) { evw::set_gemm_cluster_mode(on); }
+extern "C" void evw_set_gemm_gn_stats(int on) { evw::set_gemm_gn_stats(on); }
 
-extern "C" int evw_gemm_f16(const void* a0, const void* a1, const void* w, int B, int T, int Y, int X, int C0, int C1,
-                            int N, int num_taps, const int8_t* h_taps /*[num_taps,4] dx,dy,dt,src*/, void* out,
-                            int out_fp16, const float* bias, const float* rowvec, int64_t rv_div, int64_t rv_mod,
-                            const void* res1, int res1_fp16, float s1, const float* res2, float s2, float s0, int geglu,
-                            int block_n, void* out_lo, void* stream) {
+extern "C" int evw_gemm_f16_gn(const void* a0, const void* a1, const void* w, int B, int T, int Y, int X, int C0, int C1,
+                               int N, int num_taps, const int8_t* h_taps /*[num_taps,4] dx,dy,dt,src*/, void* out,
+                               int out_fp16, const float* bias, const float* rowvec, int64_t rv_div, int64_t rv_mod,
+                               const void* res1, int res1_fp16, float s1, const float* res2, float s2, float s0, int geglu,
+                               int block_n, void* out_lo, double* gn_stats, int64_t gn_rows_per_inst, void* stream) {
   evw::GemmProblem pr{};
   pr.a0 = a0; pr.a1 = a1; pr.w = w;
   pr.B = B; pr.T = T; pr.Y = Y; pr.X = X; pr.C0 = C0; pr.C1 = C1; pr.N = N;
@@ -1030,5 +1196,17 @@ extern "C" int evw_gemm_f16(const void* a0, const void* a1, const void* w, int B
   evw::GemmOp op;
   int rc = evw::gemm_plan(&op, pr);
   if (rc) return rc;
+  if (gn_stats) {
+    EVW_CHECK_ARG(evw::gemm_enable_gn_stats(&op, gn_stats, gn_rows_per_inst) == 0,
+                  "evw_gemm_f16_gn: this GEMM cannot accumulate GroupNorm statistics (epilogue / geometry)");
+  }
   return evw::gemm_launch(op, (cudaStream_t)stream);
+}
+
+extern "C" int evw_gemm_f16(const void* a0, const void* a1, const void* w, int B, int T, int Y, int X, int C0, int C1,
+                            int N, int num_taps, const int8_t* h_taps, void* out, int out_fp16, const float* bias,
+                            const float* rowvec, int64_t rv_div, int64_t rv_mod, const void* res1, int res1_fp16, float s1,
+                            const float* res2, float s2, float s0, int geglu, int block_n, void* out_lo, void* stream) {
+  return evw_gemm_f16_gn(a0, a1, w, B, T, Y, X, C0, C1, N, num_taps, h_taps, out, out_fp16, bias, rowvec, rv_div, rv_mod, res1,
+                         res1_fp16, s1, res2, s2, s0, geglu, block_n, out_lo, nullptr, 0, stream);
 }

@@ -27,6 +27,11 @@ struct GemmEpilogue {
   float s2 = 1.f;
   float s0 = 1.f;
   int geglu = 0;
+  // GroupNorm(32) statistics of the OUTPUT, accumulated by the epilogue so that the consumer GroupNorm skips its statistics
+  // pass over the tensor: gn_stats double [instances, 32, 2] (sum, sum of squares; cleared by gemm_launch), instance of a
+  // row = row / rows_per_inst, group of a column = n / gn_cg (gn_cg = N / 32).  Set through gemm_enable_gn_stats().
+  double* gn_stats = nullptr;
+  int gn_cg = 0;
 };
 
 // Activations are fp16 [B, T, Y, X, C] (channels last); weights fp16 [N, K_total] with
@@ -63,6 +68,8 @@ struct alignas(64) GemmOp {
 
 int gemm_plan(GemmOp* op, const GemmProblem& pr);
 int gemm_launch(const GemmOp& op, cudaStream_t stream);
+int gemm_enable_gn_stats(GemmOp* op, double* stats, long long rows_per_inst);  // 0 = enabled, 1 = not available for this GEMM
+void set_gemm_gn_stats(int on);     // -1 = EVW_GEMM_GN_STATS / default on, 0 = GroupNorms keep their own statistics pass, 1 = on
 void set_gemm_cluster_mode(int on);  // -1 = EVW_GEMM_CLUSTER / default, 0 = off, 1 = on (takes effect at plan time)
 
 }  // namespace evw

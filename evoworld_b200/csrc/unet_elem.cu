@@ -731,7 +731,8 @@ inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + th
 // ==========================================================================================
 int group_norm(const void* src0, int src0_fp16, int C0, const float* src1, int C1, long long insts,
                long long rows_per_inst, float eps, const float* gamma, const float* beta, int do_silu, double* stats,
-               __half* out, __half* raw_out, __half* out_lo, cudaStream_t st) {
+               __half* out, __half* raw_out, __half* out_lo, cudaStream_t st, int have_stats) {
+  // have_stats: `stats` already holds the sums (accumulated by the epilogue of the GEMM that produced src0)
   const int C = C0 + C1, groups = 32;
   EVW_CHECK_ARG(C % groups == 0 && C % 8 == 0 && C0 % 8 == 0, "group_norm: C=%d (C0=%d) not supported", C, C0);
   const int Q = C / 4;
@@ -743,7 +744,7 @@ int group_norm(const void* src0, int src0_fp16, int C0, const float* src1, int C
   const int threads = TQ * R;
   // stats scratch: [insts,32,2] doubles followed by the [insts, C] float2 (scale, shift) table
   float2* ab = reinterpret_cast<float2*>(stats + 2 * groups * insts);
-  EVW_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * insts, st));
+  if (!have_stats) EVW_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * insts, st));
   long long want_blocks = (long long)sm_count() * 4 / (insts > 0 ? insts : 1) + 1;
   constexpr int U1 = 8, U2 = 2;  // rows in flight per thread for NQ = 1 / 2
   const int U = NQ == 1 ? U1 : U2;
@@ -752,8 +753,9 @@ int group_norm(const void* src0, int src0_fp16, int C0, const float* src1, int C
   dim3 grid((unsigned)((rows_per_inst + rpb - 1) / rpb), (unsigned)insts);
 #define EVW_GN_STATS(T0, NQv, Uv) \
   gn_stats_kernel<T0, NQv, Uv><<<grid, threads, 0, st>>>((const T0*)src0, C0, src1, C1, rows_per_inst, rpb, groups, TQ, stats)
-  if (src0_fp16) { if (NQ == 1) EVW_GN_STATS(__half, 1, U1); else EVW_GN_STATS(__half, 2, U2); }
-  else           { if (NQ == 1) EVW_GN_STATS(float, 1, U1); else EVW_GN_STATS(float, 2, U2); }
+  if (have_stats) {}
+  else if (src0_fp16) { if (NQ == 1) EVW_GN_STATS(__half, 1, U1); else EVW_GN_STATS(__half, 2, U2); }
+  else                { if (NQ == 1) EVW_GN_STATS(float, 1, U1); else EVW_GN_STATS(float, 2, U2); }
 #undef EVW_GN_STATS
   const int nc = (int)(insts * C);
   gn_finalize_kernel<<<(nc + 255) / 256, 256, 0, st>>>(stats, (int)insts, C, groups, (double)rows_per_inst * (C / groups), eps,

@@ -11,7 +11,7 @@ namespace evw {
 // split-precision consumers.  stats: double [insts, 32, 2] scratch.
 int group_norm(const void* src0, int src0_fp16, int C0, const float* src1, int C1, long long insts,
                long long rows_per_inst, float eps, const float* gamma, const float* beta, int do_silu, double* stats,
-               __half* out, __half* raw_out, __half* out_lo, cudaStream_t st);
+               __half* out, __half* raw_out, __half* out_lo, cudaStream_t st, int have_stats = 0);
 // LayerNorm over C of (x[row] + rowvec[(row / rv_div) % rv_mod]) -> fp16
 int layer_norm(const float* x, const float* rowvec, long long rv_div, long long rv_mod, long long rows, int C, float eps,
                const float* gamma, const float* beta, __half* out, cudaStream_t st);

@@ -90,6 +90,7 @@ struct Plan {
   cudaStream_t capture_stream = nullptr;
   std::vector<std::pair<GraphKey, cudaGraphExec_t>> graphs;
   long long graph_replays = 0;
+  int gn_fused = 0;  // GroupNorms whose statistics come from the producing GEMM's epilogue
   ~Plan() {
     for (auto& g : graphs) cudaGraphExecDestroy(g.second);
     if (capture_stream) cudaStreamDestroy(capture_stream);
@@ -133,6 +134,11 @@ struct Builder {
   float *emb = nullptr, *emb2 = nullptr, *temb_all = nullptr, *xattn_all = nullptr, *tsteps = nullptr, *dargs = nullptr;
   double* stats = nullptr;
   std::string fail;
+  // GroupNorm statistics from the producer's epilogue: the most recent GEMM that wrote each tensor, and the plan position
+  // of the last op that used the statistics scratch (a GroupNorm, or a GEMM already asked to fill it)
+  struct Writer { std::shared_ptr<GemmOp> op; long long rows; int N; size_t idx; };
+  std::map<const void*, Writer> last_writer;
+  size_t stats_busy_idx = 0;
 
   Builder(UNet& u, Plan& p, void* ws, bool dry_) : U(u), P(p), bump(ws), dry(dry_) {}
 
@@ -156,6 +162,7 @@ struct Builder {
   void push(Op op, int launches = 1, const std::string& label = "", const void* out = nullptr, long long n = 0, int fp16 = 0) {
     P.launches += launches;
     if (!dry) {
+      if (out) last_writer.erase(out);
       P.ops.push_back(std::move(op));
       P.meta.push_back(OpMeta{label, out, n, fp16});
     }
@@ -178,6 +185,7 @@ struct Builder {
     const long long rows = (long long)pr.B * pr.T * pr.Y * pr.X;
     push([op](cudaStream_t st) { return gemm_launch(*op, st); }, 1, label + " " + std::to_string(rows) + "x" + std::to_string(pr.N) + "x" + std::to_string(pr.K_total),
          pr.ep.out, rows * (pr.ep.geglu ? pr.N / 2 : pr.N), pr.ep.out_fp16);
+    if (!pr.ep.geglu && !pr.ep.out_lo) last_writer[pr.ep.out] = Writer{op, rows, pr.N, P.ops.size()};
   }
   static void taps_conv3x3(GemmProblem& pr) {
     pr.num_taps = 9;
@@ -211,9 +219,21 @@ struct Builder {
     const float* g = Wf(name + ".weight");
     const float* b = Wf(name + ".bias");
     double* st_ = stats;
+    // The GEMM that produced src0 accumulates the statistics in its epilogue when it can (single source, the whole
+    // tensor written by that GEMM, nothing else using the statistics scratch in between): 2 kernels instead of 3.
+    int have = 0;
+    if (!dry && !src1) {
+      auto it = last_writer.find(src0);
+      if (it != last_writer.end() && it->second.N == C0 && it->second.rows == insts * rows && it->second.idx > stats_busy_idx &&
+          gemm_enable_gn_stats(it->second.op.get(), stats, rows) == 0) {
+        have = 1;
+        ++P.gn_fused;
+      }
+    }
     // 3 kernels (stats, finalize, apply); the statistics clear is a memset node and is not counted as a kernel launch
-    push([=](cudaStream_t st) { return group_norm(src0, src0_fp16, C0, src1, C1, insts, rows, eps, g, b, silu, st_, out, raw, out_lo, st); }, 3,
-         name, out, insts * rows * (C0 + C1), 1);
+    push([=](cudaStream_t st) { return group_norm(src0, src0_fp16, C0, src1, C1, insts, rows, eps, g, b, silu, st_, out, raw, out_lo, st, have); },
+         have ? 2 : 3, name, out, insts * rows * (C0 + C1), 1);
+    if (!dry) stats_busy_idx = P.ops.size();
   }
   void lnorm(const float* x, const float* rowvec, long long rv_div, long long rv_mod, long long rows, int C,
              const std::string& name, __half* out) {
@@ -863,6 +883,11 @@ extern "C" int evw_denoise_step(void* handle, float* latents, const float* cond_
 extern "C" int64_t evw_unet_graph_replays(void* handle) {
   UNet* U = (UNet*)handle;
   return (U && U->plan) ? U->plan->graph_replays : -1;
+}
+
+extern "C" int64_t evw_unet_gn_fused(void* handle) {
+  UNet* U = (UNet*)handle;
+  return (U && U->plan) ? U->plan->gn_fused : -1;
 }
 
 extern "C" int evw_unet_plan_info(void* handle, int64_t* launches, double* flops) {

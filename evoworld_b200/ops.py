@@ -22,8 +22,10 @@ def gemm_f16(a0: torch.Tensor, w: torch.Tensor, taps: Sequence[Tuple[int, int, i
              a1: Optional[torch.Tensor] = None, bias=None, rowvec=None, rv_div: int = 1, rv_mod: int = 1, res1=None,
              s1: float = 1.0, res2=None, s2: float = 1.0, s0: float = 1.0, geglu: bool = False,
              out_dtype=torch.float16, block_n: int = 0, out: Optional[torch.Tensor] = None,
-             out_lo: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """a0 fp16 [B,T,Y,X,C0] (or [M,C0] for a linear layer), w fp16 [N,K_total] -> [rows, N or N/2]."""
+             out_lo: Optional[torch.Tensor] = None, gn_stats: Optional[torch.Tensor] = None,
+             gn_rows_per_inst: int = 0) -> torch.Tensor:
+    """a0 fp16 [B,T,Y,X,C0] (or [M,C0] for a linear layer), w fp16 [N,K_total] -> [rows, N or N/2].
+    gn_stats (float64 [rows / gn_rows_per_inst, 32, 2]): filled with the GroupNorm(32) sums of the output (evw_gemm_f16_gn)."""
     _lib.require_cuda(a0, "a0")
     if a0.dim() == 2:
         a0 = a0[None, None, None]
@@ -39,11 +41,14 @@ def gemm_f16(a0: torch.Tensor, w: torch.Tensor, taps: Sequence[Tuple[int, int, i
     taps_arr = np.asarray(taps, dtype=np.int8).reshape(-1, 4)
     assert a0.dtype == torch.float16 and w.dtype == torch.float16
     with torch.cuda.device(a0.device):
-        _lib.check(_lib.lib().evw_gemm_f16(
+        if gn_stats is not None:
+            assert gn_stats.dtype == torch.float64 and gn_stats.is_contiguous() and gn_stats.numel() == rows // gn_rows_per_inst * 64
+        _lib.check(_lib.lib().evw_gemm_f16_gn(
             _lib.ptr(a0), _lib.ptr(a1), _lib.ptr(w), B, T, Y, X, C0, C1, N, taps_arr.shape[0], taps_arr.tobytes(),
             _lib.ptr(out), 1 if out.dtype == torch.float16 else 0, _lib.ptr(bias), _lib.ptr(rowvec), rv_div, rv_mod,
             _lib.ptr(res1), 1 if (res1 is not None and res1.dtype == torch.float16) else 0, s1, _lib.ptr(res2), s2, s0,
-            1 if geglu else 0, block_n, _lib.ptr(out_lo), _lib.stream_ptr(a0.device)), "evw_gemm_f16")
+            1 if geglu else 0, block_n, _lib.ptr(out_lo), _lib.ptr(gn_stats), gn_rows_per_inst,
+            _lib.stream_ptr(a0.device)), "evw_gemm_f16")
     return out
 
 

@@ -500,6 +500,10 @@ class UNetSpatioTemporalConditionModel:
         """Calls served by replaying the captured CUDA graph of the current plan (-1 before the first call)."""
         return int(_lib.lib().evw_unet_graph_replays(self._handle)) if self._handle is not None else -1
 
+    def gn_fused(self) -> int:
+        """GroupNorms of the current plan whose statistics come from the producing GEMM's epilogue (-1 before the first call)."""
+        return int(_lib.lib().evw_unet_gn_fused(self._handle)) if self._handle is not None else -1
+
     # ------------------------------------------------------------------ compute
     @torch.no_grad()
     def forward(self, sample: torch.Tensor, timestep: Union[torch.Tensor, float, int], encoder_hidden_states: torch.Tensor,

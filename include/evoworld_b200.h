@@ -193,12 +193,26 @@ int evw_gemm_f16(const void* a0, const void* a1, const void* w, int B, int T, in
                  const float* rowvec, int64_t rv_div, int64_t rv_mod, const void* res1, int res1_fp16, float s1,
                  const float* res2, float s2, float s0, int geglu, int block_n, void* out_lo, void* stream);
 
+/* evw_gemm_f16 whose epilogue also accumulates the GroupNorm(32) statistics of its output, so that the GroupNorm that
+ * consumes it (ResnetBlock2D.norm2 after conv1, TemporalResnetBlock.norm1 after the spatial block, ... — diffusers
+ * resnet.py) needs no statistics pass of its own: gn_stats double [rows / gn_rows_per_inst, 32, 2] = per (instance, group)
+ * sum and sum of squares of the stored values (cleared by the call).  Only for epilogues without GEGLU / res2 and with
+ * res1 fp32 (or absent); all rows of a 128-row tile must fall into one instance — EVW_ERR_INVALID otherwise. */
+int evw_gemm_f16_gn(const void* a0, const void* a1, const void* w, int B, int T, int Y, int X, int C0, int C1,
+                    int N, int num_taps, const int8_t* h_taps, void* out, int out_fp16, const float* bias,
+                    const float* rowvec, int64_t rv_div, int64_t rv_mod, const void* res1, int res1_fp16, float s1,
+                    const float* res2, float s2, float s0, int geglu, int block_n, void* out_lo, double* gn_stats,
+                    int64_t gn_rows_per_inst, void* stream);
+
 /* Launch mode of the GEMM (takes effect when an op is planned): 1 = always CTA pairs (clusters of two) on m-adjacent tiles
  * running tcgen05.mma.cta_group::2 with M = 256, each CTA holding half of the weight tile; 0 = always independent CTAs
  * (cta_group::1, M = 128); -1 = default (EVW_GEMM_CLUSTER, else automatic: pairs where K_total >= EVW_GEMM_PAIR_MIN_K,
  * 1024 by default — the main-loop-bound convolutions and wide linears — and single CTAs for the epilogue-bound K = 320 /
  * 640 linears).  All modes are bit-identical. */
 void evw_set_gemm_cluster(int on);
+/* Whether the UNet plan lets GEMM epilogues accumulate the statistics of the GroupNorm that follows (evw_gemm_f16_gn):
+ * 1 = yes, 0 = every GroupNorm runs its own statistics pass, -1 = default (EVW_GEMM_GN_STATS, on).  Read at plan time. */
+void evw_set_gemm_gn_stats(int on);
 
 /* Spatial self-attention (BasicTransformerBlock.attn1 -> F.scaled_dot_product_attention, head dim 64):
  * qkv fp16 [F*S, 3*heads*64] (columns [q|k|v], each [heads,64]) -> out fp16 [F*S, heads*64]; softmax over
@@ -251,6 +265,9 @@ int evw_denoise_step(void* handle, float* latents, const float* cond_latents, fl
  * ~830 kernel launches; the first call of a plan runs eagerly, the second captures).  -1 without a plan.  EVW_UNET_GRAPH=0
  * disables graph replay. */
 int64_t evw_unet_graph_replays(void* handle);
+/* How many GroupNorms of the current plan take their statistics from the epilogue of the GEMM that produced their input
+ * (evw_gemm_f16_gn) instead of a pass of their own.  -1 without a plan.  EVW_GEMM_GN_STATS=0 disables the fusion. */
+int64_t evw_unet_gn_fused(void* handle);
 /* Kernel launches and algorithmic FLOPs of the current plan (after the first forward / step). */
 int evw_unet_plan_info(void* handle, int64_t* launches, double* flops);
 

@@ -206,3 +206,69 @@ def test_residual_ring_at_scale(M, K, N, cuda_device):
         buf = r.clone()
         ops.gemm_f16(a, w, bias=b, res1=buf, out=buf)
         assert int(((buf - want).abs() > 1e-2).sum()) == 0 and rel_l2(buf, want) < 2e-5
+
+
+def _check_gn_sums(out, stats, insts, N, tol=2e-6):
+    """stats [insts, 32, 2] against float64 sums of the stored output."""
+    o = out.double().reshape(insts, -1, 32, N // 32)
+    want = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1)  # [insts, 32, 2]
+    scale = want[..., 1].sqrt().unsqueeze(-1) * (o.shape[1] * o.shape[3]) ** 0.5 + 1e-30  # |sum| <= sqrt(n * sum of squares)
+    err_sum = ((stats[..., 0] - want[..., 0]).abs() / scale[..., 0]).max()
+    err_sq = ((stats[..., 1] - want[..., 1]).abs() / (want[..., 1] + 1e-30)).max()
+    assert float(err_sum) < tol and float(err_sq) < tol, (float(err_sum), float(err_sq))
+
+
+@pytest.mark.parametrize("T,Y,X,C,N,per_frame", [(3, 24, 40, 64, 320, True), (4, 9, 16, 64, 640, False), (2, 36, 64, 64, 1280, True),
+                                                 (2, 72, 128, 64, 256, False), (28, 18, 32, 128, 320, False)])
+@pytest.mark.parametrize("out_dtype", [torch.float16, torch.float32])
+def test_conv3x3_group_norm_statistics(T, Y, X, C, N, per_frame, out_dtype, cuda_device):
+    """The epilogue's GroupNorm sums (evw_gemm_f16_gn) of a 3x3 convolution + bias + per-frame row vector: partial tiles
+    (rows outside the frame), groups straddling column steps and N tiles, instance = frame or = all frames."""
+    x = torch.randn(1, T, Y, X, C, device=cuda_device).half()
+    wk = (torch.randn(N, 9 * C, device=cuda_device) / (9 * C) ** 0.5).half()
+    b = torch.randn(N, device=cuda_device)
+    temb = torch.randn(T, N, device=cuda_device)
+    plain = ops.gemm_f16(x, wk, taps=ops.CONV3x3_TAPS, bias=b, rowvec=temb, rv_div=Y * X, rv_mod=T, out_dtype=out_dtype)
+    insts = T if per_frame else 1
+    stats = torch.full((insts, 32, 2), 7.0, dtype=torch.float64, device=cuda_device)  # the call clears it
+    got = ops.gemm_f16(x, wk, taps=ops.CONV3x3_TAPS, bias=b, rowvec=temb, rv_div=Y * X, rv_mod=T, out_dtype=out_dtype,
+                       gn_stats=stats, gn_rows_per_inst=(Y * X if per_frame else T * Y * X))
+    assert torch.equal(got, plain)
+    # the sums are taken before the fp16 rounding of the store: compare with the fp32 result
+    ref = got if out_dtype == torch.float32 else ops.gemm_f16(x, wk, taps=ops.CONV3x3_TAPS, bias=b, rowvec=temb, rv_div=Y * X,
+                                                               rv_mod=T, out_dtype=torch.float32)
+    _check_gn_sums(ref, stats, insts, N)
+
+
+@pytest.mark.parametrize("M,K,N,rpi", [(9216 * 2, 320, 320, 9216), (2304 * 3, 640, 640, 2304), (1280, 1280, 1280, 640),
+                                       (129024, 320, 320, 9216)])
+def test_linear_residual_group_norm_statistics(M, K, N, rpi, cuda_device):
+    """Token-row linear with the fp32 residual staged by TMA (proj_out / the temporal conv2 shape): instance = rpi rows."""
+    a = torch.randn(M, K, device=cuda_device).half()
+    w = (torch.randn(N, K, device=cuda_device) / K ** 0.5).half()
+    b = torch.randn(N, device=cuda_device)
+    r = torch.randn(M, N, device=cuda_device)
+    stats = torch.empty((M // rpi, 32, 2), dtype=torch.float64, device=cuda_device)
+    got = ops.gemm_f16(a, w, bias=b, res1=r, out_dtype=torch.float32, gn_stats=stats, gn_rows_per_inst=rpi)
+    assert torch.equal(got, ops.gemm_f16(a, w, bias=b, res1=r, out_dtype=torch.float32))
+    _check_gn_sums(got, stats, M // rpi, N)
+    # no residual, no row vector
+    got = ops.gemm_f16(a, w, bias=b, out_dtype=torch.float32, gn_stats=stats, gn_rows_per_inst=rpi)
+    _check_gn_sums(got, stats, M // rpi, N)
+
+
+def test_group_norm_statistics_refused(cuda_device):
+    """Epilogues / geometries the statistics are not built for fail loudly instead of returning wrong sums."""
+    a = torch.randn(1000, 320, device=cuda_device).half()
+    w = (torch.randn(320, 320, device=cuda_device) / 320 ** 0.5).half()
+    stats = torch.empty((10, 32, 2), dtype=torch.float64, device=cuda_device)
+    with pytest.raises(RuntimeError):  # 100 rows per instance: a 128-row tile would straddle instances
+        ops.gemm_f16(a, w, out_dtype=torch.float32, gn_stats=stats, gn_rows_per_inst=100)
+    a = torch.randn(1024, 320, device=cuda_device).half()
+    r16 = torch.randn(1024, 320, device=cuda_device).half()
+    stats = torch.empty((1, 32, 2), dtype=torch.float64, device=cuda_device)
+    with pytest.raises(RuntimeError):  # fp16 residual: not staged by TMA
+        ops.gemm_f16(a, w, res1=r16, out_dtype=torch.float32, gn_stats=stats, gn_rows_per_inst=1024)
+    w96 = (torch.randn(96, 320, device=cuda_device) / 320 ** 0.5).half()
+    with pytest.raises(RuntimeError):  # 3 channels per group: more groups per 16-column step than the epilogue has slots for
+        ops.gemm_f16(a, w96, out_dtype=torch.float32, gn_stats=stats, gn_rows_per_inst=1024)
