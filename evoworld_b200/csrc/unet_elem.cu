@@ -21,7 +21,8 @@ __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x));
 // ------------------------------------------------------------------------------------------
 // GroupNorm: (1) per-channel partial sums in registers (each thread owns fixed channel quads, rows are
 // strided over thread rows -> coalesced 16-byte loads), reduced per group in shared memory and added
-// to double accumulators; (2) finalize -> (mean, rstd) per (instance, group); (3) apply [+SiLU] -> fp16.
+// to double accumulators — or the sums arrive from the epilogue of the GEMM that produced the tensor (tc_gemm.cu);
+// (2) apply: (mean, rstd) per (instance, group) from the sums, y = a x + b [+SiLU] -> fp16.
 // ------------------------------------------------------------------------------------------
 constexpr int kGnMaxNQ = 2;  // channel quads per thread: C <= 4 * 512 * kGnMaxNQ
 
@@ -91,21 +92,6 @@ gn_stats_kernel(const T0* __restrict__ src0, int C0, const float* __restrict__ s
   }
 }
 
-// finalize: per (instance, channel) affine y = a x + b with a = rstd * gamma, b = beta - mean * rstd * gamma
-__global__ void gn_finalize_kernel(const double* __restrict__ stats, int insts, int C, int groups, double cnt, float eps,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, float2* __restrict__ ab) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= insts * C) return;
-  const int inst = i / C, c = i - inst * C;
-  const int g = c / (C / groups);
-  const double m = stats[(inst * groups + g) * 2] / cnt;
-  double var = stats[(inst * groups + g) * 2 + 1] / cnt - m * m;
-  if (var < 0) var = 0;
-  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-  const float a = rstd * gamma[c];
-  ab[i] = make_float2(a, beta[c] - (float)m * a);
-}
-
 __device__ __forceinline__ float silu_fast(float y) {
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y * -1.4426950408889634f));
@@ -114,12 +100,14 @@ __device__ __forceinline__ float silu_fast(float y) {
 }
 
 // apply: each thread owns one channel octet of one instance — its 8 (scale, shift) pairs stay in registers — and walks
-// rows with U loads in flight; y = a x + b [-> SiLU] -> fp16.  (v1 re-read the 64-byte table slice per 32 input bytes
-// and was L1-bound at 88 %.)
+// rows with U loads in flight; y = a x + b [-> SiLU] -> fp16 with a = rstd * gamma, b = beta - mean * a computed by the
+// thread itself from the (instance, group) sums (a separate finalize kernel and its [instances, C] table until round 2).
+// (v1 re-read the 64-byte table slice per 32 input bytes and was L1-bound at 88 %.)
 template <typename T0, int U>
 __global__ void __launch_bounds__(320)
 gn_apply_kernel(const T0* __restrict__ src0, int C0, const float* __restrict__ src1, int C1, long long rows_per_inst,
-                int rows_per_block, const float2* __restrict__ ab, int do_silu, __half* __restrict__ out,
+                int rows_per_block, const double* __restrict__ stats, int groups, double cnt, float eps,
+                const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu, __half* __restrict__ out,
                 __half* __restrict__ raw_out, __half* __restrict__ out_lo) {
   const int C = C0 + C1;
   const int cv = C / 8;
@@ -130,11 +118,22 @@ gn_apply_kernel(const T0* __restrict__ src0, int C0, const float* __restrict__ s
   const long long r1 = min(rows_per_inst, r0 + rows_per_block);
   float sa[8], sb[8];
   {
-    const float4* abp = reinterpret_cast<const float4*>(ab + inst * C + c);  // 8 x (a, b)
+    const int cg = C / groups;
+    int g_have = -1;
+    float mean = 0.f, rstd = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 t = __ldg(abp + i);
-      sa[2 * i] = t.x; sb[2 * i] = t.y; sa[2 * i + 1] = t.z; sb[2 * i + 1] = t.w;
+    for (int i = 0; i < 8; ++i) {
+      const int g = (c + i) / cg;
+      if (g != g_have) {  // an octet touches one or two groups (more only for toy widths)
+        const double m = stats[(inst * groups + g) * 2] / cnt;
+        double var = stats[(inst * groups + g) * 2 + 1] / cnt - m * m;
+        if (var < 0) var = 0;
+        rstd = (float)(1.0 / sqrt(var + (double)eps));
+        mean = (float)m;
+        g_have = g;
+      }
+      sa[i] = rstd * __ldg(gamma + c + i);
+      sb[i] = __ldg(beta + c + i) - mean * sa[i];
     }
   }
   const bool from0 = c < C0;
@@ -742,8 +741,7 @@ int group_norm(const void* src0, int src0_fp16, int C0, const float* src1, int C
   const int TQ = Q / NQ;
   const int R = 512 / TQ > 0 ? 512 / TQ : 1;
   const int threads = TQ * R;
-  // stats scratch: [insts,32,2] doubles followed by the [insts, C] float2 (scale, shift) table
-  float2* ab = reinterpret_cast<float2*>(stats + 2 * groups * insts);
+  // stats scratch: [insts, 32, 2] doubles
   if (!have_stats) EVW_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * insts, st));
   long long want_blocks = (long long)sm_count() * 4 / (insts > 0 ? insts : 1) + 1;
   constexpr int U1 = 8, U2 = 2;  // rows in flight per thread for NQ = 1 / 2
@@ -757,10 +755,8 @@ int group_norm(const void* src0, int src0_fp16, int C0, const float* src1, int C
   else if (src0_fp16) { if (NQ == 1) EVW_GN_STATS(__half, 1, U1); else EVW_GN_STATS(__half, 2, U2); }
   else                { if (NQ == 1) EVW_GN_STATS(float, 1, U1); else EVW_GN_STATS(float, 2, U2); }
 #undef EVW_GN_STATS
-  const int nc = (int)(insts * C);
-  gn_finalize_kernel<<<(nc + 255) / 256, 256, 0, st>>>(stats, (int)insts, C, groups, (double)rows_per_inst * (C / groups), eps,
-                                                        gamma, beta, ab);
   {
+    const double cnt = (double)rows_per_inst * (C / groups);
     const int cv = C / 8;
     EVW_CHECK_ARG(cv <= 320, "group_norm: C=%d too wide for the apply kernel", C);
     const int Ra = 320 / cv > 0 ? 320 / cv : 1;
@@ -771,11 +767,11 @@ int group_norm(const void* src0, int src0_fp16, int C0, const float* src1, int C
     if (arpb < UA * Ra) arpb = UA * Ra;
     dim3 agrid((unsigned)((rows_per_inst + arpb - 1) / arpb), (unsigned)insts);
     if (src0_fp16)
-      gn_apply_kernel<__half, UA><<<agrid, athreads, 0, st>>>((const __half*)src0, C0, src1, C1, rows_per_inst, arpb, ab, do_silu,
-                                                               out, raw_out, out_lo);
+      gn_apply_kernel<__half, UA><<<agrid, athreads, 0, st>>>((const __half*)src0, C0, src1, C1, rows_per_inst, arpb, stats, groups,
+                                                               cnt, eps, gamma, beta, do_silu, out, raw_out, out_lo);
     else
-      gn_apply_kernel<float, UA><<<agrid, athreads, 0, st>>>((const float*)src0, C0, src1, C1, rows_per_inst, arpb, ab, do_silu,
-                                                              out, raw_out, out_lo);
+      gn_apply_kernel<float, UA><<<agrid, athreads, 0, st>>>((const float*)src0, C0, src1, C1, rows_per_inst, arpb, stats, groups,
+                                                              cnt, eps, gamma, beta, do_silu, out, raw_out, out_lo);
   }
   EVW_LAUNCH_CHECK();
   return EVW_OK;

@@ -220,7 +220,7 @@ struct Builder {
     const float* b = Wf(name + ".bias");
     double* st_ = stats;
     // The GEMM that produced src0 accumulates the statistics in its epilogue when it can (single source, the whole
-    // tensor written by that GEMM, nothing else using the statistics scratch in between): 2 kernels instead of 3.
+    // tensor written by that GEMM, nothing else using the statistics scratch in between): 1 kernel instead of 2.
     int have = 0;
     if (!dry && !src1) {
       auto it = last_writer.find(src0);
@@ -230,9 +230,9 @@ struct Builder {
         ++P.gn_fused;
       }
     }
-    // 3 kernels (stats, finalize, apply); the statistics clear is a memset node and is not counted as a kernel launch
+    // 2 kernels (stats, apply); the statistics clear is a memset node and is not counted as a kernel launch
     push([=](cudaStream_t st) { return group_norm(src0, src0_fp16, C0, src1, C1, insts, rows, eps, g, b, silu, st_, out, raw, out_lo, st, have); },
-         have ? 2 : 3, name, out, insts * rows * (C0 + C1), 1);
+         have ? 1 : 2, name, out, insts * rows * (C0 + C1), 1);
     if (!dry) stats_busy_idx = P.ops.size();
   }
   void lnorm(const float* x, const float* rowvec, long long rv_div, long long rv_mod, long long rows, int C,
@@ -441,7 +441,7 @@ struct Builder {
     pp[0] = bump.take<float>(maxPP);
     pp[1] = bump.take<float>(maxPP);
     y32 = bump.take<float>(lM[0] * c.cout_pad);
-    stats = bump.take<double>((64LL + 4 * 1280) * std::max(BF, 1));  // [insts,32,2] double sums + [insts,C<=5120] float2 (scale, shift)
+    stats = bump.take<double>(64LL * std::max(BF, 1));  // [insts, 32, 2] double sums
     small16 = bump.take<__half>(5LL * kSmall);
     emb = bump.take<float>(8LL * c.temb_dim);
     emb2 = bump.take<float>(8LL * c.temb_dim);

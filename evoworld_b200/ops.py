@@ -95,7 +95,7 @@ def group_norm(src0: torch.Tensor, gamma, beta, insts: int, eps: float, silu: bo
     out = torch.empty((rows, C0 + C1), dtype=torch.float16, device=src0.device)
     raw = torch.empty_like(out) if want_raw else None
     lo = torch.empty_like(out) if want_lo else None
-    ws = torch.empty(insts * (64 + C0 + C1), dtype=torch.float64, device=src0.device)
+    ws = torch.empty(insts * 64, dtype=torch.float64, device=src0.device)
     with torch.cuda.device(src0.device):
         _lib.check(_lib.lib().evw_group_norm_f16(_lib.ptr(src0), 1 if src0.dtype == torch.float16 else 0, C0, _lib.ptr(src1),
                                                  C1, insts, rows // insts, eps, _lib.ptr(gamma), _lib.ptr(beta),

@@ -230,7 +230,7 @@ int evw_temporal_attention_f16(const void* qkv, void* out, int B, int T, int64_t
 /* GroupNorm(32) [+SiLU] over `insts` instances of `rows_per_inst` channels-last rows; input is the channel
  * concatenation of src0 (fp32 or fp16, C0 ch) and optional src1 (fp32, C1 ch); out fp16 [rows, C0+C1];
  * raw_out (optional) receives the un-normalised fp16 copy; out_lo (optional) the fp16 tail of the output (split-
- * precision operand, see evw_gemm_f16); stats_ws >= insts*(64 + C0 + C1) doubles. */
+ * precision operand, see evw_gemm_f16); stats_ws >= insts*64 doubles. */
 int evw_group_norm_f16(const void* src0, int src0_fp16, int C0, const float* src1, int C1, int64_t insts,
                        int64_t rows_per_inst, float eps, const float* gamma, const float* beta, int do_silu,
                        void* stats_ws, void* out, void* raw_out, void* out_lo, void* stream);

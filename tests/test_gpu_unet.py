@@ -228,8 +228,10 @@ def test_graph_replay_matches_eager(cuda_device, built_lib):
 
 def test_group_norm_statistics_from_gemm_epilogues(cuda_device, built_lib):
     """Most GroupNorms take their sums from the epilogue of the GEMM that produced their input (evw_gemm_f16_gn) instead of
-    a statistics pass of their own: same result as the plan with every GroupNorm computing its own (the sums differ only in
-    summation order), fewer launches, and reproducible from call to call."""
+    a statistics pass of their own: both plans meet the tolerance against the fp32 oracle, the fused one launches one kernel
+    less per fused GroupNorm and is reproducible from call to call.  (The two plans differ from each other by about as much
+    as each differs from the oracle: sums that agree to 1e-7 flip a few fp16 roundings, and 600 layers of fp16 operands
+    decorrelate from there — the sums themselves are compared exactly in tests/test_gpu_gemm.py.)"""
     T, h, w = 3, 16, 32
     torch.manual_seed(11)
     xin = torch.randn(2, T, 18, h, w, device=cuda_device)
@@ -237,7 +239,7 @@ def test_group_norm_statistics_from_gemm_epilogues(cuda_device, built_lib):
     ids = torch.tensor([[6.0, 127.0, 0.02]] * 2, device=cuda_device)
     try:
         built_lib.evw_set_gemm_gn_stats(0)
-        _, own = make_pair(SMALL, cuda_device, seed=5)
+        oracle, own = make_pair(SMALL, cuda_device, seed=5)
         y_own = own(xin, 0.3, ehs, ids).sample
         assert own.gn_fused() == 0
         launches_own, _ = own.plan_info()
@@ -246,9 +248,13 @@ def test_group_norm_statistics_from_gemm_epilogues(cuda_device, built_lib):
         y_fused = fused(xin, 0.3, ehs, ids).sample
     finally:
         built_lib.evw_set_gemm_gn_stats(-1)
+    with torch.no_grad():
+        want = oracle(xin, 0.3, ehs, ids)
     n = fused.gn_fused()
     launches_fused, _ = fused.plan_info()
-    print(f"GroupNorms with statistics from the producer's epilogue: {n}; launches {launches_own} -> {launches_fused}")
+    print(f"GroupNorms with statistics from the producer's epilogue: {n}; launches {launches_own} -> {launches_fused}; "
+          f"rel L2 vs oracle: own statistics {rel_l2(y_own, want):.3e}, from epilogues {rel_l2(y_fused, want):.3e}")
     assert n >= 20 and launches_fused == launches_own - n
-    assert rel_l2(y_fused, y_own) < 2e-4  # fp16-stored producers: sums of the unrounded values
+    assert rel_l2(y_own, want) < TOL_UNET and rel_l2(y_fused, want) < TOL_UNET
+    assert rel_l2(y_fused, y_own) < 1.5 * TOL_UNET
     assert torch.equal(fused(xin, 0.3, ehs, ids).sample, y_fused)
