@@ -64,6 +64,13 @@ SIGNATURES = {
     "evw_denoise_step": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_float, c_float,
                                  c_int, c_int, c_int, c_void_p, c_i64, c_void_p]),
     "evw_unet_plan_info": (c_int, [c_void_p, C.POINTER(c_i64), C.POINTER(C.c_double)]),
+    "evw_vae_create": (c_int, [C.POINTER(c_void_p), C.POINTER(c_int), c_int, C.POINTER(C.c_char_p), C.POINTER(c_void_p), c_int,
+                               C.POINTER(C.c_char_p), C.POINTER(C.c_double), c_int]),
+    "evw_vae_destroy": (c_int, [c_void_p]),
+    "evw_vae_workspace_bytes": (c_i64, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
+    "evw_vae_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_i64, c_void_p]),
+    "evw_vae_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_i64, c_void_p]),
+    "evw_vae_plan_info": (c_int, [c_void_p, c_int, C.POINTER(c_i64), C.POINTER(C.c_double), C.POINTER(c_i64)]),
     "evw_unet_graph_replays": (c_i64, [c_void_p]),
     "evw_unet_gn_fused": (c_i64, [c_void_p]),
     "evw_splat_cube_equirect": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p,

@@ -6,6 +6,7 @@
 // Data layout in HBM (caller-provided workspace): activations channels-last, rows = (b, t, y, x);
 // fp32 residual stream + skip tensors, fp16 GEMM operands produced by the normalisation kernels.
 #include "common.h"
+#include "plan_builder.h"
 #include "tc_gemm.h"
 #include "unet_elem.h"
 
@@ -40,7 +41,6 @@ struct Config {
   int split = 0;
 };
 
-using Op = std::function<int(cudaStream_t)>;
 constexpr int kSmall = 16384;  // halves per small staging region (B <= 8 rows of <= 2048 columns)
 
 struct CallArgs {  // per-call pointers/scalars referenced by the planned ops
@@ -55,13 +55,6 @@ struct CallArgs {  // per-call pointers/scalars referenced by the planned ops
   int mode = 0;  // 0 = forward, 1 = denoise step
 };
 
-struct OpMeta {
-  std::string label;
-  const void* out = nullptr;
-  long long n = 0;
-  int fp16 = 0;
-};
-
 // Pointers baked into a captured graph of the plan (kernel parameters); the per-step scalars are not (set_step_args).
 struct GraphKey {
   int mode = -1;
@@ -73,14 +66,10 @@ struct GraphKey {
   }
 };
 
-struct Plan {
-  std::vector<OpMeta> meta;
+struct Plan : PlanCore {
   int B = 0, T = 0, h = 0, w = 0;
   void* ws = nullptr;
   long long ws_bytes = 0;
-  std::vector<Op> ops;
-  long long launches = 0;
-  double flops = 0;
   float *tsteps = nullptr, *dargs = nullptr;  // device-side per-step scalars (in the workspace)
   // plan-owned copies of the small / per-call tensors, so that the captured graph sees constant addresses:
   // encoder_hidden_states [B, cross], added_time_ids [B, 3], and for forward() the sample and the output
@@ -90,7 +79,6 @@ struct Plan {
   cudaStream_t capture_stream = nullptr;
   std::vector<std::pair<GraphKey, cudaGraphExec_t>> graphs;
   long long graph_replays = 0;
-  int gn_fused = 0;  // GroupNorms whose statistics come from the producing GEMM's epilogue
   ~Plan() {
     for (auto& g : graphs) cudaGraphExecDestroy(g.second);
     if (capture_stream) cudaStreamDestroy(capture_stream);
@@ -106,24 +94,9 @@ struct UNet {
   std::string err;
 };
 
-struct Bump {
-  char* base;
-  long long off = 0;
-  explicit Bump(void* b) : base((char*)b) {}
-  template <typename T>
-  T* take(long long n) {
-    off = align_up(off, 1024);
-    T* p = base ? (T*)(base + off) : nullptr;
-    off += n * (long long)sizeof(T);
-    return p;
-  }
-};
-
-struct Builder {
+struct Builder : BuilderBase {
   UNet& U;
   Plan& P;
-  Bump bump;
-  bool dry;  // size computation only
   int B, T;
   int lh[4], lw[4];
   long long lS[4], lM[4];
@@ -132,77 +105,9 @@ struct Builder {
          *resamp16 = nullptr, *small16 = nullptr, *lo16 = nullptr;
   float *f0 = nullptr, *f1 = nullptr, *f2 = nullptr, *pp[2] = {nullptr, nullptr}, *y32 = nullptr;
   float *emb = nullptr, *emb2 = nullptr, *temb_all = nullptr, *xattn_all = nullptr, *tsteps = nullptr, *dargs = nullptr;
-  double* stats = nullptr;
-  std::string fail;
-  // GroupNorm statistics from the producer's epilogue: the most recent GEMM that wrote each tensor, and the plan position
-  // of the last op that used the statistics scratch (a GroupNorm, or a GEMM already asked to fill it)
-  struct Writer { std::shared_ptr<GemmOp> op; long long rows; int N; size_t idx; };
-  std::map<const void*, Writer> last_writer;
-  size_t stats_busy_idx = 0;
 
-  Builder(UNet& u, Plan& p, void* ws, bool dry_) : U(u), P(p), bump(ws), dry(dry_) {}
+  Builder(UNet& u, Plan& p, void* ws, bool dry_) : BuilderBase(u.tensors, u.scalars, p, ws, dry_), U(u), P(p) {}
 
-  const void* W(const std::string& name) {
-    auto it = U.tensors.find(name);
-    if (it == U.tensors.end()) {
-      if (fail.empty()) fail = "missing tensor '" + name + "'";
-      return nullptr;
-    }
-    return it->second;
-  }
-  const float* Wf(const std::string& name) { return (const float*)W(name); }
-  double Sc(const std::string& name) {
-    auto it = U.scalars.find(name);
-    if (it == U.scalars.end()) {
-      if (fail.empty()) fail = "missing scalar '" + name + "'";
-      return 0;
-    }
-    return it->second;
-  }
-  void push(Op op, int launches = 1, const std::string& label = "", const void* out = nullptr, long long n = 0, int fp16 = 0) {
-    P.launches += launches;
-    if (!dry) {
-      if (out) last_writer.erase(out);
-      P.ops.push_back(std::move(op));
-      P.meta.push_back(OpMeta{label, out, n, fp16});
-    }
-  }
-
-  // ---- planned GEMM
-  void gemm(GemmProblem pr, const std::string& label = "gemm") {
-    if (dry) {
-      P.launches += 1;
-      return;
-    }
-    if (!fail.empty()) return;
-    auto op = std::make_shared<GemmOp>();
-    int rc = gemm_plan(op.get(), pr);
-    if (rc != 0) {
-      fail = std::string("gemm_plan: ") + evw_last_error();
-      return;
-    }
-    P.flops += op->flops;
-    const long long rows = (long long)pr.B * pr.T * pr.Y * pr.X;
-    push([op](cudaStream_t st) { return gemm_launch(*op, st); }, 1, label + " " + std::to_string(rows) + "x" + std::to_string(pr.N) + "x" + std::to_string(pr.K_total),
-         pr.ep.out, rows * (pr.ep.geglu ? pr.N / 2 : pr.N), pr.ep.out_fp16);
-    if (!pr.ep.geglu && !pr.ep.out_lo) last_writer[pr.ep.out] = Writer{op, rows, pr.N, P.ops.size()};
-  }
-  static void taps_conv3x3(GemmProblem& pr) {
-    pr.num_taps = 9;
-    int i = 0;
-    for (int dy = -1; dy <= 1; ++dy)
-      for (int dx = -1; dx <= 1; ++dx, ++i) {
-        pr.tap_dx[i] = (int8_t)dx; pr.tap_dy[i] = (int8_t)dy; pr.tap_dt[i] = 0; pr.tap_src[i] = 0;
-      }
-  }
-  void linear(const __half* a, long long M, int K, const std::string& wname, int N, GemmEpilogue ep, bool bias = true) {
-    GemmProblem pr;
-    pr.a0 = a; pr.w = W(wname + ".weight");
-    pr.X = (int)M; pr.C0 = K; pr.N = N; pr.K_total = K; pr.num_taps = 1;
-    if (bias) ep.bias = Wf(wname + ".bias");
-    pr.ep = ep;
-    gemm(pr, wname);
-  }
   // split-precision linear: (a_hi + a_lo) (W_hi + W_lo)^T without the tail x tail term, as three taps
   // [a_hi | a_lo | a_hi] x [W_hi | W_hi | W_lo] (weight [N, 3K], packed by unet.py)
   void linear_split(const __half* a_hi, const __half* a_lo, long long M, int K, const std::string& wname, int N, GemmEpilogue ep) {
@@ -213,27 +118,6 @@ struct Builder {
     ep.bias = Wf(wname + ".bias");
     pr.ep = ep;
     gemm(pr, wname);
-  }
-  void gnorm(const void* src0, int src0_fp16, int C0, const float* src1, int C1, long long insts, long long rows, float eps,
-             const std::string& name, int silu, __half* out, __half* raw, __half* out_lo = nullptr) {
-    const float* g = Wf(name + ".weight");
-    const float* b = Wf(name + ".bias");
-    double* st_ = stats;
-    // The GEMM that produced src0 accumulates the statistics in its epilogue when it can (single source, the whole
-    // tensor written by that GEMM, nothing else using the statistics scratch in between): 1 kernel instead of 2.
-    int have = 0;
-    if (!dry && !src1) {
-      auto it = last_writer.find(src0);
-      if (it != last_writer.end() && it->second.N == C0 && it->second.rows == insts * rows && it->second.idx > stats_busy_idx &&
-          gemm_enable_gn_stats(it->second.op.get(), stats, rows) == 0) {
-        have = 1;
-        ++P.gn_fused;
-      }
-    }
-    // 2 kernels (stats, apply); the statistics clear is a memset node and is not counted as a kernel launch
-    push([=](cudaStream_t st) { return group_norm(src0, src0_fp16, C0, src1, C1, insts, rows, eps, g, b, silu, st_, out, raw, out_lo, st, have); },
-         have ? 1 : 2, name, out, insts * rows * (C0 + C1), 1);
-    if (!dry) stats_busy_idx = P.ops.size();
   }
   void lnorm(const float* x, const float* rowvec, long long rv_div, long long rv_mod, long long rows, int C,
              const std::string& name, __half* out) {
@@ -394,15 +278,6 @@ struct Builder {
       if (split) linear_split(n16, lo16, M, C, pre + ".proj_out", C, ep);
       else linear(n16, M, C, pre + ".proj_out", C, ep);
     }
-  }
-
-  void conv3x3_simple(const __half* a, int frames, int hh, int ww, int Cin, const std::string& name, int N, float* outp) {
-    GemmProblem pr;
-    pr.a0 = a; pr.w = W(name + ".weight");
-    pr.B = 1; pr.T = frames; pr.Y = hh; pr.X = ww; pr.C0 = Cin; pr.N = N; pr.K_total = 9LL * Cin;
-    taps_conv3x3(pr);
-    pr.ep.out = outp; pr.ep.out_fp16 = 0; pr.ep.bias = Wf(name + ".bias");
-    gemm(pr, name);
   }
 
   int build() {

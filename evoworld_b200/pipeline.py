@@ -54,7 +54,7 @@ class StableVideoDiffusionPipeline:
         """Reference call pattern: `from_pretrained(ckpt, unet=unet, local_files_only=True, low_cpu_mem_usage=True)`
         (forward_evoworld.py:103, navigator_evoworld.py:112, unified_loop_consistency.py:195).  Components that are not
         passed are loaded from the checkpoint's sub-folders: `unet/` and `scheduler/` natively, `image_encoder/` +
-        `feature_extractor/` through transformers, `vae/` through diffusers.  If a sub-folder exists but its library is
+        `feature_extractor/` through transformers, `vae/` natively (evoworld_b200.vae).  If a sub-folder exists but its library is
         not importable the call fails here with a clear message instead of at the first pipeline call
         (`strict_components=False` leaves the component None: then pass `image_latents=` / `image_embeddings=`)."""
         root = str(pretrained_model_name_or_path)
@@ -86,12 +86,10 @@ class StableVideoDiffusionPipeline:
 
                 return CLIPImageProcessor.from_pretrained(path, local_files_only=True)
             feature_extractor = load("feature_extractor", "transformers", _fe)
-        if vae is None:
-            def _vae(path):
-                from diffusers import AutoencoderKLTemporalDecoder
+        if vae is None and os.path.isdir(os.path.join(root, "vae")):
+            from .vae import AutoencoderKLTemporalDecoder  # native: csrc/vae_host.cu
 
-                return AutoencoderKLTemporalDecoder.from_pretrained(path, local_files_only=True).eval()
-            vae = load("vae", "diffusers (AutoencoderKLTemporalDecoder)", _vae)
+            vae = AutoencoderKLTemporalDecoder.from_pretrained(root, subfolder="vae")
         return cls(vae=vae, image_encoder=image_encoder, unet=unet, scheduler=sched, feature_extractor=feature_extractor)
 
     def to(self, device=None, dtype=None):
@@ -154,8 +152,8 @@ class StableVideoDiffusionPipeline:
     def _encode_vae_image(self, image, device, num_videos_per_prompt=1, do_classifier_free_guidance=True):
         """:307-328 — `latent_dist.mode()`, NOT multiplied by the scaling factor; zeros for the unconditional half."""
         if self.vae is None:
-            raise RuntimeError("StableVideoDiffusionPipeline: no VAE attached (SURVEY §8f: VAE is not built); pass "
-                               "`image_latents=[B, 1+T_mem, 4, h, w]` or inject a `vae`.")
+            raise RuntimeError("StableVideoDiffusionPipeline: no VAE attached (the checkpoint has no `vae/`); pass "
+                               "`image_latents=[B, 1+T_mem, 4, h, w]` or a `vae` (evoworld_b200.vae.AutoencoderKLTemporalDecoder).")
         lat = self.vae.encode(image.to(device)).latent_dist.mode()
         lat = lat.repeat(num_videos_per_prompt, 1, 1, 1)
         return torch.cat([torch.zeros_like(lat), lat]) if do_classifier_free_guidance else lat
@@ -287,7 +285,8 @@ class StableVideoDiffusionPipeline:
             frames = latents
         else:
             if self.vae is None:
-                raise RuntimeError("decoding needs a VAE (SURVEY §8f: not built); use output_type='latent' or inject a `vae`.")
+                raise RuntimeError("decoding needs a VAE (evoworld_b200.vae.AutoencoderKLTemporalDecoder); use "
+                                   "output_type='latent' or pass `vae=`.")
             frames = self.decode_latents(latents, num_frames, decode_chunk_size or num_frames)
             frames = self._postprocess(frames, output_type)
         if not return_dict:

@@ -271,6 +271,31 @@ int64_t evw_unet_gn_fused(void* handle);
 /* Kernel launches and algorithmic FLOPs of the current plan (after the first forward / step). */
 int evw_unet_plan_info(void* handle, int64_t* launches, double* flops);
 
+/* VAE around the denoise loop: diffusers AutoencoderKLTemporalDecoder as the pipeline calls it —
+ * `vae.encode(image).latent_dist.mode()` (evoworld/pipeline/pipeline_evoworld.py:307-328, call sites :610-617) and
+ * `vae.decode(latents / scaling_factor, num_frames=n).sample` (decode_latents, :358-385, call site :731).
+ * evw_vae_create takes the packed parameters by name (evoworld_b200/vae.py:pack_parameters: fp16 tap-major convolution
+ * weights, conv_shortcut merged into conv2, quant_conv folded into encoder.conv_out, to_v's bias folded into to_out's)
+ * plus named host scalars (AlphaBlender alphas); cfg_ints = {in_channels, out_channels, latent_channels,
+ * block_out_channels[4], layers_per_block}.  The caller keeps the tensors alive. */
+int evw_vae_create(void** handle, const int* cfg_ints, int n_ints, const char* const* tensor_names,
+                   const void* const* tensor_ptrs, int n_tensors, const char* const* scalar_names,
+                   const double* scalar_values, int n_scalars);
+int evw_vae_destroy(void* handle);
+/* Workspace of one call: mode 0 = encode N images of H x W, mode 1 = decode N latents of H x W (N a multiple of
+ * num_frames); -1 on error. */
+int64_t evw_vae_workspace_bytes(void* handle, int mode, int N, int num_frames, int H, int W);
+/* images fp32 [N,3,H,W] in [-1,1] -> moments fp32 [N, 2*latent, H/8, W/8] = (mean | logvar) of the posterior after
+ * quant_conv (DiagonalGaussianDistribution.mode() == mean).  H, W divisible by 8, (H/8)*(W/8) a multiple of 64. */
+int evw_vae_encode(void* handle, const float* images, float* moments, int N, int H, int W, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+/* latents fp32 [N, latent, h, w] (already divided by scaling_factor), N = videos x num_frames -> frames fp32 [N,3,8h,8w]:
+ * TemporalDecoder incl. the (3,1,1) time_conv_out over each video's frames.  h*w a multiple of 64. */
+int evw_vae_decode(void* handle, const float* latents, float* frames, int N, int num_frames, int h, int w,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+/* Kernel launches, algorithmic FLOPs and epilogue-fused GroupNorms of the current encode (0) / decode (1) plan. */
+int evw_vae_plan_info(void* handle, int mode, int64_t* launches, double* flops, int64_t* gn_fused);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,6 +3,7 @@ of evoworld/pipeline/pipeline_evoworld.py:456-741 (oracle/pipeline_torch.py), wi
 both sides and identical seeds: conditioning assembly (a3) must be bit-identical (same torch ops on the same device),
 the denoise loop agrees within the UNet tolerance."""
 import argparse
+from types import SimpleNamespace
 import math
 
 import numpy as np
@@ -202,3 +203,53 @@ def test_process_batch_through_dropin(rig, tmp_path, monkeypatch):
     ref = (want[0].permute(0, 2, 3, 1).cpu().numpy() * 255).round().astype(np.int32)
     # uint8 frames decoded from latents that agree to ~1e-3: never more than one code value apart
     assert np.abs(got - ref).max() <= 1 and (got != ref).mean() < 0.15
+
+
+class _OracleVAE(torch.nn.Module):
+    """The diffusers call surface (encode().latent_dist.mode(), decode(z, num_frames).sample) over oracle/vae_torch.py."""
+
+    def __init__(self, core):
+        super().__init__()
+        self.core = core
+        self.config = SimpleNamespace(scaling_factor=0.18215, force_upcast=True, block_out_channels=(64, 128, 128, 128))
+
+    @property
+    def dtype(self):
+        return torch.float32
+
+    def encode(self, x):
+        mean, _ = self.core.encode_moments(x)
+        return SimpleNamespace(latent_dist=SimpleNamespace(mode=lambda: mean))
+
+    def decode(self, z, num_frames=1):
+        return SimpleNamespace(sample=self.core.decode(z, num_frames))
+
+
+def test_pipeline_with_the_native_vae(rig):
+    """The whole `__call__` (pipeline_evoworld.py:456-744) with nothing but the CLIP encoder injected: VAE encode of the
+    first frame + memory frames, the denoise loop, chunked temporal decode (decode_chunk_size 2 -> videos of 2 and 1
+    frames) — against the oracle restatement of the same call with the oracle VAE."""
+    from evoworld_b200.vae import AutoencoderKLTemporalDecoder
+    from oracle import vae_torch as OV
+
+    dev = rig["dev"]
+    torch.manual_seed(21)
+    boc = (64, 128, 128, 128)
+    with torch.device(dev):
+        ovae = OV.AutoencoderKLTemporalDecoder(block_out_channels=boc).eval()
+    vae = AutoencoderKLTemporalDecoder(block_out_channels=boc).to(dev)
+    vae.load_state_dict(ovae.state_dict())
+    pipe = StableVideoDiffusionPipeline(vae=vae, image_encoder=rig["clip"], unet=rig["ours"]).to(dev)
+    steps = 2
+    got = pipe(rig["image"], height=H, width=W, num_frames=T, num_inference_steps=steps, plucker_embedding=rig["plucker"],
+               memorized_pixel_values=rig["memory"], generator=torch.Generator(device=dev).manual_seed(5), output_type="pt",
+               decode_chunk_size=2).frames
+    o = _OracleVAE(ovae)
+    with torch.no_grad():
+        st = OP.prepare(rig["oracle"], o, rig["clip"], rig["image"], rig["memory"], rig["plucker"], height=H, width=W, num_frames=T,
+                        num_inference_steps=steps, generator=torch.Generator(device=dev).manual_seed(5), mask_mem=False, device=dev)
+        want = OP.decode(o, OP.denoise_loop(rig["oracle"], st), T, 2)
+    err = rel_l2(got, want)
+    print(f"pipeline with the native VAE: frames rel L2 {err:.3e}")
+    assert got.shape == (1, T, 3, H, W) and torch.isfinite(got).all()
+    assert err < 5e-3  # VAE encode (<= 3e-3) -> 2 denoise steps -> VAE decode (<= 3e-3), frames in [0, 1]

@@ -103,20 +103,23 @@ def test_from_pretrained_components(tmp_path):
     from evoworld_b200.pipeline import StableVideoDiffusionPipeline
     from evoworld_b200.unet import UNetSpatioTemporalConditionModel
 
-    _write_checkpoint(tmp_path, subdirs=("vae",))
+    from evoworld_b200.vae import AutoencoderKLTemporalDecoder
+
+    _write_checkpoint(tmp_path)
     unet = UNetSpatioTemporalConditionModel.from_pretrained(str(tmp_path), subfolder="unet")
-    try:
-        import diffusers  # noqa: F401
-        have_diffusers = True
-    except ImportError:
-        have_diffusers = False
-    if not have_diffusers:
-        # the reference's own call pattern (forward_evoworld.py:103) must fail HERE, with a message that says why
-        with pytest.raises(ImportError, match="vae/.*diffusers"):
-            StableVideoDiffusionPipeline.from_pretrained(str(tmp_path), unet=unet, local_files_only=True, low_cpu_mem_usage=True)
     pipe = StableVideoDiffusionPipeline.from_pretrained(str(tmp_path), unet=unet, strict_components=False)
     assert pipe.vae is None and pipe.image_encoder is None and pipe.feature_extractor is None
     assert pipe.unet is unet and pipe.scheduler.init_noise_sigma == pytest.approx(700.0007142, rel=1e-7)
+    # a `vae/` sub-folder in diffusers format is loaded by the native VAE — the reference's own call pattern
+    # (forward_evoworld.py:103) then needs nothing injected for encode / decode
+    saved = AutoencoderKLTemporalDecoder(block_out_channels=(64, 64, 64, 64)).init_random(seed=1)
+    saved.save_pretrained(str(tmp_path / "vae"))
+    pipe = StableVideoDiffusionPipeline.from_pretrained(str(tmp_path), unet=unet, local_files_only=True, low_cpu_mem_usage=True)
+    assert isinstance(pipe.vae, AutoencoderKLTemporalDecoder) and pipe.vae.config.scaling_factor == 0.18215
+    assert all(torch.equal(v, saved.state_dict()[k]) for k, v in pipe.vae.state_dict().items())
+    os.remove(tmp_path / "vae" / "diffusion_pytorch_model.safetensors")
+    with pytest.raises(FileNotFoundError, match="no weights"):
+        StableVideoDiffusionPipeline.from_pretrained(str(tmp_path), unet=unet)
     # injected components are kept as they are
     vae, clip = OP.StubVAE(), OP.StubCLIP()
     pipe = StableVideoDiffusionPipeline.from_pretrained(str(tmp_path), unet=unet, vae=vae, image_encoder=clip)
