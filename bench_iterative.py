@@ -3,8 +3,8 @@
 
 Per scene (one per rank), for segment 0, 1, 2:
   1. generate      `steps` fused denoise steps (evw_denoise_step) of a T-frame clip, CFG batch 2            [built: hot path 1]
-  2. decode        VAE temporal decode -> T panoramas                                                        [NOT built: stand-in =
-                   a fixed uint8 [T,3,H,W] device buffer; stated in the JSON]
+  2. decode        VAE temporal decode of the clip's latents -> T panoramas, decode_chunk_size 8                 [built: evw_vae_decode,
+                   random-init 97.7 M-parameter AutoencoderKLTemporalDecoder] -> uint8 [T,3,H,W]
   and, when another segment follows (:442-485):
   3. pano -> pers  Equi2Pers(384, 512, fov 90) with the look-at yaw of every frame                           [built: evw_equi2pers_u8]
                    reference: ALL frames so far (25, then 49); incremental: only the segment's new frames
@@ -15,8 +15,7 @@ Per scene (one per rank), for segment 0, 1, 2:
   7. align         similarity alignment of the GT trajectory (host numpy float64, 24 poses)                  [built: host]
   8. splat         24 target views: cube splat + cube->equirect resolve (evw_splat_cube_equirect)            [built: hot path 2]
   9. memory frames 24 panoramas 1000x2000 -> 576x1024 (antialiased bilinear, as PIL Resize), [-1,1]          [torch op on device]
- 10. VAE encode    memory latents of the next clip                                                           [NOT built: stand-in =
-                   8x average pool to 4 channels]
+ 10. VAE encode    memory latents of the next clip: first frame + 24 reprojections                           [built: evw_vae_encode]
 `mode="reference"` re-warps and re-lifts every frame generated so far each segment, as the reference does;
 `mode="incremental"` (default) only touches the new frames — the scene the splat sees is bit-identical
 (tests/test_gpu_reproj.py::test_point_memory_incremental_equals_one_shot).
@@ -40,6 +39,7 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
     from evoworld_b200.memory import PointMemory
     from evoworld_b200.scheduler import EulerDiscreteScheduler
     from evoworld_b200.unet import UNetSpatioTemporalConditionModel
+    from evoworld_b200.vae import AutoencoderKLTemporalDecoder
 
     T = args.iter_frames
     steps = args.iter_steps
@@ -50,13 +50,15 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
     unet = UNetSpatioTemporalConditionModel(**bd.UNET_CFG).init_random(seed=0, device=dev)
     unet._ensure_handle()
     unet.free_master_parameters()
+    vae = AutoencoderKLTemporalDecoder().init_random(seed=1, device=dev)
+    vae.free_master_parameters()
+    sf = vae.config.scaling_factor
     lat0, cond0, ehs, ids = [t.to(dev) for t in bd.make_inputs(T, h, w, dev, seed=rank)]
     sched = EulerDiscreteScheduler()
     sched.set_timesteps(steps)
     sig = [float(s) for s in sched.sigmas]
-    # stand-ins for the two un-built networks, resident on the device before the clock starts
-    g = torch.Generator(device="cpu").manual_seed(100 + rank)
-    frames_u8 = torch.randint(0, 256, (T, 3, H, W), generator=g, dtype=torch.uint8).to(dev)      # "decoded" panoramas
+    # stand-in for the one un-built network (VGGT-1B), resident on the device before the clock starts
+    frames_u8 = torch.empty((T, 3, H, W), dtype=torch.uint8, device=dev)                         # decoded panoramas of a clip
     S_all = (n_seg - 1) * (T - 1) + 1                                                              # 49 frames after two segments
     p = synthetic.reprojection_predictions(S=S_all, H=392, W=518, seed=rank)
     vggt = {k: torch.from_numpy(p[k]).to(dev) for k in ("depth", "depth_conf", "images", "extrinsic", "intrinsic")}
@@ -90,7 +92,13 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
             for i in range(steps):
                 unet.denoise_step(x, cond, sig[i], sig[i + 1], ehs, ids, 1.0, 3.0)
             e1 = ev(); e1.record(); mark("denoise", e0, e1)
-            # decode stand-in: the segment's frames (the first frame of a later segment repeats the previous last one)
+            # decode_latents (pipeline_evoworld.py:358-385) with decode_chunk_size 8, then [-1,1] -> uint8 panoramas
+            z = x[0] / sf
+            for i in range(0, T, 8):
+                fr = vae.decode(z[i:i + 8], num_frames=z[i:i + 8].shape[0]).sample
+                frames_u8[i:i + 8] = (fr * 127.5 + 127.5).clamp_(0, 255).to(torch.uint8)
+            e1b = ev(); e1b.record(); mark("vae decode", e1, e1b)
+            # the first frame of a later segment repeats the previous last one
             new = frames_u8 if seg == 0 else frames_u8[1:]
             all_frames[n_frames:n_frames + new.shape[0]].copy_(new)
             first_new, n_frames = n_frames, n_frames + new.shape[0]
@@ -117,12 +125,11 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
             # memory frames of the next clip: slot 0 = the episode's first frame, slots 1..24 = the reprojections
             m = F.interpolate(panos.permute(0, 3, 1, 2).float(), size=(H, W), mode="bilinear", antialias=True, align_corners=False)
             m = m / 127.5 - 1.0
-            first = frames_u8[0:1].float() / 127.5 - 1.0
+            first = all_frames[0:1].float() / 127.5 - 1.0
             mem_frames = torch.cat([first, m], dim=0)[:T]                                           # [T,3,H,W]
-            mem_lat = F.avg_pool2d(mem_frames, 8)                                                    # VAE-encode stand-in
-            mem_lat = torch.cat([mem_lat, mem_lat.mean(1, keepdim=True)], dim=1)                     # 4 "latent" channels
-            cond[1, :, 4:8] = mem_lat
             e6 = ev(); e6.record(); mark("memory frames", e5, e6)
+            cond[1, :, 4:8] = vae.encode(mem_frames).latent_dist.mode()                              # :610-617
+            e7 = ev(); e7.record(); mark("vae encode", e6, e7)
             stage["points"] = stage.get("points", []) + [scene]
         return x, stage
 
@@ -154,6 +161,8 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
         "config": {"workload": f"config 3: 3-clip iterative episode, {H}x{W}x{T}f clips, {steps} denoise steps per clip, CFG batch 2, "
                                f"evolving point memory {pts} points (S = {T}, {S_all} frames), 24 target views per segment",
                    "mode": mode, "scenes_per_rank": 1,
-                   "stand_ins": "VAE decode/encode and VGGT-1B are not built: fixed uint8 frames, seeded synthetic VGGT predictions "
-                                "resident on the device, 8x average-pool 'latents' (see bench_iterative.py)"},
+                   "vae": "native AutoencoderKLTemporalDecoder (random init): temporal decode of every clip in chunks of 8, "
+                          "encode of the 25 memory frames of the next clip",
+                   "stand_ins": "VGGT-1B is not built: seeded synthetic depth / confidence / pose predictions resident on the "
+                                "device (see bench_iterative.py)"},
     }
