@@ -302,6 +302,8 @@ def main():
     ap.add_argument("--iter-steps", type=int, default=25, help="denoise steps per clip of the iterative episode (config 5: 50)")
     ap.add_argument("--iter-mode", default="incremental", choices=["incremental", "reference"])
     ap.add_argument("--iter-episodes", type=int, default=1)
+    ap.add_argument("--iter-warmup-steps", type=int, default=0,
+                    help="denoise steps per clip in the untimed warm-up episode (0 = as many as the timed one)")
     ap.add_argument("--no-iterative", action="store_true", help="skip the iterative episode in --path auto")
     ap.add_argument("--views-per-pass", type=int, default=2, choices=[1, 2, 4, 8])
     ap.add_argument("--frames", type=int, default=14)
@@ -383,7 +385,7 @@ def main():
         primary.setdefault("ms_per_step", primary["ms_per_episode"] / 3)
         primary.setdefault("e2e", None)
         primary.setdefault("roofline", None)
-        primary.setdefault("gpu_launches", None)
+        primary.setdefault("gpu_launches", primary.get("launches_per_episode"))
     line = {
         "metric": primary["metric"], "value": primary["value"], "unit": primary["unit"], "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": primary["ms_per_step"], "higher_is_better": True,
@@ -399,6 +401,11 @@ def main():
         line["reproj"] = reproj
     if iterative is not None and primary is not iterative:
         line["iterative"] = iterative
+    if primary is iterative:
+        for k in ("ms_per_episode", "episodes", "wall_s", "ms_per_stage_per_episode", "memory_points_per_segment", "finite_output",
+                  "launches_per_episode"):
+            if k in iterative:
+                line[k] = iterative[k]
     print(json.dumps(line))
     if _DIST["on"]:
         import torch.distributed as dist

@@ -2,7 +2,8 @@
 (unified_loop_consistency.py:398-492) with everything device-resident.
 
 Per scene (one per rank), for segment 0, 1, 2:
-  1. generate      `steps` fused denoise steps (evw_denoise_step) of a T-frame clip, CFG batch 2            [built: hot path 1]
+  1. generate      `steps` fused denoise steps (evw_denoise_step) of a T-frame clip, CFG batch 2, then the      [built: hot path 1]
+                   NCCL all-gather of the clip's latents over the ranks (distributed.gather_latents)
   2. decode        VAE temporal decode of the clip's latents -> T panoramas, decode_chunk_size 8                 [built: evw_vae_decode,
                    random-init 97.7 M-parameter AutoencoderKLTemporalDecoder] -> uint8 [T,3,H,W]
   and, when another segment follows (:442-485):
@@ -35,6 +36,7 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
     import bench_denoise as bd
     from evoworld_b200 import reprojection as R
     from evoworld_b200 import segments, synthetic
+    from evoworld_b200.distributed import gather_latents
     from evoworld_b200.equi2pers import Equi2Pers
     from evoworld_b200.memory import PointMemory
     from evoworld_b200.scheduler import EulerDiscreteScheduler
@@ -76,7 +78,8 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
     x = lat0.clone()
     cond = cond0.clone()
 
-    def episode(timers=None):
+    def episode(timers=None, nsteps=None):
+        nsteps = steps if nsteps is None else nsteps
         mem.reset()
         cond.copy_(cond0)
         n_frames = 0
@@ -89,8 +92,9 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
         for seg in range(n_seg):
             e0 = ev(); e0.record()
             x.copy_(lat0)
-            for i in range(steps):
+            for i in range(nsteps):
                 unet.denoise_step(x, cond, sig[i], sig[i + 1], ehs, ids, 1.0, 3.0)
+            gathered = gather_latents(x)  # clip boundary: the only collective of the path (no-op at world == 1)
             e1 = ev(); e1.record(); mark("denoise", e0, e1)
             # decode_latents (pipeline_evoworld.py:358-385) with decode_chunk_size 8, then [-1,1] -> uint8 panoramas
             z = x[0] / sf
@@ -134,8 +138,9 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
         return x, stage
 
     # warm-up: one full episode (plans, graphs, allocator)
+    # (--iter-warmup-steps: fewer denoise steps per clip in the warm-up episode; every kernel, plan and graph is still exercised)
     for _ in range(max(1, min(args.warmup, 1))):
-        episode()
+        episode(nsteps=min(steps, args.iter_warmup_steps) if args.iter_warmup_steps > 0 else None)
     torch.cuda.synchronize(dev)
     barrier(world)
     n_ep = max(1, args.iter_episodes)
@@ -154,10 +159,15 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
     clips = n_ep * n_seg
     per_stage = {k: sum(a.elapsed_time(b) for a, b in v) / n_ep for k, v in timers.items()}
     pts = [int(s.num_points()) for s in stage["points"]]
+    # our kernels per episode: the denoise plan per step + the VAE plans per chunk (reprojection kernels: a few dozen, not counted)
+    unet_launches, _ = unet.plan_info()
+    dec_launches = vae.plan_info(1)[0]
+    enc_launches = vae.plan_info(0)[0]
+    launches = n_seg * steps * unet_launches + n_seg * -(-T // 8) * dec_launches + (n_seg - 1) * -(-T // 8) * enc_launches
     return {
         "metric": "iterative clips/sec (3-clip episode, evolving point memory)", "unit": "clips/s",
         "value": world * clips / (ms * 1e-3), "ms_per_episode": ms / n_ep, "episodes": n_ep, "wall_s": wall,
-        "ms_per_stage_per_episode": per_stage, "memory_points_per_segment": pts, "finite_output": bool(torch.isfinite(x).all()),
+        "ms_per_stage_per_episode": per_stage, "memory_points_per_segment": pts, "launches_per_episode": int(launches), "finite_output": bool(torch.isfinite(x).all()),
         "config": {"workload": f"config 3: 3-clip iterative episode, {H}x{W}x{T}f clips, {steps} denoise steps per clip, CFG batch 2, "
                                f"evolving point memory {pts} points (S = {T}, {S_all} frames), 24 target views per segment",
                    "mode": mode, "scenes_per_rank": 1,

@@ -665,6 +665,12 @@ extern "C" int evw_group_norm_f16(const void* src0, int src0_fp16, int C0, const
   return evw::group_norm(src0, src0_fp16, C0, src1, C1, insts, rows_per_inst, eps, gamma, beta, do_silu, (double*)stats_ws,
                          (__half*)out, (__half*)raw_out, (__half*)out_lo, (cudaStream_t)stream);
 }
+extern "C" int evw_layer_norm_f32(const float* x, int64_t rows, int C, float eps, const float* gamma, const float* beta, float* out,
+                                  void* stream) {
+  EVW_CHECK_ARG(x && out && gamma && beta, "evw_layer_norm_f32: null pointer");
+  return evw::layer_norm(x, nullptr, 1, 1, rows, C, eps, gamma, beta, nullptr, (cudaStream_t)stream, out);
+}
+
 extern "C" int evw_layer_norm_f16(const float* x, const float* rowvec, int64_t rv_div, int64_t rv_mod, int64_t rows, int C,
                                   float eps, const float* gamma, const float* beta, void* out, void* stream) {
   return evw::layer_norm(x, rowvec, rv_div > 0 ? rv_div : 1, rv_mod > 0 ? rv_mod : 1, rows, C, eps, gamma, beta, (__half*)out,

@@ -197,7 +197,8 @@ gn_apply_kernel(const T0* __restrict__ src0, int C0, const float* __restrict__ s
 template <int MAXV, int ROWS>  // MAXV float4 per lane: C <= 128 * MAXV; ROWS rows per warp, loaded together (DRAM latency)
 __global__ void layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ rowvec, long long rv_div,
                                   long long rv_mod, long long rows, int C, float eps, const float* __restrict__ gamma,
-                                  const float* __restrict__ beta, __half* __restrict__ out) {
+                                  const float* __restrict__ beta, __half* __restrict__ out, float* __restrict__ out32) {
+  // out32 (optional, instead of out): fp32 result — the CLIP encoder's pre-LayerNorm output is its fp32 residual stream
   const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
   if (row0 >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -266,6 +267,12 @@ __global__ void layer_norm_kernel(const float* __restrict__ x, const float* __re
       const int j = lane + i * 32;
       if (j < nv) {
         float4 g = __ldg(gp + j), b = __ldg(bp + j);
+        if (out32) {
+          reinterpret_cast<float4*>(out32 + (row0 + r) * C)[j] =
+              make_float4((v[r][i].x - mu) * rs * g.x + b.x, (v[r][i].y - mu) * rs * g.y + b.y, (v[r][i].z - mu) * rs * g.z + b.z,
+                          (v[r][i].w - mu) * rs * g.w + b.w);
+          continue;
+        }
         __half2 h0 = __floats2half2_rn((v[r][i].x - mu) * rs * g.x + b.x, (v[r][i].y - mu) * rs * g.y + b.y);
         __half2 h1 = __floats2half2_rn((v[r][i].z - mu) * rs * g.z + b.z, (v[r][i].w - mu) * rs * g.w + b.w);
         uint2 o2;
@@ -778,18 +785,18 @@ int group_norm(const void* src0, int src0_fp16, int C0, const float* src1, int C
 }
 
 int layer_norm(const float* x, const float* rowvec, long long rv_div, long long rv_mod, long long rows, int C, float eps,
-               const float* gamma, const float* beta, __half* out, cudaStream_t st) {
+               const float* gamma, const float* beta, __half* out, cudaStream_t st, float* out32) {
   EVW_CHECK_ARG(C % 4 == 0 && C <= 128 * 20, "layer_norm: C=%d not supported", C);
   const int warps = 8;
   auto grid = [&](int rows_per_warp) { return (unsigned)((rows + (long long)warps * rows_per_warp - 1) / ((long long)warps * rows_per_warp)); };
   if (C <= 128 * 3)
-    layer_norm_kernel<3, 4><<<grid(4), warps * 32, 0, st>>>(x, rowvec, rv_div, rv_mod, rows, C, eps, gamma, beta, out);
+    layer_norm_kernel<3, 4><<<grid(4), warps * 32, 0, st>>>(x, rowvec, rv_div, rv_mod, rows, C, eps, gamma, beta, out, out32);
   else if (C <= 128 * 5)
-    layer_norm_kernel<5, 4><<<grid(4), warps * 32, 0, st>>>(x, rowvec, rv_div, rv_mod, rows, C, eps, gamma, beta, out);
+    layer_norm_kernel<5, 4><<<grid(4), warps * 32, 0, st>>>(x, rowvec, rv_div, rv_mod, rows, C, eps, gamma, beta, out, out32);
   else if (C <= 128 * 10)
-    layer_norm_kernel<10, 2><<<grid(2), warps * 32, 0, st>>>(x, rowvec, rv_div, rv_mod, rows, C, eps, gamma, beta, out);
+    layer_norm_kernel<10, 2><<<grid(2), warps * 32, 0, st>>>(x, rowvec, rv_div, rv_mod, rows, C, eps, gamma, beta, out, out32);
   else
-    layer_norm_kernel<20, 1><<<grid(1), warps * 32, 0, st>>>(x, rowvec, rv_div, rv_mod, rows, C, eps, gamma, beta, out);
+    layer_norm_kernel<20, 1><<<grid(1), warps * 32, 0, st>>>(x, rowvec, rv_div, rv_mod, rows, C, eps, gamma, beta, out, out32);
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }

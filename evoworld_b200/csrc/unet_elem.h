@@ -14,7 +14,7 @@ int group_norm(const void* src0, int src0_fp16, int C0, const float* src1, int C
                __half* out, __half* raw_out, __half* out_lo, cudaStream_t st, int have_stats = 0);
 // LayerNorm over C of (x[row] + rowvec[(row / rv_div) % rv_mod]) -> fp16
 int layer_norm(const float* x, const float* rowvec, long long rv_div, long long rv_mod, long long rows, int C, float eps,
-               const float* gamma, const float* beta, __half* out, cudaStream_t st);
+               const float* gamma, const float* beta, __half* out, cudaStream_t st, float* out32 = nullptr);
 // qkv fp16 [B*T*S, 3*heads*64] rows (b,t,s) -> out fp16 [B*T*S, heads*64], attention over t
 int temporal_attention(const __half* qkv, __half* out, int B, int T, long long S, int heads, cudaStream_t st);
 // qkv fp16 [F*S, 3*heads*64] rows (f,s) -> out fp16 [F*S, heads*64], attention over s (tcgen05 flash attention)

@@ -113,3 +113,36 @@ def layer_norm(x: torch.Tensor, gamma, beta, eps: float = 1e-5, rowvec=None, rv_
         _lib.check(_lib.lib().evw_layer_norm_f16(_lib.ptr(x), _lib.ptr(rowvec), rv_div, rv_mod, rows, C, eps, _lib.ptr(gamma),
                                                  _lib.ptr(beta), _lib.ptr(out), _lib.stream_ptr(x.device)), "evw_layer_norm_f16")
     return out
+
+
+def small_attention(qkv: torch.Tensor, B: int, S: int, heads: int, head_dim: int, scale: float) -> torch.Tensor:
+    """qkv fp16 [B*S, 3*heads*head_dim] (q | k | v) -> fp16 [B*S, heads*head_dim]; S <= 1024, any head width <= 256."""
+    _lib.require_cuda(qkv, "qkv")
+    assert qkv.dtype == torch.float16 and qkv.shape == (B * S, 3 * heads * head_dim)
+    out = torch.empty((B * S, heads * head_dim), dtype=torch.float16, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        _lib.check(_lib.lib().evw_small_attention_f16(_lib.ptr(qkv), _lib.ptr(out), B, S, heads, head_dim, scale,
+                                                      _lib.stream_ptr(qkv.device)), "evw_small_attention_f16")
+    return out
+
+
+def activation_f16(x: torch.Tensor, mode: str = "gelu") -> torch.Tensor:
+    """x fp32 -> fp16 through GELU (erf form) or quick_gelu."""
+    _lib.require_cuda(x, "x")
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().evw_act_f16(_lib.ptr(x), _lib.ptr(out), x.numel(), {"gelu": 0, "quick_gelu": 1}[mode],
+                                          _lib.stream_ptr(x.device)), "evw_act_f16")
+    return out
+
+
+def layer_norm_f32(x: torch.Tensor, gamma, beta, eps: float = 1e-5) -> torch.Tensor:
+    """LayerNorm over the last dimension of x fp32 [rows, C] with an fp32 result."""
+    _lib.require_cuda(x, "x")
+    rows, C = x.shape
+    out = torch.empty((rows, C), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().evw_layer_norm_f32(_lib.ptr(x), rows, C, eps, _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(out),
+                                                 _lib.stream_ptr(x.device)), "evw_layer_norm_f32")
+    return out

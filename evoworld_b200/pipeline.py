@@ -53,8 +53,9 @@ class StableVideoDiffusionPipeline:
                         scheduler=None, strict_components: bool = True, **kwargs):
         """Reference call pattern: `from_pretrained(ckpt, unet=unet, local_files_only=True, low_cpu_mem_usage=True)`
         (forward_evoworld.py:103, navigator_evoworld.py:112, unified_loop_consistency.py:195).  Components that are not
-        passed are loaded from the checkpoint's sub-folders: `unet/` and `scheduler/` natively, `image_encoder/` +
-        `feature_extractor/` through transformers, `vae/` natively (evoworld_b200.vae).  If a sub-folder exists but its library is
+        passed are loaded from the checkpoint's sub-folders: `unet/`, `scheduler/`, `vae/` (evoworld_b200.vae) and
+        `image_encoder/` (evoworld_b200.clip) natively, `feature_extractor/` through transformers (optional: without it the
+        CLIP mean / std of `image_ops` are used).  If a sub-folder exists but its library is
         not importable the call fails here with a clear message instead of at the first pipeline call
         (`strict_components=False` leaves the component None: then pass `image_latents=` / `image_embeddings=`)."""
         root = str(pretrained_model_name_or_path)
@@ -74,12 +75,10 @@ class StableVideoDiffusionPipeline:
                                       f"strict_components=False and feed precomputed latents / embeddings") from exc
                 return None
 
-        if image_encoder is None:
-            def _clip(path):
-                from transformers import CLIPVisionModelWithProjection
+        if image_encoder is None and os.path.isdir(os.path.join(root, "image_encoder")):
+            from .clip import CLIPVisionModelWithProjection  # native: evoworld_b200/clip.py
 
-                return CLIPVisionModelWithProjection.from_pretrained(path, local_files_only=True).eval()
-            image_encoder = load("image_encoder", "transformers", _clip)
+            image_encoder = CLIPVisionModelWithProjection.from_pretrained(root, subfolder="image_encoder")
         if feature_extractor is None:
             def _fe(path):
                 from transformers import CLIPImageProcessor

@@ -239,6 +239,10 @@ int evw_group_norm_f16(const void* src0, int src0_fp16, int C0, const float* src
 int evw_layer_norm_f16(const float* x, const float* rowvec, int64_t rv_div, int64_t rv_mod, int64_t rows, int C,
                        float eps, const float* gamma, const float* beta, void* out, void* stream);
 
+/* The same LayerNorm with an fp32 result (CLIP's pre_layrnorm produces the fp32 residual stream of the encoder). */
+int evw_layer_norm_f32(const float* x, int64_t rows, int C, float eps, const float* gamma, const float* beta, float* out,
+                       void* stream);
+
 /* UNetSpatioTemporalConditionModel on the device (evoworld/trainer/unet_plucker.py:30-488).
  * evw_unet_create takes the packed parameters by name (see evoworld_b200/unet.py:pack_parameters for
  * the naming and layouts; the caller keeps the tensors alive) plus named host scalars (AlphaBlender
@@ -270,6 +274,15 @@ int64_t evw_unet_graph_replays(void* handle);
 int64_t evw_unet_gn_fused(void* handle);
 /* Kernel launches and algorithmic FLOPs of the current plan (after the first forward / step). */
 int evw_unet_plan_info(void* handle, int64_t* launches, double* flops);
+
+/* CLIP ViT image encoder pieces (transformers CLIPVisionModelWithProjection, called at
+ * evoworld/pipeline/pipeline_evoworld.py:289; transformers models/clip/modeling_clip.py CLIPAttention / CLIPMLP).  The
+ * linears use evw_gemm_f16 and the LayerNorms evw_layer_norm_f16 (evoworld_b200/clip.py).
+ * evw_small_attention_f16: softmax(scale q k^T) v per (image, head) over S <= 1024 tokens with any head width <= 256
+ * (ViT-H: S = 257, 16 heads of 80): qkv fp16 [B*S, 3*heads*head_dim] (q | k | v) -> out fp16 [B*S, heads*head_dim].
+ * evw_act_f16: x fp32 -> fp16 through the MLP activation, mode 0 = GELU (erf), 1 = quick_gelu. */
+int evw_small_attention_f16(const void* qkv, void* out, int B, int S, int heads, int head_dim, float scale, void* stream);
+int evw_act_f16(const float* x, void* out, int64_t n, int mode, void* stream);
 
 /* VAE around the denoise loop: diffusers AutoencoderKLTemporalDecoder as the pipeline calls it —
  * `vae.encode(image).latent_dist.mode()` (evoworld/pipeline/pipeline_evoworld.py:307-328, call sites :610-617) and

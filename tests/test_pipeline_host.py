@@ -117,6 +117,16 @@ def test_from_pretrained_components(tmp_path):
     pipe = StableVideoDiffusionPipeline.from_pretrained(str(tmp_path), unet=unet, local_files_only=True, low_cpu_mem_usage=True)
     assert isinstance(pipe.vae, AutoencoderKLTemporalDecoder) and pipe.vae.config.scaling_factor == 0.18215
     assert all(torch.equal(v, saved.state_dict()[k]) for k, v in pipe.vae.state_dict().items())
+    # ... and an `image_encoder/` folder in transformers format by the native CLIP encoder: nothing from diffusers or
+    # transformers is needed to construct the pipeline
+    from evoworld_b200.clip import CLIPVisionModelWithProjection
+
+    clip_saved = CLIPVisionModelWithProjection(hidden_size=128, intermediate_size=256, num_hidden_layers=1, num_attention_heads=2,
+                                               image_size=28, patch_size=14, projection_dim=64).init_random(seed=2)
+    clip_saved.save_pretrained(str(tmp_path / "image_encoder"))
+    pipe = StableVideoDiffusionPipeline.from_pretrained(str(tmp_path), unet=unet, local_files_only=True, low_cpu_mem_usage=True)
+    assert isinstance(pipe.image_encoder, CLIPVisionModelWithProjection) and pipe.image_encoder.config.projection_dim == 64
+    assert isinstance(pipe.vae, AutoencoderKLTemporalDecoder) and pipe.feature_extractor is None
     os.remove(tmp_path / "vae" / "diffusion_pytorch_model.safetensors")
     with pytest.raises(FileNotFoundError, match="no weights"):
         StableVideoDiffusionPipeline.from_pretrained(str(tmp_path), unet=unet)
