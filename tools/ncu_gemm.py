@@ -26,6 +26,12 @@ elif case == "ff2":
 elif case == "conv":
     a = torch.randn(2, 14, 72, 128, 320, device=dev).half(); w = torch.randn(320, 9 * 320, device=dev).half() * 0.02
     f = lambda: ops.gemm_f16(a, w, taps=ops.CONV3x3_TAPS)
+elif case in ("conv_stats", "conv_rv"):  # level-0 conv1: 3x3 conv + bias + time-embedding row vector, fp32 out (+ GroupNorm sums)
+    a = torch.randn(1, 28, 72, 128, 320, device=dev).half(); w = torch.randn(320, 9 * 320, device=dev).half() * 0.02
+    b = torch.randn(320, device=dev); rv = torch.randn(28, 320, device=dev)
+    st = torch.empty(28, 32, 2, dtype=torch.float64, device=dev) if case == "conv_stats" else None
+    f = lambda: ops.gemm_f16(a, w, taps=ops.CONV3x3_TAPS, bias=b, rowvec=rv, rv_div=9216, rv_mod=28, out_dtype=torch.float32,
+                             gn_stats=st, gn_rows_per_inst=9216 if st is not None else 0)
 elif case == "attn":
     qkv = torch.randn(28 * 9216, 960, device=dev).half()
     f = lambda: ops.spatial_attention(qkv, 28, 9216, 5)
