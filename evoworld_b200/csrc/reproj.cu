@@ -328,129 +328,153 @@ __device__ __forceinline__ float key_float(unsigned k) {
 __host__ __device__ constexpr int radix_bits(int pass) { return pass == 2 ? 10 : 11; }
 __host__ __device__ constexpr int radix_shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
 
-__global__ void select_init_kernel(SelectState* st, unsigned* hist, long long k_lo) {
-  for (int i = threadIdx.x; i < 3 * 2048; i += blockDim.x) hist[i] = 0;
-  if (threadIdx.x == 0) {
-    st->prefix = 0;
-    st->mask = 0;
-    st->k = (unsigned long long)k_lo;
-    st->cnt_le = 0;
-    st->next_key = 0xFFFFFFFFu;
-    st->nan_count = 0;
-    st->thr = 0.f;
-  }
-}
+// Block-wide search of the histogram bin that holds rank k (the scan the round-1 version ran as a kernel of its own after
+// every histogram pass; every block of the NEXT pass now redoes it in its prologue: 8 KiB of L2 reads and a 512-thread scan
+// against a kernel launch + a dependent-launch gap).  All threads return the same result.
+struct BinHit {
+  unsigned bin;              // bin that holds rank k (the last bin if k is beyond the valid count: NaNs present -> thr = NaN anyway)
+  unsigned cnt;              // keys in that bin
+  unsigned long long k_rem;  // rank inside the bin
+  unsigned next_bin;         // next non-empty bin above it, 0xFFFFFFFF if none
+};
 
 template <int PASS>
-__global__ void select_hist_kernel(const float* __restrict__ conf, int64_t n,
-                                   const SelectState* __restrict__ st, unsigned* __restrict__ hist) {
-  __shared__ unsigned sh[2048];
-  for (int i = threadIdx.x; i < 2048; i += blockDim.x) sh[i] = 0;
-  __syncthreads();
-  const unsigned prefix = st->prefix, mask = st->mask;
-  constexpr int shift = radix_shift(PASS);
-  constexpr unsigned dmask = (1u << radix_bits(PASS)) - 1u;
-  unsigned nan_local = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    float f = conf[i];
-    if (PASS == 0 && f != f) {
-      ++nan_local;
-      continue;
-    }
-    if (f != f) continue;
-    unsigned k = float_key(f);
-    if ((k & mask) == prefix) atomicAdd(&sh[(k >> shift) & dmask], 1u);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2048; i += blockDim.x)
-    if (sh[i]) atomicAdd(&hist[PASS * 2048 + i], sh[i]);
-  if (PASS == 0 && nan_local) atomicAdd(const_cast<unsigned*>(&st->nan_count), nan_local);
-}
-
-template <int PASS>
-__global__ void __launch_bounds__(1024) select_scan_kernel(SelectState* st, const unsigned* __restrict__ hist) {
-  // one block of 1024 threads, two bins per thread: find the bin that holds rank k
+__device__ BinHit find_bin(const unsigned* __restrict__ hist, unsigned long long k) {
   constexpr int nb = 1 << radix_bits(PASS);
   __shared__ unsigned long long s_warp[32];
-  __shared__ int s_found;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned long long k = st->k;
-  unsigned c0 = (2 * tid < nb) ? hist[PASS * 2048 + 2 * tid] : 0u;
-  unsigned c1 = (2 * tid + 1 < nb) ? hist[PASS * 2048 + 2 * tid + 1] : 0u;
-  unsigned long long incl = (unsigned long long)c0 + c1;
+  __shared__ unsigned long long s_krem;
+  __shared__ unsigned s_bin, s_cnt, s_next;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+  const int per = (nb + nthreads - 1) / nthreads;
+  const int lo = tid * per;
+  __syncthreads();  // previous use of the shared scratch
+  if (tid == 0) { s_bin = 0xFFFFFFFFu; s_next = 0xFFFFFFFFu; }
+  unsigned long long mine = 0;
+  for (int b = lo; b < lo + per && b < nb; ++b) mine += hist[PASS * 2048 + b];
+  unsigned long long incl = mine;
   for (int o = 1; o < 32; o <<= 1) {
     unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += v;
   }
   if (lane == 31) s_warp[warp] = incl;
-  if (tid == 0) s_found = 0;
   __syncthreads();
-  unsigned long long base = 0;
-  for (int w = 0; w < warp; ++w) base += s_warp[w];
-  unsigned long long excl = base + incl - ((unsigned long long)c0 + c1);
-  int bin = -1;
-  unsigned long long run = 0;
-  if (excl <= k && k < excl + c0) {
-    bin = 2 * tid;
-    run = excl;
-  } else if (excl + c0 <= k && k < excl + c0 + c1) {
-    bin = 2 * tid + 1;
-    run = excl + c0;
-  }
-  if (bin >= 0) {
-    s_found = 1;
-    st->k = k - run;
-    st->prefix |= ((unsigned)bin) << radix_shift(PASS);
-    st->mask |= ((1u << radix_bits(PASS)) - 1u) << radix_shift(PASS);
+  unsigned long long run = incl - mine;
+  for (int w = 0; w < warp; ++w) run += s_warp[w];
+  if (run <= k && k < run + mine) {  // at most one thread
+    for (int b = lo; b < lo + per && b < nb; ++b) {
+      const unsigned c = hist[PASS * 2048 + b];
+      if (k < run + c) {
+        s_bin = (unsigned)b; s_cnt = c; s_krem = k - run;
+        break;
+      }
+      run += c;
+    }
   }
   __syncthreads();
-  if (tid == 0 && !s_found) {  // rank beyond the valid (non-NaN) count: threshold becomes NaN anyway
-    st->prefix |= ((unsigned)(nb - 1)) << radix_shift(PASS);
-    st->mask |= ((1u << radix_bits(PASS)) - 1u) << radix_shift(PASS);
+  if (s_bin == 0xFFFFFFFFu) {
+    if (tid == 0) { s_bin = nb - 1; s_cnt = hist[PASS * 2048 + nb - 1]; s_krem = 0; }
+    __syncthreads();
   }
+  const unsigned bin = s_bin;
+  unsigned nxt = 0xFFFFFFFFu;
+  for (int b = lo; b < lo + per && b < nb; ++b)
+    if ((unsigned)b > bin && hist[PASS * 2048 + b]) { nxt = (unsigned)b; break; }
+  for (int o = 16; o > 0; o >>= 1) nxt = min(nxt, __shfl_xor_sync(0xffffffffu, nxt, o));
+  if (lane == 0 && nxt != 0xFFFFFFFFu) atomicMin(&s_next, nxt);
+  __syncthreads();
+  BinHit h;
+  h.bin = bin; h.cnt = s_cnt; h.k_rem = s_krem; h.next_bin = s_next;
+  return h;
 }
 
-__global__ void select_next_kernel(const float* __restrict__ conf, int64_t n, SelectState* st) {
-  const unsigned key_a = st->prefix;
-  unsigned long long cnt = 0;
-  unsigned nxt = 0xFFFFFFFFu;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    float f = conf[i];
-    if (f != f) continue;
-    unsigned k = float_key(f);
-    if (k <= key_a) ++cnt;
-    else nxt = min(nxt, k);
+// Histogram pass PASS over the keys that match the digits resolved so far.  Counts go to shared memory with
+// warp-aggregated atomics (confidence maps concentrate on a few dozen top-digit bins: a plain shared atomicAdd per element
+// serialised 8-16 ways), then to the global histogram.  PASS 0 counts NaNs; PASS 2 also tracks the smallest key ABOVE the
+// 22-bit bucket, so that the successor of the selected key is known without another pass over the data.
+template <int PASS>
+__global__ void __launch_bounds__(512)
+select_hist_kernel(const float* __restrict__ conf, int64_t n, SelectState* __restrict__ st, unsigned* __restrict__ hist,
+                   unsigned long long k_lo) {
+  __shared__ unsigned sh[2048];
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) sh[i] = 0;
+  unsigned prefix = 0, mask = 0;
+  if (PASS >= 1) {
+    const BinHit h0 = find_bin<0>(hist, k_lo);
+    prefix = h0.bin << radix_shift(0);
+    mask = ((1u << radix_bits(0)) - 1u) << radix_shift(0);
+    if (PASS >= 2) {
+      const BinHit h1 = find_bin<1>(hist, h0.k_rem);
+      prefix |= h1.bin << radix_shift(1);
+      mask |= ((1u << radix_bits(1)) - 1u) << radix_shift(1);
+    }
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    nxt = min(nxt, __shfl_xor_sync(0xffffffffu, nxt, o));
+  __syncthreads();
+  constexpr int shift = radix_shift(PASS);
+  constexpr unsigned dmask = (1u << radix_bits(PASS)) - 1u;
+  unsigned nan_local = 0, above = 0xFFFFFFFFu;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += stride) {  // warp-uniform trip count
+    const int64_t i = base + threadIdx.x;
+    unsigned digit = 0xFFFFFFFFu;  // "no contribution"
+    if (i < n) {
+      const float f = conf[i];
+      if (f != f) {
+        if (PASS == 0) ++nan_local;
+      } else {
+        const unsigned k = float_key(f);
+        if ((k & mask) == prefix) digit = (k >> shift) & dmask;
+        else if (PASS == 2 && (k & mask) > prefix) above = min(above, k);
+      }
+    }
+    if (PASS == 0) {  // every element contributes and the top digits collide: one atomic per distinct digit of the warp
+      const unsigned peers = __match_any_sync(0xffffffffu, digit);
+      if (digit != 0xFFFFFFFFu && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[digit], (unsigned)__popc(peers));
+    } else if (digit != 0xFFFFFFFFu) {  // only the keys of one bucket contribute: few, and spread over the digit
+      atomicAdd(&sh[digit], 1u);
+    }
   }
-  if ((threadIdx.x & 31) == 0) {
-    if (cnt) atomicAdd(&st->cnt_le, cnt);
-    if (nxt != 0xFFFFFFFFu) atomicMin(&st->next_key, nxt);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+    if (sh[i]) atomicAdd(&hist[PASS * 2048 + i], sh[i]);
+  if (PASS == 0) {
+    for (int o = 16; o > 0; o >>= 1) nan_local += __shfl_xor_sync(0xffffffffu, nan_local, o);
+    if ((threadIdx.x & 31) == 0 && nan_local) atomicAdd(&st->nan_count, nan_local);
+  }
+  if (PASS == 2) {
+    for (int o = 16; o > 0; o >>= 1) above = min(above, __shfl_xor_sync(0xffffffffu, above, o));
+    if ((threadIdx.x & 31) == 0 && above != 0xFFFFFFFFu) atomicMin(&st->next_key, above);
   }
 }
 
 // thr = numpy _lerp(a, b, t) in float32:  a + (b-a)*t, and for t >= 0.5:  b - (b-a)*(1-t)
-__global__ void select_thr_kernel(SelectState* st, long long k_hi, float gamma, int use_threshold,
-                                  float* out_thr) {
-  if (threadIdx.x != 0) return;
-  float thr;
-  if (!use_threshold) {
-    thr = 0.0f;
-  } else if (st->nan_count) {
-    thr = CUDART_NAN_F;
-  } else {
-    float a = key_float(st->prefix);
-    float b = (st->cnt_le >= (unsigned long long)k_hi + 1ull) ? a : key_float(st->next_key);
-    float diff = __fsub_rn(b, a);
-    thr = __fadd_rn(a, __fmul_rn(diff, gamma));
-    if (gamma >= 0.5f) thr = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, gamma)));
+__global__ void __launch_bounds__(512)
+select_thr_kernel(SelectState* st, const unsigned* __restrict__ hist, long long k_lo, long long k_hi, float gamma,
+                  int use_threshold, float* out_thr) {
+  float thr = 0.0f;
+  if (use_threshold) {  // uniform
+    const BinHit h0 = find_bin<0>(hist, (unsigned long long)k_lo);
+    const BinHit h1 = find_bin<1>(hist, h0.k_rem);
+    const BinHit h2 = find_bin<2>(hist, h1.k_rem);
+    const unsigned key_a = (h0.bin << radix_shift(0)) | (h1.bin << radix_shift(1)) | h2.bin;
+    // every key of the final bin equals key_a: #keys <= key_a = (#keys below the bin) + (#keys in it)
+    const unsigned long long cnt_le = ((unsigned long long)k_lo - h2.k_rem) + h2.cnt;
+    // successor of key_a: the next non-empty bin of the same 22-bit bucket, else the smallest key above the bucket (pass 2)
+    const unsigned next_key = h2.next_bin != 0xFFFFFFFFu ? ((key_a & ~((1u << radix_bits(2)) - 1u)) | h2.next_bin) : st->next_key;
+    if (st->nan_count) {
+      thr = CUDART_NAN_F;
+    } else {
+      const float a = key_float(key_a);
+      const float b = (cnt_le >= (unsigned long long)k_hi + 1ull) ? a : key_float(next_key);
+      const float diff = __fsub_rn(b, a);
+      thr = __fadd_rn(a, __fmul_rn(diff, gamma));
+      if (gamma >= 0.5f) thr = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, gamma)));
+    }
+    if (threadIdx.x == 0) { st->prefix = key_a; st->cnt_le = cnt_le; }
   }
-  st->thr = thr;
-  if (out_thr) *out_thr = thr;
+  if (threadIdx.x == 0) {
+    st->thr = thr;
+    if (out_thr) *out_thr = thr;
+  }
 }
 
 constexpr int kCompactThreads = 256;
@@ -490,14 +514,20 @@ __global__ void compact_scan_kernel(const unsigned* __restrict__ block_counts, i
   for (int i = lo; i < hi; ++i) sum += block_counts[i];
   s_part[tid] = sum;
   __syncthreads();
-  if (tid == 0) {
-    long long run = 0;
-    for (int i = 0; i < (int)blockDim.x; ++i) {
-      long long v = s_part[i];
-      s_part[i] = run;
-      run += v;
+  {  // exclusive scan of the 1024 partial sums: warp shuffles + one pass over the 32 warp totals
+    __shared__ long long s_warp[32];
+    const int lane = tid & 31, warp = tid >> 5;
+    long long incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
     }
-    *out_count = run;
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    long long base = 0;
+    for (int w = 0; w < warp; ++w) base += s_warp[w];
+    s_part[tid] = base + incl - sum;
+    if (tid == (int)blockDim.x - 1) *out_count = base + incl;
   }
   __syncthreads();
   long long run = s_part[tid];
@@ -965,17 +995,15 @@ extern "C" int evw_conf_select(const float* conf, const float* pts4_in, int64_t 
   unsigned* bcount = (unsigned*)(ws + 256 + 3 * 2048 * 4);
   long long* boff = (long long*)((char*)bcount + evw::align_up(nb * 4, 256));
   int grid = evw::sm_count() * 4;
-  select_init_kernel<<<1, 256, 0, st>>>(state, hist, (long long)k_lo);
-  if (use_threshold) {
-    select_hist_kernel<0><<<grid, 512, 0, st>>>(conf, n, state, hist);
-    select_scan_kernel<0><<<1, 1024, 0, st>>>(state, hist);
-    select_hist_kernel<1><<<grid, 512, 0, st>>>(conf, n, state, hist);
-    select_scan_kernel<1><<<1, 1024, 0, st>>>(state, hist);
-    select_hist_kernel<2><<<grid, 512, 0, st>>>(conf, n, state, hist);
-    select_scan_kernel<2><<<1, 1024, 0, st>>>(state, hist);
-    select_next_kernel<<<grid, 512, 0, st>>>(conf, n, state);
+  // state + the three histograms: one memset node instead of an init kernel; next_key starts at "none"
+  EVW_CUDA(cudaMemsetAsync(ws, 0, 256 + 3 * 2048 * 4, st));
+  EVW_CUDA(cudaMemsetAsync(&state->next_key, 0xFF, sizeof(unsigned), st));
+  if (use_threshold) {  // 3 histogram passes (each resolves the previous digits in its prologue) + 1 block for the threshold
+    select_hist_kernel<0><<<grid, 512, 0, st>>>(conf, n, state, hist, (unsigned long long)k_lo);
+    select_hist_kernel<1><<<grid, 512, 0, st>>>(conf, n, state, hist, (unsigned long long)k_lo);
+    select_hist_kernel<2><<<grid, 512, 0, st>>>(conf, n, state, hist, (unsigned long long)k_lo);
   }
-  select_thr_kernel<<<1, 32, 0, st>>>(state, (long long)k_hi, gamma, use_threshold, out_thr);
+  select_thr_kernel<<<1, 512, 0, st>>>(state, hist, (long long)k_lo, (long long)k_hi, gamma, use_threshold, out_thr);
   compact_count_kernel<<<(unsigned)nb, kCompactThreads, 0, st>>>(conf, n, state, bcount);
   compact_scan_kernel<<<1, 1024, 0, st>>>(bcount, (int)nb, boff, (long long*)out_count);
   compact_scatter_kernel<<<(unsigned)nb, kCompactThreads, 0, st>>>(

@@ -759,7 +759,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
       if constexpr (is_geglu) {
         mbar_wait_relaxed(tfull_bar(acc), acc_phase);
         tc_fence_after();
-        // 32 accumulator columns = [16 value | 16 gate] -> 16 outputs
+        // 32 accumulator columns = [16 value | 16 gate] -> 16 outputs.  (Issuing the tensor-memory load of step k + 1 before
+        // the arithmetic of step k changed nothing — 0.493 vs 0.490 ms at 258 048 x 2560 x 320, profiles/r02t_geglu_prefetch.log:
+        // the epilogue is bound by its ~20 instructions per output, not by the load latency.)
         for (int k = cgrp; k * 32 < P.block_n; k += NG) {
           uint32_t raw[32];
           __syncwarp();

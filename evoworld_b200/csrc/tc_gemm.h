@@ -58,7 +58,7 @@ struct alignas(64) GemmOp {
   alignas(64) unsigned char tmap_b[128];
   alignas(64) unsigned char tmap_bh[128];  // half-height weight box (CTA-pair mode: each CTA loads its own half)
   alignas(64) unsigned char tmap_r[128];   // fp32 residual (res1) as a 5-D map with 32-column boxes (TMA-staged residual)
-  unsigned char params[384];
+  unsigned char params[448];
   int grid = 0;
   int cluster = 0;  // 1: launch as clusters of two CTAs sharing each weight tile (TMA multicast)
   int smem_bytes = 0;

@@ -1,5 +1,5 @@
 """Per-kernel totals of an ncu launch list (ncu --metrics gpu__time_duration.sum --csv --log-file X ...).
-usage: python tools/launch_summary.py launches.csv [--last N] [--title "..."]   (--last N: only the final N launches = one step)"""
+usage: python tools/launch_summary.py launches.csv [--last N | --step-marker KERNEL] [--title "..."]\n(--last N: only the final N launches; --step-marker K: the last complete span between two launches of kernel K = one step)"""
 import collections
 import csv
 import gzip
@@ -19,10 +19,16 @@ for r in csv.DictReader(lines):
     v = float(r["Metric Value"].replace(",", ""))
     unit = r.get("Metric Unit", "ns")
     ms = v * {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "nsecond": 1e-6, "ms": 1.0, "msecond": 1.0}.get(unit, 1e-6)
-    name = re.sub(r"<.*", "", re.sub(r"\(.*", "", r["Kernel Name"])).split("::")[-1].strip()
+    name = r["Kernel Name"].replace("void ", "").replace("<unnamed>::", "").replace("(anonymous namespace)::", "")
+    name = re.sub(r"<.*", "", re.sub(r"\(.*", "", name)).split("::")[-1].strip()
     rows.append((name, ms))
 if last:
     rows = rows[-last:]
+if "--step-marker" in sys.argv:  # the last complete span between two launches of this kernel = one step
+    mk = sys.argv[sys.argv.index("--step-marker") + 1]
+    idx = [i for i, (n, _) in enumerate(rows) if n == mk]
+    if len(idx) >= 2:
+        rows = rows[idx[-2]:idx[-1]]
 tot = collections.defaultdict(float)
 cnt = collections.Counter()
 for n, ms in rows:
