@@ -412,12 +412,10 @@ select_hist_kernel(const float* __restrict__ conf, int64_t n, SelectState* __res
   constexpr int shift = radix_shift(PASS);
   constexpr unsigned dmask = (1u << radix_bits(PASS)) - 1u;
   unsigned nan_local = 0, above = 0xFFFFFFFFu;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += stride) {  // warp-uniform trip count
-    const int64_t i = base + threadIdx.x;
+  // one element; executed by all 32 lanes of a warp together (the aggregated atomic of pass 0 is a warp collective)
+  auto take = [&](float f, bool valid) {
     unsigned digit = 0xFFFFFFFFu;  // "no contribution"
-    if (i < n) {
-      const float f = conf[i];
+    if (valid) {
       if (f != f) {
         if (PASS == 0) ++nan_local;
       } else {
@@ -432,6 +430,26 @@ select_hist_kernel(const float* __restrict__ conf, int64_t n, SelectState* __res
     } else if (digit != 0xFFFFFFFFu) {  // only the keys of one bucket contribute: few, and spread over the digit
       atomicAdd(&sh[digit], 1u);
     }
+  };
+  // 16-byte loads, two in flight per thread: with one 4-byte load per iteration the pass was bound by DRAM latency
+  // (20 us for 20 MB, profiles/r02u_reproj_launches.csv.gz), not by bandwidth or by the atomics
+  const bool vec = (reinterpret_cast<uintptr_t>(conf) & 15) == 0;
+  const int64_t n4 = vec ? (n >> 2) : 0;
+  const float4* conf4 = reinterpret_cast<const float4*>(conf);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n4; base += 2 * stride) {  // warp-uniform trip count
+    const int64_t i0 = base + threadIdx.x, i1 = i0 + stride;
+    const bool v0 = i0 < n4, v1 = i1 < n4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (v0) a = conf4[i0];
+    if (v1) b = conf4[i1];
+    take(a.x, v0); take(a.y, v0); take(a.z, v0); take(a.w, v0);
+    take(b.x, v1); take(b.y, v1); take(b.z, v1); take(b.w, v1);
+  }
+  for (int64_t base = 4 * n4 + (int64_t)blockIdx.x * blockDim.x; base < n; base += stride) {  // tail (all of it if unaligned)
+    const int64_t i = base + threadIdx.x;
+    const bool v = i < n;
+    take(v ? conf[i] : 0.f, v);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2048; i += blockDim.x)
@@ -487,10 +505,15 @@ __global__ void compact_count_kernel(const float* __restrict__ conf, int64_t n,
   const float thr = st->thr;
   int64_t base = (int64_t)blockIdx.x * kCompactTile + (int64_t)threadIdx.x * kCompactItems;
   unsigned c = 0;
+  if (base + kCompactItems <= n && (reinterpret_cast<uintptr_t>(conf) & 15) == 0) {  // two 16-byte loads
+    const float4 a = *reinterpret_cast<const float4*>(conf + base), b = *reinterpret_cast<const float4*>(conf + base + 4);
+    c = (a.x >= thr) + (a.y >= thr) + (a.z >= thr) + (a.w >= thr) + (b.x >= thr) + (b.y >= thr) + (b.z >= thr) + (b.w >= thr);
+  } else {
 #pragma unroll
-  for (int j = 0; j < kCompactItems; ++j) {
-    int64_t i = base + j;
-    if (i < n && conf[i] >= thr) ++c;
+    for (int j = 0; j < kCompactItems; ++j) {
+      int64_t i = base + j;
+      if (i < n && conf[i] >= thr) ++c;
+    }
   }
   __shared__ unsigned sw[kCompactThreads / 32];
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -544,12 +567,21 @@ __global__ void compact_scatter_kernel(const float* __restrict__ conf, const flo
   const float thr = st->thr;
   int64_t base = (int64_t)blockIdx.x * kCompactTile + (int64_t)threadIdx.x * kCompactItems;
   unsigned flags = 0, c = 0;
+  if (base + kCompactItems <= n && (reinterpret_cast<uintptr_t>(conf) & 15) == 0) {  // two 16-byte loads
+    const float4 a = *reinterpret_cast<const float4*>(conf + base), b = *reinterpret_cast<const float4*>(conf + base + 4);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-  for (int j = 0; j < kCompactItems; ++j) {
-    int64_t i = base + j;
-    if (i < n && conf[i] >= thr) {
-      flags |= 1u << j;
-      ++c;
+    for (int j = 0; j < kCompactItems; ++j)
+      if (v[j] >= thr) flags |= 1u << j;
+    c = __popc(flags);
+  } else {
+#pragma unroll
+    for (int j = 0; j < kCompactItems; ++j) {
+      int64_t i = base + j;
+      if (i < n && conf[i] >= thr) {
+        flags |= 1u << j;
+        ++c;
+      }
     }
   }
   // block exclusive scan of c

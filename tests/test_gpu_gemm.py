@@ -16,7 +16,9 @@ def rel_l2(a, b):
 
 @pytest.fixture(autouse=True, params=[1, 0], ids=["cluster", "plain"])
 def _seed(request, cuda_device, built_lib):
-    """Every case runs twice: with the 2-CTA cluster / weight-multicast launch (the default) and with the plain launch."""
+    """Every case runs twice: forced CTA pairs (tcgen05.mma.cta_group::2, each CTA holding half of the weight tile) and forced
+    single CTAs.  The library default picks per GEMM (pairs where K_total >= 1024, evw_set_gemm_cluster(-1)); both modes are
+    bit-identical, so covering the two forced modes covers the default."""
     torch.manual_seed(0)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
@@ -272,3 +274,25 @@ def test_group_norm_statistics_refused(cuda_device):
     w96 = (torch.randn(96, 320, device=cuda_device) / 320 ** 0.5).half()
     with pytest.raises(RuntimeError):  # 3 channels per group: more groups per 16-column step than the epilogue has slots for
         ops.gemm_f16(a, w96, out_dtype=torch.float32, gn_stats=stats, gn_rows_per_inst=1024)
+
+
+def test_pair_and_single_cta_modes_are_bit_identical(cuda_device, built_lib):
+    """cta_group::2 pairs (M = 256 over two SMs) and single CTAs accumulate every output element over the same K order:
+    identical bits for a convolution with GroupNorm sums, a residual linear and a GEGLU projection."""
+    x = torch.randn(1, 6, 24, 40, 128, device=cuda_device).half()
+    wk = (torch.randn(320, 9 * 128, device=cuda_device) / (9 * 128) ** 0.5).half()
+    a = torch.randn(3000, 640, device=cuda_device).half()
+    w = (torch.randn(640, 640, device=cuda_device) / 640 ** 0.5).half()
+    wg = (torch.randn(2560, 640, device=cuda_device) / 640 ** 0.5).half()
+    r = torch.randn(3000, 640, device=cuda_device)
+    outs = []
+    for mode in (1, 0):
+        built_lib.evw_set_gemm_cluster(mode)
+        st = torch.empty(6, 32, 2, dtype=torch.float64, device=cuda_device)
+        c = ops.gemm_f16(x, wk, taps=ops.CONV3x3_TAPS, out_dtype=torch.float32, gn_stats=st, gn_rows_per_inst=24 * 40)
+        outs.append((c, st.clone(), ops.gemm_f16(a, w, res1=r, out_dtype=torch.float32), ops.gemm_f16(a, wg, geglu=True)))
+    for u, v in zip(*outs):
+        if u.dtype == torch.float64:  # the per-tile sums are identical; their fp64 atomics land in any order
+            assert torch.allclose(u, v, rtol=1e-12, atol=0)
+        else:
+            assert torch.equal(u, v)

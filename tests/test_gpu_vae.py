@@ -127,3 +127,17 @@ def test_baseline_size_against_oracle(cuda_device, built_lib):
     launches, flops, fused = ours.plan_info(1)
     print(f"decode plan: {launches} launches, {flops / 1e12:.2f} TFLOP for 2 frames, {fused} GroupNorms fed by GEMM epilogues")
     assert fused >= 40
+
+
+def test_shape_errors_fail_loudly(cuda_device, built_lib):
+    ours = V.AutoencoderKLTemporalDecoder(block_out_channels=SMALL).init_random(0, cuda_device)
+    with pytest.raises(RuntimeError, match="divisible by 8"):
+        ours.encode(torch.zeros(1, 3, 60, 64, device=cuda_device))
+    with pytest.raises(RuntimeError, match="multiple of 64"):  # the mid-block attention runs as GEMMs over (H/8)*(W/8) positions
+        ours.encode(torch.zeros(1, 3, 40, 48, device=cuda_device))
+    with pytest.raises(ValueError):
+        ours.decode(torch.zeros(3, 4, 8, 8, device=cuda_device), num_frames=2)
+    with pytest.raises(ValueError):
+        ours.decode(torch.zeros(2, 5, 8, 8, device=cuda_device), num_frames=2)
+    with pytest.raises(RuntimeError):  # no CPU fallback
+        ours.decode(torch.zeros(2, 4, 8, 8), num_frames=2)
