@@ -84,6 +84,11 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
     # end to end: the step's inputs come from pinned host memory, the result goes back to the host
     xd = torch.empty_like(lat)
     cd = torch.empty_like(cond)
+    for i in range(min(args.warmup, 2)):  # untimed: these device buffers are new to the plan -> their CUDA graph is captured here
+        xd.copy_(lat_p, non_blocking=True)
+        cd.copy_(cond_p, non_blocking=True)
+        unet.denoise_step(xd, cd, sig[i % 25], sig[i % 25 + 1], ehs, ids, 1.0, 3.0)
+        out_p.copy_(xd, non_blocking=True)
     torch.cuda.synchronize(dev)
     barrier(world)
     t0 = time.perf_counter()
