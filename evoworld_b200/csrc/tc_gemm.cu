@@ -179,6 +179,11 @@ __device__ __forceinline__ void store16(const GemmEpilogue& ep, const float (&v)
       w[i] = *reinterpret_cast<uint32_t*>(&h);
     }
     __half* p = reinterpret_cast<__half*>(ep.out) + off;
+#ifdef EVW_DEBUG_NO_STORE  // A/B experiment (tools/gpu_r2_call23.sh): the kernel with its arithmetic but without its output stores
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("" ::"r"(w[i]));
+    if (ep.s2 != 12345.678f) return;
+#endif
     if (wide_ok) {
       st_global_256(p, w);
     } else {
@@ -202,6 +207,11 @@ __device__ __forceinline__ void store16(const GemmEpilogue& ep, const float (&v)
     }
   } else {
     float* p = reinterpret_cast<float*>(ep.out) + off;
+#ifdef EVW_DEBUG_NO_STORE
+#pragma unroll
+    for (int i = 0; i < 16; ++i) asm volatile("" ::"f"(v[i]));
+    if (ep.s2 != 12345.678f) return;
+#endif
     if (wide_ok) {
       uint32_t w[8];
 #pragma unroll

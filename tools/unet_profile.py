@@ -48,3 +48,22 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 print("top ops:")
 for i, ms, label in sorted(rows, key=lambda r: -r[1])[:25]:
     print(f"  {i:4d} {ms:8.3f} ms {label}")
+# GEMM shapes: time against the FLOPs of the shape (labels end in "<rows>x<N>x<K_total>"), sorted by the time above a
+# 1300 TFLOP/s floor and above the HBM floor of the operands that must move (A fp16 + output [+ fp32 residual])
+shapes = collections.defaultdict(lambda: [0, 0.0, ""])
+for _, ms, label in rows:
+    m = re.search(r" (\d+)x(\d+)x(\d+)$", label)
+    if not m:
+        continue
+    M, N, K = (int(g) for g in m.groups())
+    key = (cls(label), M, N, K)
+    s = shapes[key]; s[0] += 1; s[1] += ms; s[2] = label.split(" ")[0]
+print("GEMM shapes (class, rows, N, K): calls, total ms, TFLOP/s, ms above the 1300 TFLOP/s floor")
+out = []
+for (c, M, N, K), (n, ms, ex) in shapes.items():
+    fl = 2.0 * M * N * K * n
+    floor = fl / 1300e12 * 1e3
+    out.append((ms - floor, c, M, N, K, n, ms, fl / ms / 1e9, ex))
+for lost, c, M, N, K, n, ms, tf, ex in sorted(out, reverse=True)[:40]:
+    print(f"  {c:14s} {M:7d} x {N:5d} x {K:6d}  n={n:3d} {ms:8.3f} ms {tf:7.0f} TFLOP/s  +{lost:6.2f} ms   e.g. {ex}")
+print(f"  sum of GEMM time above the floor: {sum(o[0] for o in out):.1f} ms of {sum(o[6] for o in out):.1f} ms")
