@@ -331,10 +331,57 @@ __device__ __forceinline__ void stats_halve(float (&s)[16], int w, int lane_bit,
     }
   }
 }
-template <bool RV, bool R1, bool R2, bool RT, bool ST>
+// TS: TMA-store epilogue.  A warp's 32 rows x 16 columns of one step are staged in the warp's own shared-memory slab
+// (fp32: 64-byte rows, SWIZZLE_64B; fp16: 32-byte rows, SWIZZLE_32B — conflict-free 16-byte stores) and leave through one
+// cp.async.bulk.tensor store issued by lane 0: the LSU / L1 path handled one scattered 32-byte sector per lane and store
+// instruction and cost 8-46 % of the level-0 linears (profiles/r02x_gemm_bench_nostore.log); the copy engine drains the
+// slab asynchronously and clips rows / columns outside the tensor.  Two slabs per warp: before a slab is rewritten lane 0
+// waits until at most one of its store groups is still reading shared memory (every step commits a group, empty or not,
+// so that "one pending" always means "the other slab").
+struct StoreCtx {
+  const CUtensorMap* map;
+  uint32_t slab;   // shared-memory address of this warp's two slabs (2 x 2 KiB)
+  uint32_t count;  // steps staged so far by this warp (slab parity)
+  int col0;        // output column of the tile's first column
+  int x, y, t, b;  // coordinates of the warp's first row
+  int lane;
+  bool valid;      // tile inside the problem (CTA pairs run a dummy tile when the m-tile count is odd)
+};
+template <bool kFp16>
+__device__ __forceinline__ void stage_store16(StoreCtx& sc, const float (&v)[16], int col) {
+  const uint32_t buf = sc.slab + (sc.count & 1u) * 2048u;
+  if (sc.lane == 0) tc::bulk_wait_read<1>();
+  __syncwarp();
+  if constexpr (kFp16) {
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    const uint32_t row = buf + (uint32_t)sc.lane * 32u, sw = ((uint32_t)sc.lane >> 2) & 1u;  // SWIZZLE_32B: chunk ^= (row / 4) % 2
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((0u ^ sw) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((1u ^ sw) << 4)), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+  } else {
+    const uint32_t row = buf + (uint32_t)sc.lane * 64u, sw = ((uint32_t)sc.lane >> 1) & 3u;  // SWIZZLE_64B: chunk ^= (row / 2) % 4
+#pragma unroll
+    for (uint32_t c = 0; c < 4; ++c)
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((c ^ sw) << 4)), "f"(v[4 * c]), "f"(v[4 * c + 1]),
+                   "f"(v[4 * c + 2]), "f"(v[4 * c + 3]) : "memory");
+  }
+  tc::fence_proxy_async_smem();
+  __syncwarp();
+  if (sc.lane == 0) {
+    if (sc.valid) tc::tma_store_5d(sc.map, buf, sc.col0 + col, sc.x, sc.y, sc.t, sc.b);
+    tc::bulk_commit();
+  }
+  ++sc.count;
+}
+
+template <bool RV, bool R1, bool R2, bool RT, bool ST, bool TS>
 __device__ __forceinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_addr, const float* bs, int cgrp, int NG, int nsteps,
                                           bool row_ok, int ncols, long long out_off, long long rv_off, bool wide_ok,
-                                          uint32_t bar_full, uint32_t phase, const ResRing& rr, const StatsCtx& sx) {
+                                          uint32_t bar_full, uint32_t phase, const ResRing& rr, const StatsCtx& sx, StoreCtx& sc) {
   auto load_r1 = [&](float (&x)[16], int k) {
     if constexpr (!R1 || RT) return;
     const int c = k * 16;
@@ -371,9 +418,13 @@ __device__ __forceinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_add
 #pragma unroll
       for (int i = 0; i < 16; ++i) sv[i] = 0.f;
     }
+    float v[16];
+    if constexpr (TS) {  // rows outside the tensor are staged too (and clipped by the store): keep them defined
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    }
     if (row_ok && c < ncols) {
       const bool full = c + 16 <= ncols;
-      float v[16];
       const float4* b4 = reinterpret_cast<const float4*>(bs + k * 16);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -414,14 +465,22 @@ __device__ __forceinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_add
 #pragma unroll
         for (int i = 0; i < 16; ++i) sv[i] = (full || i < 8) ? v[i] : 0.f;
       }
-      if (full) {
-        store16(ep, v, out_off + c, wide_ok);
-      } else {  // N tail: only the first 8 columns exist (N is a multiple of 8)
-        float v8[8];
+      if constexpr (!TS) {
+        if (full) {
+          store16(ep, v, out_off + c, wide_ok);
+        } else {  // N tail: only the first 8 columns exist (N is a multiple of 8)
+          float v8[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v8[i] = v[i];
-        if (ep.out_fp16) store8(reinterpret_cast<__half*>(ep.out) + out_off + c, v8);
-        else store8(reinterpret_cast<float*>(ep.out) + out_off + c, v8);
+          for (int i = 0; i < 8; ++i) v8[i] = v[i];
+          if (ep.out_fp16) store8(reinterpret_cast<__half*>(ep.out) + out_off + c, v8);
+          else store8(reinterpret_cast<float*>(ep.out) + out_off + c, v8);
+        }
+      }
+    }
+    if constexpr (TS) {
+      if (c < ncols) {  // warp-uniform; columns past N are clipped by the store
+        if (ep.out_fp16) stage_store16<true>(sc, v, c);
+        else stage_store16<false>(sc, v, c);
       }
     }
     if constexpr (ST) {  // executed by every lane (rows outside the tensor contribute zeros)
@@ -483,7 +542,8 @@ template <bool k2Cta, int kEpiWarps, int kEpi>
 __global__ void __launch_bounds__(kCtrlThreads + 32 * kEpiWarps, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
                const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_bh,
-               const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ KernelParams P) {
+               const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_o,
+               const __grid_constant__ KernelParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -493,8 +553,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
   const uint32_t stage_bytes = kATileBytes + b_tile_bytes;
   constexpr bool kResTma = (kEpi & 16) != 0;  // res1 staged through shared memory by TMA (warp 3)
   constexpr bool kStats = (kEpi & 32) != 0;   // GroupNorm statistics of the output accumulated by the epilogue
+  constexpr bool kStoreTma = (kEpi & 64) != 0;  // outputs leave through per-warp shared-memory slabs and TMA stores
   const uint32_t res_base = smem_base + stages * stage_bytes;  // kResTma: P.res_slots boxes of 16 KiB
-  const uint32_t bar_base = res_base + (kResTma ? (uint32_t)P.res_slots * 16384u : 0u);  // 8-byte barriers
+  const uint32_t st_base = res_base + (kResTma ? (uint32_t)P.res_slots * 16384u : 0u);  // kStoreTma: 2 x 2 KiB per epilogue warp
+  const uint32_t bar_base = st_base + (kStoreTma ? (uint32_t)kEpiWarps * 4096u : 0u);  // 8-byte barriers
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * stages + a); };
@@ -576,6 +638,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
+#ifdef EVW_DEBUG_SKIP_W
+    int dbg_loads = 0;
+#endif
     for (int v = v_first; v < v_limit; v += v_step) {
       const int tile = to_tile(v);
       int n_tile, tx, ty, tt, tb;
@@ -597,12 +662,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
               tma_load_5d_2cta(ma, sa, lead_full, kc * kBlockK, cx, cy, ct, tb);
               tma_load_2d_2cta(&tmap_bh, sa + kATileBytes, lead_full, kglob * kBlockK, n0 + (int)crank * (P.block_n >> 1));
             } else {
-              mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
-              tma_load_5d(ma, sa, full_bar(stage), kc * kBlockK, cx, cy, ct, tb);
-              tma_load_2d(&tmap_b, sa + kATileBytes, full_bar(stage), kglob * kBlockK, n0);
+#ifdef EVW_DEBUG_SKIP_W  // timing experiment only (wrong results): after the ring's first pass the weight tile is not re-loaded
+              if (dbg_loads >= stages) {
+                mbar_arrive_expect_tx(full_bar(stage), kATileBytes);
+                tma_load_5d(ma, sa, full_bar(stage), kc * kBlockK, cx, cy, ct, tb);
+              } else
+#endif
+              {
+                mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+                tma_load_5d(ma, sa, full_bar(stage), kc * kBlockK, cx, cy, ct, tb);
+                tma_load_2d(&tmap_b, sa + kATileBytes, full_bar(stage), kglob * kBlockK, n0);
+              }
             }
           }
           __syncwarp();
+#ifdef EVW_DEBUG_SKIP_W
+          ++dbg_loads;
+#endif
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -705,7 +781,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
       }
     };
     const int mx = r & (P.bx - 1), my = r >> P.bx_shift;  // bx is a power of two
-    constexpr bool is_geglu = kEpi == kEpiGeglu;
+    constexpr bool is_geglu = (kEpi & ~64) == kEpiGeglu;
     // residual operands stream from DRAM exactly once: pull the row segment of the NEXT tile into L2 one tile ahead
     // (prefetch.global.L2, no registers / shared memory), so the epilogue's loads find it there
     auto prefetch_residuals = [&](int v_p) {
@@ -730,6 +806,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
       }
     };
     prefetch_residuals(v_first);
+    StoreCtx sc;
+    sc.map = &tmap_o; sc.slab = st_base + (uint32_t)(warp - 4) * 4096u; sc.count = 0; sc.lane = lane;
+    sc.col0 = 0; sc.x = sc.y = sc.t = sc.b = 0; sc.valid = false;
+    if (kStoreTma && warp == 4 && lane == 0) tma_prefetch_desc(&tmap_o);
+    // first row of this warp's 32 rows inside the tile: (x, y) offset of row 32 q
+    const int wx = (q * 32) & (P.bx - 1), wy = (q * 32) >> P.bx_shift;
     int it = 0;
     for (int v = v_first; v < v_limit; v += v_step, ++it) {
       const int tile = to_tile(v);
@@ -765,6 +847,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
         prev_cols = ncols_t;
       }
 
+      if (kStoreTma) {
+        sc.col0 = is_geglu ? n0 / 2 : n0;
+        sc.x = tx * P.bx + wx; sc.y = ty * P.by + wy; sc.t = tt; sc.b = tb;
+        sc.valid = tile < P.total_tiles;
+      }
       const uint32_t t_addr = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
       if constexpr (is_geglu) {
         mbar_wait_relaxed(tfull_bar(acc), acc_phase);
@@ -778,7 +865,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
           tmem_ld_32x32b_x32(t_addr + k * 32, raw);
           tmem_ld_wait();
           const int nh = n0 + k * 32;
-          if (row_ok && nh < P.N) {
+          if ((kStoreTma || row_ok) && nh < P.N) {  // TMA store: every lane stages its row, the store clips
             float vv[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -786,7 +873,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
               const float gv = __uint_as_float(raw[16 + i]) + bs[k * 32 + 16 + i];
               vv[i] = hv * gelu_erf(gv);
             }
-            store16(ep, vv, row * ldo + nh / 2, wide_ok);
+            if constexpr (kStoreTma) stage_store16<true>(sc, vv, k * 16);
+            else store16(ep, vv, row * ldo + nh / 2, wide_ok);
           }
         }
       } else {
@@ -805,9 +893,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
         rr.base = res_base; rr.full_bar = res_full_bar(0); rr.empty_bar = res_empty_bar(0);
         rr.slots_mask = (uint32_t)(P.res_slots - 1); rr.shift = (uint32_t)P.res_shift;
         rr.box0 = (uint32_t)it * (uint32_t)(P.block_n >> 5); rr.row = r; rr.lane = lane;
-        epi_plain<(kEpi & 1) != 0, (kEpi & 2) != 0, (kEpi & 4) != 0, kResTma, kStats>(ep, t_addr, bs, cgrp, NG, nsteps, row_ok, ncols,
-                                                                                       out_off, rv_off, wide_ok, bar_full, acc_phase,
-                                                                                       rr, sx);
+        epi_plain<(kEpi & 1) != 0, (kEpi & 2) != 0, (kEpi & 4) != 0, kResTma, kStats, kStoreTma>(
+            ep, t_addr, bs, cgrp, NG, nsteps, row_ok, ncols, out_off, rv_off, wide_ok, bar_full, acc_phase, rr, sx, sc);
       }
       tc_fence_before();
       __syncwarp();
@@ -820,6 +907,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       flush_stats((it - 1) & 1);
     }
+    if (kStoreTma && lane == 0) tc::bulk_wait<0>();  // this warp's stores are complete before the CTA's shared memory goes away
   }
 
   tc_fence_before();
@@ -852,7 +940,14 @@ EncodeTiledFn get_encode_fn() {
 }  // namespace
 
 static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
-                       const uint64_t* strides_bytes, const uint32_t* box);
+                       const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B);
+int encode_tmap_swz(CUtensorMap* out, int fp16, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int swizzle_bytes) {
+  const CUtensorMapSwizzle swz = swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                               : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  return encode_tmap(out, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes,
+                     box, swz);
+}
 int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box) {
   return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, base, rank, dims, strides_bytes, box);
@@ -862,7 +957,7 @@ int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t
   return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box);
 }
 static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
-                       const uint64_t* strides_bytes, const uint32_t* box) {
+                       const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -877,7 +972,7 @@ static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* 
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
   CUresult r = fn(out, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu box %u %u %u base %p", (int)r, rank,
@@ -974,8 +1069,24 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   P.res_shift = 2;
   // operand stages + residual ring + barriers, TMEM slot, residual barriers + staged bias + GroupNorm partial sums + 1 KiB
   // of alignment slack: as many stages (<= 8) as fit into the 227 KiB a CTA may use
+  // TMA-store epilogue (EVW_GEMM_STORE_TMA=0 disables): one output, 16-byte aligned rows, and every warp's 32 tile rows must be
+  // a box of the output's (x, y) grid — 32 consecutive x positions, or whole image rows when the tile spans the image width
+  // EVW_GEMM_STORE_TMA: 0 = never, 1 = wherever possible, 2 = only the single-CTA (K_total < pair threshold) GEMMs,
+  // 3 = only fp32 outputs (A/B runs)
+  static const int store_tma_mode = [] { const char* e = getenv("EVW_GEMM_STORE_TMA"); return e ? atoi(e) : 1; }();
+  {
+    const int ldo = pr.ep.geglu ? pr.N / 2 : pr.N;
+    const int esz = pr.ep.out_fp16 ? 2 : 4;
+    const bool rows_ok = P.bx >= 32 || (P.tiles_x == 1 && P.bx == pr.X && 32 % P.bx == 0);
+    bool want = store_tma_mode != 0;
+    if (store_tma_mode == 2 && op->cluster) want = false;
+    if (store_tma_mode == 3 && pr.ep.out_fp16) want = false;
+    op->store_tma = (want && !pr.ep.out_lo && rows_ok && ((long long)ldo * esz) % 16 == 0 && ldo % 16 == 0 &&
+                     (!pr.ep.geglu || bn % 32 == 0)) ? 1 : 0;
+  }
   auto smem_for = [&](int s) {
-    return (long long)s * stage_bytes + P.res_slots * 16384 + 8 * (2 * s + 4) + 16 + 128 + 2 * 256 * 4 + kStatsBytes + 1024;
+    return (long long)s * stage_bytes + P.res_slots * 16384 + (op->store_tma ? kEpiWarpsDefault * 4096 : 0) + 8 * (2 * s + 4) + 16 +
+           128 + 2 * 256 * 4 + kStatsBytes + 1024;
   };
   int stages = 8;
   while (stages > 1 && smem_for(stages) > 227 * 1024) --stages;
@@ -1024,6 +1135,18 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
     if (rc) return rc;
   } else {
     memcpy(op->tmap_r, op->tmap_a0, sizeof(op->tmap_a0));
+  }
+  if (op->store_tma) {
+    const uint64_t ldo = pr.ep.geglu ? pr.N / 2 : pr.N, esz = pr.ep.out_fp16 ? 2 : 4;
+    uint64_t odims[5] = {ldo, (uint64_t)pr.X, (uint64_t)pr.Y, (uint64_t)pr.T, (uint64_t)pr.B};
+    uint64_t ostr[4] = {ldo * esz, ldo * esz * pr.X, ldo * esz * pr.X * pr.Y, ldo * esz * pr.X * pr.Y * pr.T};
+    const uint32_t bxw = P.bx >= 32 ? 32u : (uint32_t)P.bx;
+    uint32_t obox[5] = {16u, bxw, 32u / bxw, 1, 1};
+    rc = encode_tmap_swz(reinterpret_cast<CUtensorMap*>(op->tmap_o), pr.ep.out_fp16, pr.ep.out, 5, odims, ostr, obox,
+                         pr.ep.out_fp16 ? 32 : 64);
+    if (rc) return rc;
+  } else {
+    memcpy(op->tmap_o, op->tmap_a0, sizeof(op->tmap_a0));
   }
   op->flops = 2.0 * pr.X * pr.Y * pr.T * pr.B * (double)pr.N * (double)pr.K_total;
   return EVW_OK;
@@ -1090,7 +1213,7 @@ static int gemm_geglu_wide_epilogue() {
 
 int gemm_launch(const GemmOp& op, cudaStream_t stream) {
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
-                           const KernelParams);
+                           const CUtensorMap, const KernelParams);
   // [pair mode][epilogue]: 0..5 = plain epilogue by operand set {none, rv, r1, rv+r1, r1+r2, rv+r1+r2}, 6 = GEGLU with
   // 8 epilogue warps, 7 = GEGLU with 16, 8..11 = the four residual sets {r1, rv+r1, r1+r2, rv+r1+r2} with res1 staged by TMA
 #define EVW_GEMM_ROW(C)                                                                                                          \
@@ -1101,13 +1224,21 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream) {
    tc_gemm_kernel<C, kEpiWarpsDefault, 16 + 6>, tc_gemm_kernel<C, kEpiWarpsDefault, 16 + 7>,                                     \
    tc_gemm_kernel<C, kEpiWarpsGeglu, 0>, tc_gemm_kernel<C, kEpiWarpsGeglu, 1>, /* 12, 13: no-residual epilogues, 16 warps */ \
    tc_gemm_kernel<C, kEpiWarpsDefault, 32 + 0>, tc_gemm_kernel<C, kEpiWarpsDefault, 32 + 1>,                                     \
-   tc_gemm_kernel<C, kEpiWarpsDefault, 32 + 16 + 2>} /* 14..16: GroupNorm statistics of the output {none, rv, r1 by TMA} */
-  static const KernelFn fns[2][17] = {EVW_GEMM_ROW(false), EVW_GEMM_ROW(true)};
+   tc_gemm_kernel<C, kEpiWarpsDefault, 32 + 16 + 2>, /* 14..16: GroupNorm statistics of the output {none, rv, r1 by TMA} */   \
+   /* 17..27: the same epilogues with the TMA-store path (index 17 + i = variant i of {0,1,2,3,6: GEGLU,8,9,10,11,14,15,16}) */   \
+   tc_gemm_kernel<C, kEpiWarpsDefault, 64 + 0>, tc_gemm_kernel<C, kEpiWarpsDefault, 64 + 1>,                                     \
+   tc_gemm_kernel<C, kEpiWarpsDefault, 64 + 2>, tc_gemm_kernel<C, kEpiWarpsDefault, 64 + 3>,                                     \
+   tc_gemm_kernel<C, kEpiWarpsDefault, 64 + kEpiGeglu>,                                                                          \
+   tc_gemm_kernel<C, kEpiWarpsDefault, 64 + 16 + 2>, tc_gemm_kernel<C, kEpiWarpsDefault, 64 + 16 + 3>,                           \
+   tc_gemm_kernel<C, kEpiWarpsDefault, 64 + 16 + 6>, tc_gemm_kernel<C, kEpiWarpsDefault, 64 + 16 + 7>,                           \
+   tc_gemm_kernel<C, kEpiWarpsDefault, 64 + 32 + 0>, tc_gemm_kernel<C, kEpiWarpsDefault, 64 + 32 + 1>,                           \
+   tc_gemm_kernel<C, kEpiWarpsDefault, 64 + 32 + 16 + 2>}
+  static const KernelFn fns[2][29] = {EVW_GEMM_ROW(false), EVW_GEMM_ROW(true)};
 #undef EVW_GEMM_ROW
   static bool attr_set = false;
   if (!attr_set) {
     for (int c = 0; c < 2; ++c)
-      for (int w = 0; w < 17; ++w) {
+      for (int w = 0; w < 29; ++w) {
         cudaError_t e = cudaFuncSetAttribute(fns[c][w], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
           set_error("cudaFuncSetAttribute(tc_gemm_kernel): %s", cudaGetErrorString(e));
@@ -1147,8 +1278,13 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream) {
       return EVW_ERR_CUDA;
     }
   }
+  if (op.store_tma) {  // twin of the selected epilogue with the TMA-store path, where one is built
+    static const int twin[17] = {17, 18, 19, 20, -1, -1, 21, -1, 22, 23, 24, 25, -1, -1, 26, 27, 28};
+    if (twin[epi] >= 0) epi = twin[epi];
+  }
   KernelFn fn = fns[op.cluster ? 1 : 0][epi];
   const CUtensorMap& tr = *reinterpret_cast<const CUtensorMap*>(op.tmap_r);
+  const CUtensorMap& to = *reinterpret_cast<const CUtensorMap*>(op.tmap_o);
   cudaError_t e;
   if (op.cluster) {
     cudaLaunchConfig_t cfg{};
@@ -1163,9 +1299,9 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, fn, ta0, ta1, tb, tbh, tr, P);
+    e = cudaLaunchKernelEx(&cfg, fn, ta0, ta1, tb, tbh, tr, to, P);
   } else {
-    fn<<<op.grid, threads, op.smem_bytes, stream>>>(ta0, ta1, tb, tbh, tr, P);
+    fn<<<op.grid, threads, op.smem_bytes, stream>>>(ta0, ta1, tb, tbh, tr, to, P);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) {

@@ -58,11 +58,13 @@ struct alignas(64) GemmOp {
   alignas(64) unsigned char tmap_b[128];
   alignas(64) unsigned char tmap_bh[128];  // half-height weight box (CTA-pair mode: each CTA loads its own half)
   alignas(64) unsigned char tmap_r[128];   // fp32 residual (res1) as a 5-D map with 32-column boxes (TMA-staged residual)
+  alignas(64) unsigned char tmap_o[128];   // output as a 5-D map with 32-row x 16-column boxes (TMA-store epilogue)
   unsigned char params[448];
   int grid = 0;
   int cluster = 0;  // 1: launch as clusters of two CTAs sharing each weight tile (TMA multicast)
   int smem_bytes = 0;
   int res_tma = 0;  // 1: res1 streams through a shared-memory ring filled by TMA (fp32 residual, BLOCK_N % 32 == 0)
+  int store_tma = 0;  // 1: the epilogue stages each warp's 32 x 16 outputs in shared memory and stores them with TMA
   double flops = 0;
 };
 
