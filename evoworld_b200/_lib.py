@@ -49,6 +49,7 @@ SIGNATURES = {
     "evw_set_attention_variant": (None, [c_int]),
     "evw_set_gemm_cluster": (None, [c_int]),
     "evw_set_gemm_gn_stats": (None, [c_int]),
+    "evw_set_gemm_store_tma": (None, [c_int]),
     "evw_temporal_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_i64, c_int, c_void_p]),
     "evw_group_norm_f16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_i64, c_i64, c_float, c_void_p, c_void_p,
                                    c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -991,6 +991,7 @@ static int pow2_floor(int v) {
 
 int gemm_cluster_mode();
 int gemm_pair_min_k();
+int gemm_store_tma_mode();
 
 int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   EVW_CHECK_ARG(pr.C0 > 0 && pr.C0 % kBlockK == 0, "gemm: C0=%d must be a positive multiple of 64", pr.C0);
@@ -1073,7 +1074,7 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   // a box of the output's (x, y) grid — 32 consecutive x positions, or whole image rows when the tile spans the image width
   // EVW_GEMM_STORE_TMA: 0 = never, 1 = wherever possible, 2 = only the single-CTA (K_total < pair threshold) GEMMs,
   // 3 = only fp32 outputs (A/B runs)
-  static const int store_tma_mode = [] { const char* e = getenv("EVW_GEMM_STORE_TMA"); return e ? atoi(e) : 1; }();
+  const int store_tma_mode = gemm_store_tma_mode();
   {
     const int ldo = pr.ep.geglu ? pr.N / 2 : pr.N;
     const int esz = pr.ep.out_fp16 ? 2 : 4;
@@ -1203,6 +1204,15 @@ int gemm_pair_min_k() {
   static const int k = [] { const char* e = getenv("EVW_GEMM_PAIR_MIN_K"); return e ? atoi(e) : 1024; }();
   return k;
 }
+static int g_gemm_store_tma = -1;
+int gemm_store_tma_mode() {
+  if (g_gemm_store_tma < 0) {
+    const char* e = getenv("EVW_GEMM_STORE_TMA");
+    g_gemm_store_tma = e ? atoi(e) : 1;
+  }
+  return g_gemm_store_tma;
+}
+void set_gemm_store_tma(int mode) { g_gemm_store_tma = mode < 0 ? -1 : mode; }
 void set_gemm_cluster_mode(int on) { g_gemm_cluster = on < 0 ? -1 : (on ? 1 : 0); }
 // EVW_GEMM_GEGLU_WARPS=16 selects the 16-warp GEGLU epilogue.  Measured slower than 8 warps (0.554 vs 0.514 ms at
 // 258048 x 2560 x 320, profiles/r01h_gemm_geglu_warps.log): the epilogue is bound by instruction count, not by latency.
@@ -1318,6 +1328,7 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------
 extern "C" void evw_set_gemm_cluster(int on) { evw::set_gemm_cluster_mode(on); }
 extern "C" void evw_set_gemm_gn_stats(int on) { evw::set_gemm_gn_stats(on); }
+extern "C" void evw_set_gemm_store_tma(int mode) { evw::set_gemm_store_tma(mode); }
 
 extern "C" int evw_gemm_f16_gn(const void* a0, const void* a1, const void* w, int B, int T, int Y, int X, int C0, int C1,
                                int N, int num_taps, const int8_t* h_taps /*[num_taps,4] dx,dy,dt,src*/, void* out,

@@ -72,6 +72,7 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr);
 int gemm_launch(const GemmOp& op, cudaStream_t stream);
 int gemm_enable_gn_stats(GemmOp* op, double* stats, long long rows_per_inst);  // 0 = enabled, 1 = not available for this GEMM
 void set_gemm_gn_stats(int on);     // -1 = EVW_GEMM_GN_STATS / default on, 0 = GroupNorms keep their own statistics pass, 1 = on
+void set_gemm_store_tma(int mode);  // -1 = EVW_GEMM_STORE_TMA / default (1 = wherever possible), 0 = direct stores only
 void set_gemm_cluster_mode(int on);  // -1 = EVW_GEMM_CLUSTER / default, 0 = off, 1 = on (takes effect at plan time)
 
 }  // namespace evw

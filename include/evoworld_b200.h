@@ -213,6 +213,9 @@ void evw_set_gemm_cluster(int on);
 /* Whether the UNet plan lets GEMM epilogues accumulate the statistics of the GroupNorm that follows (evw_gemm_f16_gn):
  * 1 = yes, 0 = every GroupNorm runs its own statistics pass, -1 = default (EVW_GEMM_GN_STATS, on).  Read at plan time. */
 void evw_set_gemm_gn_stats(int on);
+/* Output path of the GEMM epilogue (read at plan time): 1 = TMA stores from per-warp shared-memory slabs wherever the
+ * geometry allows (default), 0 = per-thread global stores only, -1 = default (EVW_GEMM_STORE_TMA).  Bit-identical. */
+void evw_set_gemm_store_tma(int mode);
 
 /* Spatial self-attention (BasicTransformerBlock.attn1 -> F.scaled_dot_product_attention, head dim 64):
  * qkv fp16 [F*S, 3*heads*64] (columns [q|k|v], each [heads,64]) -> out fp16 [F*S, heads*64]; softmax over

@@ -296,3 +296,49 @@ def test_pair_and_single_cta_modes_are_bit_identical(cuda_device, built_lib):
             assert torch.allclose(u, v, rtol=1e-12, atol=0)
         else:
             assert torch.equal(u, v)
+
+
+def test_tma_store_and_direct_store_are_bit_identical(cuda_device, built_lib):
+    """The TMA-store epilogue (per-warp swizzled slabs, stores clipped by the output's tensor map) against per-thread global
+    stores: partial tiles in x, y and N, 16-wide image rows (a warp's 32 rows = two image rows), fp16 / fp32 outputs, residual,
+    GroupNorm sums, GEGLU, in-place residual update."""
+    torch.manual_seed(1)
+    cases = []
+    x = torch.randn(1, 3, 24, 40, 64, device=cuda_device).half()      # bx = 32, partial tiles in x and y
+    w = (torch.randn(328, 9 * 64, device=cuda_device) / 24).half()    # N = 328: 8-column tail
+    cases.append(lambda: ops.gemm_f16(x, w, taps=ops.CONV3x3_TAPS, out_dtype=torch.float32))
+    cases.append(lambda: ops.gemm_f16(x, w[:320], taps=ops.CONV3x3_TAPS, out_dtype=torch.float16))
+    x16 = torch.randn(2, 2, 9, 16, 128, device=cuda_device).half()    # X = 16 = bx: tile spans the image width
+    w16 = (torch.randn(64, 9 * 128, device=cuda_device) / 34).half()
+    cases.append(lambda: ops.gemm_f16(x16, w16, taps=ops.CONV3x3_TAPS, out_dtype=torch.float32))
+    a = torch.randn(1000, 320, device=cuda_device).half()
+    wl = (torch.randn(320, 320, device=cuda_device) / 18).half()
+    r = torch.randn(1000, 320, device=cuda_device)
+    b = torch.randn(320, device=cuda_device)
+    cases.append(lambda: ops.gemm_f16(a, wl, bias=b, res1=r, out_dtype=torch.float32))
+    cases.append(lambda: ops.gemm_f16(a, wl, bias=b, out_dtype=torch.float16))
+    wg = (torch.randn(2560, 320, device=cuda_device) / 18).half()
+    cases.append(lambda: ops.gemm_f16(a, wg, geglu=True))
+
+    def in_place():
+        buf = r.clone()
+        ops.gemm_f16(a, wl, bias=b, res1=buf, out=buf)
+        return buf
+
+    cases.append(in_place)
+
+    def with_sums():
+        st = torch.empty(3, 32, 2, dtype=torch.float64, device=cuda_device)
+        out = ops.gemm_f16(x, w[:320], taps=ops.CONV3x3_TAPS, out_dtype=torch.float32, gn_stats=st, gn_rows_per_inst=24 * 40)
+        return torch.cat([out.flatten(), st.flatten().float()])
+
+    cases.append(with_sums)
+    try:
+        outs = []
+        for mode in (1, 0):
+            built_lib.evw_set_gemm_store_tma(mode)
+            outs.append([f() for f in cases])
+    finally:
+        built_lib.evw_set_gemm_store_tma(-1)
+    for i, (u, v) in enumerate(zip(*outs)):
+        assert torch.equal(u, v), f"case {i}"
