@@ -15,7 +15,7 @@ Per scene (one per rank), for segment 0, 1, 2:
   6. filter        joint 50th-percentile confidence filter + compaction (evw_conf_select)                    [built]
   7. align         similarity alignment of the GT trajectory (host numpy float64, 24 poses)                  [built: host]
   8. splat         24 target views: cube splat + cube->equirect resolve (evw_splat_cube_equirect)            [built: hot path 2]
-  9. memory frames 24 panoramas 1000x2000 -> 576x1024 (antialiased bilinear, as PIL Resize), [-1,1]          [torch op on device]
+  9. memory frames 24 panoramas 1000x2000 -> 576x1024, bit-exact PIL bilinear Resize (evw_resize_pil_u8), [-1,1]  [built]
  10. VAE encode    memory latents of the next clip: first frame + 24 reprojections                           [built: evw_vae_encode]
 `mode="reference"` re-warps and re-lifts every frame generated so far each segment, as the reference does;
 `mode="incremental"` (default) only touches the new frames — the scene the splat sees is bit-identical
@@ -35,7 +35,7 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
 
     import bench_denoise as bd
     from evoworld_b200 import reprojection as R
-    from evoworld_b200 import segments, synthetic
+    from evoworld_b200 import image_ops, segments, synthetic
     from evoworld_b200.distributed import gather_latents
     from evoworld_b200.equi2pers import Equi2Pers
     from evoworld_b200.memory import PointMemory
@@ -127,8 +127,8 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
             R.splat_to_panoramas_device(scene, w2c, 2000, 1000, 512, G, out=panos, zbuf=zbuf)
             e5 = ev(); e5.record(); mark("splat", e4, e5)
             # memory frames of the next clip: slot 0 = the episode's first frame, slots 1..24 = the reprojections
-            m = F.interpolate(panos.permute(0, 3, 1, 2).float(), size=(H, W), mode="bilinear", antialias=True, align_corners=False)
-            m = m / 127.5 - 1.0
+            # transforms.Resize((H, W)) + ToTensor on the PIL copy of every panorama (CameraTrajDataset.py:597-600): Pillow-exact
+            m = image_ops.resize_pil_u8(panos, H, W).permute(0, 3, 1, 2).float() / 127.5 - 1.0
             first = all_frames[0:1].float() / 127.5 - 1.0
             mem_frames = torch.cat([first, m], dim=0)[:T]                                           # [T,3,H,W]
             e6 = ev(); e6.record(); mark("memory frames", e5, e6)

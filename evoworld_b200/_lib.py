@@ -66,6 +66,8 @@ SIGNATURES = {
     "evw_denoise_step": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_float, c_float,
                                  c_int, c_int, c_int, c_void_p, c_i64, c_void_p]),
     "evw_unet_plan_info": (c_int, [c_void_p, C.POINTER(c_i64), C.POINTER(C.c_double)]),
+    "evw_resize_pil_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                  c_void_p, c_void_p, c_int, c_void_p]),
     "evw_small_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "evw_act_f16": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "evw_vae_create": (c_int, [C.POINTER(c_void_p), C.POINTER(c_int), c_int, C.POINTER(C.c_char_p), C.POINTER(c_void_p), c_int,

@@ -8,6 +8,7 @@ the build container (tests/golden/make_pipeline_golden.py -> tests/golden/pipeli
 """
 from __future__ import annotations
 
+import math
 from typing import Sequence, Tuple
 
 import torch
@@ -76,3 +77,67 @@ def clip_preprocess(image01: torch.Tensor, feature_extractor=None) -> torch.Tens
     mean = torch.tensor(CLIP_MEAN, dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
     std = torch.tensor(CLIP_STD, dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
     return (x - mean) / std
+
+
+# ---------------------------------------------------------------------------------------------
+# Pillow-exact bilinear resize of 8-bit images (dataset/CameraTrajDataset.py:597-600: transforms.Resize on PIL images)
+# ---------------------------------------------------------------------------------------------
+_PIL_PRECISION_BITS = 32 - 8 - 2
+_pil_tables: dict = {}
+
+
+def pil_resize_tables(in_size: int, out_size: int):
+    """Pillow's bilinear coefficient tables for one axis (libImaging/Resample.c precompute_coeffs + normalize_coeffs_8bpc, box =
+    the whole axis): (bounds int32 [out, 2] = (first input index, tap count), k int32 [out, ksize], ksize).  Double precision
+    with Pillow's operation order (the weights of an output sample are summed tap by tap)."""
+    import numpy as np
+
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    ss = 1.0 / filterscale
+    center = 0.0 + (np.arange(out_size, dtype=np.float64) + 0.5) * scale
+    xmin = np.maximum(np.trunc(center - support + 0.5), 0.0).astype(np.int64)
+    xmax = np.minimum(np.trunc(center + support + 0.5), float(in_size)).astype(np.int64) - xmin
+    k = np.zeros((out_size, ksize), dtype=np.float64)
+    ww = np.zeros(out_size, dtype=np.float64)
+    for t in range(ksize):
+        w = np.abs((t + xmin - center + 0.5) * ss)
+        w = np.where(w < 1.0, 1.0 - w, 0.0)
+        w = np.where(t < xmax, w, 0.0)
+        k[:, t] = w
+        ww = ww + w
+    k = np.where(ww[:, None] != 0.0, k / np.where(ww == 0.0, 1.0, ww)[:, None], k)
+    kk = np.trunc(0.5 + k * float(1 << _PIL_PRECISION_BITS)).astype(np.int32)
+    bounds = np.stack([xmin, xmax], axis=1).astype(np.int32)
+    return bounds, kk, ksize
+
+
+def resize_pil_u8(images: torch.Tensor, height: int, width: int) -> torch.Tensor:
+    """uint8 [N, H, W, 3] (or [H, W, 3]) on a CUDA device -> uint8 [N, height, width, 3], bit-identical to
+    `PIL.Image.resize((width, height), BILINEAR)` of every image — i.e. to `transforms.Resize((height, width))` on the PIL copy
+    (evw_resize_pil_u8).  Tables are cached per (size pair, device)."""
+    from . import _lib
+
+    _lib.require_cuda(images, "images")
+    single = images.dim() == 3
+    x = images[None] if single else images
+    if x.dtype != torch.uint8 or x.dim() != 4 or x.shape[-1] != 3:
+        raise ValueError(f"resize_pil_u8 expects uint8 [N,H,W,3], got {images.dtype} {tuple(images.shape)}")
+    x = x.contiguous()
+    N, H, W, _ = x.shape
+    key = (H, W, height, width, str(x.device))
+    if key not in _pil_tables:
+        bx, kx, ksx = pil_resize_tables(W, width)
+        by, ky, ksy = pil_resize_tables(H, height)
+        to = lambda a: torch.from_numpy(a).contiguous().to(x.device)
+        _pil_tables[key] = (to(bx), to(kx), ksx, to(by), to(ky), ksy)
+    bx, kx, ksx, by, ky, ksy = _pil_tables[key]
+    out = torch.empty((N, height, width, 3), dtype=torch.uint8, device=x.device)
+    tmp = torch.empty((N, H, width, 3), dtype=torch.uint8, device=x.device) if (width != W and height != H) else None
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().evw_resize_pil_u8(_lib.ptr(x), _lib.ptr(tmp), _lib.ptr(out), N, H, W, height, width, _lib.ptr(bx),
+                                                _lib.ptr(kx), ksx, _lib.ptr(by), _lib.ptr(ky), ksy, _lib.stream_ptr(x.device)),
+                   "evw_resize_pil_u8")
+    return out[0] if single else out

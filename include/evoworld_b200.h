@@ -278,6 +278,14 @@ int64_t evw_unet_gn_fused(void* handle);
 /* Kernel launches and algorithmic FLOPs of the current plan (after the first forward / step). */
 int evw_unet_plan_info(void* handle, int64_t* launches, double* flops);
 
+/* Pillow-exact bilinear resize of 8-bit images: `transforms.Resize((height, width))` on the PIL copies of the reprojected
+ * memory panoramas (dataset/CameraTrajDataset.py:597-600, applied at unified_loop_consistency.py:422) = PIL.Image.resize
+ * (BILINEAR): horizontal pass into an 8-bit intermediate, then vertical, 22-bit fixed-point coefficients (libImaging
+ * Resample.c).  in uint8 [N,H,W,3] -> out uint8 [N,h,w,3]; tmp uint8 [N,H,w,3]; the coefficient tables come from
+ * evoworld_b200/image_ops.py::pil_resize_tables (device int32: bounds [out,2] = first input index and tap count, k [out,ks]). */
+int evw_resize_pil_u8(const uint8_t* in, uint8_t* tmp, uint8_t* out, int N, int H, int W, int h, int w, const int* bounds_x,
+                      const int* kx, int ksx, const int* bounds_y, const int* ky, int ksy, void* stream);
+
 /* CLIP ViT image encoder pieces (transformers CLIPVisionModelWithProjection, called at
  * evoworld/pipeline/pipeline_evoworld.py:289; transformers models/clip/modeling_clip.py CLIPAttention / CLIPMLP).  The
  * linears use evw_gemm_f16 and the LayerNorms evw_layer_norm_f16 (evoworld_b200/clip.py).

@@ -1,0 +1,55 @@
+"""evw_resize_pil_u8 (csrc/resize.cu) against Pillow itself: bit-exact for down- and up-scaling, odd sizes, the panorama size."""
+import numpy as np
+import pytest
+import torch
+
+from evoworld_b200.image_ops import resize_pil_u8
+from oracle import resize_np as R
+
+pytestmark = pytest.mark.gpu
+PIL = pytest.importorskip("PIL")
+
+
+def _pil(img, h, w):
+    from PIL import Image
+
+    return np.asarray(Image.fromarray(img).resize((w, h), Image.BILINEAR))
+
+
+@pytest.mark.parametrize("N,H,W,h,w", [(2, 100, 200, 58, 102), (1, 37, 53, 11, 20), (3, 40, 64, 40, 32), (1, 31, 17, 64, 40),
+                                       (2, 50, 50, 50, 50), (1, 9, 300, 3, 7), (2, 33, 35, 33, 70)])
+def test_resize_equals_pillow(N, H, W, h, w, cuda_device, built_lib):
+    rng = np.random.default_rng(N * 7 + H)
+    imgs = rng.integers(0, 256, (N, H, W, 3), dtype=np.uint8)
+    imgs[:, : H // 3] = 255
+    imgs[:, -(H // 4):] = 0
+    got = resize_pil_u8(torch.from_numpy(imgs).to(cuda_device), h, w).cpu().numpy()
+    for i in range(N):
+        assert np.array_equal(got[i], _pil(imgs[i], h, w)), f"image {i}"
+        assert np.array_equal(got[i], R.resize_bilinear_u8(imgs[i], h, w))
+
+
+def test_memory_panoramas(cuda_device, built_lib):
+    """The reference's case: 24 reprojected panoramas 1000 x 2000 -> 576 x 1024 (unified_loop_consistency.py:422)."""
+    rng = np.random.default_rng(5)
+    imgs = rng.integers(0, 256, (24, 1000, 2000, 3), dtype=np.uint8)
+    imgs[:, 400:600, 500:900] = 0  # holes of the splat
+    x = torch.from_numpy(imgs).to(cuda_device)
+    got = resize_pil_u8(x, 576, 1024)
+    assert got.shape == (24, 576, 1024, 3)
+    g = got.cpu().numpy()
+    for i in (0, 11, 23):
+        assert np.array_equal(g[i], _pil(imgs[i], 576, 1024))
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(5):
+        resize_pil_u8(x, 576, 1024)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"24 panoramas 1000x2000 -> 576x1024: {e0.elapsed_time(e1) / 5 * 1e3:.0f} us")
+    single = resize_pil_u8(x[3], 576, 1024)
+    assert torch.equal(single, got[3])
+    with pytest.raises(ValueError):
+        resize_pil_u8(x.float(), 576, 1024)
+    with pytest.raises(RuntimeError):
+        resize_pil_u8(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), 4, 4)
