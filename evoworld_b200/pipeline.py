@@ -161,8 +161,8 @@ class StableVideoDiffusionPipeline:
         """:255-305 — `image` is a tensor in [0,1]: x*2-1 -> `_resize_with_antialiasing`(224,224) -> (x+1)/2 -> CLIP
         normalisation (`feature_extractor` when attached, else the CLIP mean/std) -> image_encoder(...).image_embeds."""
         if self.image_encoder is None:
-            raise RuntimeError("StableVideoDiffusionPipeline: no CLIP image encoder attached (SURVEY §8f: not built); pass "
-                               "`image_embeddings=[B, 1, 1024]` or inject an `image_encoder`.")
+            raise RuntimeError("StableVideoDiffusionPipeline: no CLIP image encoder attached (the checkpoint has no `image_encoder/`); pass "
+                               "`image_embeddings=[B, 1, 1024]` or an `image_encoder` (evoworld_b200.clip.CLIPVisionModelWithProjection).")
         if not isinstance(image, torch.Tensor):
             arr = np.stack([np.asarray(im, dtype=np.float32) / 255.0 for im in (image if isinstance(image, list) else [image])])
             image = torch.from_numpy(arr).permute(0, 3, 1, 2)

@@ -253,3 +253,44 @@ def test_pipeline_with_the_native_vae(rig):
     print(f"pipeline with the native VAE: frames rel L2 {err:.3e}")
     assert got.shape == (1, T, 3, H, W) and torch.isfinite(got).all()
     assert err < 5e-3  # VAE encode (<= 3e-3) -> 2 denoise steps -> VAE decode (<= 3e-3), frames in [0, 1]
+
+
+def test_whole_pipeline_at_the_baseline_size_with_native_components(cuda_device, built_lib):
+    """`__call__` at 576 x 1024 x 14 frames with nothing injected: full-width UNet (1.525 B), VAE (97.7 M) and CLIP ViT-H/14
+    (632 M), random-init, 3 denoise steps, decode_chunk_size 8 — CLIP embedding, VAE encode of the first frame + 14 memory
+    frames, the fused steps and the temporal decode all run on this repository's kernels.  (Numerical parity of each part is
+    covered at this size by test_gpu_unet / test_gpu_vae / test_gpu_clip; here: it runs, shapes, finiteness, determinism.)"""
+    import time
+
+    from evoworld_b200.clip import CLIPVisionModelWithProjection
+    from evoworld_b200.vae import AutoencoderKLTemporalDecoder
+
+    dev = cuda_device
+    Tn, Hn, Wn = 14, 576, 1024
+    unet = UNetSpatioTemporalConditionModel(in_channels=18, num_frames=Tn).init_random(seed=0, device=dev)
+    unet._ensure_handle()
+    unet.free_master_parameters()
+    vae = AutoencoderKLTemporalDecoder().init_random(seed=1, device=dev)
+    vae.free_master_parameters()
+    clip = CLIPVisionModelWithProjection().init_random(seed=2, device=dev)
+    clip.free_master_parameters()
+    pipe = StableVideoDiffusionPipeline(vae=vae, image_encoder=clip, unet=unet).to(dev)
+    g = torch.Generator().manual_seed(3)
+    image = (torch.rand(1, 3, Hn, Wn, generator=g) * 2 - 1).to(dev)
+    memory = (torch.rand(1, Tn, 3, Hn, Wn, generator=g) * 2 - 1).to(dev)
+    plucker = torch.randn(1, Tn, 6, Hn // 8, Wn // 8, generator=g).to(dev)
+
+    def run():
+        return pipe(image, height=Hn, width=Wn, num_frames=Tn, num_inference_steps=3, plucker_embedding=plucker,
+                    memorized_pixel_values=memory, generator=torch.Generator(device=dev).manual_seed(7), output_type="pt",
+                    decode_chunk_size=8).frames
+
+    a = run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    b = run()
+    torch.cuda.synchronize()
+    print(f"whole pipeline call at 576x1024x14f, 3 steps, native VAE / CLIP / UNet: {time.perf_counter() - t0:.2f} s")
+    assert a.shape == (1, Tn, 3, Hn, Wn) and torch.isfinite(a).all()
+    assert float(a.min()) >= 0.0 and float(a.max()) <= 1.0
+    assert torch.equal(a, b)
