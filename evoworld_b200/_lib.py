@@ -45,6 +45,7 @@ SIGNATURES = {
     "evw_gemm_f16_gn": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                 C.c_char_p, c_void_p, c_int, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_int, c_float,
                                 c_void_p, c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_i64, c_void_p]),
+    "evw_upconv2x_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "evw_spatial_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "evw_set_attention_variant": (None, [c_int]),
     "evw_set_gemm_cluster": (None, [c_int]),

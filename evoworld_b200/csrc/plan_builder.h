@@ -135,6 +135,20 @@ struct BuilderBase {
     pr.ep.out = outp; pr.ep.out_fp16 = 0; pr.ep.bias = Wf(name + ".bias");
     gemm(pr, name);
   }
+  // diffusers Upsample2D (nearest x2 + Conv2d 3x3) as four 2x2 phase convolutions of the low-resolution input a16
+  // [frames, hh, ww, C] -> outp fp32 [frames, 2hh, 2ww, N]; weights [4][N, 4C] packed by ops.upconv_weights
+  void upconv2x(const __half* a16, int frames, int hh, int ww, int C, const std::string& name, int N, float* outp) {
+    const __half* w4 = (const __half*)W(name + ".weight4");
+    for (int phase = 0; phase < 4; ++phase) {
+      GemmProblem pr;
+      pr.a0 = a16; pr.w = (w4 && !dry) ? w4 + (size_t)phase * N * 4 * C : w4;
+      pr.B = 1; pr.T = frames; pr.Y = hh; pr.X = ww; pr.C0 = C; pr.N = N;
+      upconv2x_phase(pr, phase);
+      pr.ep.out = outp; pr.ep.out_fp16 = 0; pr.ep.bias = Wf(name + ".bias");
+      gemm(pr, name + ".phase" + std::to_string(phase));
+    }
+    if (!dry) last_writer.erase(outp);  // four partial writers: nobody owns the whole tensor's GroupNorm sums
+  }
   void gnorm(const void* src0, int src0_fp16, int C0, const float* src1, int C1, long long insts, long long rows, float eps,
              const std::string& name, int silu, __half* out, __half* raw, __half* out_lo = nullptr) {
     const float* g = Wf(name + ".weight");

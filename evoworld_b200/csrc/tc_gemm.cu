@@ -1079,9 +1079,10 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
     const int ldo = pr.ep.geglu ? pr.N / 2 : pr.N;
     const int esz = pr.ep.out_fp16 ? 2 : 4;
     const bool rows_ok = P.bx >= 32 || (P.tiles_x == 1 && P.bx == pr.X && 32 % P.bx == 0);
-    bool want = store_tma_mode != 0;
-    if (store_tma_mode == 2 && op->cluster) want = false;
-    if (store_tma_mode == 3 && pr.ep.out_fp16) want = false;
+    const bool strided_req = pr.out_sx != 1 || pr.out_sy != 1 || pr.out_ox != 0 || pr.out_oy != 0;
+    bool want = store_tma_mode != 0 || strided_req;  // a strided output view exists only on the TMA-store path
+    if (store_tma_mode == 2 && op->cluster && !strided_req) want = false;
+    if (store_tma_mode == 3 && pr.ep.out_fp16 && !strided_req) want = false;
     op->store_tma = (want && !pr.ep.out_lo && rows_ok && ((long long)ldo * esz) % 16 == 0 && ldo % 16 == 0 &&
                      (!pr.ep.geglu || bn % 32 == 0)) ? 1 : 0;
   }
@@ -1137,13 +1138,22 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   } else {
     memcpy(op->tmap_r, op->tmap_a0, sizeof(op->tmap_a0));
   }
+  const bool strided_out = pr.out_sx != 1 || pr.out_sy != 1 || pr.out_ox != 0 || pr.out_oy != 0;
+  op->strided_out = strided_out ? 1 : 0;
+  EVW_CHECK_ARG(!strided_out || (op->store_tma && pr.out_sx >= 1 && pr.out_sy >= 1 && pr.out_ox >= 0 && pr.out_ox < pr.out_sx &&
+                                 pr.out_oy >= 0 && pr.out_oy < pr.out_sy && !pr.ep.res1 && !pr.ep.res2 && !pr.ep.geglu),
+                "gemm: a strided output view needs the TMA-store epilogue (no residuals, no GEGLU)");
   if (op->store_tma) {
     const uint64_t ldo = pr.ep.geglu ? pr.N / 2 : pr.N, esz = pr.ep.out_fp16 ? 2 : 4;
+    const uint64_t sx = (uint64_t)pr.out_sx, sy = (uint64_t)pr.out_sy;
+    const uint64_t px = ldo * esz;                // bytes per output pixel
+    const uint64_t line = px * sx * pr.X;         // bytes per output image row
     uint64_t odims[5] = {ldo, (uint64_t)pr.X, (uint64_t)pr.Y, (uint64_t)pr.T, (uint64_t)pr.B};
-    uint64_t ostr[4] = {ldo * esz, ldo * esz * pr.X, ldo * esz * pr.X * pr.Y, ldo * esz * pr.X * pr.Y * pr.T};
+    uint64_t ostr[4] = {px * sx, line * sy, line * sy * pr.Y, line * sy * pr.Y * pr.T};
     const uint32_t bxw = P.bx >= 32 ? 32u : (uint32_t)P.bx;
     uint32_t obox[5] = {16u, bxw, 32u / bxw, 1, 1};
-    rc = encode_tmap_swz(reinterpret_cast<CUtensorMap*>(op->tmap_o), pr.ep.out_fp16, pr.ep.out, 5, odims, ostr, obox,
+    const char* obase = reinterpret_cast<const char*>(pr.ep.out) + (uint64_t)pr.out_oy * line + (uint64_t)pr.out_ox * px;
+    rc = encode_tmap_swz(reinterpret_cast<CUtensorMap*>(op->tmap_o), pr.ep.out_fp16, obase, 5, odims, ostr, obox,
                          pr.ep.out_fp16 ? 32 : 64);
     if (rc) return rc;
   } else {
@@ -1151,6 +1161,29 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   }
   op->flops = 2.0 * pr.X * pr.Y * pr.T * pr.B * (double)pr.N * (double)pr.K_total;
   return EVW_OK;
+}
+
+bool gemm_strided_out_ok(int X, int Y, int N) {
+  int bx = X >= kBlockM ? kBlockM : pow2_floor(X);
+  if (Y == 1) bx = kBlockM;
+  const int tiles_x = (X + bx - 1) / bx;
+  const bool rows_ok = bx >= 32 || (tiles_x == 1 && bx == X && 32 % bx == 0);
+  return rows_ok && N % 16 == 0;
+}
+
+void upconv2x_phase(GemmProblem& pr, int phase) {
+  const int py = phase >> 1, px = phase & 1;
+  pr.num_taps = 4;
+  int t = 0;
+  for (int iy = 0; iy < 2; ++iy)
+    for (int ix = 0; ix < 2; ++ix, ++t) {
+      pr.tap_dy[t] = (int8_t)(py == 0 ? iy - 1 : iy);
+      pr.tap_dx[t] = (int8_t)(px == 0 ? ix - 1 : ix);
+      pr.tap_dt[t] = 0;
+      pr.tap_src[t] = 0;
+    }
+  pr.K_total = 4LL * pr.C0;
+  pr.out_sx = 2; pr.out_sy = 2; pr.out_ox = px; pr.out_oy = py;
 }
 
 // -1: EVW_GEMM_GN_STATS (default on), 0 / 1: forced (tests, A/B runs); read when a GroupNorm asks its producer for statistics
@@ -1171,7 +1204,7 @@ int gemm_enable_gn_stats(GemmOp* op, double* stats, long long rows_per_inst) {
   KernelParams P;
   memcpy(&P, op->params, sizeof(P));
   const long long rows = (long long)P.B * P.T * P.Y * P.X;
-  if (P.ep.geglu || P.ep.res2 || (P.ep.res1 && !op->res_tma) || P.N % 32 != 0 || !stats || rows_per_inst <= 0) return 1;
+  if (P.ep.geglu || P.ep.res2 || (P.ep.res1 && !op->res_tma) || P.N % 32 != 0 || !stats || rows_per_inst <= 0 || op->strided_out) return 1;
   const int cg = P.N / 32;
   if (cg < 8) return 1;  // a 16-column step may touch at most kStatsSub groups
   if (rows % rows_per_inst != 0) return 1;
@@ -1292,6 +1325,10 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream) {
     static const int twin[17] = {17, 18, 19, 20, -1, -1, 21, -1, 22, 23, 24, 25, -1, -1, 26, 27, 28};
     if (twin[epi] >= 0) epi = twin[epi];
   }
+  if (op.strided_out && epi < 17) {
+    set_error("gemm: strided output view without a TMA-store kernel for this epilogue");
+    return EVW_ERR_INVALID;
+  }
   KernelFn fn = fns[op.cluster ? 1 : 0][epi];
   const CUtensorMap& tr = *reinterpret_cast<const CUtensorMap*>(op.tmap_r);
   const CUtensorMap& to = *reinterpret_cast<const CUtensorMap*>(op.tmap_o);
@@ -1360,6 +1397,26 @@ extern "C" int evw_gemm_f16_gn(const void* a0, const void* a1, const void* w, in
                   "evw_gemm_f16_gn: this GEMM cannot accumulate GroupNorm statistics (epilogue / geometry)");
   }
   return evw::gemm_launch(op, (cudaStream_t)stream);
+}
+
+// nearest-x2 up-sampling + 3x3 convolution (diffusers Upsample2D): a fp16 [F, h, w, C] -> out fp32 [F, 2h, 2w, N];
+// w4 = the four phase weight matrices [4][N, 4C] (evoworld_b200/ops.py::upconv_weights), bias fp32 [N] or null
+extern "C" int evw_upconv2x_f16(const void* a, const void* w4, const float* bias, void* out, int F, int h, int w, int C, int N,
+                                void* stream) {
+  EVW_CHECK_ARG(a && w4 && out, "evw_upconv2x_f16: null pointer");
+  for (int phase = 0; phase < 4; ++phase) {
+    evw::GemmProblem pr{};
+    pr.a0 = a; pr.w = reinterpret_cast<const __half*>(w4) + (size_t)phase * N * 4 * C;
+    pr.B = 1; pr.T = F; pr.Y = h; pr.X = w; pr.C0 = C; pr.N = N;
+    evw::upconv2x_phase(pr, phase);
+    pr.ep.out = out; pr.ep.out_fp16 = 0; pr.ep.bias = bias;
+    evw::GemmOp op;
+    int rc = evw::gemm_plan(&op, pr);
+    if (rc) return rc;
+    rc = evw::gemm_launch(op, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return EVW_OK;
 }
 
 extern "C" int evw_gemm_f16(const void* a0, const void* a1, const void* w, int B, int T, int Y, int X, int C0, int C1,

@@ -49,6 +49,9 @@ struct GemmProblem {
   int num_taps = 1;
   int8_t tap_dx[kMaxTaps] = {0}, tap_dy[kMaxTaps] = {0}, tap_dt[kMaxTaps] = {0}, tap_src[kMaxTaps] = {0};
   int block_n = 0;  // 0 = choose
+  // Strided output view (TMA-store epilogue only): the output of pixel (x, y) goes to pixel (out_sx x + out_ox,
+  // out_sy y + out_oy) of an image of out_sx X by out_sy Y pixels — one phase of a fused nearest-x2-upsample + 3x3 conv
+  int out_sx = 1, out_sy = 1, out_ox = 0, out_oy = 0;
   GemmEpilogue ep;
 };
 
@@ -65,10 +68,18 @@ struct alignas(64) GemmOp {
   int smem_bytes = 0;
   int res_tma = 0;  // 1: res1 streams through a shared-memory ring filled by TMA (fp32 residual, BLOCK_N % 32 == 0)
   int store_tma = 0;  // 1: the epilogue stages each warp's 32 x 16 outputs in shared memory and stores them with TMA
+  int strided_out = 0;  // 1: the output map is a strided view (GemmProblem::out_sx ...): only the TMA-store kernels honour it
   double flops = 0;
 };
 
 int gemm_plan(GemmOp* op, const GemmProblem& pr);
+// Taps and output phase of a fused nearest-x2 up-sampling + 3x3 convolution (padding 1): output pixel (2y + py, 2x + px) is a
+// 2x2 convolution of the LOW-resolution input — rows {y - 1, y} for py = 0, {y, y + 1} for py = 1 (columns likewise) — with
+// the 3x3 weights that fall on the same source pixel summed: 4 GEMMs of K = 4 C instead of one of K = 9 C on a 4x larger
+// input.  phase = 2 py + px; weights [N, 4 C], taps ordered (dy, dx) as filled here (packed by unet.py / vae.py: upconv_weights).
+void upconv2x_phase(GemmProblem& pr, int phase);
+// whether a GEMM over an X x Y image with N fp32 output columns can store through a strided output view (TMA-store geometry)
+bool gemm_strided_out_ok(int X, int Y, int N);
 int gemm_launch(const GemmOp& op, cudaStream_t stream);
 int gemm_enable_gn_stats(GemmOp* op, double* stats, long long rows_per_inst);  // 0 = enabled, 1 = not available for this GEMM
 void set_gemm_gn_stats(int on);     // -1 = EVW_GEMM_GN_STATS / default on, 0 = GroupNorms keep their own statistics pass, 1 = on

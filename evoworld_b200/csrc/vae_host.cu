@@ -381,9 +381,15 @@ struct VaeBuilder : BuilderBase {
         cur ^= 1; x = pp[cur]; xC = rev[s];
       }
       if (s < 3) {
-        { const float* xi = x; __half* o = resamp16; const long long n = N; const int hh = lh[s], ww = lw[s], C = xC;
-          push([=](cudaStream_t st) { return upsample2x(xi, o, n, hh, ww, C, st); }, 1, "upsample2x"); }
-        conv3x3_simple(resamp16, N, lh[s + 1], lw[s + 1], xC, bp + ".upsamplers.0.conv", xC, pp[cur ^ 1]);
+        if (gemm_strided_out_ok(lw[s], lh[s], xC)) {  // four 2x2 phase convolutions of the low-resolution tensor
+          { const float* xi = x; __half* o = resamp16; const long long n = lM[s] * xC;
+            push([=](cudaStream_t st) { return cast_f16(xi, o, n, st); }, 1, "cast (upsampler operand)"); }
+          upconv2x(resamp16, N, lh[s], lw[s], xC, bp + ".upsamplers.0.conv", xC, pp[cur ^ 1]);
+        } else {  // the literal form on the up-sampled fp16 image
+          { const float* xi = x; __half* o = resamp16; const long long n = N; const int hh = lh[s], ww = lw[s], C = xC;
+            push([=](cudaStream_t st) { return upsample2x(xi, o, n, hh, ww, C, st); }, 1, "upsample2x"); }
+          conv3x3_simple(resamp16, N, lh[s + 1], lw[s + 1], xC, bp + ".upsamplers.0.conv", xC, pp[cur ^ 1]);
+        }
         cur ^= 1; x = pp[cur];
       }
     }

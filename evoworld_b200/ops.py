@@ -146,3 +146,33 @@ def layer_norm_f32(x: torch.Tensor, gamma, beta, eps: float = 1e-5) -> torch.Ten
         _lib.check(_lib.lib().evw_layer_norm_f32(_lib.ptr(x), rows, C, eps, _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(out),
                                                  _lib.stream_ptr(x.device)), "evw_layer_norm_f32")
     return out
+
+
+def upconv_weights(w: torch.Tensor) -> torch.Tensor:
+    """Conv2d weight [N, C, 3, 3] of an Upsample2D (nearest x2 then 3x3 conv, padding 1) -> the four phase matrices fp16
+    [4, N, 4C] of the fused form: phase = 2 py + px, taps (dy, dx) in the order of csrc/tc_gemm.cu::upconv2x_phase, the 3x3
+    weights that fall on the same low-resolution pixel summed in fp32 (rows: py = 0 -> {k0}, {k1 + k2}; py = 1 -> {k0 + k1}, {k2})."""
+    w = w.to(torch.float32)
+    groups = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+    phases = []
+    for py in (0, 1):
+        for px in (0, 1):
+            taps = []
+            for ky in groups[py]:
+                for kx in groups[px]:
+                    taps.append(w[:, :, ky][:, :, :, kx].sum(dim=(2, 3)))  # [N, C]
+            phases.append(torch.cat(taps, dim=1))                            # [N, 4C]
+    return torch.stack(phases).to(torch.float16).contiguous()
+
+
+def upconv2x(a: torch.Tensor, w4: torch.Tensor, bias=None) -> torch.Tensor:
+    """a fp16 [F, h, w, C] -> fp32 [F, 2h, 2w, N]: nearest x2 + 3x3 conv as four 2x2 phase convolutions (evw_upconv2x_f16)."""
+    _lib.require_cuda(a, "a")
+    F_, h, w, C = a.shape
+    N = w4.shape[1]
+    assert a.dtype == torch.float16 and w4.dtype == torch.float16 and w4.shape == (4, N, 4 * C)
+    out = torch.empty((F_, 2 * h, 2 * w, N), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().evw_upconv2x_f16(_lib.ptr(a), _lib.ptr(w4), _lib.ptr(bias), _lib.ptr(out), F_, h, w, C, N,
+                                               _lib.stream_ptr(a.device)), "evw_upconv2x_f16")
+    return out

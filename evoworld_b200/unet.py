@@ -20,7 +20,7 @@ from typing import Dict, Optional, Tuple, Union
 
 import torch
 
-from . import _lib
+from . import _lib, ops
 
 MAX_FRAMES = 32
 
@@ -438,6 +438,8 @@ class UNetSpatioTemporalConditionModel:
         T["xattn_all.weight"] = h(torch.cat(xw, 0).float()); T["xattn_all.bias"] = f(torch.cat(xb, 0))
         for p, c in lay["samplers"]:
             T[p + ".weight"] = h(conv2d_w(P[p + ".weight"])); T[p + ".bias"] = f(P[p + ".bias"])
+            if ".upsamplers." in p:  # nearest x2 + 3x3 conv fused into four 2x2 phase convolutions (ops.upconv_weights)
+                T[p + ".weight4"] = ops.upconv_weights(P[p + ".weight"])
         norm("conv_norm_out")
         co = cfg["out_channels"]
         if split:  # rows [0,co): [9 taps W_hi (head operand) | 9 taps W_hi (tail operand)]; rows [co,2co): [W_lo | 0]

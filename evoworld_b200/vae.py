@@ -20,7 +20,7 @@ from typing import Dict, Optional, Tuple
 
 import torch
 
-from . import _lib
+from . import _lib, ops
 
 DEFAULT_CONFIG = dict(
     in_channels=3, out_channels=3, down_block_types=("DownEncoderBlock2D",) * 4, block_out_channels=(128, 256, 512, 512),
@@ -346,6 +346,8 @@ class AutoencoderKLTemporalDecoder:
             T[p + ".to_out.0.bias"] = f(P[p + ".to_out.0.bias"].double() + wo.double() @ P[p + ".to_v.bias"].double())
         for p, c in lay["samplers"]:
             T[p + ".weight"] = h(conv2d_w(P[p + ".weight"])); T[p + ".bias"] = f(P[p + ".bias"])
+            if ".upsamplers." in p:  # nearest x2 + 3x3 conv fused into four 2x2 phase convolutions (ops.upconv_weights)
+                T[p + ".weight4"] = ops.upconv_weights(P[p + ".weight"])
         norm("encoder.conv_norm_out"); norm("decoder.conv_norm_out")
         # quant_conv (1x1) composed with encoder.conv_out: W' = Wq Wc, b' = Wq bc + bq
         lat2 = 2 * cfg["latent_channels"]

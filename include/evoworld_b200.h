@@ -204,6 +204,14 @@ int evw_gemm_f16_gn(const void* a0, const void* a1, const void* w, int B, int T,
                     const float* res2, float s2, float s0, int geglu, int block_n, void* out_lo, double* gn_stats,
                     int64_t gn_rows_per_inst, void* stream);
 
+/* diffusers Upsample2D (nearest x2, then Conv2d 3x3 padding 1) without materialising the up-sampled image: every output phase
+ * (2y + py, 2x + px) is a 2x2 convolution of the low-resolution input with the 3x3 weights that land on the same source pixel
+ * summed — four GEMMs of K = 4C that store through strided TMA maps.  a fp16 [F,h,w,C] -> out fp32 [F,2h,2w,N]; w4 fp16
+ * [4][N,4C] (evoworld_b200/ops.py::upconv_weights).  Used by the UNet up blocks (unet_plucker.py:203-233 -> diffusers
+ * UpBlockSpatioTemporal.upsamplers) and the VAE decoder. */
+int evw_upconv2x_f16(const void* a, const void* w4, const float* bias, void* out, int F, int h, int w, int C, int N,
+                     void* stream);
+
 /* Launch mode of the GEMM (takes effect when an op is planned): 1 = always CTA pairs (clusters of two) on m-adjacent tiles
  * running tcgen05.mma.cta_group::2 with M = 256, each CTA holding half of the weight tile; 0 = always independent CTAs
  * (cta_group::1, M = 128); -1 = default (EVW_GEMM_CLUSTER, else automatic: pairs where K_total >= EVW_GEMM_PAIR_MIN_K,

@@ -342,3 +342,19 @@ def test_tma_store_and_direct_store_are_bit_identical(cuda_device, built_lib):
         built_lib.evw_set_gemm_store_tma(-1)
     for i, (u, v) in enumerate(zip(*outs)):
         assert torch.equal(u, v), f"case {i}"
+
+
+@pytest.mark.parametrize("Fr,h,w,C,N", [(2, 9, 16, 64, 64), (3, 18, 32, 128, 320), (1, 36, 64, 64, 128), (2, 5, 40, 64, 80)])
+def test_fused_upsample_conv(Fr, h, w, C, N, cuda_device, built_lib):
+    """diffusers Upsample2D (nearest x2, then Conv2d 3x3 padding 1) as four 2x2 phase convolutions of the low-resolution input
+    stored through strided TMA maps (evw_upconv2x_f16) against the literal torch form on the same fp16-rounded operands; the
+    phase weights are fp32 sums of fp16-rounded taps here so that only the accumulation order differs."""
+    x = torch.randn(Fr, C, h, w, device=cuda_device).half()
+    wt = (torch.randn(N, C, 3, 3, device=cuda_device) / (9 * C) ** 0.5).half()
+    b = torch.randn(N, device=cuda_device)
+    want = F.conv2d(F.interpolate(x.float(), scale_factor=2.0, mode="nearest"), wt.float(), b, padding=1).permute(0, 2, 3, 1)
+    w4 = ops.upconv_weights(wt)
+    got = ops.upconv2x(x.permute(0, 2, 3, 1).contiguous(), w4, b)
+    assert got.shape == (Fr, 2 * h, 2 * w, N)
+    # the summed phase weights are rounded to fp16 once more: 2.8e-4 relative per weight, averaged over K
+    assert rel_l2(got, want) < 3e-4
