@@ -881,7 +881,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
         const long long out_off = row * ldo + n0;
         long long rv_off = 0;
         if (ep.rowvec) {
-          const uint32_t rq = fd_div((uint32_t)row, P.fd_rv_div);
+          const uint32_t rq = fd_div((uint32_t)(row + ep.rv_row0), P.fd_rv_div);
           uint32_t qq, rem;
           fd_divmod(rq, P.fd_rv_mod, qq, rem);
           rv_off = (long long)rem * rv_ld + n0;
@@ -1029,6 +1029,7 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   P.n_tiles = (pr.N + bn - 1) / bn;
   {
     const long long rows_total = (long long)pr.B * pr.T * pr.Y * pr.X;
+    EVW_CHECK_ARG(pr.ep.rv_row0 >= 0 && rows_total + pr.ep.rv_row0 < (1ll << 31), "gemm: rv_row0 out of range");
     EVW_CHECK_ARG(rows_total < (1ll << 31) && pr.ep.rv_div < (1ll << 31) && pr.ep.rv_mod < (1ll << 31) && pr.ep.rv_div > 0 &&
                       pr.ep.rv_mod > 0,
                   "gemm: more than 2^31 rows (or a broadcast period out of range)");

@@ -8,7 +8,7 @@ namespace evw {
 
 constexpr int kMaxTaps = 20;  // 3x3 conv with split-precision activations: 9 head taps + 9 tail taps
 
-// out[row, n] = s0 * (acc + bias[n]) + rowvec[((row / rv_div) % rv_mod) * rv_ld + n] + s1 * res1[row, n] + s2 * res2[row, n]
+// out[row, n] = s0 * (acc + bias[n]) + rowvec[(((row + rv_row0) / rv_div) % rv_mod) * rv_ld + n] + s1 * res1[row, n] + s2 * res2[row, n]
 // geglu: acc columns come in interleaved [16 value | 16 gate] groups, out has N/2 columns:
 //        out = (value + bias_v) * gelu(gate + bias_g), then the same affine tail.
 struct GemmEpilogue {
@@ -19,6 +19,7 @@ struct GemmEpilogue {
   const float* bias = nullptr;
   const float* rowvec = nullptr;
   long long rv_div = 1, rv_mod = 1;
+  long long rv_row0 = 0;  // row offset added before the broadcast index (a GEMM over a row panel of a larger tensor)
   int rv_ld = 0;  // row stride of rowvec in floats (0 = output width)
   const void* res1 = nullptr;
   int res1_fp16 = 0;

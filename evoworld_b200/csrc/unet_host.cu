@@ -194,6 +194,38 @@ struct Builder : BuilderBase {
     (void)M;
   }
 
+  // FeedForward (GEGLU projection -> net.2), optionally over row panels (EVW_FF_PANEL_MB > 0): the 4C-wide fp16 intermediate
+  // of a panel would be written and read back while still in the 126 MB L2, every panel re-using the same buffer — at
+  // level 0 the intermediate is 660 MB per feed-forward (1.3 GB of HBM traffic for 0.6 TFLOP).  MEASURED SLOWER and therefore
+  // off by default: 114.7 ms per step without panels, 114.8 / 117.7 / 119.0 ms with 160 / 80 / 40 MB panels
+  // (profiles/r02ag_bench_ff_panel_ab.log) — the extra launches and partial last waves cost more than the L2 hits return.
+  // ep2 = epilogue of net.2 for the whole tensor; its row-indexed operands are offset per panel here.
+  void feed_forward(const __half* a16, long long M, int C, const std::string& ff, GemmEpilogue ep2) {
+    static const long long panel_mb = [] { const char* e = getenv("EVW_FF_PANEL_MB"); return e ? atoll(e) : 0ll; }();
+    const long long bytes_per_row = 4LL * C * 2;
+    long long rows_per_panel = M;
+    if (panel_mb > 0 && M * bytes_per_row > panel_mb * (1ll << 20) * 3 / 2) {
+      const long long panels = (M * bytes_per_row + panel_mb * (1ll << 20) - 1) / (panel_mb * (1ll << 20));
+      rows_per_panel = ((M + panels - 1) / panels + 127) / 128 * 128;  // whole 128-row tiles
+    }
+    const int o_esz = ep2.out_fp16 ? 2 : 4;
+    for (long long r0 = 0; r0 < M; r0 += rows_per_panel) {
+      const long long rows = std::min(rows_per_panel, M - r0);
+      GemmEpilogue e1;
+      e1.out = ff16; e1.out_fp16 = 1; e1.geglu = 1;
+      linear(dry ? a16 : a16 + r0 * C, rows, C, ff + ".net.0.proj", 8 * C, e1);
+      GemmEpilogue e2 = ep2;
+      if (!dry) {
+        e2.out = (char*)ep2.out + r0 * C * o_esz;
+        if (ep2.out_lo) e2.out_lo = (char*)ep2.out_lo + r0 * C * 2;
+        if (ep2.res1) e2.res1 = (const char*)ep2.res1 + r0 * C * (ep2.res1_fp16 ? 2 : 4);
+        if (ep2.res2) e2.res2 = ep2.res2 + r0 * C;
+      }
+      e2.rv_row0 = ep2.rv_row0 + r0;
+      linear(ff16, rows, 4 * C, ff + ".net.2", C, e2);
+    }
+  }
+
   // ---- TransformerSpatioTemporalModel (diffusers transformer_temporal.py); in-place on x allowed (out may == x)
   void transformer(const std::string& pre, int lvl, const float* x, int C, int heads, float* out) {
     const long long M = lM[lvl], S = lS[lvl];
@@ -226,26 +258,16 @@ struct Builder : BuilderBase {
     }
     lnorm(f0, nullptr, 1, 1, M, C, sb + ".norm3", n16);
     {
-      GemmEpilogue ep = ep_f16(ff16);
-      ep.geglu = 1;
-      linear(n16, M, C, sb + ".ff.net.0.proj", 8 * C, ep);
-    }
-    {
       GemmEpilogue ep = ep_f32(f0);
       ep.res1 = f0;
-      linear(ff16, M, 4 * C, sb + ".ff.net.2", C, ep);  // f0 = x_spatial
+      feed_forward(n16, M, C, sb + ".ff", ep);  // f0 = x_spatial
     }
     // --- temporal block on x_spatial + time_pos_embed[t]
     lnorm(f0, tpos, S, T, M, C, tb + ".norm_in", n16);
     {
-      GemmEpilogue ep = ep_f16(ff16);
-      ep.geglu = 1;
-      linear(n16, M, C, tb + ".ff_in.net.0.proj", 8 * C, ep);
-    }
-    {
       GemmEpilogue ep = ep_f32(f1);
       ep.res1 = f0; ep.rowvec = tpos; ep.rv_ld = C; ep.rv_div = S; ep.rv_mod = T;
-      linear(ff16, M, 4 * C, tb + ".ff_in.net.2", C, ep);  // f1 = ff_in(...) + (x_s + emb)
+      feed_forward(n16, M, C, tb + ".ff_in", ep);  // f1 = ff_in(...) + (x_s + emb)
     }
     lnorm(f1, nullptr, 1, 1, M, C, tb + ".norm1", n16);
     linear(n16, M, C, tb + ".attn1.qkv", 3 * C, ep_f16(qkv16), false);
@@ -261,16 +283,12 @@ struct Builder : BuilderBase {
     }
     lnorm(f1, nullptr, 1, 1, M, C, tb + ".norm3", n16);
     {
-      GemmEpilogue ep = ep_f16(ff16);
-      ep.geglu = 1;
-      linear(n16, M, C, tb + ".ff.net.0.proj", 8 * C, ep);
-    }
-    {
       // time_mixer: alpha x_s + (1 - alpha)(y + ff(y))  -> fp16 operand of proj_out
+      // (in place over n16: a panel's rows are rewritten only after its own GEGLU projection has consumed them)
       GemmEpilogue ep = ep_f16(n16);
       ep.s0 = 1.f - alpha; ep.res1 = f1; ep.s1 = 1.f - alpha; ep.res2 = f0; ep.s2 = alpha;
       if (split) ep.out_lo = lo16;
-      linear(ff16, M, 4 * C, tb + ".ff.net.2", C, ep);
+      feed_forward(n16, M, C, tb + ".ff", ep);
     }
     {
       GemmEpilogue ep = ep_f32(out);
