@@ -578,7 +578,7 @@ int run_plan_profiled(UNet* U, cudaStream_t st, const char* path) {
 }
 
 // Replay the plan as ONE CUDA graph launch.  The first call of a plan runs eagerly (it also performs the one-time
-// cudaFuncSetAttribute calls of the kernels); the second call captures the ~830 launches on an internal stream (the
+// cudaFuncSetAttribute calls of the kernels); the second call captures the ~550 launches on an internal stream (the
 // caller's stream may be the legacy default stream, which cannot be captured) and from then on every call with the same
 // caller pointers is: set_step_args kernel + cudaGraphLaunch on the caller's stream.  EVW_UNET_GRAPH=0 disables.
 int run_plan_graph(UNet* U, cudaStream_t st, bool* done) {

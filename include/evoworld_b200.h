@@ -277,7 +277,7 @@ int evw_denoise_step(void* handle, float* latents, const float* cond_latents, fl
                      const float* ehs, const float* added_time_ids, float g_min, float g_max, int T, int h, int w,
                      void* workspace, int64_t workspace_bytes, void* stream);
 /* How many calls on the current plan were served by replaying its captured CUDA graph (one cudaGraphLaunch instead of
- * ~830 kernel launches; the first call of a plan runs eagerly, the second captures).  -1 without a plan.  EVW_UNET_GRAPH=0
+ * ~550 kernel launches; the first call of a plan runs eagerly, the second captures).  -1 without a plan.  EVW_UNET_GRAPH=0
  * disables graph replay. */
 int64_t evw_unet_graph_replays(void* handle);
 /* How many GroupNorms of the current plan take their statistics from the epilogue of the GEMM that produced their input
