@@ -86,6 +86,12 @@ SIGNATURES = {
                                            c_void_p, c_i64, c_void_p]),
     "evw_splat_faces_debug": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_float, c_float, c_void_p,
                                       c_void_p, c_i64, c_void_p]),
+    "evw_qknorm_rope_f16": (c_int, [c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_float, c_void_p]),
+    "evw_bilinear_ac_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "evw_relu_inplace_f16": (c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
+    "evw_adaln_modulate_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "evw_dpt_activate_f32": (c_int, [c_void_p, c_i64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
 

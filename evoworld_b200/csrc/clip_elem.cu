@@ -83,12 +83,20 @@ small_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
   }
 }
 
-// MLP activation: x fp32 -> fp16.  mode 0 = GELU (erf form, nn.GELU / transformers "gelu"), 1 = quick_gelu x sigmoid(1.702 x)
+// Activation + cast: x fp32 -> fp16.  mode 0 = GELU (erf form, nn.GELU / transformers "gelu"), 1 = quick_gelu x sigmoid(1.702 x),
+// 2 = ReLU, 3 = identity (cast only), 4 = SiLU (the last three: VGGT's DPT / camera heads, evoworld_b200/vggt.py)
 __global__ void act_f16_kernel(const float* __restrict__ x, __half* __restrict__ out, long long n, int mode) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = x[i];
-  const float r = mode == 0 ? 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)) : v / (1.0f + __expf(-1.702f * v));
+  float r;
+  switch (mode) {
+    case 0: r = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); break;
+    case 1: r = v / (1.0f + __expf(-1.702f * v)); break;
+    case 2: r = fmaxf(v, 0.0f); break;
+    case 3: r = v; break;
+    default: r = v / (1.0f + expf(-v)); break;
+  }
   out[i] = __float2half_rn(r);
 }
 
@@ -117,7 +125,7 @@ extern "C" int evw_small_attention_f16(const void* qkv, void* out, int B, int S,
 }
 
 extern "C" int evw_act_f16(const float* x, void* out, int64_t n, int mode, void* stream) {
-  EVW_CHECK_ARG(x && out && n >= 0 && (mode == 0 || mode == 1), "evw_act_f16: bad arguments");
+  EVW_CHECK_ARG(x && out && n >= 0 && mode >= 0 && mode <= 4, "evw_act_f16: bad arguments");
   if (n == 0) return EVW_OK;
   evw::act_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (__half*)out, n, mode);
   EVW_LAUNCH_CHECK();

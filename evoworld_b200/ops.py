@@ -127,12 +127,12 @@ def small_attention(qkv: torch.Tensor, B: int, S: int, heads: int, head_dim: int
 
 
 def activation_f16(x: torch.Tensor, mode: str = "gelu") -> torch.Tensor:
-    """x fp32 -> fp16 through GELU (erf form) or quick_gelu."""
+    """x fp32 -> fp16 through GELU (erf form), quick_gelu, relu, identity (cast) or silu."""
     _lib.require_cuda(x, "x")
     assert x.dtype == torch.float32 and x.is_contiguous()
     out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().evw_act_f16(_lib.ptr(x), _lib.ptr(out), x.numel(), {"gelu": 0, "quick_gelu": 1}[mode],
+        _lib.check(_lib.lib().evw_act_f16(_lib.ptr(x), _lib.ptr(out), x.numel(), {"gelu": 0, "quick_gelu": 1, "relu": 2, "identity": 3, "silu": 4}[mode],
                                           _lib.stream_ptr(x.device)), "evw_act_f16")
     return out
 
@@ -176,3 +176,69 @@ def upconv2x(a: torch.Tensor, w4: torch.Tensor, bias=None) -> torch.Tensor:
         _lib.check(_lib.lib().evw_upconv2x_f16(_lib.ptr(a), _lib.ptr(w4), _lib.ptr(bias), _lib.ptr(out), F_, h, w, C, N,
                                                _lib.stream_ptr(a.device)), "evw_upconv2x_f16")
     return out
+
+
+def qknorm_rope_(qkv: torch.Tensor, heads: int, tokens_per_frame: int, pos_yx: torch.Tensor, q_gamma, q_beta, k_gamma, k_beta,
+                 cos_t: torch.Tensor, sin_t: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """In place on qkv fp16 [rows, 3*heads*64]: LayerNorm(64) of every q / k head, then the 2-D rotary embedding with the
+    integer (y, x) position pos_yx int32 [tokens_per_frame, 2] of token row % tokens_per_frame (evw_qknorm_rope_f16)."""
+    _lib.require_cuda(qkv, "qkv")
+    rows = qkv.shape[0]
+    assert qkv.dtype == torch.float16 and qkv.shape[1] == 3 * heads * 64 and rows % tokens_per_frame == 0
+    assert pos_yx.dtype == torch.int32 and pos_yx.shape == (tokens_per_frame, 2)
+    assert cos_t.dtype == torch.float32 and cos_t.shape[1] == 16 and sin_t.shape == cos_t.shape
+    assert int(pos_yx.max()) < cos_t.shape[0]
+    with torch.cuda.device(qkv.device):
+        _lib.check(_lib.lib().evw_qknorm_rope_f16(_lib.ptr(qkv), rows, heads, tokens_per_frame, _lib.ptr(pos_yx), _lib.ptr(q_gamma),
+                                                  _lib.ptr(q_beta), _lib.ptr(k_gamma), _lib.ptr(k_beta), _lib.ptr(cos_t),
+                                                  _lib.ptr(sin_t), eps, _lib.stream_ptr(qkv.device)), "evw_qknorm_rope_f16")
+    return qkv
+
+
+def bilinear_ac(src: torch.Tensor, H: int, W: int, out_dtype=torch.float16, addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """src fp32 [F, h, w, C] -> [F, H, W, C]: F.interpolate(mode="bilinear", align_corners=True), channels last, plus an
+    optional per-pixel addend fp32 [H*W, C] (evw_bilinear_ac_f32)."""
+    _lib.require_cuda(src, "src")
+    F_, h, w, C = src.shape
+    assert src.dtype == torch.float32 and (addend is None or (addend.dtype == torch.float32 and addend.numel() == H * W * C))
+    out = torch.empty((F_, H, W, C), dtype=out_dtype, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.lib().evw_bilinear_ac_f32(_lib.ptr(src), _lib.ptr(out), 1 if out_dtype == torch.float16 else 0,
+                                                  _lib.ptr(addend), F_, h, w, H, W, C, _lib.stream_ptr(src.device)),
+                   "evw_bilinear_ac_f32")
+    return out
+
+
+def relu_inplace_f16(x: torch.Tensor) -> torch.Tensor:
+    """x fp32 <- relu(x) in place; returns the fp16 copy (evw_relu_inplace_f16: nn.ReLU(inplace=True) feeding a convolution)."""
+    _lib.require_cuda(x, "x")
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() % 4 == 0
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().evw_relu_inplace_f16(_lib.ptr(x), _lib.ptr(out), x.numel(), _lib.stream_ptr(x.device)), "evw_relu_inplace_f16")
+    return out
+
+
+def adaln_modulate(xn: torch.Tensor, mod: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """gate * (xn * (1 + scale) + shift) + x with mod fp32 [rows, 3C] = (shift | scale | gate) (evw_adaln_modulate_f32)."""
+    _lib.require_cuda(x, "x")
+    rows, C = x.shape
+    assert xn.shape == x.shape and mod.shape == (rows, 3 * C) and all(t.dtype == torch.float32 for t in (xn, mod, x))
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().evw_adaln_modulate_f32(_lib.ptr(xn), _lib.ptr(mod), _lib.ptr(x), _lib.ptr(out), rows, C,
+                                                     _lib.stream_ptr(x.device)), "evw_adaln_modulate_f32")
+    return out
+
+
+def dpt_activate(x: torch.Tensor, n_ch: int, mode: str):
+    """x fp32 [rows, ld] -> (pts fp32 [rows, n_ch-1] through exp / inv_log, conf fp32 [rows] = 1 + exp) (evw_dpt_activate_f32)."""
+    _lib.require_cuda(x, "x")
+    rows, ld = x.shape
+    assert x.dtype == torch.float32
+    pts = torch.empty((rows, n_ch - 1), dtype=torch.float32, device=x.device)
+    conf = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().evw_dpt_activate_f32(_lib.ptr(x), rows, ld, n_ch, {"exp": 0, "inv_log": 1}[mode], _lib.ptr(pts),
+                                                   _lib.ptr(conf), _lib.stream_ptr(x.device)), "evw_dpt_activate_f32")
+    return pts, conf

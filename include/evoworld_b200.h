@@ -299,7 +299,8 @@ int evw_resize_pil_u8(const uint8_t* in, uint8_t* tmp, uint8_t* out, int N, int 
  * linears use evw_gemm_f16 and the LayerNorms evw_layer_norm_f16 (evoworld_b200/clip.py).
  * evw_small_attention_f16: softmax(scale q k^T) v per (image, head) over S <= 1024 tokens with any head width <= 256
  * (ViT-H: S = 257, 16 heads of 80): qkv fp16 [B*S, 3*heads*head_dim] (q | k | v) -> out fp16 [B*S, heads*head_dim].
- * evw_act_f16: x fp32 -> fp16 through the MLP activation, mode 0 = GELU (erf), 1 = quick_gelu. */
+ * evw_act_f16: x fp32 -> fp16 through an activation, mode 0 = GELU (erf), 1 = quick_gelu, 2 = ReLU, 3 = identity (cast),
+ * 4 = SiLU (2-4: VGGT's DPT residual units and camera-head modulation). */
 int evw_small_attention_f16(const void* qkv, void* out, int B, int S, int heads, int head_dim, float scale, void* stream);
 int evw_act_f16(const float* x, void* out, int64_t n, int mode, void* stream);
 
@@ -327,6 +328,31 @@ int evw_vae_decode(void* handle, const float* latents, float* frames, int N, int
                    void* workspace, int64_t workspace_bytes, void* stream);
 /* Kernel launches, algorithmic FLOPs and epilogue-fused GroupNorms of the current encode (0) / decode (1) plan. */
 int evw_vae_plan_info(void* handle, int mode, int64_t* launches, double* flops, int64_t* gn_fused);
+
+/* VGGT forward pieces (third_party/vggt/vggt/models/vggt.py:56-92 as called at
+ * unified_loop_consistency.py:114-136).  Linears / convolutions: evw_gemm_f16; frame and global attention (head width 64):
+ * evw_spatial_attention_f16; camera trunk attention: evw_small_attention_f16; LayerNorms: evw_layer_norm_f16 / _f32
+ * (evoworld_b200/vggt.py).
+ * evw_qknorm_rope_f16: layers/attention.py:54-58 in place on qkv fp16 [rows, 3*heads*64] — LayerNorm(64, eps) of every q and
+ *   k head (gamma / beta fp32 [64]) followed by the 2-D rotary embedding (layers/rope.py:116-188): token (row %
+ *   tokens_per_frame) has integer position pos_yx[tok] = (y, x); cos_t / sin_t fp32 [max_pos, 16] = cos / sin(pos * 100^(-j/16)).
+ * evw_bilinear_ac_f32: heads/dpt_head.py:463-484 (F.interpolate bilinear, align_corners=True) on channels-last src fp32
+ *   [F,h,w,C] -> dst [F,H,W,C] fp16 (out_fp16) or fp32, optional addend fp32 [H*W, C] added per pixel (the uv positional
+ *   embedding of dpt_head.py:258-259).  C a multiple of 4.
+ * evw_relu_inplace_f16: ResidualConvUnit's nn.ReLU(inplace=True) (heads/dpt_head.py:333,397,410): x fp32 [n] <- relu(x) in place
+ *   (the skip connection then adds relu(x)) and out fp16 [n] = the same values (the convolution's operand).  n % 4 == 0.
+ * evw_adaln_modulate_f32: heads/camera_head.py:118-122  out = gate * (xn * (1 + scale) + shift) + x, mod fp32 [rows, 3C] =
+ *   (shift | scale | gate).
+ * evw_dpt_activate_f32: heads/head_act.py:62-112 on x fp32 [rows, ld]: channels 0..n_ch-2 -> pts fp32 [rows, n_ch-1] (mode 0 =
+ *   exp, 1 = inv_log), channel n_ch-1 -> conf fp32 [rows] = 1 + exp. */
+int evw_qknorm_rope_f16(void* qkv, int64_t rows, int heads, int tokens_per_frame, const int* pos_yx, const float* q_gamma,
+                        const float* q_beta, const float* k_gamma, const float* k_beta, const float* cos_t, const float* sin_t,
+                        float eps, void* stream);
+int evw_bilinear_ac_f32(const float* src, void* dst, int out_fp16, const float* addend, int F, int h, int w, int H, int W, int C,
+                        void* stream);
+int evw_relu_inplace_f16(float* x, void* out, int64_t n, void* stream);
+int evw_adaln_modulate_f32(const float* xn, const float* mod, const float* x, float* out, int64_t rows, int C, void* stream);
+int evw_dpt_activate_f32(const float* x, int64_t rows, int ld, int n_ch, int mode, float* pts, float* conf, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,171 @@
+"""VGGT forward on the GPU (evoworld_b200/vggt.py) against (a) outputs of the REFERENCE's own modules on seeded weights
+(tests/golden/vggt_golden.npz) and (b) the fp32 oracle restatement (oracle/vggt_torch.py, pinned against the same golden
+vectors by tests/test_oracle_vggt.py) run on the same GPU with TF32 off, at sizes up to the full VGGT-1B at 392 x 518.
+
+Tolerance: fp16 GEMM / attention operands with fp32 accumulation and an fp32 residual stream (the reference itself runs the
+aggregator under bf16 autocast, unified_loop_consistency.py:131-136).  Predicted by the CPU emulation of the same rounding
+points (tests/test_vggt_host.py): tokens 5e-4, depth 7e-4, points 1e-3, pose 6e-4; asserted <= 2e-3 relative L2."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from evoworld_b200 import ops
+from evoworld_b200 import vggt as V
+from oracle import vggt_torch as O
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+import ops_emulation as E  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+TOL_VGGT = 2e-3
+CFG = O.SMALL_TEST_CONFIG
+
+
+def rel_l2(a, b):
+    if not isinstance(b, torch.Tensor):
+        b = torch.from_numpy(np.asarray(b))
+    return float((a.double().cpu() - b.double().cpu()).norm() / (b.double().norm() + 1e-30))
+
+
+def no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+# ----------------------------------------------------------------------------- kernels
+@pytest.mark.parametrize("frames,h0,w0,heads", [(3, 5, 7, 6), (2, 28, 37, 16), (1, 1, 1, 2)])
+def test_qknorm_rope(frames, h0, w0, heads, cuda_device, built_lib):
+    torch.manual_seed(0)
+    dev = cuda_device
+    P = 5 + h0 * w0
+    qkv = (torch.randn(frames * P, 3 * heads * 64, device=dev) * 2 + 0.3).half()
+    g = [torch.randn(64, device=dev) * 0.3 + 1 for _ in range(2)]
+    b = [torch.randn(64, device=dev) * 0.2 for _ in range(2)]
+    grid = torch.cartesian_prod(torch.arange(h0, device=dev), torch.arange(w0, device=dev)) + 1
+    pos = torch.cat([torch.zeros(5, 2, dtype=grid.dtype, device=dev), grid], 0)
+    cos_t, sin_t = V._rope_tables(max(h0, w0) + 1, 100.0, dev)
+    # the reference formulation (oracle.rope2d on [B, heads, N, 64]) of q and k, v untouched
+    C = heads * 64
+    want = qkv.clone().float()
+    for which in range(2):
+        t = qkv[:, which * C: (which + 1) * C].float().view(frames, P, heads, 64).transpose(1, 2)
+        t = F.layer_norm(t, (64,), g[which], b[which], 1e-5)
+        t = O.rope2d(t, pos[None].expand(frames, -1, -1), 100.0)
+        want[:, which * C: (which + 1) * C] = t.transpose(1, 2).reshape(frames * P, C)
+    got = ops.qknorm_rope_(qkv.clone(), heads, P, pos.to(torch.int32).contiguous(), g[0], b[0], g[1], b[1], cos_t, sin_t, 1e-5)
+    assert torch.equal(got[:, 2 * C:], qkv[:, 2 * C:])
+    assert rel_l2(got[:, : 2 * C], want[:, : 2 * C]) < 4e-4        # fp16 rounding of the result
+    assert float((got[:, : 2 * C].float() - want[:, : 2 * C]).abs().max()) < 6e-3
+
+
+@pytest.mark.parametrize("F_,h,w,H,W,C", [(2, 3, 4, 5, 7, 128), (3, 5, 7, 10, 14, 64), (1, 40, 56, 70, 98, 64), (1, 1, 1, 3, 2, 8),
+                                          (2, 7, 9, 7, 9, 4), (1, 224, 296, 392, 518, 128)])
+@pytest.mark.parametrize("out_dtype", [torch.float16, torch.float32])
+def test_bilinear_align_corners(F_, h, w, H, W, C, out_dtype, cuda_device, built_lib):
+    torch.manual_seed(1)
+    src = torch.randn(F_, h, w, C, device=cuda_device)
+    add = torch.randn(H * W, C, device=cuda_device)
+    want = F.interpolate(src.permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    got = ops.bilinear_ac(src, H, W, out_dtype)
+    tol = 4e-4 if out_dtype == torch.float16 else 2e-6
+    assert got.shape == (F_, H, W, C) and got.dtype == out_dtype and rel_l2(got, want) < tol
+    got = ops.bilinear_ac(src, H, W, out_dtype, addend=add)
+    assert rel_l2(got, want + add.view(1, H, W, C)) < tol
+
+
+def test_elementwise_kernels(cuda_device, built_lib):
+    torch.manual_seed(2)
+    dev = cuda_device
+    x = torch.randn(1000, 256, device=dev) * 2
+    for mode, f in (("relu", F.relu), ("identity", lambda t: t), ("silu", F.silu)):
+        assert rel_l2(ops.activation_f16(x, mode), f(x)) < 4e-4
+    y = x.clone()
+    h = ops.relu_inplace_f16(y)
+    assert torch.equal(y, F.relu(x)) and torch.equal(h, F.relu(x).half())
+    xn, mod = torch.randn(7, 768, device=dev), torch.randn(7, 3 * 768, device=dev)
+    assert rel_l2(ops.adaln_modulate(xn, mod, x[:7, :1].expand(7, 768).contiguous()), E.adaln_modulate(xn, mod, x[:7, :1].expand(7, 768))) < 1e-6
+    o = torch.randn(5000, 16, device=dev) * 2
+    o[0, :4] = 0
+    for mode, n_ch in (("exp", 2), ("inv_log", 4)):
+        pts, conf = ops.dpt_activate(o, n_ch, mode)
+        wp, wc = E.dpt_activate(o, n_ch, mode)
+        assert pts.shape == (5000, n_ch - 1) and rel_l2(pts, wp) < 1e-6 and rel_l2(conf, wc) < 1e-6
+
+
+# ----------------------------------------------------------------------------- the network
+def build(cfg, dev, seed, gpu_init=False):
+    mcfg = {k: v for k, v in cfg.items() if k != "seed"}
+    sd = V.random_state_dict(mcfg, seed=seed, device=dev if gpu_init else "cpu")
+    m = V.VGGT(**mcfg).to(dev)
+    m.load_state_dict(sd)
+    return m, {k: v.to(dev) for k, v in sd.items()}, mcfg
+
+
+def test_small_config_against_the_reference_modules(cuda_device, built_lib):
+    """Seeded weights and clip of tests/golden/make_vggt_golden.py: the CUDA path vs the REFERENCE Aggregator / CameraHead /
+    DPTHead outputs (fp32, CPU)."""
+    vg = np.load(Path(__file__).resolve().parent / "golden" / "vggt_golden.npz")
+    m, _, _ = build(CFG, cuda_device, CFG["seed"])
+    images = O.small_test_images().to(cuda_device)
+    toks, start = m.aggregator(images)
+    assert start == 5 and len(toks) == CFG["depth"]
+    errs = {f"tokens_{i}": rel_l2(t, vg[f"tokens_{i}"]) for i, t in enumerate(toks)}
+    out = m(images[0])
+    for k in ("depth", "depth_conf", "world_points", "world_points_conf"):
+        assert tuple(out[k].shape) == vg[k].shape, k
+        errs[k] = rel_l2(out[k], vg[k])
+    errs["pose_enc"] = rel_l2(out["pose_enc"], vg["pose_enc_3"])
+    print("vggt small vs reference:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < TOL_VGGT, errs
+    assert out["images"].shape == (1, 3, 3, 70, 98) and out["depth"].dtype == torch.float32
+    # chunked DPT == unchunked, run-to-run determinism
+    again = m(images[0], frames_chunk_size=2)
+    assert torch.equal(again["depth"], out["depth"]) and torch.equal(again["pose_enc"], out["pose_enc"])
+
+
+@pytest.mark.parametrize("B,S,H,W", [(2, 2, 56, 84), (1, 5, 98, 70), (1, 1, 70, 70)])
+def test_other_shapes_against_the_oracle(B, S, H, W, cuda_device, built_lib):
+    """Batch > 1, a single frame (no 'other frames' tokens), portrait and square clips (square 5 x 5 = the position table
+    itself, no resize) vs the oracle on the GPU."""
+    no_tf32()
+    m, sd, mcfg = build(CFG, cuda_device, 11)
+    g = torch.Generator(device="cpu"); g.manual_seed(B * 100 + S)
+    images = torch.rand((B, S, 3, H, W), generator=g).to(cuda_device)
+    with torch.no_grad():
+        want = O.vggt_forward(images, sd, mcfg)
+    out = m(images)
+    errs = {k: rel_l2(out[k], want[k]) for k in ("pose_enc", "depth", "depth_conf", "world_points", "world_points_conf")}
+    print(f"vggt B={B} S={S} {H}x{W}:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < TOL_VGGT, errs
+
+
+def test_vggt_1b_at_the_loop_resolution(cuda_device, built_lib):
+    """The full VGGT-1B architecture (random weights; 1.2 B parameters) on 3 frames of 392 x 518 — the resolution
+    load_and_preprocess_images hands to the model in the reference loop — vs the fp32 oracle on the same GPU."""
+    no_tf32()
+    cfg = dict(V.DEFAULT_CONFIG)
+    m, sd, mcfg = build(cfg, cuda_device, 5, gpu_init=True)
+    assert 1.15e9 < m.num_parameters() < 1.30e9
+    g = torch.Generator(device="cpu"); g.manual_seed(3)
+    low = torch.rand((3, 3, 28, 37), generator=g)
+    images = (F.interpolate(low, size=(392, 518), mode="bilinear") * 0.8 + 0.2 * torch.rand((3, 3, 392, 518), generator=g)).to(cuda_device)
+    with torch.no_grad():
+        want = O.vggt_forward(images, sd, mcfg)
+    m.free_master_parameters()
+    del sd
+    out = m(images)
+    errs = {k: rel_l2(out[k], want[k]) for k in ("pose_enc", "depth", "depth_conf", "world_points", "world_points_conf")}
+    print("vggt-1b 3 x 392 x 518:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert out["depth"].shape == (1, 3, 392, 518, 1) and out["world_points"].shape == (1, 3, 392, 518, 3)
+    assert max(errs.values()) < TOL_VGGT, errs
+
+
+def test_no_cpu_fallback(built_lib):
+    m = V.VGGT(**{k: v for k, v in CFG.items() if k != "seed"})
+    m.load_state_dict(V.random_state_dict(CFG, seed=1))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 2, 3, 70, 98))
