@@ -301,6 +301,9 @@ def main():
     ap.add_argument("--iter-frames", type=int, default=25, help="frames per clip of the iterative episode (the reference's 25)")
     ap.add_argument("--iter-steps", type=int, default=25, help="denoise steps per clip of the iterative episode (config 5: 50)")
     ap.add_argument("--iter-mode", default="incremental", choices=["incremental", "reference"])
+    ap.add_argument("--iter-vggt", dest="iter_vggt", action="store_true", default=True,
+                    help="iterative path: run the native VGGT-1B (random init) on the perspective frames of every segment")
+    ap.add_argument("--no-iter-vggt", dest="iter_vggt", action="store_false")
     ap.add_argument("--iter-episodes", type=int, default=1)
     ap.add_argument("--iter-warmup-steps", type=int, default=0,
                     help="denoise steps per clip in the untimed warm-up episode (0 = as many as the timed one)")

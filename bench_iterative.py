@@ -9,8 +9,11 @@ Per scene (one per rank), for segment 0, 1, 2:
   and, when another segment follows (:442-485):
   3. pano -> pers  Equi2Pers(384, 512, fov 90) with the look-at yaw of every frame                           [built: evw_equi2pers_u8]
                    reference: ALL frames so far (25, then 49); incremental: only the segment's new frames
-  4. VGGT-1B       depth / confidence / pose of the perspective frames                                       [NOT built: stand-in =
-                   seeded synthetic predictions already resident on the device]
+  4. VGGT-1B       Pillow-exact bicubic 384x512 -> 392x518 of EVERY frame so far (25, then 49: global attention couples  [built: evoworld_b200.vggt,
+                   all frames, so nothing is incremental here), then the 1.19 B-parameter network (random init)          random init]
+                   -> depth / confidence / pose.  With random weights these predictions describe no scene, so the
+                   geometry handed to stages 5-8 stays the seeded synthetic prediction set; the network's
+                   time is inside the timed region and its outputs are checked finite
   5. lift + pack   new frames appended to the device-resident PointMemory (evw_lift_pack_points)             [built]
   6. filter        joint 50th-percentile confidence filter + compaction (evw_conf_select)                    [built]
   7. align         similarity alignment of the GT trajectory (host numpy float64, 24 poses)                  [built: host]
@@ -42,6 +45,7 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
     from evoworld_b200.scheduler import EulerDiscreteScheduler
     from evoworld_b200.unet import UNetSpatioTemporalConditionModel
     from evoworld_b200.vae import AutoencoderKLTemporalDecoder
+    from evoworld_b200.vggt import VGGT, DEFAULT_CONFIG as VGGT_CFG, random_state_dict as vggt_random, run_vggt_inference
 
     T = args.iter_frames
     steps = args.iter_steps
@@ -59,7 +63,14 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
     sched = EulerDiscreteScheduler()
     sched.set_timesteps(steps)
     sig = [float(s) for s in sched.sigmas]
-    # stand-in for the one un-built network (VGGT-1B), resident on the device before the clock starts
+    vggt_net = None
+    if args.iter_vggt:
+        vcfg = dict(VGGT_CFG, point_head=False)   # the loop reads depth / depth_conf / pose_enc only (unified_loop_consistency.py:352-366)
+        vggt_net = VGGT(**vcfg).to(dev)
+        vggt_net.load_state_dict(vggt_random(vcfg, seed=2, device=dev))
+        vggt_net.free_master_parameters()
+    vggt_ok = []
+    # geometry of the scene (random VGGT weights describe none): seeded synthetic predictions, resident before the clock starts
     frames_u8 = torch.empty((T, 3, H, W), dtype=torch.uint8, device=dev)                         # decoded panoramas of a clip
     S_all = (n_seg - 1) * (T - 1) + 1                                                              # 49 frames after two segments
     p = synthetic.reprojection_predictions(S=S_all, H=392, W=518, seed=rank)
@@ -112,8 +123,18 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
             _, _, look_at = segments.calculate_segment_indices(seg)
             lo = 0 if mode == "reference" else first_new
             rots = [{"pitch": 0.0, "roll": 0.0, "yaw": segments.calculate_target_yaw(poses, i + 1, look_at)} for i in range(lo, n_frames)]
-            pers = e2p(all_frames[lo:n_frames], rots)                                                # -> VGGT (not built)
+            pers = e2p(all_frames[lo:n_frames], rots)
             e3 = ev(); e3.record(); mark("equi2pers", e2, e3)
+            if vggt_net is not None:
+                if lo != 0:   # VGGT sees every frame generated so far, re-warped towards this segment's look-at frame (:444-462)
+                    rots_all = [{"pitch": 0.0, "roll": 0.0, "yaw": segments.calculate_target_yaw(poses, i + 1, look_at)} for i in range(n_frames)]
+                    pers_all = e2p(all_frames[0:n_frames], rots_all)
+                else:
+                    pers_all = pers
+                vp = run_vggt_inference(vggt_net, pers_all.permute(0, 2, 3, 1).contiguous())
+                vggt_ok.append(torch.isfinite(vp["depth"]).all() & torch.isfinite(vp["pose_enc"]).all() & torch.isfinite(vp["depth_conf"]).all())
+                e3b = ev(); e3b.record(); mark("vggt", e3, e3b)
+                e3 = e3b
             if mode == "reference":
                 mem.reset()
                 sl = slice(0, n_frames)
@@ -173,6 +194,8 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
                    "mode": mode, "scenes_per_rank": 1,
                    "vae": "native AutoencoderKLTemporalDecoder (random init): temporal decode of every clip in chunks of 8, "
                           "encode of the 25 memory frames of the next clip",
-                   "stand_ins": "VGGT-1B is not built: seeded synthetic depth / confidence / pose predictions resident on the "
-                                "device (see bench_iterative.py)"},
+                   "vggt": ("native VGGT-1B (1.19 B parameters, random init, point head off) on every frame generated so far, inside the "
+                            "timed region; outputs finite: " + str(bool(all(bool(t) for t in vggt_ok))) if vggt_net is not None else "off (--no-iter-vggt)"),
+                   "stand_ins": "random VGGT weights describe no scene: the geometry consumed by lift / filter / splat is the seeded "
+                                "synthetic prediction set resident on the device (see bench_iterative.py)"},
     }

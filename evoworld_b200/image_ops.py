@@ -86,15 +86,17 @@ _PIL_PRECISION_BITS = 32 - 8 - 2
 _pil_tables: dict = {}
 
 
-def pil_resize_tables(in_size: int, out_size: int):
-    """Pillow's bilinear coefficient tables for one axis (libImaging/Resample.c precompute_coeffs + normalize_coeffs_8bpc, box =
-    the whole axis): (bounds int32 [out, 2] = (first input index, tap count), k int32 [out, ksize], ksize).  Double precision
-    with Pillow's operation order (the weights of an output sample are summed tap by tap)."""
+def pil_resize_tables(in_size: int, out_size: int, filt: str = "bilinear"):
+    """Pillow's bilinear / bicubic coefficient tables for one axis (libImaging/Resample.c precompute_coeffs +
+    normalize_coeffs_8bpc, box = the whole axis): (bounds int32 [out, 2] = (first input index, tap count), k int32 [out, ksize],
+    ksize).  Double precision with Pillow's operation order (the weights of an output sample are summed tap by tap)."""
     import numpy as np
 
+    if filt not in ("bilinear", "bicubic"):
+        raise ValueError(f"pil_resize_tables: filter {filt!r}")
     scale = in_size / out_size
     filterscale = max(scale, 1.0)
-    support = 1.0 * filterscale
+    support = (1.0 if filt == "bilinear" else 2.0) * filterscale
     ksize = int(math.ceil(support)) * 2 + 1
     ss = 1.0 / filterscale
     center = 0.0 + (np.arange(out_size, dtype=np.float64) + 0.5) * scale
@@ -104,19 +106,23 @@ def pil_resize_tables(in_size: int, out_size: int):
     ww = np.zeros(out_size, dtype=np.float64)
     for t in range(ksize):
         w = np.abs((t + xmin - center + 0.5) * ss)
-        w = np.where(w < 1.0, 1.0 - w, 0.0)
+        if filt == "bilinear":
+            w = np.where(w < 1.0, 1.0 - w, 0.0)
+        else:  # Resample.c bicubic_filter, a = -0.5
+            a = -0.5
+            w = np.where(w < 1.0, ((a + 2.0) * w - (a + 3.0)) * w * w + 1, np.where(w < 2.0, (((w - 5) * w + 8) * w - 4) * a, 0.0))
         w = np.where(t < xmax, w, 0.0)
         k[:, t] = w
         ww = ww + w
     k = np.where(ww[:, None] != 0.0, k / np.where(ww == 0.0, 1.0, ww)[:, None], k)
-    kk = np.trunc(0.5 + k * float(1 << _PIL_PRECISION_BITS)).astype(np.int32)
+    kk = np.trunc(np.where(k < 0, -0.5, 0.5) + k * float(1 << _PIL_PRECISION_BITS)).astype(np.int32)
     bounds = np.stack([xmin, xmax], axis=1).astype(np.int32)
     return bounds, kk, ksize
 
 
-def resize_pil_u8(images: torch.Tensor, height: int, width: int) -> torch.Tensor:
+def resize_pil_u8(images: torch.Tensor, height: int, width: int, filt: str = "bilinear") -> torch.Tensor:
     """uint8 [N, H, W, 3] (or [H, W, 3]) on a CUDA device -> uint8 [N, height, width, 3], bit-identical to
-    `PIL.Image.resize((width, height), BILINEAR)` of every image — i.e. to `transforms.Resize((height, width))` on the PIL copy
+    `PIL.Image.resize((width, height), BILINEAR | BICUBIC)` of every image — i.e. to `transforms.Resize((height, width))` on the PIL copy
     (evw_resize_pil_u8).  Tables are cached per (size pair, device)."""
     from . import _lib
 
@@ -127,10 +133,10 @@ def resize_pil_u8(images: torch.Tensor, height: int, width: int) -> torch.Tensor
         raise ValueError(f"resize_pil_u8 expects uint8 [N,H,W,3], got {images.dtype} {tuple(images.shape)}")
     x = x.contiguous()
     N, H, W, _ = x.shape
-    key = (H, W, height, width, str(x.device))
+    key = (H, W, height, width, str(x.device), filt)
     if key not in _pil_tables:
-        bx, kx, ksx = pil_resize_tables(W, width)
-        by, ky, ksy = pil_resize_tables(H, height)
+        bx, kx, ksx = pil_resize_tables(W, width, filt)
+        by, ky, ksy = pil_resize_tables(H, height, filt)
         to = lambda a: torch.from_numpy(a).contiguous().to(x.device)
         _pil_tables[key] = (to(bx), to(kx), ksx, to(by), to(ky), ksy)
     bx, kx, ksx, by, ky, ksy = _pil_tables[key]
@@ -141,3 +147,19 @@ def resize_pil_u8(images: torch.Tensor, height: int, width: int) -> torch.Tensor
                                                 _lib.ptr(kx), ksx, _lib.ptr(by), _lib.ptr(ky), ksy, _lib.stream_ptr(x.device)),
                    "evw_resize_pil_u8")
     return out[0] if single else out
+
+
+def vggt_preprocess_u8(frames: torch.Tensor) -> torch.Tensor:
+    """`load_and_preprocess_images(paths)` (third_party/vggt/vggt/utils/load_fn.py:135-170, mode "crop") for RGB frames uint8
+    [N, H, W, 3] already on the device — the reference writes them to PNG files and reads them back
+    (unified_loop_consistency.py:339-348; PNG is lossless): width -> 518, height -> round(H * 518 / W / 14) * 14 with Pillow's
+    BICUBIC (bit-exact: evw_resize_pil_u8 with the bicubic tables), ToTensor, centre crop of the height to 518
+    -> float32 [N, 3, h, 518] in [0, 1]."""
+    N, H, W, _ = frames.shape
+    new_w = 518
+    new_h = round(H * (new_w / W) / 14) * 14
+    x = resize_pil_u8(frames, new_h, new_w, "bicubic").permute(0, 3, 1, 2).to(torch.float32) / 255.0
+    if new_h > 518:
+        y0 = (new_h - 518) // 2
+        x = x[:, :, y0:y0 + 518]
+    return x.contiguous()

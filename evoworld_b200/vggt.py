@@ -322,6 +322,8 @@ class VGGT:
         w = P[v + "patch_embed.proj.weight"].reshape(cfg["embed_dim"], -1)             # (c, ky, kx) order = unfold's
         T["patch.weight"] = h(F.pad(w, (0, (-w.shape[1]) % 64)))
         T["patch.bias"] = f(P[v + "patch_embed.proj.bias"])
+        T["vit.cls"] = f(P[v + "cls_token"][0, 0]); T["vit.reg"] = f(P[v + "register_tokens"][0]); T["vit.pos"] = f(P[v + "pos_embed"])
+        T["agg.camera"] = f(P["aggregator.camera_token"][0, :, 0]); T["agg.register"] = f(P["aggregator.register_token"][0])
         for i in range(cfg["vit_depth"]):
             self._pack_block(T, f"{v}blocks.{i}.")
         T[v + "norm.weight"] = f(P[v + "norm.weight"]); T[v + "norm.bias"] = f(P[v + "norm.bias"])
@@ -334,6 +336,7 @@ class VGGT:
         for n in ("token_norm", "trunk_norm"):
             T[c + n + ".weight"] = f(P[c + n + ".weight"]); T[c + n + ".bias"] = f(P[c + n + ".bias"])
         dc = 2 * cfg["embed_dim"]
+        T[c + "empty_pose"] = f(P[c + "empty_pose_tokens"].reshape(1, 9))
         T[c + "ones"] = torch.ones(dc, device=self._device); T[c + "zeros"] = torch.zeros(dc, device=self._device)
         T[c + "embed_pose.weight"] = h(F.pad(P[c + "embed_pose.weight"], (0, 64 - 9))); T[c + "embed_pose.bias"] = f(P[c + "embed_pose.bias"])
         T[c + "mod.weight"] = h(P[c + "poseLN_modulation.1.weight"]); T[c + "mod.bias"] = f(P[c + "poseLN_modulation.1.bias"])
@@ -386,7 +389,7 @@ class VGGT:
         interpolate_offset 0): (class-token row [d], patch rows [h0 w0, d]) — parameter preparation, cached per grid."""
         key = ("pos", h0, w0)
         if key not in self._cache:
-            pe = self._params["aggregator.patch_embed.pos_embed"].float()
+            pe = self._packed["vit.pos"]
             N = pe.shape[1] - 1
             M = int(math.sqrt(N))
             patch = pe[:, 1:]
@@ -422,8 +425,8 @@ class VGGT:
         # PatchEmbed conv (k = stride = patch) + bias + the patch rows of the position table in one GEMM epilogue
         patches = ops.gemm_f16(a, T["patch.weight"], bias=T["patch.bias"], rowvec=patch_pos, rv_div=1, rv_mod=n, out_dtype=torch.float32)
         tok = torch.empty((Fr, P, d), dtype=torch.float32, device=dev)
-        tok[:, 0] = self._params[v + "cls_token"][0, 0] + cls_pos
-        tok[:, 1: 1 + r] = self._params[v + "register_tokens"][0]
+        tok[:, 0] = T["vit.cls"] + cls_pos
+        tok[:, 1: 1 + r] = T["vit.reg"]
         tok[:, 1 + r:] = patches.view(Fr, n, d)
         xs = tok.view(Fr * P, d)
         heads = cfg["vit_heads"]
@@ -435,8 +438,8 @@ class VGGT:
         first[1:] = 1
         first = first.repeat(B)
         tok = torch.empty((Fr, P, d), dtype=torch.float32, device=dev)
-        tok[:, 0] = self._params["aggregator.camera_token"][0, :, 0][first]
-        tok[:, 1: 1 + r] = self._params["aggregator.register_token"][0][first]
+        tok[:, 0] = T["agg.camera"][first]
+        tok[:, 1: 1 + r] = T["agg.register"][first]
         tok[:, 1 + r:] = xs[:, 1 + r:]
         xs = tok.view(Fr * P, d)
         key = ("rope", h0, w0)
@@ -493,7 +496,7 @@ class VGGT:
         outs = []
         attn = lambda qkv: ops.small_attention(qkv, B, S, heads, hd, hd ** -0.5)
         for _ in range(cfg["camera_iterations"]):
-            inp = self._params[c + "empty_pose_tokens"].reshape(1, 9).expand(rows, 9) if pred is None else pred
+            inp = T[c + "empty_pose"].expand(rows, 9) if pred is None else pred
             a = torch.zeros((rows, 64), dtype=torch.float16, device=x.device)
             a[:, :9] = inp
             emb = ops.gemm_f16(a, T[c + "embed_pose.weight"], bias=T[c + "embed_pose.bias"], out_dtype=torch.float32)
@@ -619,3 +622,28 @@ class VGGT:
         return out
 
     __call__ = forward
+
+
+@torch.no_grad()
+def run_vggt_inference(model: VGGT, perspective_frames, lift_dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """`UnifiedLoopConsistencyPipeline.run_vggt_inference` (unified_loop_consistency.py:336-367) with everything resident on
+    the device: RGB frames uint8 [N, H, W, 3] (a CUDA tensor, or a list of host arrays as the reference passes) -> the
+    preprocessing of load_and_preprocess_images without the PNG round trip (image_ops.vggt_preprocess_u8, Pillow-exact) -> VGGT ->
+    pose encoding to extrinsic / intrinsic (:352) -> batch dimension squeezed (:357-362) -> `world_points_from_depth` by the
+    depth lift (:366, evw_lift_depth).  Returns CUDA tensors (the reference converts to numpy at this point)."""
+    import numpy as np
+
+    from . import image_ops
+    from .geometry import pose_encoding_to_extri_intri
+    from .lift import lift_depth_device
+
+    if not isinstance(perspective_frames, torch.Tensor):
+        perspective_frames = torch.from_numpy(np.stack([np.asarray(f).astype(np.uint8) for f in perspective_frames]))
+    frames = perspective_frames.to(model.device, non_blocking=True)
+    images = image_ops.vggt_preprocess_u8(frames)[None]
+    preds = model(images)
+    extr, intr = pose_encoding_to_extri_intri(preds["pose_enc"], images.shape[-2:])
+    preds["extrinsic"], preds["intrinsic"] = extr, intr
+    out = {k: (v[0] if isinstance(v, torch.Tensor) else v) for k, v in preds.items()}
+    out["world_points_from_depth"] = lift_depth_device(out["depth"], out["extrinsic"], out["intrinsic"], out_dtype=lift_dtype)
+    return out

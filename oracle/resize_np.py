@@ -20,12 +20,33 @@ import numpy as np
 PRECISION_BITS = 32 - 8 - 2
 
 
-def coeffs(in_size: int, out_size: int):
-    """Resample.c precompute_coeffs + normalize_coeffs_8bpc for the bilinear filter over the whole axis (box = full image):
-    returns (bounds int32 [out, 2] = (first input index, tap count), kk int32 [out, ksize], ksize)."""
+def _bilinear(x: float) -> float:
+    x = abs(x)
+    return 1.0 - x if x < 1.0 else 0.0
+
+
+def _bicubic(x: float) -> float:
+    """Resample.c bicubic_filter (a = -0.5, support 2) — `Image.resize(..., BICUBIC)`, the resize of
+    third_party/vggt/vggt/utils/load_fn.py:166."""
+    a = -0.5
+    x = abs(x)
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+FILTERS = {"bilinear": (_bilinear, 1.0), "bicubic": (_bicubic, 2.0)}
+
+
+def coeffs(in_size: int, out_size: int, filt: str = "bilinear"):
+    """Resample.c precompute_coeffs + normalize_coeffs_8bpc for the bilinear / bicubic filter over the whole axis (box = full
+    image): returns (bounds int32 [out, 2] = (first input index, tap count), kk int32 [out, ksize], ksize)."""
+    fn, base_support = FILTERS[filt]
     scale = in_size / out_size
     filterscale = max(scale, 1.0)
-    support = 1.0 * filterscale
+    support = base_support * filterscale
     ksize = int(math.ceil(support)) * 2 + 1
     bounds = np.zeros((out_size, 2), dtype=np.int32)
     kk = np.zeros((out_size, ksize), dtype=np.int32)
@@ -42,8 +63,7 @@ def coeffs(in_size: int, out_size: int):
         k = [0.0] * ksize
         ww = 0.0
         for x in range(xmax):
-            w = abs((x + xmin - center + 0.5) * ss)
-            w = 1.0 - w if w < 1.0 else 0.0
+            w = fn((x + xmin - center + 0.5) * ss)
             k[x] = w
             ww += w
         for x in range(xmax):
@@ -55,9 +75,9 @@ def coeffs(in_size: int, out_size: int):
     return bounds, kk, ksize
 
 
-def _pass(img: np.ndarray, axis: int, out_size: int) -> np.ndarray:
+def _pass(img: np.ndarray, axis: int, out_size: int, filt: str = "bilinear") -> np.ndarray:
     """One 8-bit resampling pass along `axis` of a [H, W, C] uint8 image."""
-    bounds, kk, ksize = coeffs(img.shape[axis], out_size)
+    bounds, kk, ksize = coeffs(img.shape[axis], out_size, filt)
     src = np.moveaxis(img, axis, 0).astype(np.int64)
     out = np.empty((out_size,) + src.shape[1:], dtype=np.uint8)
     for i in range(out_size):
@@ -69,12 +89,32 @@ def _pass(img: np.ndarray, axis: int, out_size: int) -> np.ndarray:
     return np.moveaxis(out, 0, axis)
 
 
-def resize_bilinear_u8(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
-    """[H, W, C] uint8 -> [out_h, out_w, C] uint8 exactly as PIL.Image.resize((out_w, out_h), BILINEAR): horizontal pass first
-    (skipped when the width does not change), then the vertical one."""
+def resize_u8(img: np.ndarray, out_h: int, out_w: int, filt: str = "bilinear") -> np.ndarray:
+    """[H, W, C] uint8 -> [out_h, out_w, C] uint8 exactly as PIL.Image.resize((out_w, out_h), BILINEAR | BICUBIC): horizontal
+    pass first (skipped when the width does not change), then the vertical one."""
     x = img
     if x.shape[1] != out_w:
-        x = _pass(x, 1, out_w)
+        x = _pass(x, 1, out_w, filt)
     if x.shape[0] != out_h:
-        x = _pass(x, 0, out_h)
+        x = _pass(x, 0, out_h, filt)
     return np.ascontiguousarray(x)
+
+
+def resize_bilinear_u8(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    return resize_u8(img, out_h, out_w, "bilinear")
+
+
+def vggt_preprocess(frames_u8: np.ndarray) -> np.ndarray:
+    """third_party/vggt/vggt/utils/load_fn.py:135-170 (`load_and_preprocess_images`, mode "crop") on RGB frames uint8
+    [N, H, W, 3] of one size: width -> 518, height -> round(H * 518 / W / 14) * 14 by PIL BICUBIC, ToTensor, centre crop of the
+    height to 518 -> float32 [N, 3, h, 518] in [0, 1].  (The reference reaches it through a lossless PNG round trip,
+    unified_loop_consistency.py:339-348.)"""
+    N, H, W, _ = frames_u8.shape
+    new_w = 518
+    new_h = round(H * (new_w / W) / 14) * 14
+    out = np.stack([resize_u8(f, new_h, new_w, "bicubic") for f in frames_u8]).astype(np.float32) / 255.0
+    out = out.transpose(0, 3, 1, 2)
+    if new_h > 518:
+        y0 = (new_h - 518) // 2
+        out = out[:, :, y0:y0 + 518]
+    return np.ascontiguousarray(out)

@@ -53,3 +53,26 @@ def test_memory_panoramas(cuda_device, built_lib):
         resize_pil_u8(x.float(), 576, 1024)
     with pytest.raises(RuntimeError):
         resize_pil_u8(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), 4, 4)
+
+
+@pytest.mark.parametrize("N,H,W,h,w", [(2, 384, 512, 392, 518), (1, 37, 53, 11, 20), (1, 31, 17, 64, 40), (2, 9, 300, 3, 7)])
+def test_bicubic_resize_equals_pillow(N, H, W, h, w, cuda_device, built_lib):
+    """The same kernels with Pillow's BICUBIC tables (negative coefficients): the resize in front of VGGT (load_fn.py:166)."""
+    from PIL import Image
+
+    rng = np.random.default_rng(N * 11 + H)
+    imgs = rng.integers(0, 256, (N, H, W, 3), dtype=np.uint8)
+    imgs[:, : H // 3] = 255
+    imgs[:, -(H // 4):] = 0
+    got = resize_pil_u8(torch.from_numpy(imgs).to(cuda_device), h, w, "bicubic").cpu().numpy()
+    for i in range(N):
+        assert np.array_equal(got[i], np.asarray(Image.fromarray(imgs[i]).resize((w, h), Image.BICUBIC))), f"image {i}"
+
+
+def test_vggt_preprocess(cuda_device, built_lib):
+    from evoworld_b200.image_ops import vggt_preprocess_u8
+
+    frames = np.random.default_rng(9).integers(0, 256, (5, 384, 512, 3), dtype=np.uint8)
+    got = vggt_preprocess_u8(torch.from_numpy(frames).to(cuda_device))
+    assert got.shape == (5, 3, 392, 518) and got.dtype == torch.float32
+    assert np.array_equal(got.cpu().numpy(), R.vggt_preprocess(frames))

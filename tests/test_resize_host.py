@@ -49,3 +49,59 @@ def test_product_tables_equal_the_restatement(n_in, n_out):
     b0, k0, s0 = R.coeffs(n_in, n_out)
     b1, k1, s1 = pil_resize_tables(n_in, n_out)
     assert s0 == s1 and np.array_equal(b0, b1) and np.array_equal(k0, k1)
+
+
+BICUBIC_CASES = [(384, 512, 392, 518), (100, 200, 58, 102), (37, 53, 11, 20), (31, 17, 64, 40), (9, 300, 3, 7), (50, 50, 50, 50)]
+
+
+@pytest.mark.parametrize("H,W,h,w", BICUBIC_CASES)
+def test_bicubic_restatement_equals_pillow(H, W, h, w):
+    """Pillow's BICUBIC (negative lobes, support 2): the resize of load_and_preprocess_images (vggt/utils/load_fn.py:166)."""
+    from PIL import Image
+
+    from evoworld_b200.image_ops import pil_resize_tables
+
+    rng = np.random.default_rng(H)
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    img[: H // 3] = 255
+    img[-(H // 4):] = 0
+    want = np.asarray(Image.fromarray(img).resize((w, h), Image.BICUBIC))
+    assert np.array_equal(R.resize_u8(img, h, w, "bicubic"), want)
+    for a, b in ((W, w), (H, h)):
+        t0, t1 = R.coeffs(a, b, "bicubic"), pil_resize_tables(a, b, "bicubic")
+        assert t0[2] == t1[2] and np.array_equal(t0[0], t1[0]) and np.array_equal(t0[1], t1[1])
+    assert (R.coeffs(W, w, "bicubic")[1] < 0).any() or w == W
+
+
+def test_vggt_preprocess_equals_the_reference_loader(tmp_path):
+    """oracle.vggt_preprocess against the loader itself: PNG files -> load_and_preprocess_images (imported from the reference
+    checkout when it is present, else its PIL / ToTensor steps written out here)."""
+    import os
+    import sys
+
+    import torch
+    from PIL import Image
+
+    rng = np.random.default_rng(3)
+    frames = rng.integers(0, 256, (3, 384, 512, 3), dtype=np.uint8)
+    paths = []
+    for i, f in enumerate(frames):
+        paths.append(str(tmp_path / f"temp_{i:03d}.png"))
+        Image.fromarray(f).save(paths[-1])
+    got = R.vggt_preprocess(frames)
+    assert got.shape == (3, 3, 392, 518) and got.dtype == np.float32
+    ref_root = "/root/reference/third_party/vggt"
+    if os.path.isdir(ref_root):
+        sys.path.insert(0, ref_root)
+        try:
+            from vggt.utils.load_fn import load_and_preprocess_images
+
+            want = load_and_preprocess_images(paths).numpy()
+        finally:
+            sys.path.remove(ref_root)
+    else:
+        want = np.stack([np.asarray(Image.open(p).convert("RGB").resize((518, 392), Image.Resampling.BICUBIC), dtype=np.float32) / 255.0
+                         for p in paths]).transpose(0, 3, 1, 2)
+    assert np.array_equal(got, want)
+    tall = R.vggt_preprocess(rng.integers(0, 256, (1, 600, 400, 3), dtype=np.uint8))   # height 777 -> centre crop to 518
+    assert tall.shape == (1, 3, 518, 518)

@@ -78,6 +78,7 @@ def main():
     ap.add_argument("--width", type=int, default=518)
     ap.add_argument("--no-eager", action="store_true")
     ap.add_argument("--no-point-head", action="store_true")
+    ap.add_argument("--profile-once", action="store_true", help="one warm forward, then one forward between cudaProfilerStart / Stop (ncu --profile-from-start off)")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -89,6 +90,15 @@ def main():
     m.load_state_dict(sd)
     m._pack()
     images = torch.rand((1, a.frames, 3, a.height, a.width), device=dev)
+    if a.profile_once:
+        m.free_master_parameters()
+        m(images)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        m(images)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     with Counter() as c:
         m(images)
     torch.cuda.synchronize()
