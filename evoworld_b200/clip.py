@@ -243,8 +243,11 @@ class CLIPVisionModelWithProjection:
             att = ops.small_attention(qkv, B, S, heads, hd, scale)
             hs = ops.gemm_f16(att, T[f"{l}.out.weight"], bias=T[f"{l}.out.bias"], res1=hs, out_dtype=torch.float32)
             n2 = ops.layer_norm(hs, T[f"{l}.layer_norm2.weight"], T[f"{l}.layer_norm2.bias"], eps)
-            f1 = ops.gemm_f16(n2, T[f"{l}.fc1.weight"], bias=T[f"{l}.fc1.bias"], out_dtype=torch.float32)
-            act = ops.activation_f16(f1, cfg["hidden_act"])
+            if cfg["hidden_act"] == "gelu":   # GELU in the GEMM epilogue: no fp32 intermediate, no activation pass
+                act = ops.gemm_f16(n2, T[f"{l}.fc1.weight"], bias=T[f"{l}.fc1.bias"], act="gelu", out_dtype=torch.float16)
+            else:
+                f1 = ops.gemm_f16(n2, T[f"{l}.fc1.weight"], bias=T[f"{l}.fc1.bias"], out_dtype=torch.float32)
+                act = ops.activation_f16(f1, cfg["hidden_act"])
             hs = ops.gemm_f16(act, T[f"{l}.fc2.weight"], bias=T[f"{l}.fc2.bias"], res1=hs, out_dtype=torch.float32)
         last = hs.view(B, S, d)
         pooled = ops.layer_norm(last[:, 0].contiguous(), T["post_layernorm.weight"], T["post_layernorm.bias"], eps)   # fp16 [B, d]

@@ -378,7 +378,7 @@ __device__ __forceinline__ void stage_store16(StoreCtx& sc, const float (&v)[16]
   ++sc.count;
 }
 
-template <bool RV, bool R1, bool R2, bool RT, bool ST, bool TS>
+template <bool RV, bool R1, bool R2, bool RT, bool ST, bool TS, bool GL = false>
 __device__ __forceinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_addr, const float* bs, int cgrp, int NG, int nsteps,
                                           bool row_ok, int ncols, long long out_off, long long rv_off, bool wide_ok,
                                           uint32_t bar_full, uint32_t phase, const ResRing& rr, const StatsCtx& sx, StoreCtx& sc) {
@@ -460,6 +460,10 @@ __device__ __forceinline__ void epi_plain(const GemmEpilogue& ep, uint32_t t_add
             for (int i = 0; i < 8; ++i) v[8 * hf + i] = fmaf(ep.s2, r2[i], v[8 * hf + i]);
           }
         }
+      }
+      if constexpr (GL) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
       }
       if constexpr (ST) {
 #pragma unroll
@@ -893,7 +897,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constan
         rr.base = res_base; rr.full_bar = res_full_bar(0); rr.empty_bar = res_empty_bar(0);
         rr.slots_mask = (uint32_t)(P.res_slots - 1); rr.shift = (uint32_t)P.res_shift;
         rr.box0 = (uint32_t)it * (uint32_t)(P.block_n >> 5); rr.row = r; rr.lane = lane;
-        epi_plain<(kEpi & 1) != 0, (kEpi & 2) != 0, (kEpi & 4) != 0, kResTma, kStats, kStoreTma>(
+        epi_plain<(kEpi & 1) != 0, (kEpi & 2) != 0, (kEpi & 4) != 0, kResTma, kStats, kStoreTma, (kEpi & 128) != 0>(
             ep, t_addr, bs, cgrp, NG, nsteps, row_ok, ncols, out_off, rv_off, wide_ok, bar_full, acc_phase, rr, sx, sc);
       }
       tc_fence_before();
@@ -1023,6 +1027,8 @@ int gemm_plan(GemmOp* op, const GemmProblem& pr) {
   EVW_CHECK_ARG(bn % 16 == 0 && bn >= 16 && bn <= 256, "gemm: BLOCK_N=%d invalid", bn);
   EVW_CHECK_ARG(!pr.ep.geglu || (bn % 32 == 0 && pr.N % 32 == 0), "gemm: GEGLU needs N and BLOCK_N multiples of 32");
   EVW_CHECK_ARG(!pr.ep.res2 || pr.ep.res1, "gemm: res2 needs res1 (the two-residual epilogue loads both)");
+  EVW_CHECK_ARG(!pr.ep.act || (pr.ep.act == 1 && !pr.ep.geglu && !pr.ep.res1 && !pr.ep.rowvec && !pr.ep.out_lo && !pr.ep.gn_stats),
+                "gemm: the GELU epilogue takes no row vector, residual, split output or GroupNorm statistics");
   EVW_CHECK_ARG(!pr.ep.out_lo || (pr.ep.out_fp16 && !pr.ep.geglu && pr.N % 16 == 0 && ((uintptr_t)pr.ep.out_lo & 15) == 0),
                 "gemm: out_lo needs an fp16, non-GEGLU output with N a multiple of 16");
   P.block_n = bn;
@@ -1276,13 +1282,15 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream) {
    tc_gemm_kernel<C, kEpiWarpsDefault, 64 + 16 + 2>, tc_gemm_kernel<C, kEpiWarpsDefault, 64 + 16 + 3>,                           \
    tc_gemm_kernel<C, kEpiWarpsDefault, 64 + 16 + 6>, tc_gemm_kernel<C, kEpiWarpsDefault, 64 + 16 + 7>,                           \
    tc_gemm_kernel<C, kEpiWarpsDefault, 64 + 32 + 0>, tc_gemm_kernel<C, kEpiWarpsDefault, 64 + 32 + 1>,                           \
-   tc_gemm_kernel<C, kEpiWarpsDefault, 64 + 32 + 16 + 2>}
-  static const KernelFn fns[2][29] = {EVW_GEMM_ROW(false), EVW_GEMM_ROW(true)};
+   tc_gemm_kernel<C, kEpiWarpsDefault, 64 + 32 + 16 + 2>,                                                                        \
+   /* 29, 30: GELU of (acc + bias), no other operand: direct stores / TMA stores */                                             \
+   tc_gemm_kernel<C, kEpiWarpsDefault, 128 + 0>, tc_gemm_kernel<C, kEpiWarpsDefault, 128 + 64 + 0>}
+  static const KernelFn fns[2][31] = {EVW_GEMM_ROW(false), EVW_GEMM_ROW(true)};
 #undef EVW_GEMM_ROW
   static bool attr_set = false;
   if (!attr_set) {
     for (int c = 0; c < 2; ++c)
-      for (int w = 0; w < 29; ++w) {
+      for (int w = 0; w < 31; ++w) {
         cudaError_t e = cudaFuncSetAttribute(fns[c][w], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {
           set_error("cudaFuncSetAttribute(tc_gemm_kernel): %s", cudaGetErrorString(e));
@@ -1326,6 +1334,7 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream) {
     static const int twin[17] = {17, 18, 19, 20, -1, -1, 21, -1, 22, 23, 24, 25, -1, -1, 26, 27, 28};
     if (twin[epi] >= 0) epi = twin[epi];
   }
+  if (P.ep.act) epi = op.store_tma ? 30 : 29;  // gemm_plan admits it only without row vector / residual / statistics / GEGLU
   if (op.strided_out && epi < 17) {
     set_error("gemm: strided output view without a TMA-store kernel for this epilogue");
     return EVW_ERR_INVALID;
@@ -1389,7 +1398,10 @@ extern "C" int evw_gemm_f16_gn(const void* a0, const void* a1, const void* w, in
   pr.ep.out = out; pr.ep.out_fp16 = out_fp16; pr.ep.out_lo = out_lo; pr.ep.bias = bias; pr.ep.rowvec = rowvec;
   pr.ep.rv_div = rv_div > 0 ? rv_div : 1; pr.ep.rv_mod = rv_mod > 0 ? rv_mod : 1;
   pr.ep.res1 = res1; pr.ep.res1_fp16 = res1_fp16; pr.ep.s1 = s1; pr.ep.res2 = res2; pr.ep.s2 = s2; pr.ep.s0 = s0;
-  pr.ep.geglu = geglu;
+  EVW_CHECK_ARG(geglu >= 0 && geglu <= 2, "evw_gemm_f16: geglu must be 0, 1 (GEGLU) or 2 (GELU of acc + bias)");
+  pr.ep.geglu = geglu == 1 ? 1 : 0;
+  pr.ep.act = geglu == 2 ? 1 : 0;
+  EVW_CHECK_ARG(!(pr.ep.act && gn_stats), "evw_gemm_f16_gn: no GroupNorm statistics with the GELU epilogue");
   evw::GemmOp op;
   int rc = evw::gemm_plan(&op, pr);
   if (rc) return rc;

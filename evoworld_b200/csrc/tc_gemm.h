@@ -28,6 +28,8 @@ struct GemmEpilogue {
   float s2 = 1.f;
   float s0 = 1.f;
   int geglu = 0;
+  int act = 0;  // 1: exact GELU applied to s0 * acc + bias (epilogues without row vector / residuals only): the MLP fc1 of the
+                // ViT-style blocks (VGGT, CLIP) writes its fp16 activation directly instead of an fp32 tensor + an activation pass
   // GroupNorm(32) statistics of the OUTPUT, accumulated by the epilogue so that the consumer GroupNorm skips its statistics
   // pass over the tensor: gn_stats double [instances, 32, 2] (sum, sum of squares; cleared by gemm_launch), instance of a
   // row = row / rows_per_inst, group of a column = n / gn_cg (gn_cg = N / 32).  Set through gemm_enable_gn_stats().

@@ -158,7 +158,10 @@ def vggt_preprocess_u8(frames: torch.Tensor) -> torch.Tensor:
     N, H, W, _ = frames.shape
     new_w = 518
     new_h = round(H * (new_w / W) / 14) * 14
-    x = resize_pil_u8(frames, new_h, new_w, "bicubic").permute(0, 3, 1, 2).to(torch.float32) / 255.0
+    key = ("to_tensor", str(frames.device))
+    if key not in _pil_tables:   # ToTensor's byte / 255 as a table computed on the host: a CUDA division by a scalar multiplies by 1 / 255
+        _pil_tables[key] = (torch.arange(256, dtype=torch.float32) / 255).to(frames.device)
+    x = _pil_tables[key][resize_pil_u8(frames, new_h, new_w, "bicubic").permute(0, 3, 1, 2).to(torch.int32)]
     if new_h > 518:
         y0 = (new_h - 518) // 2
         x = x[:, :, y0:y0 + 518]

@@ -23,8 +23,9 @@ def gemm_f16(a0: torch.Tensor, w: torch.Tensor, taps: Sequence[Tuple[int, int, i
              s1: float = 1.0, res2=None, s2: float = 1.0, s0: float = 1.0, geglu: bool = False,
              out_dtype=torch.float16, block_n: int = 0, out: Optional[torch.Tensor] = None,
              out_lo: Optional[torch.Tensor] = None, gn_stats: Optional[torch.Tensor] = None,
-             gn_rows_per_inst: int = 0) -> torch.Tensor:
+             gn_rows_per_inst: int = 0, act: Optional[str] = None) -> torch.Tensor:
     """a0 fp16 [B,T,Y,X,C0] (or [M,C0] for a linear layer), w fp16 [N,K_total] -> [rows, N or N/2].
+    act="gelu": exact GELU of s0 * (acc + bias) in the epilogue (no row vector / residual operands).
     gn_stats (float64 [rows / gn_rows_per_inst, 32, 2]): filled with the GroupNorm(32) sums of the output (evw_gemm_f16_gn)."""
     _lib.require_cuda(a0, "a0")
     if a0.dim() == 2:
@@ -47,9 +48,18 @@ def gemm_f16(a0: torch.Tensor, w: torch.Tensor, taps: Sequence[Tuple[int, int, i
             _lib.ptr(a0), _lib.ptr(a1), _lib.ptr(w), B, T, Y, X, C0, C1, N, taps_arr.shape[0], taps_arr.tobytes(),
             _lib.ptr(out), 1 if out.dtype == torch.float16 else 0, _lib.ptr(bias), _lib.ptr(rowvec), rv_div, rv_mod,
             _lib.ptr(res1), 1 if (res1 is not None and res1.dtype == torch.float16) else 0, s1, _lib.ptr(res2), s2, s0,
-            1 if geglu else 0, block_n, _lib.ptr(out_lo), _lib.ptr(gn_stats), gn_rows_per_inst,
+            _epilogue_mode(geglu, act), block_n, _lib.ptr(out_lo), _lib.ptr(gn_stats), gn_rows_per_inst,
             _lib.stream_ptr(a0.device)), "evw_gemm_f16")
     return out
+
+
+def _epilogue_mode(geglu: bool, act: Optional[str]) -> int:
+    """The `geglu` argument of evw_gemm_f16: 0 = plain, 1 = GEGLU, 2 = GELU of acc + bias."""
+    if act not in (None, "gelu"):
+        raise ValueError(f"gemm_f16: activation {act!r} is not built into the epilogue")
+    if act and geglu:
+        raise ValueError("gemm_f16: GEGLU and act are exclusive")
+    return 1 if geglu else (2 if act else 0)
 
 
 def geglu_interleave(w: torch.Tensor, b: Optional[torch.Tensor] = None):

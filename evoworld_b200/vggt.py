@@ -381,8 +381,8 @@ class VGGT:
         qkv = ops.gemm_f16(n1, T[pre + "qkv.weight"], bias=T[pre + "qkv.bias"], out_dtype=torch.float16)
         x = ops.gemm_f16(attn(qkv), T[pre + "proj.weight"], bias=T[pre + "proj.bias"], res1=x, out_dtype=torch.float32)
         n2 = ops.layer_norm(x, T[pre + "norm2.weight"], T[pre + "norm2.bias"], eps)
-        f1 = ops.gemm_f16(n2, T[pre + "fc1.weight"], bias=T[pre + "fc1.bias"], out_dtype=torch.float32)
-        return ops.gemm_f16(ops.activation_f16(f1, "gelu"), T[pre + "fc2.weight"], bias=T[pre + "fc2.bias"], res1=x, out_dtype=torch.float32)
+        f1 = ops.gemm_f16(n2, T[pre + "fc1.weight"], bias=T[pre + "fc1.bias"], act="gelu", out_dtype=torch.float16)   # GELU in the epilogue
+        return ops.gemm_f16(f1, T[pre + "fc2.weight"], bias=T[pre + "fc2.bias"], res1=x, out_dtype=torch.float32)
 
     def _pos_tokens(self, h0: int, w0: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """DINOv2 position table resized to the h0 x w0 patch grid (vision_transformer.py:183-213: bicubic, antialias,
@@ -505,8 +505,8 @@ class VGGT:
             for i in range(cfg["camera_trunk_depth"]):
                 t = self._block(t, f"{c}trunk.{i}.", 1e-5, attn)
             tn = ops.layer_norm(t, T[c + "trunk_norm.weight"], T[c + "trunk_norm.bias"], 1e-5)
-            h1 = ops.gemm_f16(tn, T[c + "pb1.weight"], bias=T[c + "pb1.bias"], out_dtype=torch.float32)
-            delta = ops.gemm_f16(ops.activation_f16(h1, "gelu"), T[c + "pb2.weight"], bias=T[c + "pb2.bias"], out_dtype=torch.float32)[:, :9]
+            h1 = ops.gemm_f16(tn, T[c + "pb1.weight"], bias=T[c + "pb1.bias"], act="gelu", out_dtype=torch.float16)
+            delta = ops.gemm_f16(h1, T[c + "pb2.weight"], bias=T[c + "pb2.bias"], out_dtype=torch.float32)[:, :9]
             pred = delta.contiguous() if pred is None else pred + delta
             outs.append(torch.cat([pred[:, :7], torch.relu(pred[:, 7:])], dim=-1).view(B, S, 9))   # head_act.py:11-34: FoV through relu
         return outs

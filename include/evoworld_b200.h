@@ -182,7 +182,8 @@ int evw_cube_to_equirect_u8(const uint8_t* faces, const uint32_t* lut, int B, in
  *   a0 fp16 [B,T,Y,X,C0] channels-last, a1 optional fp16 [B,T,Y,X,C1], w fp16 [N, K_total] tap-major,
  *   h_taps (HOST) int8 [num_taps,4] = (dx,dy,dt,src); reads outside the tensor are zero (padding).
  *   out[row,n] = s0*(acc+bias[n]) + rowvec[(row/rv_div)%rv_mod, n] + s1*res1[row,n] + s2*res2[row,n];
- *   geglu: columns interleaved [16 value|16 gate], out has N/2 columns = (v+b)*gelu(g+b).
+ *   geglu = 1: columns interleaved [16 value|16 gate], out has N/2 columns = (v+b)*gelu(g+b).
+ *   geglu = 2: out = gelu(s0 * (acc + bias)) (exact erf form; no rowvec / res1 / res2 / out_lo): the fc1 of ViT-style MLPs.
  *   out/res1 are fp16 or fp32 (flags), bias/rowvec/res2 fp32.  C0, C1 multiples of 64; N multiple of 8.
  *   out_lo (optional, fp16 output only, N multiple of 16): fp16 tail half(v - float(half(v))) of every stored value —
  *   the split-precision operand format: a consumer reads head and tail as two tap sources (a0, a1) against

@@ -8,7 +8,8 @@ import torch.nn.functional as F
 
 def gemm_f16(a0, w, taps=((0, 0, 0, 0),), a1=None, bias=None, rowvec=None, rv_div=1, rv_mod=1, res1=None, s1=1.0, res2=None,
              s2=1.0, s0=1.0, geglu=False, out_dtype=torch.float16, block_n=0, out=None, out_lo=None, gn_stats=None,
-             gn_rows_per_inst=0):
+             gn_rows_per_inst=0, act=None):
+    assert act in (None, "gelu") and not (act and (rowvec is not None or res1 is not None))
     assert a0.dtype == torch.float16 and w.dtype == torch.float16 and not geglu and out_lo is None and gn_stats is None
     if a0.dim() == 2:
         a0 = a0[None, None, None]
@@ -34,6 +35,8 @@ def gemm_f16(a0, w, taps=((0, 0, 0, 0),), a1=None, bias=None, rowvec=None, rv_di
     if bias is not None:
         r = r + bias
     r = s0 * r
+    if act == "gelu":
+        r = F.gelu(r)
     if rowvec is not None:
         idx = (torch.arange(rows) // rv_div) % rv_mod
         r = r + rowvec.reshape(-1, r.shape[1])[idx]

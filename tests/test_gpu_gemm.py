@@ -358,3 +358,27 @@ def test_fused_upsample_conv(Fr, h, w, C, N, cuda_device, built_lib):
     assert got.shape == (Fr, 2 * h, 2 * w, N)
     # the summed phase weights are rounded to fp16 once more: 2.8e-4 relative per weight, averaged over K
     assert rel_l2(got, want) < 3e-4
+
+
+@pytest.mark.parametrize("M,K,N", [(1000, 320, 1280), (4164, 1024, 4096), (3, 2048, 1024), (777, 64, 16), (300, 384, 1536)])
+@pytest.mark.parametrize("out_dtype", [torch.float16, torch.float32])
+def test_linear_gelu_epilogue(M, K, N, out_dtype, cuda_device, built_lib):
+    """fc1 of the ViT-style MLPs (VGGT / CLIP): exact GELU of acc + bias in the epilogue (evw_gemm_f16 geglu = 2), single CTAs
+    and CTA pairs (K >= 1024), direct and TMA stores bit-identical; operand combinations it is not built for are refused."""
+    a = torch.randn(M, K, device=cuda_device).half()
+    w = (torch.randn(N, K, device=cuda_device) / K ** 0.5).half()
+    b = torch.randn(N, device=cuda_device)
+    want = F.gelu(a.float() @ w.float().T + b)
+    try:
+        outs = []
+        for mode in (1, 0):
+            built_lib.evw_set_gemm_store_tma(mode)
+            outs.append(ops.gemm_f16(a, w, bias=b, act="gelu", out_dtype=out_dtype))
+    finally:
+        built_lib.evw_set_gemm_store_tma(-1)
+    assert torch.equal(outs[0], outs[1])
+    assert outs[0].dtype == out_dtype and rel_l2(outs[0], want) < (2e-3 if out_dtype == torch.float16 else 2e-5)
+    with pytest.raises(RuntimeError):
+        ops.gemm_f16(a, w, bias=b, act="gelu", res1=torch.zeros(M, N, device=cuda_device), out_dtype=torch.float32)
+    with pytest.raises(ValueError):
+        ops.gemm_f16(a, w, bias=b, act="relu")
