@@ -20,45 +20,83 @@
 namespace evw {
 namespace {
 
-// One warp per (token row, head, q|k): lane l holds features l (vertical half) and l + 32 (horizontal half).
-// LayerNorm over the 64 features, then per 32-feature half: out[j] = t[j] cos[p][j % 16] + rot[j] sin[p][j % 16] with
-// rot = (-t[16:], t[:16]) — the partner feature sits in lane l ^ 16.  cos / sin: fp32 [max_pos, 16].
+// Eight threads per (token row, q|k, head): thread `sub` holds features 8 sub .. 8 sub + 7 of the 64 (one 16-byte load; a
+// warp covers 4 consecutive heads = 512 contiguous bytes).  LayerNorm over the 64 features (3 shuffle stages inside the
+// 8-lane group), then per 32-feature half (sub < 4: vertical, position y; else horizontal, position x):
+// out[j] = t[j] cos[p][j % 16] + rot[j] sin[p][j % 16] with rot = (-t[16:], t[:16]) — the partner feature j +- 16 sits in
+// the thread two lanes away (sub ^ 2), same slot.  cos / sin: fp32 [max_pos, 16].
 __global__ void __launch_bounds__(256)
-qknorm_rope_kernel(__half* __restrict__ qkv, long long rows, int heads, int tokens_per_frame, const int* __restrict__ pos_yx,
+qknorm_rope_kernel(__half* __restrict__ qkv, long long items, int heads, int tokens_per_frame, const int* __restrict__ pos_yx,
                    const float* __restrict__ q_gamma, const float* __restrict__ q_beta, const float* __restrict__ k_gamma,
                    const float* __restrict__ k_beta, const float* __restrict__ cos_t, const float* __restrict__ sin_t, float eps) {
-  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long total = rows * heads * 2;
-  if (w >= total) return;
-  const int lane = threadIdx.x & 31;
-  const int which = (int)(w % 2);
-  const int head = (int)((w / 2) % heads);
-  const long long row = w / (2ll * heads);
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = (t >> 3) < items;
+  const long long item = live ? (t >> 3) : items - 1;  // tail lanes shadow the last item (they take part in the shuffles)
+  const int sub = (int)(t & 7);
+  const int per_row = 2 * heads;
+  const long long row = item / per_row;
+  const int rem = (int)(item - row * per_row);
+  const int which = rem >= heads ? 1 : 0;
   const int C = heads * 64;
-  __half* p = qkv + row * (3ll * C) + (long long)which * C + head * 64;
-  float a = __half2float(p[lane]), b = __half2float(p[lane + 32]);
-  float s = a + b;
+  __half* p = qkv + row * (3ll * C) + (long long)rem * 64 + sub * 8;  // q heads then k heads: rem * 64 = which * C + head * 64
+  const uint4 raw = *reinterpret_cast<const uint4*>(p);
+  float x[8];
+  {
+    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h2[i]);
+      x[2 * i] = f.x; x[2 * i + 1] = f.y;
+    }
+  }
+  float s = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+#pragma unroll
+  for (int o = 4; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s * (1.0f / 64.0f);
-  const float da = a - mean, db = b - mean;
-  float q = da * da + db * db;
+  float q = 0.f;
 #pragma unroll
-  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  for (int i = 0; i < 8; ++i) {
+    x[i] -= mean;
+    q = fmaf(x[i], x[i], q);
+  }
+#pragma unroll
+  for (int o = 4; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q * (1.0f / 64.0f) + eps);
-  const float* g = which ? k_gamma : q_gamma;
-  const float* be = which ? k_beta : q_beta;
-  a = da * rstd * g[lane] + be[lane];
-  b = db * rstd * g[lane + 32] + be[lane + 32];
+  const float4* g4 = reinterpret_cast<const float4*>((which ? k_gamma : q_gamma) + sub * 8);
+  const float4* b4 = reinterpret_cast<const float4*>((which ? k_beta : q_beta) + sub * 8);
   const int tok = (int)(row % tokens_per_frame);
-  const int py = pos_yx[2 * tok], px = pos_yx[2 * tok + 1];
-  const int j = lane & 15;
-  const float pa = __shfl_xor_sync(0xffffffffu, a, 16), pb = __shfl_xor_sync(0xffffffffu, b, 16);
-  const float sgn = lane < 16 ? -1.0f : 1.0f;
-  const float ra = a * cos_t[py * 16 + j] + sgn * pa * sin_t[py * 16 + j];
-  const float rb = b * cos_t[px * 16 + j] + sgn * pb * sin_t[px * 16 + j];
-  p[lane] = __float2half_rn(ra);
-  p[lane + 32] = __float2half_rn(rb);
+  const int pos = pos_yx[2 * tok + (sub < 4 ? 0 : 1)];
+  const float4* c4 = reinterpret_cast<const float4*>(cos_t + pos * 16 + (sub & 1) * 8);
+  const float4* s4 = reinterpret_cast<const float4*>(sin_t + pos * 16 + (sub & 1) * 8);
+  const float sgn = (sub & 2) ? 1.0f : -1.0f;
+  float y[8];
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    const float4 g = __ldg(g4 + hf), b = __ldg(b4 + hf);
+    y[4 * hf] = fmaf(x[4 * hf] * rstd, g.x, b.x);
+    y[4 * hf + 1] = fmaf(x[4 * hf + 1] * rstd, g.y, b.y);
+    y[4 * hf + 2] = fmaf(x[4 * hf + 2] * rstd, g.z, b.z);
+    y[4 * hf + 3] = fmaf(x[4 * hf + 3] * rstd, g.w, b.w);
+  }
+  float o[8];
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    const float4 c = __ldg(c4 + hf), sn = __ldg(s4 + hf);
+    const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float partner = __shfl_xor_sync(0xffffffffu, y[4 * hf + i], 2);
+      o[4 * hf + i] = fmaf(y[4 * hf + i], cc[i], sgn * partner * ss[i]);
+    }
+  }
+  if (live) {
+    uint4 w;
+    __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
+    __half2 h2 = __floats2half2_rn(o[4], o[5]), h3 = __floats2half2_rn(o[6], o[7]);
+    w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
+    w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(p) = w;
+  }
 }
 
 // src fp32 [F, h, w, C] -> dst [F, H, W, C] (fp16 or fp32), 4 channels per thread; index arithmetic as ATen's
@@ -148,10 +186,13 @@ extern "C" int evw_qknorm_rope_f16(void* qkv, int64_t rows, int heads, int token
   EVW_CHECK_ARG(qkv && pos_yx && q_gamma && q_beta && k_gamma && k_beta && cos_t && sin_t, "evw_qknorm_rope_f16: null pointer");
   EVW_CHECK_ARG(rows >= 0 && heads >= 1 && tokens_per_frame >= 1, "evw_qknorm_rope_f16: bad extents");
   if (rows == 0) return EVW_OK;
-  const long long warps = rows * heads * 2;
-  const long long blocks = (warps + 7) / 8;
+  const long long items = rows * heads * 2;  // (row, q|k, head): 8 threads each
+  const long long blocks = (items * 8 + 255) / 256;
   EVW_CHECK_ARG(blocks < (1ll << 31), "evw_qknorm_rope_f16: too many rows");
-  evw::qknorm_rope_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((__half*)qkv, rows, heads, tokens_per_frame, pos_yx,
+  EVW_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)q_gamma & 15) == 0 && ((uintptr_t)q_beta & 15) == 0 && ((uintptr_t)k_gamma & 15) == 0 &&
+                    ((uintptr_t)k_beta & 15) == 0 && ((uintptr_t)cos_t & 15) == 0 && ((uintptr_t)sin_t & 15) == 0,
+                "evw_qknorm_rope_f16: pointers must be 16-byte aligned");
+  evw::qknorm_rope_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((__half*)qkv, items, heads, tokens_per_frame, pos_yx,
                                                                                q_gamma, q_beta, k_gamma, k_beta, cos_t, sin_t, eps);
   EVW_LAUNCH_CHECK();
   return EVW_OK;
