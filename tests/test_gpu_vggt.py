@@ -201,3 +201,18 @@ def test_no_cpu_fallback(built_lib):
     m.load_state_dict(V.random_state_dict(CFG, seed=1))
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(1, 2, 3, 70, 98))
+
+
+def test_global_attention_sequence_length(cuda_device, built_lib):
+    """VGGT's global attention is ONE sequence of S x 1041 tokens (26 025 at 25 frames: 204 key tiles, a ragged last tile, many
+    lazy-rescale decisions) — far beyond the UNet's 9 216: the flash kernel against softmax(q k^T / 8) v in fp32."""
+    no_tf32()
+    torch.manual_seed(3)
+    S, heads = 25 * 1041, 2
+    qkv = torch.randn(S, 3 * heads * 64, device=cuda_device).half()
+    qkv[:, : heads * 64] *= 2.0                      # sharper rows: exercise the running-maximum updates
+    got = ops.spatial_attention(qkv, 1, S, heads)
+    q, k, v = [t.reshape(S, heads, 64).transpose(0, 1).float() for t in qkv.chunk(3, dim=1)]
+    for h in range(heads):
+        want = torch.softmax((q[h] * 0.125) @ k[h].T, dim=-1) @ v[h]
+        assert rel_l2(got[:, h * 64: (h + 1) * 64], want) < 1e-3
