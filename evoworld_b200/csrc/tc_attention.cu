@@ -349,7 +349,10 @@ constexpr int kA8OffToken = kA7OffBar + 256;          // 512 words
 constexpr int kA8OffMax = kA8OffToken + 2048;         // [2 parities][2 groups][2 halves][128 rows] fp32
 constexpr int kA8Smem = kA8OffMax + 4096 + 1024;
 
-template <int kPolyN, bool kStagger>
+// kPairBar: the half-row maxima / sums are exchanged under a barrier of the TWO warps that share the rows (one named barrier
+// per group and TMEM lane quarter, 64 threads) instead of all eight warps of the group (256 threads): the quarters of a
+// group no longer wait for each other's slowest warp at every key tile.
+template <int kPolyN, bool kStagger, bool kPairBar = false>
 __global__ void __launch_bounds__(kA6Threads, 1)
 spatial_attn8_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ out, int S, int C, float scale_log2e) {
   extern __shared__ uint8_t smem_raw[];
@@ -504,7 +507,8 @@ spatial_attn8_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
         {
           float* slot = mxbuf + (((j & 1) * 2 + g) * 2) * 128;
           slot[half * 128 + r] = mx;
-          named_bar_sync(3 + g, 256);
+          if constexpr (kPairBar) named_bar_sync(3 + g * 4 + quarter, 64);
+          else named_bar_sync(3 + g, 256);
           mx = fmaxf(mx, slot[(half ^ 1) * 128 + r]);
         }
         const float m_tile = mx * scale_log2e;
@@ -573,7 +577,8 @@ spatial_attn8_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
       {
         float* slot = mxbuf + (((n_kv & 1) * 2 + g) * 2) * 128;  // the parity the last tile did not use
         slot[half * 128 + r] = l_run;
-        named_bar_sync(3 + g, 256);
+        if constexpr (kPairBar) named_bar_sync(3 + g * 4 + quarter, 64);
+          else named_bar_sync(3 + g, 256);
         l_run += slot[(half ^ 1) * 128 + r];
       }
       mbar_wait(o_full(g), (n_kv - 1) & 1);
@@ -612,7 +617,7 @@ spatial_attn8_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restric
 
 // default kernel: v8 (P in tensor memory, two threads per row), all exponentials on MUFU, no stagger
 // variants: 0 = v8, 1 = v8 with every 8th exponential on the FMA pipe, 2 = v8 with the two groups staggered on the MUFU
-// pipe, 3 = v7 (one thread per row), 4 = v7 with every 4th exponential on the FMA pipe
+// pipe, 3 = v7 (one thread per row), 4 = v7 with every 4th exponential on the FMA pipe, 5 = v8 with pair barriers (kPairBar)
 constexpr int kDefaultAttnVariant = 0;
 static int g_attn_variant_override = -2;
 void set_attention_variant(int v) { g_attn_variant_override = v; }
@@ -627,7 +632,7 @@ int spatial_attention(const __half* qkv, __half* out, int F, int S, int heads, c
   static const Variant table[] = {
       {spatial_attn8_kernel<0, false>, kA6Threads, kA8Smem}, {spatial_attn8_kernel<8, false>, kA6Threads, kA8Smem},
       {spatial_attn8_kernel<0, true>, kA6Threads, kA8Smem},  {spatial_attn7_kernel<0, false>, kA2Threads, kA7Smem},
-      {spatial_attn7_kernel<4, false>, kA2Threads, kA7Smem}};
+      {spatial_attn7_kernel<4, false>, kA2Threads, kA7Smem}, {spatial_attn8_kernel<0, false, true>, kA6Threads, kA8Smem}};
   constexpr int kVariants = (int)(sizeof(table) / sizeof(table[0]));
   if (!attr_set) {
     for (const Variant& v : table) EVW_CUDA(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem));

@@ -39,7 +39,7 @@ def test_spatial_attention(frames, S, heads, scale, cuda_device):
     assert rel_l2(got, want) < 3e-3
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("frames,S,heads", [(2, 576, 3), (1, 129, 2), (1, 2304, 2), (3, 144, 5), (1, 300, 1), (1, 1, 1)])
 def test_spatial_attention_variants(variant, frames, S, heads, cuda_device):
     """Every variant behind evw_set_attention_variant (v8 default / partial FMA-pipe exponentials / staggered groups,

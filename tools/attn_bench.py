@@ -25,16 +25,19 @@ def timeit(fn, n=5):
     return e0.elapsed_time(e1) / n
 
 
-VARIANTS = {0: "v8 (default)", 1: "v8 poly1/8", 2: "v8 stagger", 3: "v7 1thr/row", 4: "v7 poly1/4"}
+VARIANTS = {0: "v8 (default)", 1: "v8 poly1/8", 2: "v8 stagger", 3: "v7 1thr/row", 4: "v7 poly1/4", 5: "v8 pair barriers"}
 if "--new-only" in sys.argv:
     VARIANTS = {0: VARIANTS[0]}
-shapes = {"L0 spatial": (28, 9216, 5), "L1 spatial": (28, 2304, 10), "L2 spatial": (28, 576, 20), "mid": (28, 144, 20)}
+if "--pair" in sys.argv:
+    VARIANTS = {0: VARIANTS[0], 5: VARIANTS[5], 10: VARIANTS[0] + " again", 15: VARIANTS[5] + " again"}
+shapes = {"L0 spatial": (28, 9216, 5), "L1 spatial": (28, 2304, 10), "L2 spatial": (28, 576, 20), "mid": (28, 144, 20),
+          "VGGT global S25": (1, 25 * 1041, 16), "VGGT frame S25": (25, 1041, 16)}
 qkvs = {k: torch.randn(f * s, 3 * h * 64, device=dev).half() for k, (f, s, h) in shapes.items()}
 f_, s_, h_ = shapes["L1 spatial"]
 x = qkvs["L1 spatial"][: 2 * s_].float().view(2, s_, 3, h_, 64).permute(2, 0, 3, 1, 4)
 want = F.scaled_dot_product_attention(x[0], x[1], x[2]).permute(0, 2, 1, 3).reshape(2 * s_, h_ * 64)
 for var, label in VARIANTS.items():
-    L.evw_set_attention_variant(var)
+    L.evw_set_attention_variant(var % 10)
     got = ops.spatial_attention(qkvs["L1 spatial"][: 2 * s_].contiguous(), 2, s_, h_).float()
     err = float((got - want).norm() / want.norm())
     row = []
