@@ -185,10 +185,28 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
     dec_launches = vae.plan_info(1)[0]
     enc_launches = vae.plan_info(0)[0]
     launches = n_seg * steps * unet_launches + n_seg * -(-T // 8) * dec_launches + (n_seg - 1) * -(-T // 8) * enc_launches
+    vggt_forward = None
+    if vggt_net is not None:   # the network alone on one segment's frames (depth head only), 3 timed forwards after a warm one
+        vi = torch.rand((1, T, 3, 392, 518), device=dev)
+        vggt_net(vi)
+        ve = [ev() for _ in range(4)]
+        ve[0].record()
+        for i in range(3):
+            vggt_net(vi)
+            ve[i + 1].record()
+        torch.cuda.synchronize(dev)
+        vms = ve[0].elapsed_time(ve[3]) / 3
+        P_tok = 28 * 37 + 5
+        # executed FLOPs of the attention (4 S^2 d per head and sequence): 24 DINOv2 + 24 frame blocks over T sequences of P_tok
+        # tokens, 24 global blocks over one sequence of T * P_tok tokens; GEMM FLOPs counted by tools/vggt_bench.py (60.0 TFLOP at T = 25)
+        att = 4.0 * 64 * 16 * (48 * T * P_tok ** 2 + 24 * (T * P_tok) ** 2) / 1e12
+        vggt_forward = {"frames": T, "size": [392, 518], "ms": vms, "frames_per_s": T / vms * 1e3, "attention_tflop": att,
+                        "note": "VGGT-1B (random init, depth + camera heads), device-resident input; see profiles/r02am_vggt_bench_S25.json "
+                                "for the FLOP count and the PyTorch-eager legs"}
     return {
         "metric": "iterative clips/sec (3-clip episode, evolving point memory)", "unit": "clips/s",
         "value": world * clips / (ms * 1e-3), "ms_per_episode": ms / n_ep, "episodes": n_ep, "wall_s": wall,
-        "ms_per_stage_per_episode": per_stage, "memory_points_per_segment": pts, "launches_per_episode": int(launches), "finite_output": bool(torch.isfinite(x).all()),
+        "ms_per_stage_per_episode": per_stage, "memory_points_per_segment": pts, "launches_per_episode": int(launches), "vggt_forward": vggt_forward, "finite_output": bool(torch.isfinite(x).all()),
         "config": {"workload": f"config 3: 3-clip iterative episode, {H}x{W}x{T}f clips, {steps} denoise steps per clip, CFG batch 2, "
                                f"evolving point memory {pts} points (S = {T}, {S_all} frames), 24 target views per segment",
                    "mode": mode, "scenes_per_rank": 1,
