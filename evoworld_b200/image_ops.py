@@ -149,20 +149,90 @@ def resize_pil_u8(images: torch.Tensor, height: int, width: int, filt: str = "bi
     return out[0] if single else out
 
 
-def vggt_preprocess_u8(frames: torch.Tensor) -> torch.Tensor:
-    """`load_and_preprocess_images(paths)` (third_party/vggt/vggt/utils/load_fn.py:135-170, mode "crop") for RGB frames uint8
-    [N, H, W, 3] already on the device — the reference writes them to PNG files and reads them back
-    (unified_loop_consistency.py:339-348; PNG is lossless): width -> 518, height -> round(H * 518 / W / 14) * 14 with Pillow's
-    BICUBIC (bit-exact: evw_resize_pil_u8 with the bicubic tables), ToTensor, centre crop of the height to 518
-    -> float32 [N, 3, h, 518] in [0, 1]."""
+def _to_tensor_lut(device) -> torch.Tensor:
+    """ToTensor's byte / 255 as a table computed on the host: a CUDA division by a scalar multiplies by 1 / 255 instead."""
+    key = ("to_tensor", str(device))
+    if key not in _pil_tables:
+        _pil_tables[key] = (torch.arange(256, dtype=torch.float32) / 255).to(device)
+    return _pil_tables[key]
+
+
+def _vggt_target_size(H: int, W: int, mode: str):
+    """load_fn.py:150-163: (new_height, new_width) of the BICUBIC resize for a W x H image."""
+    target = 518
+    if mode == "pad":
+        if W >= H:
+            return round(H * (target / W) / 14) * 14, target
+        return target, round(W * (target / H) / 14) * 14
+    return round(H * (target / W) / 14) * 14, target
+
+
+def vggt_preprocess_u8(frames: torch.Tensor, mode: str = "crop") -> torch.Tensor:
+    """`load_and_preprocess_images(paths, mode)` (third_party/vggt/vggt/utils/load_fn.py:135-193) for RGB frames uint8
+    [N, H, W, 3] of one size already on the device — the reference writes them to PNG files and reads them back
+    (unified_loop_consistency.py:339-348; PNG is lossless): Pillow BICUBIC resize (bit-exact: evw_resize_pil_u8 with the
+    bicubic tables) to width 518 ("crop": height round(H * 518 / W / 14) * 14, centre-cropped to 518 when taller) or to the
+    larger side 518 ("pad": then white padding to 518 x 518), ToTensor -> float32 [N, 3, h, w] in [0, 1]."""
+    if mode not in ("crop", "pad"):
+        raise ValueError("Mode must be either 'crop' or 'pad'")
     N, H, W, _ = frames.shape
-    new_w = 518
-    new_h = round(H * (new_w / W) / 14) * 14
-    key = ("to_tensor", str(frames.device))
-    if key not in _pil_tables:   # ToTensor's byte / 255 as a table computed on the host: a CUDA division by a scalar multiplies by 1 / 255
-        _pil_tables[key] = (torch.arange(256, dtype=torch.float32) / 255).to(frames.device)
-    x = _pil_tables[key][resize_pil_u8(frames, new_h, new_w, "bicubic").permute(0, 3, 1, 2).to(torch.int32)]
-    if new_h > 518:
+    new_h, new_w = _vggt_target_size(H, W, mode)
+    x = _to_tensor_lut(frames.device)[resize_pil_u8(frames, new_h, new_w, "bicubic").permute(0, 3, 1, 2).to(torch.int32)]
+    if mode == "crop" and new_h > 518:
         y0 = (new_h - 518) // 2
         x = x[:, :, y0:y0 + 518]
+    if mode == "pad":
+        hp, wp = 518 - x.shape[2], 518 - x.shape[3]
+        if hp > 0 or wp > 0:
+            x = torch.nn.functional.pad(x, (wp // 2, wp - wp // 2, hp // 2, hp - hp // 2), mode="constant", value=1.0)
     return x.contiguous()
+
+
+def decode_rgb(path) -> "np.ndarray":
+    """load_fn.py:138-149: open an image file, composite an alpha channel onto white, convert to RGB -> uint8 [H, W, 3] (host)."""
+    import numpy as np
+    from PIL import Image
+
+    img = Image.open(path)
+    if img.mode == "RGBA":
+        background = Image.new("RGBA", img.size, (255, 255, 255, 255))
+        img = Image.alpha_composite(background, img)
+    return np.asarray(img.convert("RGB"))
+
+
+def load_and_preprocess_images(image_path_list, mode: str = "crop", device=None) -> torch.Tensor:
+    """Drop-in for `vggt.utils.load_fn.load_and_preprocess_images` (third_party/vggt/vggt/utils/load_fn.py:95-230; call site
+    unified_loop_consistency.py:348): the files are decoded on the host (PIL), everything after — Pillow-exact BICUBIC
+    resize, ToTensor, centre crop / white padding, padding of differently shaped images to the largest — runs on the device.
+    Returns float32 [N, 3, H, W] ON THE DEVICE (the caller's `.to(device)` is then a no-op).  Same errors as the reference."""
+    if len(image_path_list) == 0:
+        raise ValueError("At least 1 image is required")
+    if mode not in ("crop", "pad"):
+        raise ValueError("Mode must be either 'crop' or 'pad'")
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+    if dev is None or dev.type != "cuda":
+        raise RuntimeError("evoworld_b200 load_and_preprocess_images needs a CUDA device (no CPU fallback)")
+    decoded = [decode_rgb(p) for p in image_path_list]
+    out = [None] * len(decoded)
+    by_size: dict = {}
+    for i, a in enumerate(decoded):
+        by_size.setdefault(a.shape[:2], []).append(i)
+    import numpy as np
+
+    for idx in by_size.values():          # one resize call per source size (the loop's frames all share one)
+        batch = torch.from_numpy(np.stack([decoded[i] for i in idx])).to(dev, non_blocking=True)
+        res = vggt_preprocess_u8(batch, mode)
+        for j, i in enumerate(idx):
+            out[i] = res[j]
+    shapes = {(t.shape[1], t.shape[2]) for t in out}
+    if len(shapes) > 1:
+        print(f"Warning: Found images with different shapes: {shapes}")
+        mh, mw = max(s[0] for s in shapes), max(s[1] for s in shapes)
+        padded = []
+        for t in out:
+            hp, wp = mh - t.shape[1], mw - t.shape[2]
+            if hp > 0 or wp > 0:
+                t = torch.nn.functional.pad(t, (wp // 2, wp - wp // 2, hp // 2, hp - hp // 2), mode="constant", value=1.0)
+            padded.append(t)
+        out = padded
+    return torch.stack(out)

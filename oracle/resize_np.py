@@ -118,3 +118,45 @@ def vggt_preprocess(frames_u8: np.ndarray) -> np.ndarray:
         y0 = (new_h - 518) // 2
         out = out[:, :, y0:y0 + 518]
     return np.ascontiguousarray(out)
+
+
+def load_and_preprocess_images_np(image_path_list, mode: str = "crop") -> np.ndarray:
+    """third_party/vggt/vggt/utils/load_fn.py:95-230 restated with the numpy BICUBIC above: decode (alpha composited on
+    white), resize, ToTensor, centre crop ("crop") / white padding to 518 x 518 ("pad"), white padding of differently shaped
+    images to the largest -> float32 [N, 3, H, W]."""
+    from PIL import Image
+
+    if len(image_path_list) == 0:
+        raise ValueError("At least 1 image is required")
+    if mode not in ["crop", "pad"]:
+        raise ValueError("Mode must be either 'crop' or 'pad'")
+    target = 518
+    images = []
+    for path in image_path_list:
+        img = Image.open(path)
+        if img.mode == "RGBA":
+            img = Image.alpha_composite(Image.new("RGBA", img.size, (255, 255, 255, 255)), img)
+        a = np.asarray(img.convert("RGB"))
+        H, W = a.shape[:2]
+        if mode == "pad":
+            if W >= H:
+                nw, nh = target, round(H * (target / W) / 14) * 14
+            else:
+                nh, nw = target, round(W * (target / H) / 14) * 14
+        else:
+            nw, nh = target, round(H * (target / W) / 14) * 14
+        t = resize_u8(a, nh, nw, "bicubic").astype(np.float32).transpose(2, 0, 1) / np.float32(255.0)
+        if mode == "crop" and nh > target:
+            y0 = (nh - target) // 2
+            t = t[:, y0:y0 + target]
+        if mode == "pad":
+            hp, wp = target - t.shape[1], target - t.shape[2]
+            if hp > 0 or wp > 0:
+                t = np.pad(t, ((0, 0), (hp // 2, hp - hp // 2), (wp // 2, wp - wp // 2)), constant_values=1.0)
+        images.append(t)
+    shapes = {(t.shape[1], t.shape[2]) for t in images}
+    if len(shapes) > 1:
+        mh, mw = max(s[0] for s in shapes), max(s[1] for s in shapes)
+        images = [np.pad(t, ((0, 0), ((mh - t.shape[1]) // 2, mh - t.shape[1] - (mh - t.shape[1]) // 2),
+                             ((mw - t.shape[2]) // 2, mw - t.shape[2] - (mw - t.shape[2]) // 2)), constant_values=1.0) for t in images]
+    return np.ascontiguousarray(np.stack(images))

@@ -24,6 +24,7 @@ def test_import_surface(monkeypatch):
         "third_party.vggt.vggt.utils.geometry": ["unproject_depth_map_to_point_map"],
         "third_party.vggt.vggt.utils.pose_enc": ["pose_encoding_to_extri_intri"],
         "third_party.vggt.vggt.models.vggt": ["VGGT"],
+        "third_party.vggt.vggt.utils.load_fn": ["load_and_preprocess_images"],
     }
     for mod, names in surface.items():
         m = importlib.import_module(mod)

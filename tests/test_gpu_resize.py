@@ -76,3 +76,24 @@ def test_vggt_preprocess(cuda_device, built_lib):
     got = vggt_preprocess_u8(torch.from_numpy(frames).to(cuda_device))
     assert got.shape == (5, 3, 392, 518) and got.dtype == torch.float32
     assert np.array_equal(got.cpu().numpy(), R.vggt_preprocess(frames))
+
+
+@pytest.mark.parametrize("names,mode", [(("a", "b"), "crop"), (("a", "rgba"), "crop"), (("a", "tall", "wide"), "crop"),
+                                        (("a", "tall", "wide"), "pad"), (("tall",), "crop")])
+def test_load_and_preprocess_images(names, mode, cuda_device, built_lib, tmp_path, capsys):
+    """The drop-in loader (files decoded on the host, resize / ToTensor / crop / pad on the device) against the numpy
+    restatement of the reference loader (pinned against the reference itself in tests/test_resize_host.py), bit for bit."""
+    from PIL import Image
+
+    from evoworld_b200.image_ops import load_and_preprocess_images
+
+    rng = np.random.default_rng(11)
+    paths = []
+    for n in names:
+        H, W, ch = {"a": (384, 512, 3), "b": (384, 512, 3), "rgba": (384, 512, 4), "tall": (640, 400, 3), "wide": (200, 640, 3)}[n]
+        paths.append(str(tmp_path / f"{n}.png"))
+        Image.fromarray(rng.integers(0, 256, (H, W, ch), dtype=np.uint8), "RGBA" if ch == 4 else "RGB").save(paths[-1])
+    got = load_and_preprocess_images(paths, mode=mode)
+    want = R.load_and_preprocess_images_np(paths, mode=mode)
+    assert got.is_cuda and got.dtype == torch.float32 and tuple(got.shape) == want.shape
+    assert np.array_equal(got.cpu().numpy(), want)

@@ -105,3 +105,57 @@ def test_vggt_preprocess_equals_the_reference_loader(tmp_path):
     assert np.array_equal(got, want)
     tall = R.vggt_preprocess(rng.integers(0, 256, (1, 600, 400, 3), dtype=np.uint8))   # height 777 -> centre crop to 518
     assert tall.shape == (1, 3, 518, 518)
+
+
+def _write_loader_cases(tmp_path):
+    from PIL import Image
+
+    rng = np.random.default_rng(11)
+    paths = {}
+    for name, (H, W, ch) in {"a": (384, 512, 3), "b": (384, 512, 3), "rgba": (384, 512, 4), "tall": (640, 400, 3), "wide": (200, 640, 3)}.items():
+        arr = rng.integers(0, 256, (H, W, ch), dtype=np.uint8)
+        paths[name] = str(tmp_path / f"{name}.png")
+        Image.fromarray(arr, "RGBA" if ch == 4 else "RGB").save(paths[name])
+    return paths
+
+
+@pytest.mark.parametrize("names,mode", [(("a", "b"), "crop"), (("a", "rgba"), "crop"), (("a", "tall", "wide"), "crop"),
+                                        (("a", "tall", "wide"), "pad"), (("tall",), "crop"), (("wide",), "pad")])
+def test_loader_restatement_equals_the_reference_loader(names, mode, tmp_path, capsys):
+    """oracle.load_and_preprocess_images_np (every branch: alpha compositing, crop, pad, mixed shapes) against the reference's
+    load_and_preprocess_images, imported from the checkout when it is present (build container)."""
+    import os
+    import sys
+
+    ref_root = "/root/reference/third_party/vggt"
+    if not os.path.isdir(ref_root):
+        pytest.skip("reference checkout not present (GPU box): the restatement is pinned in the build container")
+    paths = _write_loader_cases(tmp_path)
+    sys.path.insert(0, ref_root)
+    try:
+        from vggt.utils.load_fn import load_and_preprocess_images
+
+        want = load_and_preprocess_images([paths[n] for n in names], mode=mode).numpy()
+    finally:
+        sys.path.remove(ref_root)
+    got = R.load_and_preprocess_images_np([paths[n] for n in names], mode=mode)
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_loader_errors_and_host_decoding(tmp_path):
+    from evoworld_b200 import image_ops
+
+    with pytest.raises(ValueError, match="At least 1 image"):
+        image_ops.load_and_preprocess_images([])
+    with pytest.raises(ValueError, match="Mode must be"):
+        image_ops.load_and_preprocess_images(["x.png"], mode="stretch")
+    with pytest.raises(ValueError, match="Mode must be"):
+        R.load_and_preprocess_images_np(["x.png"], mode="stretch")
+    paths = _write_loader_cases(tmp_path)
+    rgb = image_ops.decode_rgb(paths["rgba"])
+    from PIL import Image
+
+    src = Image.open(paths["rgba"])
+    want = np.asarray(Image.alpha_composite(Image.new("RGBA", src.size, (255, 255, 255, 255)), src).convert("RGB"))
+    assert rgb.shape == (384, 512, 3) and np.array_equal(rgb, want)
+    assert image_ops._vggt_target_size(384, 512, "crop") == (392, 518) and image_ops._vggt_target_size(640, 400, "pad") == (518, 322)
