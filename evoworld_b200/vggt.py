@@ -474,7 +474,8 @@ class VGGT:
         _lib.require_cuda(images, "images")
         if images.dim() == 4:
             images = images[None]
-        pairs, (B, S, P, _, _) = self._aggregate(images)
+        with torch.autocast(device_type=images.device.type, enabled=False):
+            pairs, (B, S, P, _, _) = self._aggregate(images)
         d = self._cfg["embed_dim"]
         return [torch.cat([pairs[i][0].view(B, S, P, d), pairs[i][1].view(B, S, P, d)], dim=-1) for i in range(self._cfg["depth"])], \
             1 + self._cfg["num_register_tokens"]
@@ -611,13 +612,16 @@ class VGGT:
             images = images[None]
         cfg = self._cfg
         last = cfg["depth"] - 1
-        pairs, dims = self._aggregate(images, keep=set(cfg["dpt_layers"]) | {last})
-        B, S, P, H, W = dims
-        out = {"pose_enc": self._camera(pairs[last], B, S, P)[-1]}
-        depth, out["depth_conf"] = self._dpt_chunked(pairs, dims, "depth_head.", "exp", 2, frames_chunk_size)
-        out["depth"] = depth
-        if cfg["point_head"]:
-            out["world_points"], out["world_points_conf"] = self._dpt_chunked(pairs, dims, "point_head.", "inv_log", 4, frames_chunk_size)
+        # the reference wraps the call in bf16 autocast (unified_loop_consistency.py:131-136); the precision here is fixed by the
+        # kernels, and the few torch helpers (einsum of the sin / cos tables, interpolate of the position table) must stay fp32
+        with torch.autocast(device_type=images.device.type, enabled=False):
+            pairs, dims = self._aggregate(images, keep=set(cfg["dpt_layers"]) | {last})
+            B, S, P, H, W = dims
+            out = {"pose_enc": self._camera(pairs[last], B, S, P)[-1]}
+            depth, out["depth_conf"] = self._dpt_chunked(pairs, dims, "depth_head.", "exp", 2, frames_chunk_size)
+            out["depth"] = depth
+            if cfg["point_head"]:
+                out["world_points"], out["world_points_conf"] = self._dpt_chunked(pairs, dims, "point_head.", "inv_log", 4, frames_chunk_size)
         out["images"] = images
         return out
 

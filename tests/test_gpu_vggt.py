@@ -216,3 +216,52 @@ def test_global_attention_sequence_length(cuda_device, built_lib):
     for h in range(heads):
         want = torch.softmax((q[h] * 0.125) @ k[h].T, dim=-1) @ v[h]
         assert rel_l2(got[:, h * 64: (h + 1) * 64], want) < 1e-3
+
+
+def test_reference_vggt_call_sequence_through_dropin(cuda_device, built_lib, tmp_path, monkeypatch):
+    """The lines of the reference that touch VGGT — VGGTProcessor (unified_loop_consistency.py:114-136) and run_vggt_inference
+    (:336-367) — executed statement by statement with every name resolved through the dropin overlay
+    (third_party.vggt.vggt.{models.vggt, utils.load_fn, utils.pose_enc, utils.geometry}); the result equals
+    evoworld_b200.vggt.run_vggt_inference (the same steps without the PNG / numpy round trips)."""
+    import importlib
+    import tempfile
+
+    from PIL import Image
+
+    root = Path(__file__).resolve().parent.parent
+    monkeypatch.syspath_prepend(str(root / "dropin"))
+    for mname in [k for k in sys.modules if k.split(".")[0] == "third_party"]:
+        monkeypatch.delitem(sys.modules, mname)
+    VGGT = importlib.import_module("third_party.vggt.vggt.models.vggt").VGGT
+    load_and_preprocess_images = importlib.import_module("third_party.vggt.vggt.utils.load_fn").load_and_preprocess_images
+    pose_encoding_to_extri_intri = importlib.import_module("third_party.vggt.vggt.utils.pose_enc").pose_encoding_to_extri_intri
+    unproject_depth_map_to_point_map = importlib.import_module("third_party.vggt.vggt.utils.geometry").unproject_depth_map_to_point_map
+    for fn in (VGGT, load_and_preprocess_images, pose_encoding_to_extri_intri, unproject_depth_map_to_point_map):
+        assert fn.__module__.startswith("evoworld_b200"), fn
+    mcfg = {k: v for k, v in CFG.items() if k not in ("seed", "img_size", "patch_size", "embed_dim")}
+    state = V.random_state_dict(CFG, seed=8)
+    state["track_head.feature_extractor.norm.weight"] = torch.zeros(4)          # model.pt carries the track head as well
+    # VGGTProcessor.__init__ (:120-127) and __call__ (:129-136)
+    model = VGGT(img_size=CFG["img_size"], patch_size=CFG["patch_size"], embed_dim=CFG["embed_dim"], **mcfg).to(cuda_device).eval()
+    model.load_state_dict(state)
+    perspective_frames = [f for f in np.random.default_rng(2).integers(0, 256, (3, 384, 512, 3), dtype=np.uint8)]
+    # run_vggt_inference (:336-367)
+    with tempfile.TemporaryDirectory() as tmp:
+        img_paths = []
+        for i, frame in enumerate(perspective_frames):
+            p = f"{tmp}/temp_{i:03d}.png"
+            Image.fromarray(frame.astype(np.uint8)).save(p)
+            img_paths.append(p)
+        images = load_and_preprocess_images(img_paths).to(cuda_device)
+        with torch.inference_mode(), torch.autocast(device_type="cuda", dtype=torch.bfloat16):
+            preds = model(images)
+    extrinsic, intrinsic = pose_encoding_to_extri_intri(preds["pose_enc"], images.shape[-2:])
+    preds["extrinsic"], preds["intrinsic"] = extrinsic, intrinsic
+    out = {k: (v.detach().cpu().numpy().squeeze(0) if isinstance(v, torch.Tensor) else v) for k, v in preds.items()}
+    world_points = unproject_depth_map_to_point_map(out["depth"], out["extrinsic"], out["intrinsic"])
+    assert out["depth"].shape == (3, 392, 518, 1) and out["depth_conf"].shape == (3, 392, 518) and world_points.shape == (3, 392, 518, 3)
+    assert out["extrinsic"].shape == (3, 3, 4) and out["intrinsic"].shape == (3, 3, 3) and out["images"].shape == (3, 3, 392, 518)
+    ours = V.run_vggt_inference(model, perspective_frames, lift_dtype=torch.float64)
+    for k in ("depth", "depth_conf", "pose_enc", "extrinsic", "intrinsic", "images", "world_points"):
+        assert np.array_equal(out[k], ours[k].cpu().numpy()), k
+    assert np.array_equal(world_points, ours["world_points_from_depth"].cpu().numpy())
