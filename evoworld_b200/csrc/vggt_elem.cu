@@ -20,82 +20,86 @@
 namespace evw {
 namespace {
 
-// Eight threads per (token row, q|k, head): thread `sub` holds features 8 sub .. 8 sub + 7 of the 64 (one 16-byte load; a
-// warp covers 4 consecutive heads = 512 contiguous bytes).  LayerNorm over the 64 features (3 shuffle stages inside the
-// 8-lane group), then per 32-feature half (sub < 4: vertical, position y; else horizontal, position x):
+// Eight threads per (token row, q|k): thread `sub` owns features 8 sub .. 8 sub + 7 of EVERY head of its row (one 16-byte
+// load per head; the 8 threads cover a head's 128 contiguous bytes) and keeps the LayerNorm weights and the row's cos / sin
+// in registers across the heads — read per head they made the kernel L1-bound (l1tex 81 %, 128 B of table reads per 16 B of
+// data: profiles/r02aq_ncu_full_vggt_elem.txt).  LayerNorm over the 64 features (3 shuffle stages inside the 8-lane group),
+// then per 32-feature half (sub < 4: vertical, position y; else horizontal, position x):
 // out[j] = t[j] cos[p][j % 16] + rot[j] sin[p][j % 16] with rot = (-t[16:], t[:16]) — the partner feature j +- 16 sits in
 // the thread two lanes away (sub ^ 2), same slot.  cos / sin: fp32 [max_pos, 16].
 __global__ void __launch_bounds__(256)
-qknorm_rope_kernel(__half* __restrict__ qkv, long long items, int heads, int tokens_per_frame, const int* __restrict__ pos_yx,
-                   const float* __restrict__ q_gamma, const float* __restrict__ q_beta, const float* __restrict__ k_gamma,
-                   const float* __restrict__ k_beta, const float* __restrict__ cos_t, const float* __restrict__ sin_t, float eps) {
+qknorm_rope_kernel(__half* __restrict__ qkv, long long items /* rows * 2 */, int heads, int tokens_per_frame,
+                   const int* __restrict__ pos_yx, const float* __restrict__ q_gamma, const float* __restrict__ q_beta,
+                   const float* __restrict__ k_gamma, const float* __restrict__ k_beta, const float* __restrict__ cos_t,
+                   const float* __restrict__ sin_t, float eps) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = (t >> 3) < items;
   const long long item = live ? (t >> 3) : items - 1;  // tail lanes shadow the last item (they take part in the shuffles)
   const int sub = (int)(t & 7);
-  const int per_row = 2 * heads;
-  const long long row = item / per_row;
-  const int rem = (int)(item - row * per_row);
-  const int which = rem >= heads ? 1 : 0;
+  const long long row = item >> 1;
+  const int which = (int)(item & 1);
   const int C = heads * 64;
-  __half* p = qkv + row * (3ll * C) + (long long)rem * 64 + sub * 8;  // q heads then k heads: rem * 64 = which * C + head * 64
-  const uint4 raw = *reinterpret_cast<const uint4*>(p);
-  float x[8];
+  __half* p = qkv + row * (3ll * C) + (long long)which * C + sub * 8;
+  float g[8], b[8], cs[8], sn[8];
   {
-    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+    const float4* g4 = reinterpret_cast<const float4*>((which ? k_gamma : q_gamma) + sub * 8);
+    const float4* b4 = reinterpret_cast<const float4*>((which ? k_beta : q_beta) + sub * 8);
+    const int tok = (int)(row % tokens_per_frame);
+    const int pos = pos_yx[2 * tok + (sub < 4 ? 0 : 1)];
+    const float4* c4 = reinterpret_cast<const float4*>(cos_t + pos * 16 + (sub & 1) * 8);
+    const float4* s4 = reinterpret_cast<const float4*>(sin_t + pos * 16 + (sub & 1) * 8);
+    const float sgn = (sub & 2) ? 1.0f : -1.0f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __half22float2(h2[i]);
-      x[2 * i] = f.x; x[2 * i + 1] = f.y;
+    for (int hf = 0; hf < 2; ++hf) {
+      const float4 gv = __ldg(g4 + hf), bv = __ldg(b4 + hf), cv = __ldg(c4 + hf), sv = __ldg(s4 + hf);
+      g[4 * hf] = gv.x; g[4 * hf + 1] = gv.y; g[4 * hf + 2] = gv.z; g[4 * hf + 3] = gv.w;
+      b[4 * hf] = bv.x; b[4 * hf + 1] = bv.y; b[4 * hf + 2] = bv.z; b[4 * hf + 3] = bv.w;
+      cs[4 * hf] = cv.x; cs[4 * hf + 1] = cv.y; cs[4 * hf + 2] = cv.z; cs[4 * hf + 3] = cv.w;
+      sn[4 * hf] = sgn * sv.x; sn[4 * hf + 1] = sgn * sv.y; sn[4 * hf + 2] = sgn * sv.z; sn[4 * hf + 3] = sgn * sv.w;
     }
   }
-  float s = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+  uint4 raw = *reinterpret_cast<const uint4*>(p);
+  for (int h = 0; h < heads; ++h) {
+    uint4 nxt = raw;
+    if (h + 1 < heads) nxt = *reinterpret_cast<const uint4*>(p + (h + 1) * 64);  // next head in flight during this one's math
+    float x[8];
+    {
+      const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
-  for (int o = 4; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s * (1.0f / 64.0f);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    x[i] -= mean;
-    q = fmaf(x[i], x[i], q);
-  }
-#pragma unroll
-  for (int o = 4; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q * (1.0f / 64.0f) + eps);
-  const float4* g4 = reinterpret_cast<const float4*>((which ? k_gamma : q_gamma) + sub * 8);
-  const float4* b4 = reinterpret_cast<const float4*>((which ? k_beta : q_beta) + sub * 8);
-  const int tok = (int)(row % tokens_per_frame);
-  const int pos = pos_yx[2 * tok + (sub < 4 ? 0 : 1)];
-  const float4* c4 = reinterpret_cast<const float4*>(cos_t + pos * 16 + (sub & 1) * 8);
-  const float4* s4 = reinterpret_cast<const float4*>(sin_t + pos * 16 + (sub & 1) * 8);
-  const float sgn = (sub & 2) ? 1.0f : -1.0f;
-  float y[8];
-#pragma unroll
-  for (int hf = 0; hf < 2; ++hf) {
-    const float4 g = __ldg(g4 + hf), b = __ldg(b4 + hf);
-    y[4 * hf] = fmaf(x[4 * hf] * rstd, g.x, b.x);
-    y[4 * hf + 1] = fmaf(x[4 * hf + 1] * rstd, g.y, b.y);
-    y[4 * hf + 2] = fmaf(x[4 * hf + 2] * rstd, g.z, b.z);
-    y[4 * hf + 3] = fmaf(x[4 * hf + 3] * rstd, g.w, b.w);
-  }
-  float o[8];
-#pragma unroll
-  for (int hf = 0; hf < 2; ++hf) {
-    const float4 c = __ldg(c4 + hf), sn = __ldg(s4 + hf);
-    const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {sn.x, sn.y, sn.z, sn.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float partner = __shfl_xor_sync(0xffffffffu, y[4 * hf + i], 2);
-      o[4 * hf + i] = fmaf(y[4 * hf + i], cc[i], sgn * partner * ss[i]);
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h2[i]);
+        x[2 * i] = f.x; x[2 * i + 1] = f.y;
+      }
     }
-  }
-  if (live) {
-    uint4 w;
-    __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
-    __half2 h2 = __floats2half2_rn(o[4], o[5]), h3 = __floats2half2_rn(o[6], o[7]);
-    w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
-    w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
-    *reinterpret_cast<uint4*>(p) = w;
+    float s = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+#pragma unroll
+    for (int o = 4; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / 64.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      x[i] -= mean;
+      q = fmaf(x[i], x[i], q);
+    }
+#pragma unroll
+    for (int o = 4; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.0f / 64.0f) + eps);
+    float o8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float y = fmaf(x[i] * rstd, g[i], b[i]);
+      const float partner = __shfl_xor_sync(0xffffffffu, y, 2);
+      o8[i] = fmaf(y, cs[i], partner * sn[i]);
+    }
+    if (live) {
+      uint4 w;
+      __half2 h0 = __floats2half2_rn(o8[0], o8[1]), h1 = __floats2half2_rn(o8[2], o8[3]);
+      __half2 h2 = __floats2half2_rn(o8[4], o8[5]), h3 = __floats2half2_rn(o8[6], o8[7]);
+      w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
+      w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(p + h * 64) = w;
+    }
+    raw = nxt;
   }
 }
 
@@ -104,15 +108,15 @@ qknorm_rope_kernel(__half* __restrict__ qkv, long long items, int heads, int tok
 template <bool OUT_HALF>
 __global__ void __launch_bounds__(256)
 bilinear_ac_kernel(const float* __restrict__ src, void* __restrict__ dst, const float* __restrict__ addend, int F, int h, int w,
-                   int H, int W, int C4, float sy, float sx) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)F * H * W * C4;
-  if (i >= total) return;
-  const int c = (int)(i % C4);
-  long long t = i / C4;
-  const int x = (int)(t % W); t /= W;
-  const int y = (int)(t % H);
-  const int f = (int)(t / H);
+                   int H, int W, int C4, int c4_shift, float sy, float sx) {
+  // grid (ceil(W C4 / 256), H, F): the row / frame come from the block index, one division (a shift when C4 is a power of
+  // two) splits the rest into (x, channel quad) — three 64-bit divisions per thread made the first version issue-bound
+  // (80 % issue, 5 % DRAM: profiles/r02aq_ncu_full_vggt_elem.txt)
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= W * C4) return;
+  const int x = c4_shift >= 0 ? (idx >> c4_shift) : idx / C4;
+  const int c = idx - x * C4;
+  const int y = blockIdx.y, f = blockIdx.z;
   const float fy = sy * y, fx = sx * x;
   const int y0 = (int)fy, x0 = (int)fx;
   const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
@@ -125,17 +129,19 @@ bilinear_ac_kernel(const float* __restrict__ src, void* __restrict__ dst, const 
   r.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
   r.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
   r.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+  const long long pix = (long long)y * W + x;
   if (addend) {
-    const float4 ad = __ldg(reinterpret_cast<const float4*>(addend) + ((long long)y * W + x) * C4 + c);
+    const float4 ad = __ldg(reinterpret_cast<const float4*>(addend) + pix * C4 + c);
     r.x += ad.x; r.y += ad.y; r.z += ad.z; r.w += ad.w;
   }
+  const long long o = ((long long)f * H * W + pix) * C4 + c;
   if (OUT_HALF) {
     __half2 h0 = __floats2half2_rn(r.x, r.y), h1 = __floats2half2_rn(r.z, r.w);
     uint2 u;
     u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-    reinterpret_cast<uint2*>(dst)[i] = u;
+    reinterpret_cast<uint2*>(dst)[o] = u;
   } else {
-    reinterpret_cast<float4*>(dst)[i] = r;
+    reinterpret_cast<float4*>(dst)[o] = r;
   }
 }
 
@@ -186,7 +192,7 @@ extern "C" int evw_qknorm_rope_f16(void* qkv, int64_t rows, int heads, int token
   EVW_CHECK_ARG(qkv && pos_yx && q_gamma && q_beta && k_gamma && k_beta && cos_t && sin_t, "evw_qknorm_rope_f16: null pointer");
   EVW_CHECK_ARG(rows >= 0 && heads >= 1 && tokens_per_frame >= 1, "evw_qknorm_rope_f16: bad extents");
   if (rows == 0) return EVW_OK;
-  const long long items = rows * heads * 2;  // (row, q|k, head): 8 threads each
+  const long long items = rows * 2;  // (row, q|k): 8 threads each, looping over the heads
   const long long blocks = (items * 8 + 255) / 256;
   EVW_CHECK_ARG(blocks < (1ll << 31), "evw_qknorm_rope_f16: too many rows");
   EVW_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)q_gamma & 15) == 0 && ((uintptr_t)q_beta & 15) == 0 && ((uintptr_t)k_gamma & 15) == 0 &&
@@ -202,15 +208,20 @@ extern "C" int evw_bilinear_ac_f32(const float* src, void* dst, int out_fp16, co
                                    int C, void* stream) {
   EVW_CHECK_ARG(src && dst && F >= 1 && h >= 1 && w >= 1 && H >= 1 && W >= 1 && C >= 4 && C % 4 == 0,
                 "evw_bilinear_ac_f32: bad arguments (C must be a multiple of 4)");
-  const long long total = (long long)F * H * W * (C / 4);
-  const long long blocks = (total + 255) / 256;
-  EVW_CHECK_ARG(blocks < (1ll << 31), "evw_bilinear_ac_f32: output too large");
+  EVW_CHECK_ARG(H <= 65535 && F <= 65535 && (long long)W * (C / 4) < (1ll << 31), "evw_bilinear_ac_f32: output too large");
+  const int C4 = C / 4;
+  int shift = -1;
+  if ((C4 & (C4 - 1)) == 0) {
+    shift = 0;
+    while ((1 << shift) < C4) ++shift;
+  }
+  const dim3 grid((unsigned)((W * C4 + 255) / 256), (unsigned)H, (unsigned)F);
   const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.0f;
   const float sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.0f;
   if (out_fp16)
-    evw::bilinear_ac_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, addend, F, h, w, H, W, C / 4, sy, sx);
+    evw::bilinear_ac_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, addend, F, h, w, H, W, C4, shift, sy, sx);
   else
-    evw::bilinear_ac_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, addend, F, h, w, H, W, C / 4, sy, sx);
+    evw::bilinear_ac_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, addend, F, h, w, H, W, C4, shift, sy, sx);
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }

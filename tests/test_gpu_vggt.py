@@ -65,7 +65,7 @@ def test_qknorm_rope(frames, h0, w0, heads, cuda_device, built_lib):
 
 
 @pytest.mark.parametrize("F_,h,w,H,W,C", [(2, 3, 4, 5, 7, 128), (3, 5, 7, 10, 14, 64), (1, 40, 56, 70, 98, 64), (1, 1, 1, 3, 2, 8),
-                                          (2, 7, 9, 7, 9, 4), (1, 224, 296, 392, 518, 128)])
+                                          (2, 7, 9, 7, 9, 4), (1, 224, 296, 392, 518, 128), (2, 5, 6, 11, 13, 12)])
 @pytest.mark.parametrize("out_dtype", [torch.float16, torch.float32])
 def test_bilinear_align_corners(F_, h, w, H, W, C, out_dtype, cuda_device, built_lib):
     torch.manual_seed(1)
