@@ -89,6 +89,7 @@ SIGNATURES = {
     "evw_qknorm_rope_f16": (c_int, [c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_float, c_void_p]),
     "evw_bilinear_ac_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "evw_patchify_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, C.POINTER(c_float), C.POINTER(c_float), c_void_p]),
     "evw_relu_inplace_f16": (c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
     "evw_adaln_modulate_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "evw_dpt_activate_f32": (c_int, [c_void_p, c_i64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

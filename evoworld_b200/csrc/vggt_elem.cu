@@ -10,6 +10,7 @@
 //                        last, optional per-pixel addend (the uv positional embedding of dpt_head.py:258-259), fp16 or fp32 out
 //   adaln_modulate_kernel heads/camera_head.py:118-122  gate * (LN(x) * (1 + scale) + shift) + x
 //   dpt_activate_kernel  heads/head_act.py:62-112 (exp / inv_log points, 1 + exp confidence)
+//   patchify_kernel      models/aggregator.py:201 + layers/patch_embed.py:66-77: normalised 14 x 14 patches as GEMM rows
 #include "common.h"
 
 #include <cuda_fp16.h>
@@ -145,6 +146,31 @@ bilinear_ac_kernel(const float* __restrict__ src, void* __restrict__ dst, const 
   }
 }
 
+// DINOv2 patch embedding operand (layers/patch_embed.py:66-77 + the image normalisation of models/aggregator.py:201): images
+// fp32 [F, 3, H, W] in [0, 1] -> fp16 [F * (H/p) * (W/p), Kp] rows = patches, columns = (channel, ky, kx) of the normalised
+// pixel (x - mean[c]) / std[c], zero-padded from 3 p^2 to Kp (a whole number of 64-wide GEMM K blocks).
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float* __restrict__ img, __half* __restrict__ out, long long rows, int H, int W, int p, int Kp, float m0, float m1,
+                float m2, float s0, float s1, float s2) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * Kp) return;
+  const long long row = i / Kp;
+  const int k = (int)(i - row * Kp);
+  const int pp = p * p;
+  float v = 0.f;
+  if (k < 3 * pp) {
+    const int c = k / pp, r = k - c * pp;
+    const int ky = r / p, kx = r - ky * p;
+    const int w0 = W / p, h0 = H / p;
+    const long long f = row / ((long long)h0 * w0);
+    const int pr = (int)(row - f * h0 * w0);
+    const int py = pr / w0, px = pr - py * w0;
+    const float x = img[((f * 3 + c) * H + (py * p + ky)) * (long long)W + px * p + kx];
+    v = __fdiv_rn(x - (c == 0 ? m0 : (c == 1 ? m1 : m2)), c == 0 ? s0 : (c == 1 ? s1 : s2));
+  }
+  out[i] = __float2half_rn(v);
+}
+
 // x <- relu(x) in place (fp32) and its fp16 copy: ResidualConvUnit's nn.ReLU(inplace=True) (heads/dpt_head.py:333,397) — the
 // convolution reads the fp16 copy, the skip connection (:410) the overwritten fp32 tensor.
 __global__ void relu_inplace_kernel(float* __restrict__ x, __half* __restrict__ out, long long n4) {
@@ -222,6 +248,20 @@ extern "C" int evw_bilinear_ac_f32(const float* src, void* dst, int out_fp16, co
     evw::bilinear_ac_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, addend, F, h, w, H, W, C4, shift, sy, sx);
   else
     evw::bilinear_ac_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, addend, F, h, w, H, W, C4, shift, sy, sx);
+  EVW_LAUNCH_CHECK();
+  return EVW_OK;
+}
+
+extern "C" int evw_patchify_f16(const float* images, void* out, int F, int H, int W, int patch, int Kp, const float* mean3,
+                                const float* std3, void* stream) {
+  EVW_CHECK_ARG(images && out && mean3 && std3 && F >= 1 && patch >= 1 && H >= patch && W >= patch && H % patch == 0 && W % patch == 0,
+                "evw_patchify_f16: bad arguments (H and W must be multiples of the patch size)");
+  EVW_CHECK_ARG(Kp >= 3 * patch * patch && Kp % 8 == 0, "evw_patchify_f16: Kp=%d must cover 3 p^2 and be a multiple of 8", Kp);
+  const long long rows = (long long)F * (H / patch) * (W / patch);
+  const long long blocks = (rows * Kp + 255) / 256;
+  EVW_CHECK_ARG(blocks < (1ll << 31), "evw_patchify_f16: too many patches");
+  evw::patchify_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(images, (__half*)out, rows, H, W, patch, Kp, mean3[0], mean3[1],
+                                                                           mean3[2], std3[0], std3[1], std3[2]);
   EVW_LAUNCH_CHECK();
   return EVW_OK;
 }

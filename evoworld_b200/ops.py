@@ -219,6 +219,21 @@ def bilinear_ac(src: torch.Tensor, H: int, W: int, out_dtype=torch.float16, adde
     return out
 
 
+def patchify_f16(images: torch.Tensor, patch: int, Kp: int, mean: Sequence[float], std: Sequence[float]) -> torch.Tensor:
+    """images fp32 [F, 3, H, W] -> fp16 [F (H/p) (W/p), Kp]: rows = patches, columns = (channel, ky, kx) of (x - mean[c]) / std[c],
+    zero-padded to Kp — the operand of the patch-embedding GEMM (evw_patchify_f16)."""
+    _lib.require_cuda(images, "images")
+    F_, Cc, H, W = images.shape
+    assert Cc == 3 and images.dtype == torch.float32 and images.is_contiguous()
+    out = torch.empty((F_ * (H // patch) * (W // patch), Kp), dtype=torch.float16, device=images.device)
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    s = (C.c_float * 3)(*[float(v) for v in std])
+    with torch.cuda.device(images.device):
+        _lib.check(_lib.lib().evw_patchify_f16(_lib.ptr(images), _lib.ptr(out), F_, H, W, patch, Kp, m, s, _lib.stream_ptr(images.device)),
+                   "evw_patchify_f16")
+    return out
+
+
 def relu_inplace_f16(x: torch.Tensor) -> torch.Tensor:
     """x fp32 <- relu(x) in place; returns the fp16 copy (evw_relu_inplace_f16: nn.ReLU(inplace=True) feeding a convolution)."""
     _lib.require_cuda(x, "x")

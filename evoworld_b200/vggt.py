@@ -414,12 +414,8 @@ class VGGT:
         Fr, h0, w0 = B * S, H // p, W // p
         n = h0 * w0
         P = n + 1 + r
-        mean = torch.tensor(RESNET_MEAN, device=dev).view(1, 3, 1, 1)
-        std = torch.tensor(RESNET_STD, device=dev).view(1, 3, 1, 1)
-        x = (images.reshape(Fr, 3, H, W).to(torch.float32) - mean) / std
-        cols = F.unfold(x, kernel_size=p, stride=p).transpose(1, 2).reshape(Fr * n, -1)
-        a = torch.zeros((Fr * n, T["patch.weight"].shape[1]), dtype=torch.float16, device=dev)
-        a[:, : cols.shape[1]] = cols
+        # image normalisation (aggregator.py:201) + the 14 x 14 patches as rows of the patch-embedding GEMM, in one kernel
+        a = ops.patchify_f16(images.reshape(Fr, 3, H, W).to(torch.float32).contiguous(), p, T["patch.weight"].shape[1], RESNET_MEAN, RESNET_STD)
         cls_pos, patch_pos = self._pos_tokens(h0, w0)
         v = "aggregator.patch_embed."
         # PatchEmbed conv (k = stride = patch) + bias + the patch rows of the position table in one GEMM epilogue

@@ -340,6 +340,9 @@ int evw_vae_plan_info(void* handle, int mode, int64_t* launches, double* flops, 
  * evw_bilinear_ac_f32: heads/dpt_head.py:463-484 (F.interpolate bilinear, align_corners=True) on channels-last src fp32
  *   [F,h,w,C] -> dst [F,H,W,C] fp16 (out_fp16) or fp32, optional addend fp32 [H*W, C] added per pixel (the uv positional
  *   embedding of dpt_head.py:258-259).  C a multiple of 4.
+ * evw_patchify_f16: the operand of the DINOv2 patch-embedding GEMM (models/aggregator.py:201 image normalisation +
+ *   layers/patch_embed.py:66-77 Conv2d(k = stride = patch)): images fp32 [F,3,H,W] -> out fp16 [F (H/p) (W/p), Kp], columns
+ *   (channel, ky, kx) of (x - mean3[c]) / std3[c] (mean3 / std3: HOST pointers), zero-padded from 3 p^2 to Kp.
  * evw_relu_inplace_f16: ResidualConvUnit's nn.ReLU(inplace=True) (heads/dpt_head.py:333,397,410): x fp32 [n] <- relu(x) in place
  *   (the skip connection then adds relu(x)) and out fp16 [n] = the same values (the convolution's operand).  n % 4 == 0.
  * evw_adaln_modulate_f32: heads/camera_head.py:118-122  out = gate * (xn * (1 + scale) + shift) + x, mod fp32 [rows, 3C] =
@@ -351,6 +354,8 @@ int evw_qknorm_rope_f16(void* qkv, int64_t rows, int heads, int tokens_per_frame
                         float eps, void* stream);
 int evw_bilinear_ac_f32(const float* src, void* dst, int out_fp16, const float* addend, int F, int h, int w, int H, int W, int C,
                         void* stream);
+int evw_patchify_f16(const float* images, void* out, int F, int H, int W, int patch, int Kp, const float* mean3, const float* std3,
+                     void* stream);
 int evw_relu_inplace_f16(float* x, void* out, int64_t n, void* stream);
 int evw_adaln_modulate_f32(const float* xn, const float* mod, const float* x, float* out, int64_t rows, int C, void* stream);
 int evw_dpt_activate_f32(const float* x, int64_t rows, int ld, int n_ch, int mode, float* pts, float* conf, void* stream);

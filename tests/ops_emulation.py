@@ -76,6 +76,14 @@ def activation_f16(x, mode="gelu"):
     return f(x).half()
 
 
+def patchify_f16(images, patch, Kp, mean, std):
+    x = (images - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    cols = F.unfold(x, kernel_size=patch, stride=patch).transpose(1, 2).reshape(-1, 3 * patch * patch)
+    out = torch.zeros((cols.shape[0], Kp), dtype=torch.float16)
+    out[:, : cols.shape[1]] = cols
+    return out
+
+
 def relu_inplace_f16(x):
     x.clamp_(min=0)
     return x.half()
@@ -119,5 +127,5 @@ def dpt_activate(x, n_ch, mode):
     return pts.contiguous(), 1 + torch.exp(x[:, n_ch - 1])
 
 
-ALL = ("gemm_f16", "spatial_attention", "small_attention", "layer_norm", "layer_norm_f32", "activation_f16", "relu_inplace_f16",
+ALL = ("patchify_f16", "gemm_f16", "spatial_attention", "small_attention", "layer_norm", "layer_norm_f32", "activation_f16", "relu_inplace_f16",
        "qknorm_rope_", "bilinear_ac", "adaln_modulate", "dpt_activate")

@@ -79,6 +79,17 @@ def test_bilinear_align_corners(F_, h, w, H, W, C, out_dtype, cuda_device, built
     assert rel_l2(got, want + add.view(1, H, W, C)) < tol
 
 
+@pytest.mark.parametrize("F_,H,W", [(3, 70, 98), (2, 392, 518), (1, 14, 14)])
+def test_patchify(F_, H, W, cuda_device, built_lib):
+    """Image normalisation + 14 x 14 patches as GEMM rows (evw_patchify_f16) == (x - mean) / std, F.unfold, fp16 cast, zero pad."""
+    g = torch.Generator(device="cpu"); g.manual_seed(H)
+    img = torch.rand((F_, 3, H, W), generator=g)
+    got = ops.patchify_f16(img.to(cuda_device), 14, 640, V.RESNET_MEAN, V.RESNET_STD)
+    want = E.patchify_f16(img, 14, 640, V.RESNET_MEAN, V.RESNET_STD)
+    assert got.shape == want.shape == (F_ * (H // 14) * (W // 14), 640) and torch.equal(got.cpu(), want)
+    assert not got[:, 588:].any()
+
+
 def test_elementwise_kernels(cuda_device, built_lib):
     torch.manual_seed(2)
     dev = cuda_device
