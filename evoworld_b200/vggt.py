@@ -597,10 +597,12 @@ class VGGT:
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward(self, images: torch.Tensor, query_points=None, frames_chunk_size: Optional[int] = 8) -> Dict[str, torch.Tensor]:
+    def forward(self, images: torch.Tensor, query_points=None, frames_chunk_size: Optional[int] = 32) -> Dict[str, torch.Tensor]:
         """models/vggt.py:27-92: images [S,3,H,W] or [B,S,3,H,W] in [0,1] -> pose_enc [B,S,9], depth [B,S,H,W,1], depth_conf
         [B,S,H,W], world_points [B,S,H,W,3], world_points_conf [B,S,H,W], images.  frames_chunk_size: the DPT heads process
-        this many frames at a time (heads/dpt_head.py:119-157; None = all at once)."""
+        this many frames at a time (heads/dpt_head.py:119-157 chunks by 8 to bound memory; frames are independent in the heads, so
+        the chunk size does not change the result — 32 keeps a segment's 25 frames in one pass, whose low-resolution layers then
+        fill the GPU; None = all at once)."""
         _lib.require_cuda(images, "images")
         if query_points is not None:
             raise NotImplementedError("VGGT track head (query_points) is not part of the reference loop and is not built")

@@ -79,6 +79,7 @@ def main():
     ap.add_argument("--no-eager", action="store_true")
     ap.add_argument("--no-point-head", action="store_true")
     ap.add_argument("--profile-once", action="store_true", help="one warm forward, then one forward between cudaProfilerStart / Stop (ncu --profile-from-start off)")
+    ap.add_argument("--dpt-chunk", type=int, default=32, help="frames per DPT-head pass (the reference: 8)")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -104,7 +105,7 @@ def main():
     torch.cuda.synchronize()
     res = {"frames": a.frames, "size": [a.height, a.width], "params": m.num_parameters(), "launches": c.launches,
            "tflop": {k: v / 1e12 for k, v in c.flops.items()}}
-    ms, best = timed(lambda: m(images), a.steps, a.warmup)
+    ms, best = timed(lambda: m(images, frames_chunk_size=a.dpt_chunk), a.steps, a.warmup)
     tf = sum(c.flops.values()) / 1e12
     res["native"] = {"ms": ms, "ms_best": best, "frames_per_s": a.frames / ms * 1e3, "tflops": tf / ms * 1e3}
     # sections
@@ -115,7 +116,7 @@ def main():
     pairs, dims = m._aggregate(images, keep=keep)
     B, S, P, H, W = dims
     sec["camera_head_ms"], _ = timed(lambda: m._camera(pairs[last], B, S, P), max(1, a.steps - 1), 1)
-    sec["depth_head_ms"], _ = timed(lambda: m._dpt_chunked(pairs, dims, "depth_head.", "exp", 2, 8), max(1, a.steps - 1), 1)
+    sec["depth_head_ms"], _ = timed(lambda: m._dpt_chunked(pairs, dims, "depth_head.", "exp", 2, a.dpt_chunk), max(1, a.steps - 1), 1)
     res["sections"] = sec
     del pairs
     print(json.dumps(res), flush=True)
