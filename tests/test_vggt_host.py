@@ -50,3 +50,20 @@ def test_host_orchestration_against_the_reference(emulated):
     print(errs)
     assert max(errs.values()) < 5e-3, errs
     assert out["images"].shape == (1, 3, 3, 70, 98)
+
+
+def test_batched_chunked_orchestration_against_the_oracle(emulated):
+    """Batch of two sequences, DPT heads chunked 2 + 1 frames: the row order (batch, frame, patch) through the aggregator, the
+    camera head and the chunked heads against the oracle restatement on the CPU."""
+    g = torch.Generator().manual_seed(5)
+    images = torch.rand((2, 3, 3, 56, 84), generator=g)
+    mcfg = {k: v for k, v in CFG.items() if k != "seed"}
+    sd = V.random_state_dict(CFG, seed=CFG["seed"])
+    with torch.no_grad():
+        want = O.vggt_forward(images, sd, mcfg)
+    out = emulated(images, frames_chunk_size=2)
+    for k in ("pose_enc", "depth", "depth_conf", "world_points", "world_points_conf"):
+        assert out[k].shape == want[k].shape, k
+        assert rel_l2(out[k], want[k].double().numpy()) < 5e-3, k
+    whole = emulated(images, frames_chunk_size=None)
+    assert torch.equal(whole["depth"], out["depth"]) and torch.equal(whole["world_points_conf"], out["world_points_conf"])
