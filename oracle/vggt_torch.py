@@ -305,3 +305,23 @@ def small_test_images(S: int = 3, H: int = 70, W: int = 98, seed: int = 7) -> to
     low = torch.rand((S, 3, H // 7, W // 7), generator=g)
     img = F.interpolate(low, size=(H, W), mode="bilinear", align_corners=False) * 0.8 + 0.2 * torch.rand((S, 3, H, W), generator=g)
     return img.clamp(0, 1)[None].contiguous()
+
+
+# ----------------------------------------------------------------------------- the full-size golden vectors (VGGT-1B, 2 x 392 x 518)
+FULL_TEST_SEED = 20251018
+
+
+def full_test_images(S: int = 2, H: int = 392, W: int = 518, seed: int = 9) -> torch.Tensor:
+    return small_test_images(S, H, W, seed)
+
+
+def subsample_full(out: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """The slices of a full-size result kept in tests/golden/vggt_1b_golden.npz (every 4th pixel of the maps, the special
+    tokens and every 16th patch token of two aggregator layers)."""
+    keep = {"pose_enc": out["pose_enc"]}
+    for k in ("depth", "depth_conf", "world_points", "world_points_conf"):
+        keep[k] = out[k][:, :, ::4, ::4].contiguous()
+    for k in ("tokens_last", "tokens_4"):
+        if k in out:
+            keep[k] = torch.cat([out[k][:, :, :5], out[k][:, :, 5::16]], dim=2).contiguous()
+    return keep

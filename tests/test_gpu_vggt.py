@@ -24,6 +24,7 @@ import ops_emulation as E  # noqa: E402
 pytestmark = pytest.mark.gpu
 TOL_VGGT = 2e-3
 TOL_POINTS = 4e-3
+TOL_POSE_1B = 4e-3
 CFG = O.SMALL_TEST_CONFIG
 
 
@@ -110,12 +111,12 @@ def test_elementwise_kernels(cuda_device, built_lib):
 
 
 # ----------------------------------------------------------------------------- the network
-def check(errs):
+def check(errs, pose_tol=TOL_VGGT):
     """depth / confidence / pose within TOL_VGGT; the point head's inv_log activation sign(v) expm1(|v|) multiplies the relative
     error of its pre-activation v by |v| e^|v| / (e^|v| - 1) >= 1 (about 2 at the |v| ~ 1.5 of random weights): TOL_POINTS."""
     pts = errs.get("world_points", 0.0)
-    rest = max(v for k, v in errs.items() if k != "world_points")
-    assert rest < TOL_VGGT and pts < TOL_POINTS, errs
+    rest = max(v for k, v in errs.items() if k not in ("world_points", "pose_enc"))
+    assert rest < TOL_VGGT and pts < TOL_POINTS and errs.get("pose_enc", 0.0) < pose_tol, errs
 
 
 def build(cfg, dev, seed, gpu_init=False):
@@ -276,3 +277,22 @@ def test_reference_vggt_call_sequence_through_dropin(cuda_device, built_lib, tmp
     for k in ("depth", "depth_conf", "pose_enc", "extrinsic", "intrinsic", "images", "world_points"):
         assert np.array_equal(out[k], ours[k].cpu().numpy()), k
     assert np.array_equal(world_points, ours["world_points_from_depth"].cpu().numpy())
+
+
+def test_vggt_1b_against_the_reference_modules(cuda_device, built_lib):
+    """The full VGGT-1B on two 392 x 518 frames against sub-sampled outputs of the REFERENCE's own modules at their default
+    configuration (tests/golden/vggt_1b_golden.npz, made by tests/golden/make_vggt_1b_golden.py) — host-seeded weights."""
+    vg = np.load(Path(__file__).resolve().parent / "golden" / "vggt_1b_golden.npz")
+    cfg = dict(V.DEFAULT_CONFIG)
+    m = V.VGGT(**cfg).to(cuda_device)
+    m.load_state_dict(V.random_state_dict(cfg, seed=O.FULL_TEST_SEED))
+    m.free_master_parameters()
+    out = m(O.full_test_images().to(cuda_device))
+    got = O.subsample_full({k: v for k, v in out.items() if k != "images"})
+    errs = {k: rel_l2(got[k], vg[k]) for k in ("pose_enc", "depth", "depth_conf", "world_points", "world_points_conf")}
+    print("vggt-1b vs reference modules:", {k: f"{v:.2e}" for k, v in errs.items()})
+    # measured (profiles/r02ay_vggt_1b_golden.log): depth 9.2e-4, confidence 1.3e-4, points 1.7e-3, pose 2.2e-3.  The pose encoding
+    # of two frames is 18 numbers (4 of them zero) out of four refinement iterations x four width-2048 blocks that the
+    # reference runs in fp32 and this path with fp16 operands; with these random weights its relative L2 ranges from 8.5e-4
+    # (test_vggt_1b_at_the_loop_resolution) to 2.2e-3 here: asserted <= TOL_POSE_1B
+    check(errs, pose_tol=TOL_POSE_1B)
