@@ -113,6 +113,9 @@ def run_ours(args, dev, rank, world, barrier, allreduce_max, peaks):
         "roofline": {"bound": "tensor", "kernel": "whole denoise step (tc_gemm_kernel + spatial_attn8_kernel dominate; per-kernel figures under kernels)",
                      "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
                      "traffic": None, "algorithmic_tflop_per_step": fl, "executed_tflop_per_step": plan_flops / 1e12,
+                     # the same fraction on the FLOPs the plan executes (folded cross-attention projections, fused up-sampling
+                     # convolutions): what the tensor pipe really does per second
+                     "frac_executed": plan_flops / 1e12 * (args.steps / (ms * 1e-3)) / peaks["tf_sustained"],
                      "kernels": kernels,
                      "peak_source": peaks["source"] + " (sustained bf16/fp16 dense)"},
         "gpu_launches": launches * args.steps,
