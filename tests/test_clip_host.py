@@ -51,3 +51,48 @@ def test_checkpoint_round_trip_and_errors(tmp_path):
     bad.pop("visual_projection.weight")
     with pytest.raises(RuntimeError):
         m.load_state_dict(bad)
+
+
+@pytest.mark.parametrize("act", ["gelu", "quick_gelu"])
+def test_host_orchestration_against_transformers(act, monkeypatch):
+    """The host logic of clip.py (weight packing, fused q/k/v, class / position rows, GELU in the GEMM epilogue or as a cast
+    pass) with the kernels swapped for the torch restatements of tests/ops_emulation.py, against transformers on the CPU."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    import ops_emulation as E
+
+    from evoworld_b200 import _lib, ops
+
+    for n in E.ALL:
+        monkeypatch.setattr(ops, n, getattr(E, n))
+    monkeypatch.setattr(_lib, "require_cuda", lambda t, name: None)
+    cfg = dict(SMALL, hidden_act=act)
+    torch.manual_seed(0)
+    hf = _hf(cfg)
+    with torch.no_grad():
+        for n, p in hf.named_parameters():
+            if "norm" in n:
+                p.copy_(torch.randn_like(p) * 0.2 + (1.0 if n.endswith("weight") else 0.0))
+            elif n.endswith("bias"):
+                p.copy_(torch.randn_like(p) * 0.05)
+    m = K.CLIPVisionModelWithProjection(**cfg)
+    m.load_state_dict(hf.state_dict())
+    x = torch.randn(2, 3, 56, 56)
+
+    class _Dev:   # the pack step only asks the device for its type
+        type = "cuda"
+
+    real = m._device
+    m._device = _Dev()
+    try:
+        T = m._pack()
+    finally:
+        m._device = real
+    assert T is m._packed
+    with torch.no_grad():
+        want = hf(pixel_values=x).image_embeds
+    got = m(x).image_embeds
+    err = float((got.double() - want.double()).norm() / want.double().norm())
+    assert got.shape == want.shape and err < 2e-3, err
